@@ -1,0 +1,220 @@
+"""Pins the CPU oracle against the known answers the reference's own tests assert
+(SURVEY.md section 4 / section 8c).  No GPU, no reference tree needed at run time."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import triqs_oracle as O
+
+F, B = O.FERMION, O.BOSON
+
+
+def one_pole_tau(En, tau, beta, stat):
+    """closed form used by test/c++/gfs/fourier_matsubara.cpp:56-66."""
+    s = -1.0 if stat == F else 1.0
+    if En > 0:
+        return -np.exp(-En * tau) / (1 - s * math.exp(-En * beta))
+    return s * np.exp(En * (beta - tau)) / (1 - s * math.exp(En * beta))
+
+
+@pytest.mark.parametrize("stat", [F, B])
+@pytest.mark.parametrize("ncols", [1, 4])
+def test_fourier_matsubara_cpp(stat, ncols):
+    """test/c++/gfs/fourier_matsubara.cpp:23-114: beta=10, N_iw=1000, N_tau=10000, E=-1."""
+    beta, n_iw, n_tau, E = 10.0, 1000, 10000, -1.0
+    iw = O.imfreq_values(beta, stat, n_iw)
+    gw1 = 1 / (iw - E) + 1 / (iw + 2 * E) - 4.5 / (iw - 1.25 * E)
+    gw = np.repeat(gw1[:, None], ncols, axis=1)
+    gt = O.fourier_iw_to_tau(gw, beta, stat, n_tau)
+    gwb = O.fourier_tau_to_iw(gt, beta, stat, n_iw)
+    assert np.max(np.abs(gw - gwb)) < 1e-8
+    tau = O.tau_values(beta, n_tau)
+    exact = one_pole_tau(E, tau, beta, stat) + one_pole_tau(-2 * E, tau, beta, stat) - 4.5 * one_pole_tau(1.25 * E, tau, beta, stat)
+    assert np.max(np.abs(gt - exact[:, None])) < 1e-8
+    # tail from fit_tail passed explicitly (:68-72)
+    tail, err = O.fit_tail(gw, beta, stat)
+    gt_tail = O.fourier_iw_to_tau(gw, beta, stat, n_tau, tail)
+    assert np.max(np.abs(gt_tail - exact[:, None])) < 1e-8
+    # only 0th and 1st moment known (:74-83)
+    km = np.zeros((2, ncols), dtype=complex)
+    km[1] = -2.5
+    gt_km = O.fourier_iw_to_tau(gw, beta, stat, n_tau, km)
+    assert np.max(np.abs(gt_km - exact[:, None])) < 1e-8
+    # real-valued G(tau) input (:91-96)
+    gwc = O.fourier_tau_to_iw(np.repeat(exact[:, None], ncols, axis=1), beta, stat, n_iw)
+    assert np.max(np.abs(gw - gwc)) < 1e-8
+    # with a self energy, then 10 repeated round trips (:98-113)
+    sig = 1 / (iw - 2) + 3 / (iw + 3)
+    gw2 = np.repeat((1 / (iw - E - sig))[:, None], ncols, axis=1)
+    g = gw2
+    for _ in range(11):
+        g = O.fourier_tau_to_iw(O.fourier_iw_to_tau(g, beta, stat, n_tau), beta, stat, n_iw)
+    assert np.max(np.abs(g - gw2)) < 1e-8
+
+
+def test_fourier_positive_only_throws():
+    """test/c++/gfs/fourier_matsubara.cpp:127-136 (a positive-only mesh has odd/half size)."""
+    gw = np.zeros((1000 + 1, 1), dtype=complex)
+    with pytest.raises(O.TriqsRuntimeError):
+        O.fourier_iw_to_tau(gw, 10.0, F, 6001)
+
+
+def test_fit_tail_basic():
+    """test/c++/gfs/fit_tail_matsubara.cpp:27-72: c={0,1,3,5}, tail_fraction 0.3, 1e-8."""
+    beta, N = 10.0, 100
+    iw = O.imfreq_values(beta, F, N)
+    c = np.array([0, 1, 3, 5], dtype=complex)
+    gw = (c[0] + c[1] / iw + c[2] / iw / iw + c[3] / iw / iw / iw)[:, None]
+    for km in (np.zeros((1, 1), complex), np.array([[0.0], [1.0]], complex)):
+        tail, err = O.fit_tail(gw, beta, F, km, tail_fraction=0.3)
+        assert np.max(np.abs(tail[:4, 0] - c)) < 1e-8
+
+
+def test_fit_tail_real_f_and_b():
+    """fit_tail_matsubara.cpp:76-106: 1/(iw-1) moments {0,1,1,1,1}, 1e-9, Fermion and Boson."""
+    beta, N = 10.0, 100
+    km = np.array([[0.0], [1.0]], complex)
+    for stat, n_iw in ((F, N), (B, N - 1)):
+        iw = O.imfreq_values(beta, stat, n_iw)
+        tail, err = O.fit_tail((1 / (iw - 1))[:, None], beta, stat, km, tail_fraction=0.3)
+        assert np.max(np.abs(tail[:5, 0] - np.array([0, 1, 1, 1, 1]))) < 1e-9
+
+
+def test_fit_tail_complex():
+    """fit_tail_matsubara.cpp:110-130: complex pole a=1+0.4i, N=200, 1e-7."""
+    beta, N = 10.0, 200
+    a = 1.0 + 0.4j
+    iw = O.imfreq_values(beta, F, N)
+    tail, err = O.fit_tail((1 / (iw - a))[:, None], beta, F, np.array([[0.0], [1.0]], complex))
+    assert np.max(np.abs(tail[:5, 0] - np.array([0, 1, a, a ** 2, a ** 3]))) < 1e-7
+
+
+@pytest.mark.parametrize("eps", [0.001, 0.01, 0.1, 1, 10, 100])
+def test_fit_hermitian_tail_exact_moments(eps):
+    """test/python/base/tail_issues.py:74-102."""
+    Nw = int(max(25, eps * 60))
+    beta = 1.0
+    H = eps * np.array([[1.0, 0.1j], [-0.1j, 2.0]])
+    iw = O.imfreq_values(beta, F, Nw)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(2)[None] - H[None]).reshape(-1, 4)
+    mx = lambda x: np.max(np.abs(x))
+    for km in (None, np.vstack([np.zeros(4), np.eye(2).reshape(4)]).astype(complex)):
+        tail, err = O.fit_hermitian_tail(g, beta, F, km, inner_dim=2)
+        for n in range(3):
+            exact = np.linalg.matrix_power(H, n)
+            assert mx(exact - tail[1 + n].reshape(2, 2)) / mx(exact) < 1e-4
+        # result is hermitian moment by moment
+        for m in tail:
+            mm = m.reshape(2, 2)
+            assert mx(mm - mm.conj().T) < 1e-12 * max(1.0, mx(mm))
+
+
+def test_fit_iomega_n_error_large():
+    """tail_issues.py:30-37: fitting G = iw gives err > 1e-2."""
+    iw = O.imfreq_values(10.0, F, 1000)
+    g = np.stack([iw, 0 * iw, 0 * iw, iw], axis=1)
+    tail, err = O.fit_tail(g, 10.0, F)
+    assert err > 1e-2
+
+
+@pytest.mark.parametrize("eps", [0.001, 1, 100])
+def test_multi_fft(eps):
+    """tail_issues.py:41-72 (10 iterations instead of 100 to keep the CPU suite short)."""
+    Nw = int(max(25, eps * 60))
+    Ntau = 6 * Nw + 1
+    beta = 1.0
+    iw = O.imfreq_values(beta, F, Nw)
+    g_ref = np.linalg.inv((iw[:, None, None] + eps) * np.eye(2)[None]).reshape(-1, 4)
+    g = g_ref.copy()
+    fitter = O.TailFitter(beta, F, Nw)
+    for _ in range(10):
+        gt = O.fourier_iw_to_tau(g, beta, F, Ntau, fitter=fitter)
+        g = O.fourier_tau_to_iw(gt, beta, F, Nw)
+        assert np.max(np.abs(g - g_ref)) < 1e-9
+        assert np.linalg.norm(g[0].reshape(2, 2) - g[-1].reshape(2, 2).conj().T) < 1e-9
+
+
+def test_imag_gt_semicircular():
+    """tail_issues.py:104-112: Im G(tau) < 1e-11 for a semicircular DOS, beta=50, n=2000."""
+    beta, n = 50.0, 2000
+    iw = O.imfreq_values(beta, F, n)
+    D = 1.0
+    om = iw.imag
+    # SemiCircular(1): G(iw) = 2 (iw - i sign(w) sqrt(w^2 + D^2)) / D^2
+    g = (2 * (iw - 1j * np.sign(om) * np.sqrt(om ** 2 + D ** 2)) / D ** 2)[:, None]
+    gt = O.fourier_iw_to_tau(g, beta, F, O.adjoint_n_tau(n))
+    assert np.max(np.abs(gt.imag)) < 1e-11
+
+
+def test_hermiticity_default_meshes():
+    """test/c++/gfs/functions/hermiticity.cpp:34-48: n_iw=1025 -> n_tau=6151; G(iw)=G(-iw)^dagger kept to 1e-12."""
+    beta, n_iw = 10.0, 1025
+    assert O.adjoint_n_tau(n_iw) == 6151
+    iw = O.imfreq_values(beta, F, n_iw)
+    H = np.array([[1.0, 1j], [-1j, 2.0]])
+    g = np.linalg.inv(iw[:, None, None] * np.eye(2)[None] - H[None]).reshape(-1, 4)
+    gt = O.fourier_iw_to_tau(g, beta, F, 6151)
+    gt2 = gt.reshape(-1, 2, 2)
+    assert np.max(np.abs(gt2 - gt2.conj().transpose(0, 2, 1))) < 1e-12
+
+
+def test_g_r_k_exact():
+    """test/c++/gfs/g_r_k.cpp:28-62: FT of -2(cos kx + cos ky) on 10x10 is -1 at r=(+-1,0),(0,+-1)."""
+    N = 10
+    k = 2 * math.pi * np.arange(N) / N
+    gk = (-2 * (np.cos(k)[:, None] + np.cos(k)[None, :])).reshape(N * N, 1).astype(complex)
+    gr = O.fourier_lattice_k_to_r(gk, (N, N, 1)).reshape(N, N)
+    expect = np.zeros((N, N), complex)
+    expect[1, 0] = expect[N - 1, 0] = expect[0, 1] = expect[0, N - 1] = -1
+    assert np.max(np.abs(gr - expect)) < 1e-13
+    back = O.fourier_lattice_r_to_k(gr.reshape(N * N, 1), (N, N, 1))
+    assert np.max(np.abs(back - gk)) < 1e-13
+
+
+def test_lattice_round_trip_3d():
+    """test/c++/gfs/fourier_lattice.cpp:27-62 style round trip, plus sign convention on a plane wave."""
+    rng = np.random.default_rng(7)
+    dims = (4, 3, 5)
+    x = rng.normal(size=(60, 3)) + 1j * rng.normal(size=(60, 3))
+    assert np.max(np.abs(O.fourier_lattice_k_to_r(O.fourier_lattice_r_to_k(x, dims), dims) - x)) < 1e-13
+    # delta at r=(1,0,0) -> e^{+2 pi i k0/d0}
+    d = np.zeros((60, 1), complex)
+    d[1 * 15] = 1
+    gk = O.fourier_lattice_r_to_k(d, dims).reshape(dims)
+    assert np.allclose(gk[:, 0, 0], np.exp(2j * math.pi * np.arange(4) / 4))
+
+
+def test_interp_weights():
+    """test/c++/meshes/eval.cpp:62-89: imtime(beta=10, 5 pts): tau=2 -> .2 g0 + .8 g1; 3.5 -> .6 g1 + .4 g2."""
+    tab = np.array([[1.0], [10.0], [100.0], [1000.0], [1e4]], complex)
+    out = O.interp_tau(tab, 10.0, np.array([2.0, 3.5, 10.0, 0.0]))
+    assert np.allclose(out[:, 0], [0.2 * 1 + 0.8 * 10, 0.6 * 10 + 0.4 * 100, 1e4, 1.0], rtol=1e-14)
+
+
+def test_tail_fit_indices_c1():
+    """n_iw=1025 fermion -> 60 rows, first -1025 step 6.8333, second start 819."""
+    f = O.TailFitter(10.0, F, 1025)
+    assert len(f.fit_idx) == 60
+    assert f.fit_idx[0] == -1025 and f.fit_idx[1] == 1024 - 205
+    assert f.fit_idx[2] == int(-1025 + 205 / 30)
+
+
+def test_dyson_small_against_direct():
+    rng = np.random.default_rng(3)
+    n, nk, n_iw = 3, 17, 8
+    eps = rng.normal(size=(nk, n, n)) + 1j * rng.normal(size=(nk, n, n))
+    eps = eps + eps.conj().transpose(0, 2, 1)
+    iw = O.imfreq_values(10.0, F, n_iw)
+    sig = np.stack([np.eye(n) / (w - 0.5) for w in iw])
+    G = O.dyson_ksum(eps, sig, 10.0, F, 0.1, k_chunk=5)
+    for wi, w in enumerate(iw):
+        ref = sum(np.linalg.inv((w + 0.1) * np.eye(n) - e - sig[wi]) for e in eps) / nk
+        assert np.max(np.abs(G[wi] - ref)) < 1e-13
+
+
+def test_slice_bounds_matches_mpi_rule():
+    """python/triqs/utility/mpi_mpi4py.py:96-109."""
+    n, size = 11, 4
+    pieces = [O.slice_bounds(n, size, r) for r in range(size)]
+    assert pieces == [(0, 3), (3, 6), (6, 9), (9, 11)]
