@@ -1,0 +1,190 @@
+/* tqgpu.h -- C ABI of the B200-native TRIQS Green's-function hot path (libtqgpu.so).
+ *
+ * Every entry point replaces one seam of the reference (TRIQS 3.3.1, paths relative
+ * to its tree); the seam is cited next to the declaration.  All arrays are row-major
+ * ("C order") interleaved complex<double> (re, im) exactly as the reference's
+ * flattened 2-D views `[rows, n_others]` (c++/triqs/gfs/gf/flatten.hpp:33-47).
+ *
+ * Pointers may be host or device pointers; the library detects which
+ * (cudaPointerGetAttributes).  Host buffers are staged through pinned/device memory
+ * inside the call; device buffers are used in place on the context's stream.
+ * Every function returns TQ_OK (0) or a negative tq_status; tq_last_error(ctx) holds
+ * the message the reference would have thrown (triqs::runtime_error text,
+ * c++/triqs/utility/exceptions.hpp:31-37).  There is no CPU fallback: without a CUDA
+ * device tq_create fails.
+ */
+#ifndef TQGPU_H
+#define TQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tq_ctx tq_ctx;
+
+/* interleaved complex<double>; layout-compatible with std::complex<double>, fftw_complex, numpy complex128 */
+typedef struct { double re, im; } tq_complex;
+
+typedef enum {
+  TQ_OK = 0,
+  TQ_ERR_CUDA = -1,            /* a CUDA runtime call failed (message has the cudaError string)           */
+  TQ_ERR_INVALID = -2,         /* bad argument                                                            */
+  TQ_ERR_RUNTIME = -3,         /* a condition on which the reference throws triqs::runtime_error          */
+  TQ_ERR_UNSUPPORTED = -4,     /* shape outside what the kernels implement (e.g. FFT length with a prime
+                                  factor > TQ_MAX_GENERIC_RADIX that does not fit the two-pass scheme)     */
+  TQ_ERR_NO_DEVICE = -5,       /* no CUDA device: the library never computes on the CPU                   */
+  TQ_ERR_COMM = -6             /* NCCL failure                                                            */
+} tq_status;
+
+/* c++/triqs/mesh/domains/matsubara.hpp: enum statistic_enum { Boson = 0, Fermion = 1 } */
+enum { TQ_BOSON = 0, TQ_FERMION = 1 };
+
+/* warning bits: the reference prints these to std::cerr; the C++ shim re-prints the same text */
+enum {
+  TQ_WARN_NOISY_TAU = 1,      /* fourier_matsubara.cpp:109-110 (moments cannot be deduced, zero tail used)  */
+  TQ_WARN_SHORT_TAU_MESH = 2, /* fourier_matsubara.cpp:131-133 (L < 6 n_iw)                                 */
+  TQ_WARN_TAIL_ERR = 4        /* fourier_matsubara.cpp:208-210 (tail error > 1e-4)                          */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* One context per host thread / GPU (the reference is single threaded; its FFTW planner and the
+ * mutable tail_fitter cache are not thread safe: fourier_common.cpp:30, tail_fitter.hpp:310-324).
+ * The context owns a stream, the plan/twiddle/tail-fitter caches keyed by mesh parameters, staging
+ * buffers and (optionally) an NCCL communicator. */
+tq_status tq_create(int device, tq_ctx **out);
+void tq_destroy(tq_ctx *ctx);
+const char *tq_last_error(const tq_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void *tq_stream(tq_ctx *ctx);
+/* block until all work enqueued by this context has finished */
+tq_status tq_synchronize(tq_ctx *ctx);
+/* number of kernel launches issued by this context since creation (bench.py reports the delta) */
+uint64_t tq_launch_count(const tq_ctx *ctx);
+/* library build id string ("tqgpu <version> sm_100a") */
+const char *tq_version(void);
+
+/* ---- Matsubara transforms ------------------------------------------------------------------ */
+
+/* Replaces  gf_vec_t<imfreq> _fourier_impl(imfreq const&, gf_vec_cvt<imtime>, array_const_view<dcomplex,2>)
+ *           c++/triqs/gfs/transform/fourier.hpp:39-40, fourier_matsubara.cpp:96-186
+ * for `batch` independent gfs of identical mesh/shape (the reference loops blocks sequentially,
+ * c++/triqs/gfs/block/map.hpp:35-40).
+ *   gt       [batch][n_tau][n_others]
+ *   moments  [batch][n_moments][n_others] known high-frequency moments, or NULL / n_moments = 0:
+ *            then the tau-derivative estimate fit_tail(gt) (fourier_matsubara.cpp:39-92) is used, with
+ *            the noise heuristic of :100-114.
+ *   gw       [batch][n_w][n_others], n_w = 2 n_iw (Fermion) or 2 n_iw - 1 (Boson), index n - first_index
+ *   warn     host int[batch] receiving TQ_WARN_* bits, or NULL
+ * Errors (TQ_ERR_RUNTIME): |0th moment| >= 1e-8 (:116-118); n_tau - 1 < 2 n_iw (:127-129). */
+tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                               const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn);
+
+/* Replaces  gf_vec_t<imtime> _fourier_impl(imtime const&, gf_vec_cvt<imfreq>, array_const_view<dcomplex,2>)
+ *           c++/triqs/gfs/transform/fourier.hpp:47-48, fourier_matsubara.cpp:190-271.
+ *   gw       [batch][n_w][n_others] on the FULL mesh (a positive-only mesh throws, :192)
+ *   moments  as above; with fewer than 4 moments the least-squares fit_tail(gw, known) of the mesh's
+ *            tail fitter (default parameters, tail_fitter.hpp:92,95) completes them (:203-212)
+ *   gt       [batch][n_tau][n_others]
+ *   tail_err host double[batch] receiving the fit error of each gf (0 if no fit), or NULL
+ * Errors: 0th moment (:199-201); fit error >= 1e-2 (:205-207); < 4 moments after fit (:211); mesh too short (:218-220). */
+tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                               const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
+                               double *tail_err);
+
+/* ---- least-squares tail fit ------------------------------------------------------------------ */
+
+/* Replaces  tail_fitter::fit<0, hermitian>(mesh, g_data, normalize=true, known_moments, inner_matrix_dim)
+ *           c++/triqs/mesh/tail_fitter.hpp:192-297 and the free functions fit_tail / fit_hermitian_tail
+ *           c++/triqs/gfs/functions/functions2.hpp:50-56, 94-110.
+ *   g            [batch][n_w][n_cols] on the full imfreq mesh (beta, statistic, n_iw)
+ *   known        [batch][n_known][n_cols] or NULL
+ *   tail_fraction, n_tail_max, expansion_order (-1 = adaptive)  tail_fitter.hpp:302-321
+ *   hermitian    0 / 1;  inner_dim = d of the d x d target (n_cols must be a multiple of d*d), 1 for scalar
+ *   out_moments  [batch][*out_n_moments][n_cols]; the caller provides room for TQ_MAX_MOMENTS rows per gf;
+ *                rows are written densely with *out_n_moments rows
+ *   out_err      host double[batch]
+ * Errors: "Insufficient data points for least square procedure" (:157), "Conditioning of tail-fit violates
+ * boundary" (:180), known_moments shape mismatch. */
+#define TQ_MAX_MOMENTS 10
+tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max,
+                      int expansion_order, int hermitian, int inner_dim, long n_cols, long batch, const tq_complex *g,
+                      const tq_complex *known, int n_known, tq_complex *out_moments, int *out_n_moments, double *out_err);
+
+/* The mesh-only part of the fit (fit indices, Vandermonde, SVD pseudo-inverse, chosen order), i.e. what the
+ * reference caches in tail_fitter::_lss (tail_fitter.hpp:140-181).  Pure host code (plan creation, no GPU
+ * needed, no ctx): exposed so that tests can compare it with LAPACK.
+ *   idx_out   long[2 n_tail]                   fit indices (Matsubara n)
+ *   pinv_out  [n_var][rows] complex, rows = n_idx (plain) or 2 n_idx (hermitian: stacked [A; conj A])
+ *   sv_out    double[n_var] singular values of A (plain, un-stacked; used for the order choice)
+ * Buffers must hold 2*n_tail_max indices, TQ_MAX_MOMENTS * 4 * n_tail_max complex, TQ_MAX_MOMENTS doubles. */
+tq_status tq_tail_fitter_setup_host(double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max,
+                                    int expansion_order, int n_fixed, int hermitian, int *n_idx_out, long *idx_out,
+                                    int *n_var_out, tq_complex *pinv_out, double *sv_out, char *errbuf, size_t errbuf_len);
+
+/* ---- plain batched DFT and lattice transforms --------------------------------------------------- */
+
+/* Replaces  _fourier_base(in, out, rank, dims, howmany, sign)   c++/triqs/gfs/transform/fourier_common.cpp:25-45
+ * (fftw_plan_many_dft with stride = howmany, dist = 1): unnormalised DFT of rank 1..3 over the leading
+ * (C-order flattened) axis of [prod(dims)][howmany]; sign = +1 is FFTW_BACKWARD (e^{+2 pi i jk/N}), -1 FORWARD.
+ * in == out (in place) is allowed. */
+tq_status tq_fft_many(tq_ctx *ctx, int rank, const int *dims, long howmany, const tq_complex *in, tq_complex *out, int sign);
+
+/* Replaces  _fourier_impl(brzone const&, gf_vec_cvt<cyclat>) / _fourier_impl(cyclat const&, gf_vec_cvt<brzone>)
+ *           c++/triqs/gfs/transform/fourier_lattice.cpp:30-59.
+ *   to_k = 1: cyclat -> brzone (BACKWARD, no scaling);  to_k = 0: brzone -> cyclat (FORWARD, then / N_k).
+ *   in, out  [d0*d1*d2][n_others], linear index i0*d1*d2 + i1*d2 + i2 (mesh/brzone.hpp:187-190). */
+tq_status tq_fourier_lattice(tq_ctx *ctx, const long dims[3], int to_k, long n_others, const tq_complex *in, tq_complex *out);
+
+/* ---- matrix inversion and the lattice Dyson k-sum ------------------------------------------------ */
+
+/* Replaces  invert_in_place(gf_view<M, matrix_valued>)  c++/triqs/gfs/functions/functions2.hpp:197-201
+ *           _gf_invert_data_in_place(array_view<dcomplex,3>)  c++/triqs/gfs/gf/gf_expr.hpp:219-222
+ * a [n_pts][n][n], inverted in place, 1 <= n <= TQ_MAX_MATRIX_DIM (partial pivoting). */
+#define TQ_MAX_MATRIX_DIM 8
+tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_complex *a);
+
+/* Replaces the k-sum of  SumkDiscrete.__call__   python/triqs/sumk/sumk_discrete.py:140-166
+ * (C++ spelling: clef fill + inverse + sum over k, test/c++/gfs/multivar/g_k_om.cpp:64, bubble.cpp:65):
+ *   out[w] = sum_k weights[k] * inverse( (i w_n + mu) 1 - eps_k[k] - sigma[w] )
+ * fused: G(k, w) is never materialised.
+ *   eps_k    [n_k][n][n]   this rank's k-points (the caller slices like mpi.slice_array, mpi_mpi4py.py:96-109)
+ *   weights  double[n_k] or NULL (then every weight is `uniform_weight`, e.g. 1/N_k_total)
+ *   sigma    [n_w][n][n] on the full imfreq mesh (beta, statistic, n_iw)
+ *   out      [n_w][n][n]
+ *   all_reduce != 0: sum `out` over the ranks of the context's communicator (tq_comm_init) in place,
+ *                    the equivalent of  G << mpi.all_reduce(G)  (sumk_discrete.py:163). */
+tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, double beta, int statistic, double mu, const tq_complex *eps_k,
+                        const double *weights, double uniform_weight, const tq_complex *sigma, tq_complex *out, int all_reduce);
+
+/* ---- off-mesh evaluation ----------------------------------------------------------------------- */
+
+/* Replaces  gf_evaluator<imtime>::operator()(g, double tau)  c++/triqs/gfs/evaluator.hpp:35-43 with
+ *           linear::evaluate  c++/triqs/mesh/bases/linear.hpp:221-228, batched over n_pts points.
+ *   table [n_tau][n_elem] (one gf block), taus double[n_pts] in [0, beta], out [n_pts][n_elem]. */
+tq_status tq_interp_tau(tq_ctx *ctx, double beta, long n_tau, long n_elem, const tq_complex *table, long n_pts, const double *taus,
+                        tq_complex *out);
+
+/* ---- multi-GPU (one process per GPU; replaces mpi::all_reduce of gf data, c++/triqs/gfs/gf/gf.hpp:347-351) --- */
+
+#define TQ_COMM_ID_BYTES 128
+/* rank 0 creates the id and broadcasts the bytes by whatever means the host program has (MPI_Bcast in a
+ * TRIQS application, torch.distributed in this repo's harness); then every rank calls tq_comm_init. */
+tq_status tq_comm_unique_id(unsigned char id[TQ_COMM_ID_BYTES]);
+tq_status tq_comm_init(tq_ctx *ctx, int n_ranks, int rank, const unsigned char id[TQ_COMM_ID_BYTES]);
+/* in-place sum over ranks of `count` doubles at device pointer `data` (NCCL all-reduce on the ctx stream) */
+tq_status tq_all_reduce_sum(tq_ctx *ctx, double *data, size_t count);
+
+/* ---- device memory helpers for hosts that want to keep gfs resident in HBM ------------------------ */
+tq_status tq_device_alloc(tq_ctx *ctx, size_t bytes, void **dptr);
+tq_status tq_device_free(tq_ctx *ctx, void *dptr);
+tq_status tq_memcpy_h2d(tq_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+tq_status tq_memcpy_d2h(tq_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQGPU_H */

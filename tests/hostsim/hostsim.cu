@@ -1,0 +1,66 @@
+// TEST-ONLY host emulation of the device math of libtqgpu (never linked into the product library).
+// The tile-FFT engine and the small dense kernels are __host__ __device__; here a CTA is emulated by
+// calling each pass with (tid = 0, nthreads = 1), which is equivalent because passes are hazard free.
+#include "../../triqs_b200/csrc/tq_fft.cuh"
+#include <vector>
+#include <cstring>
+
+
+extern "C" int hostsim_fft(int N, int TC, int sign, int direct_tw, int skew, double *data /* [N][TC] complex */) {
+  FftPlan P;
+  if (!tq_fft_factorize(N, P)) return -1;
+  std::vector<cd> tw;
+  tq_fft_twiddles_host(N, tw);
+  P.tw = tw.data();
+  int sm = skew ? ~0 : 0;
+  int rows = fft_rows_alloc(N, sm);
+  std::vector<cd> s((size_t)rows * TC);
+  cd *in = (cd *)data;
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < TC; ++c) s[(size_t)fft_row(n, sm) * TC + c] = in[(size_t)n * TC + c];
+  for (int p = 0; p < P.npass; ++p) {
+    if (sign > 0)
+      fft_pass<1>(P, p, s.data(), TC, TC, 0, 1, direct_tw != 0, sm);
+    else
+      fft_pass<-1>(P, p, s.data(), TC, TC, 0, 1, direct_tw != 0, sm);
+  }
+  for (int k = 0; k < N; ++k) {
+    int pos = fft_pos(P, k);
+    for (int c = 0; c < TC; ++c) in[(size_t)k * TC + c] = s[(size_t)fft_row(pos, sm) * TC + c];
+  }
+  return P.npass;
+}
+
+extern "C" int hostsim_radices(int N, int *radix) {
+  FftPlan P;
+  if (!tq_fft_factorize(N, P)) return -1;
+  for (int i = 0; i < P.npass; ++i) radix[i] = P.radix[i];
+  return P.npass;
+}
+
+#include "../../triqs_b200/csrc/tq_linalg.cuh"
+template <int N> static void inv_all(long n_pts, cd *a) {
+  for (long p = 0; p < n_pts; ++p) {
+    cd M[N][N];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) M[i][j] = a[(size_t)p * N * N + i * N + j];
+    tq_invert_inplace<N>(M);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) a[(size_t)p * N * N + i * N + j] = M[i][j];
+  }
+}
+extern "C" int hostsim_invert(int n, long n_pts, double *data) {
+  cd *a = (cd *)data;
+  switch (n) {
+    case 1: inv_all<1>(n_pts, a); break;
+    case 2: inv_all<2>(n_pts, a); break;
+    case 3: inv_all<3>(n_pts, a); break;
+    case 4: inv_all<4>(n_pts, a); break;
+    case 5: inv_all<5>(n_pts, a); break;
+    case 6: inv_all<6>(n_pts, a); break;
+    case 7: inv_all<7>(n_pts, a); break;
+    case 8: inv_all<8>(n_pts, a); break;
+    default: return -1;
+  }
+  return 0;
+}

@@ -1,0 +1,402 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerance (BASELINE.json north_star): 1e-12 relative in the max norm,  max|x - x_ref| / max|x_ref|,
+the convention of c++/triqs/gfs/gf_tests.hpp:26-32.  Every test needs a B200 (-m gpu).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import triqs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+F, B = O.FERMION, O.BOSON
+
+
+def rel(x, ref):
+    return float(np.max(np.abs(np.asarray(x) - ref)) / np.max(np.abs(ref)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import triqs_b200
+    c = triqs_b200.Context(0, print_warnings=False)
+    yield c
+    c.close()
+
+
+def poles_gtau(beta, n_tau, E, r, stat=F):
+    """G(tau) = sum_p r_p * pole(E_p) in the overflow-safe form of test/c++/gfs/fourier_matsubara.cpp:59-65."""
+    tau = O.tau_values(beta, n_tau)
+    s = -1.0 if stat == F else 1.0
+    g = np.zeros(n_tau)
+    for e, w in zip(E, r):
+        if e > 0:
+            g += w * (-np.exp(-e * tau) / (1 - s * math.exp(-e * beta)))
+        else:
+            g += w * (s * np.exp(e * (beta - tau)) / (1 - s * math.exp(e * beta)))
+    return g.astype(np.complex128)
+
+
+def c1_input(b):
+    rng = np.random.default_rng(1001 + b)
+    E = rng.uniform(-2, 2, 4)
+    r = rng.dirichlet(np.ones(4))
+    return poles_gtau(10.0, 10001, E, r)[:, None]
+
+
+def matrix_gf(beta, n_iw, n, seed, stat=F):
+    """G(iw) = (iw - H)^-1 with H random Hermitian, spectrum in [-2, 2]; returns (gw [n_w, n*n], H)."""
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    h = a + a.conj().T
+    w, v = np.linalg.eigh(h)
+    w = -2 + 4 * (w - w.min()) / (w.max() - w.min())
+    H = (v * w) @ v.conj().T
+    iw = O.imfreq_values(beta, stat, n_iw)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(n)[None] - H[None])
+    return g.reshape(len(iw), n * n), H
+
+
+def matrix_gtau(beta, n_tau, H):
+    w, v = np.linalg.eigh(H)
+    tau = O.tau_values(beta, n_tau)
+    f = np.where(w[None, :] > 0, -np.exp(-w[None, :] * tau[:, None]) / (1 + np.exp(-beta * np.abs(w[None, :]))),
+                 -np.exp(-w[None, :] * (tau[:, None] - beta)) / (1 + np.exp(-beta * np.abs(w[None, :]))))
+    g = np.einsum("ik,tk,jk->tij", v, f, v.conj())
+    return g.reshape(n_tau, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# direct transform
+# ---------------------------------------------------------------------------------------------
+def test_c1_tau_to_iw_single_and_batch(ctx):
+    """configs[0]: beta=10, n_tau=10001, n_iw=1025, scalar."""
+    gts = np.stack([c1_input(b) for b in range(5)])
+    gw = ctx.fourier_tau_to_iw(gts, 10.0, F, 1025)
+    for b in range(5):
+        ref = O.fourier_tau_to_iw(gts[b], 10.0, F, 1025)
+        assert rel(gw[b], ref) < TOL
+    gw0 = ctx.fourier_tau_to_iw(gts[:1], 10.0, F, 1025)
+    assert np.array_equal(gw0[0], gw[0])  # batching does not change a bit
+
+
+@pytest.mark.parametrize("stat", [F, B])
+@pytest.mark.parametrize("ncols", [1, 4])
+def test_reference_test_mesh_round_trip(ctx, stat, ncols):
+    """test/c++/gfs/fourier_matsubara.cpp: beta=10, N_iw=1000, N_tau=10000 (L = 9999 = 3^2 * 11 * 101)."""
+    beta, n_iw, n_tau, E = 10.0, 1000, 10000, -1.0
+    iw = O.imfreq_values(beta, stat, n_iw)
+    gw1 = 1 / (iw - E) + 1 / (iw + 2 * E) - 4.5 / (iw - 1.25 * E)
+    gw = np.repeat(gw1[:, None], ncols, axis=1) * (1 + 0.25 * np.arange(ncols))[None, :]
+    ref_t, info = O.fourier_iw_to_tau(gw, beta, stat, n_tau, return_info=True)
+    # inverse with the oracle's fitted tail supplied: isolates the transform from the SVD
+    gt = ctx.fourier_iw_to_tau(gw[None], beta, stat, n_tau, moments=info["tail"][None])[0]
+    assert rel(gt, ref_t) < TOL
+    # inverse with the library's own tail fit
+    gt2 = ctx.fourier_iw_to_tau(gw[None], beta, stat, n_tau)[0]
+    assert rel(gt2, ref_t) < 1e-11
+    # direct, with the tau-derivative tail estimate
+    ref_w = O.fourier_tau_to_iw(ref_t, beta, stat, n_iw)
+    gwb = ctx.fourier_tau_to_iw(ref_t[None], beta, stat, n_iw)[0]
+    assert rel(gwb, ref_w) < TOL
+    assert np.max(np.abs(gwb - gw)) < 1e-8  # the reference test's own criterion
+    # known moments (:74-83)
+    km = np.zeros((2, ncols), complex)
+    km[1] = -2.5 * (1 + 0.25 * np.arange(ncols))
+    ref_km = O.fourier_iw_to_tau(gw, beta, stat, n_tau, km)
+    gt_km = ctx.fourier_iw_to_tau(gw[None], beta, stat, n_tau, moments=km[None])[0]
+    assert rel(gt_km, ref_km) < 1e-11
+
+
+def test_default_python_mesh_6150(ctx):
+    """n_iw = 1025 (Python default) -> n_tau = 6151, L = 6150 = 2 * 3 * 5^2 * 41 (hermiticity.cpp:34-48)."""
+    beta, n_iw = 10.0, 1025
+    gw, H = matrix_gf(beta, n_iw, 2, 11)
+    n_tau = O.adjoint_n_tau(n_iw)
+    ref_t, info = O.fourier_iw_to_tau(gw, beta, F, n_tau, return_info=True)
+    gt = ctx.fourier_iw_to_tau(gw[None], beta, F, n_tau, moments=info["tail"][None])[0]
+    assert rel(gt, ref_t) < TOL
+    g3 = gt.reshape(-1, 2, 2)
+    assert np.max(np.abs(g3 - g3.conj().transpose(0, 2, 1))) < 1e-12
+    ref_w = O.fourier_tau_to_iw(ref_t, beta, F, n_iw)
+    assert rel(ctx.fourier_tau_to_iw(ref_t[None], beta, F, n_iw)[0], ref_w) < TOL
+
+
+def test_c2_blockgf_round_trip(ctx):
+    """configs[1]: 2 blocks x 5x5, beta=100, n_tau=100001 (L=10^5, four-step path), n_iw=10000."""
+    beta, n_tau, n_iw = 100.0, 100001, 10000
+    gts, gws = [], []
+    for b in range(2):
+        gw, H = matrix_gf(beta, n_iw, 5, 2001 + b)
+        gts.append(matrix_gtau(beta, n_tau, H))
+        gws.append(gw)
+    gts = np.stack(gts)
+    out_w = ctx.fourier_tau_to_iw(gts, beta, F, n_iw)
+    for b in range(2):
+        ref_w = O.fourier_tau_to_iw(gts[b], beta, F, n_iw)
+        assert rel(out_w[b], ref_w) < TOL
+        assert np.max(np.abs(out_w[b] - gws[b])) < 1e-6
+    # return leg on the transformed data, tail supplied by the oracle (transform parity) ...
+    refs, tails = [], []
+    for b in range(2):
+        r, info = O.fourier_iw_to_tau(np.asarray(out_w[b]), beta, F, n_tau, return_info=True)
+        refs.append(r)
+        tails.append(info["tail"])
+    out_t = ctx.fourier_iw_to_tau(out_w, beta, F, n_tau, moments=np.stack(tails))
+    for b in range(2):
+        assert rel(out_t[b], refs[b]) < TOL
+    # ... and with the library's own least-squares tail (end-to-end)
+    out_t2, err = ctx.fourier_iw_to_tau(out_w, beta, F, n_tau, return_err=True)
+    for b in range(2):
+        assert rel(out_t2[b], refs[b]) < 1e-11
+        assert np.max(np.abs(out_t2[b] - gts[b])) < 1e-7
+    assert np.all(err < 1e-4)
+
+
+def test_tau_to_iw_known_moments_and_noise_warning(ctx):
+    import triqs_b200
+    beta, n_tau, n_iw = 10.0, 1201, 200
+    rng = np.random.default_rng(5)
+    gt = poles_gtau(beta, n_tau, [0.7, -1.1], [0.4, 0.6])[:, None] + 1e-3 * rng.normal(size=(n_tau, 1))
+    ref, info = O.fourier_tau_to_iw(gt, beta, F, n_iw, return_info=True)
+    assert info["warn"] & O.WARN_NOISY_TAU
+    out = ctx.fourier_tau_to_iw(gt[None], beta, F, n_iw)
+    assert ctx.last_warn[0] & triqs_b200.TQ_WARN_NOISY_TAU
+    assert rel(out[0], ref) < TOL
+    km = np.array([[0.0], [1.0], [0.1], [0.3]], complex)
+    ref = O.fourier_tau_to_iw(gt, beta, F, n_iw, km)
+    assert rel(ctx.fourier_tau_to_iw(gt[None], beta, F, n_iw, moments=km[None])[0], ref) < TOL
+    # short tau mesh warning (L < 6 n_iw)
+    ctx.fourier_tau_to_iw(gt[None], beta, F, 300)
+    assert ctx.last_warn[0] & triqs_b200.TQ_WARN_SHORT_TAU_MESH
+
+
+def test_errors_match_reference(ctx):
+    import triqs_b200
+    gt = np.zeros((1, 101, 1), complex)
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="at least twice as long"):
+        ctx.fourier_tau_to_iw(gt, 1.0, F, 60)
+    km = np.ones((1, 2, 1), complex)
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="vanishing 0th moment"):
+        ctx.fourier_tau_to_iw(np.zeros((1, 1001, 1), complex), 1.0, F, 50, moments=km)
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="full mesh"):
+        ctx.fourier_iw_to_tau(np.zeros((1, 101, 1), complex), 1.0, F, 1001)
+    # G = iw cannot be fitted: error > 1e-2 (tail_issues.py:30-37 + fourier_matsubara.cpp:205-207)
+    iw = O.imfreq_values(10.0, F, 1000)
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="greater than 1e-2"):
+        ctx.fourier_iw_to_tau(iw[None, :, None].copy(), 10.0, F, 6001)
+
+
+# ---------------------------------------------------------------------------------------------
+# tail fit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("herm", [False, True])
+@pytest.mark.parametrize("n_fixed", [0, 2])
+def test_fit_tail_kernel_against_same_pinv(ctx, herm, n_fixed):
+    """The batched kernel against NumPy using the SAME pseudo-inverse (the library's, exported by
+    tq_tail_fitter_setup_host): pins gather, known-moment shift, GEMM, residual, rescale, symmetrisation."""
+    import triqs_b200
+    beta, n_iw, n = 10.0, 1025, 3
+    gws = np.stack([matrix_gf(beta, n_iw, n, 40 + b)[0] for b in range(3)])
+    known = None
+    if n_fixed:
+        known = np.zeros((3, 2, n * n), complex)
+        known[:, 1] = np.eye(n).reshape(-1)
+    s = triqs_b200.tail_fitter_setup(beta, F, n_iw, n_fixed=n_fixed, hermitian=herm)
+    mom, err = ctx.fit_tail(gws, beta, F, known_moments=known, hermitian=herm, inner_dim=n)
+    f = O.TailFitter(beta, F, n_iw)
+    lss = f.setup_lss(n_fixed, herm)
+    assert mom.shape[1] == s["n_var"] + n_fixed
+    for b in range(3):
+        # oracle fit with the library's pinv swapped in
+        lss2 = dict(lss)
+        lss2["pinv"] = s["pinv"]
+        f._lss[(n_fixed, herm)] = lss2
+        ref, ref_err = f.fit(gws[b], None if known is None else known[b], hermitian=herm, inner_dim=n)
+        for p in range(ref.shape[0]):
+            scale = max(np.max(np.abs(ref[p])), f.w_max ** p * 1e-16)
+            assert np.max(np.abs(mom[b, p] - ref[p])) / scale < 1e-10, (p,)
+        assert abs(err[b] - ref_err) < 1e-12 * np.max(np.abs(gws[b]))
+
+
+@pytest.mark.parametrize("eps", [0.001, 0.1, 1, 10, 100])
+def test_fit_hermitian_tail_exact_moments(ctx, eps):
+    """test/python/base/tail_issues.py:74-102 through the GPU path."""
+    Nw = int(max(25, eps * 60))
+    H = eps * np.array([[1.0, 0.1j], [-0.1j, 2.0]])
+    iw = O.imfreq_values(1.0, F, Nw)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(2)[None] - H[None]).reshape(1, -1, 4)
+    mx = lambda x: np.max(np.abs(x))
+    for km in (None, np.vstack([np.zeros(4), np.eye(2).reshape(4)]).astype(complex)[None]):
+        tail, err = ctx.fit_tail(g, 1.0, F, known_moments=km, hermitian=True, inner_dim=2)
+        for n in range(3):
+            exact = np.linalg.matrix_power(H, n)
+            assert mx(exact - tail[0, 1 + n].reshape(2, 2)) / mx(exact) < 1e-4
+        ref, ref_err = O.fit_hermitian_tail(g[0], 1.0, F, None if km is None else km[0], inner_dim=2)
+        # low moments agree with the LAPACK-based oracle far below the test's own 1e-4
+        for n in range(1, 4):
+            assert mx(tail[0, n] - ref[n]) / max(mx(ref[n]), 1e-300) < 1e-6
+
+
+def test_fit_tail_reference_known_answers(ctx):
+    """test/c++/gfs/fit_tail_matsubara.cpp:27-106 through the GPU path."""
+    beta, N = 10.0, 100
+    iw = O.imfreq_values(beta, F, N)
+    c = np.array([0, 1, 3, 5], dtype=complex)
+    gw = (c[0] + c[1] / iw + c[2] / iw / iw + c[3] / iw / iw / iw)[None, :, None]
+    for km in (np.zeros((1, 1, 1), complex), np.array([[[0.0], [1.0]]], complex)):
+        tail, err = ctx.fit_tail(gw, beta, F, known_moments=km, tail_fraction=0.3)
+        assert np.max(np.abs(tail[0, :4, 0] - c)) < 1e-8
+    km = np.array([[[0.0], [1.0]]], complex)
+    for stat, n_iw in ((F, N), (B, N - 1)):
+        iw = O.imfreq_values(beta, stat, n_iw)
+        tail, err = ctx.fit_tail((1 / (iw - 1))[None, :, None], beta, stat, known_moments=km, tail_fraction=0.3)
+        assert np.max(np.abs(tail[0, :5, 0] - np.array([0, 1, 1, 1, 1]))) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# lattice
+# ---------------------------------------------------------------------------------------------
+def test_g_r_k_exact(ctx):
+    """test/c++/gfs/g_r_k.cpp:52-58."""
+    N = 10
+    k = 2 * math.pi * np.arange(N) / N
+    gk = (-2 * (np.cos(k)[:, None] + np.cos(k)[None, :])).reshape(N * N, 1).astype(complex)
+    gr = ctx.fourier_lattice(gk, (N, N, 1), to_k=False).reshape(N, N)
+    expect = np.zeros((N, N), complex)
+    expect[1, 0] = expect[N - 1, 0] = expect[0, 1] = expect[0, N - 1] = -1
+    assert np.max(np.abs(gr - expect)) < 1e-13
+    assert np.max(np.abs(ctx.fourier_lattice(gr.reshape(-1, 1), (N, N, 1), to_k=True) - gk)) < 1e-12
+
+
+@pytest.mark.parametrize("dims,n_others", [((64, 64, 1), 36), ((4, 3, 5), 7), ((16, 16, 16), 9), ((2, 2, 1), 1), ((7, 1, 11), 3),
+                                           ((256, 256, 1), 18)])
+def test_lattice_vs_oracle(ctx, dims, n_others):
+    """configs[2] shape family: data = complex normal * exp(-|r|_inf / 8), seed 3001."""
+    rng = np.random.default_rng(3001)
+    nk = int(np.prod(dims))
+    x = rng.normal(size=(nk, n_others)) + 1j * rng.normal(size=(nk, n_others))
+    idx = np.stack(np.unravel_index(np.arange(nk), dims), axis=1)
+    dist = np.max(np.minimum(idx, np.array(dims)[None, :] - idx), axis=1)
+    x *= np.exp(-dist / 8.0)[:, None]
+    ref = O.fourier_lattice_r_to_k(x, dims)
+    out = ctx.fourier_lattice(x, dims, to_k=True)
+    assert rel(out, ref) < TOL
+    back = ctx.fourier_lattice(out, dims, to_k=False)
+    assert rel(back, x) < TOL
+    assert rel(back, O.fourier_lattice_k_to_r(ref, dims)) < TOL
+
+
+def test_fft_many_semantics(ctx):
+    """_fourier_base: rank-1 over L rows of an (L+1)-row buffer is the caller's business; here plain rank 1..3."""
+    rng = np.random.default_rng(9)
+    for dims in [(12,), (6150,), (5, 8), (3, 4, 5)]:
+        n = int(np.prod(dims))
+        x = rng.normal(size=(n, 3)) + 1j * rng.normal(size=(n, 3))
+        for sign in (1, -1):
+            assert rel(ctx.fft_many(x, dims, sign), O.fft_many(x, dims, sign)) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# inversion and the Dyson k-sum
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 8])
+def test_invert_batched(ctx, n):
+    rng = np.random.default_rng(100 + n)
+    a = rng.normal(size=(1000, n, n)) + 1j * rng.normal(size=(1000, n, n))
+    ref = O.invert_batched(a)
+    out = ctx.invert_in_place(a.copy())
+    err = np.max(np.abs(out - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
+    cond = np.linalg.cond(a)
+    assert np.all(err < 1e-15 * cond * 50)
+    assert np.median(err) < 1e-13
+
+
+def c4_inputs(nk1, n_iw, n=5, beta=10.0):
+    """configs[3] family: NN tight-binding eps_k (seed 4001), 2-pole Sigma (seed 4002)."""
+    rng = np.random.default_rng(4001)
+    t = []
+    for _ in range(3):
+        m = 0.25 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / math.sqrt(n)
+        t.append(m)
+    e0 = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    e0 = 0.1 * (e0 + e0.conj().T)
+    ks = 2 * math.pi * np.arange(nk1) / nk1
+    kx, ky, kz = np.meshgrid(ks, ks, ks, indexing="ij")
+    eps = np.broadcast_to(e0, (nk1, nk1, nk1, n, n)).copy()
+    for d, kk in enumerate((kx, ky, kz)):
+        ph = np.exp(1j * kk)[..., None, None]
+        eps += ph * t[d] + ph.conj() * t[d].conj().T
+    eps = eps.reshape(-1, n, n)
+    rng = np.random.default_rng(4002)
+    iw = O.imfreq_values(beta, F, n_iw)
+    sig = np.zeros((len(iw), n, n), complex)
+    for p in range(2):
+        v = rng.normal(size=(n, 1)) + 1j * rng.normal(size=(n, 1))
+        e = rng.uniform(-1, 1)
+        sig += (v @ v.conj().T)[None] / (iw[:, None, None] - e)
+    return eps, sig
+
+
+def test_dyson_ksum_vs_oracle(ctx):
+    eps, sig = c4_inputs(8, 64)
+    ref = O.dyson_ksum(eps, sig, 10.0, F, 0.1)
+    out = ctx.dyson_ksum(eps, sig, 10.0, F, 0.1)
+    assert rel(out, ref) < TOL
+    # explicit weights and a ragged k count
+    w = np.random.default_rng(1).uniform(0.5, 1.5, 301)
+    w /= w.sum()
+    ref = O.dyson_ksum(eps[:301], sig, 10.0, F, 0.1, weights=w)
+    assert rel(ctx.dyson_ksum(eps[:301], sig, 10.0, F, 0.1, weights=w), ref) < TOL
+
+
+def test_dyson_other_dims(ctx):
+    for n in (1, 2, 3):
+        eps, sig = c4_inputs(4, 16, n=n)
+        assert rel(ctx.dyson_ksum(eps, sig, 10.0, F, -0.3), O.dyson_ksum(eps, sig, 10.0, F, -0.3)) < TOL
+
+
+def test_dyson_sharded_sum_equals_whole(ctx):
+    """k-slices like mpi.slice_array (mpi_mpi4py.py:96-109), partial sums added = the all-reduce result."""
+    eps, sig = c4_inputs(6, 32)
+    nk = eps.shape[0]
+    whole = ctx.dyson_ksum(eps, sig, 10.0, F, 0.1)
+    acc = np.zeros_like(whole)
+    for r in range(3):
+        lo, hi = O.slice_bounds(nk, 3, r)
+        acc += ctx.dyson_ksum(eps[lo:hi], sig, 10.0, F, 0.1, uniform_weight=1.0 / nk)
+    assert rel(acc, whole) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# interpolation
+# ---------------------------------------------------------------------------------------------
+def test_interp_tau(ctx):
+    beta, n_tau = 10.0, 8192
+    _, H = matrix_gf(beta, 8, 5, 77)
+    table = matrix_gtau(beta, n_tau, H)
+    rng = np.random.default_rng(5001)
+    taus = np.concatenate([rng.uniform(0, beta, 100000), [0.0, beta, beta / 2, 1e-300, beta - 1e-13]])
+    ref = O.interp_tau(table, beta, taus)
+    out = ctx.interp_tau(table, beta, taus)
+    assert np.array_equal(out, ref)  # same operations in the same order: bit exact
+    # test/c++/meshes/eval.cpp:62-89
+    tab = np.array([[1.0], [10.0], [100.0], [1000.0], [1e4]], complex)
+    o = ctx.interp_tau(tab, 10.0, np.array([2.0, 3.5]))
+    assert np.allclose(o[:, 0], [0.2 * 1 + 0.8 * 10, 0.6 * 10 + 0.4 * 100], rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident (torch CUDA tensor) path gives the same bits as the host-staged path
+# ---------------------------------------------------------------------------------------------
+def test_device_pointers_same_result(ctx):
+    import torch
+    gts = np.stack([c1_input(b) for b in range(3)])
+    host = ctx.fourier_tau_to_iw(gts, 10.0, F, 1025)
+    dev = ctx.fourier_tau_to_iw(torch.from_numpy(gts).cuda(), 10.0, F, 1025)
+    assert dev.is_cuda
+    assert np.array_equal(dev.cpu().numpy(), host)

@@ -1,0 +1,60 @@
+"""Device math (tile-FFT engine, register-resident inversion) compiled for the HOST and emulated
+single-threaded: pins butterflies, twiddles, digit reversal and pivoting logic on the CPU-only box.
+The emulation library is test infrastructure; the product never links it."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "hostsim", "libhostsim.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        pytest.skip("tests/hostsim/libhostsim.so not built (run __graft_entry__.build())")
+    return ctypes.CDLL(LIB)
+
+
+SIZES = [1, 2, 3, 4, 5, 6, 8, 10, 16, 20, 25, 32, 49, 64, 100, 125, 128, 250, 256, 400, 1000, 246, 6150, 9999, 10000, 1001, 404]
+
+
+@pytest.mark.parametrize("N", SIZES)
+def test_tile_fft_engine(lib, N):
+    rng = np.random.default_rng(N)
+    for TC in (1, 3):
+        for sign in (1, -1):
+            for direct in (0, 1):
+                for skew in (0, 1):
+                    x = rng.normal(size=(N, TC)) + 1j * rng.normal(size=(N, TC))
+                    y = x.copy()
+                    assert lib.hostsim_fft(N, TC, sign, direct, skew, y.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) >= 0
+                    ref = np.fft.ifft(x, axis=0) * N if sign > 0 else np.fft.fft(x, axis=0)
+                    assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 5e-15
+
+
+def test_radix_choice(lib):
+    rad = (ctypes.c_int * 16)()
+    n = lib.hostsim_radices(10000, rad)
+    assert list(rad[:n]) == [10, 10, 10, 10]
+    n = lib.hostsim_radices(6150, rad)
+    assert sorted(rad[:n]) == [3, 5, 10, 41]
+    assert lib.hostsim_radices(2 * 131, rad) == -1  # prime factor above the generic-radix limit
+
+
+@pytest.mark.parametrize("n", range(1, 9))
+def test_register_inverse(lib, n):
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=(500, n, n)) + 1j * rng.normal(size=(500, n, n))
+    # force pivoting: zero some diagonal entries
+    if n > 1:
+        a[::3, 0, 0] = 0
+    if n > 2:
+        a[::5, 1, 1] = 1e-18
+    b = a.copy()
+    assert lib.hostsim_invert(n, 500, b.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+    ref = np.linalg.inv(a)
+    err = np.max(np.abs(b - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
+    assert np.all(err < 1e-15 * 100 * np.linalg.cond(a))

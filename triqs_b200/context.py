@@ -1,0 +1,303 @@
+"""Thin, array-level Python face of the C ABI (include/tqgpu.h).
+
+Arrays are either NumPy arrays (host memory: the library stages them through the GPU inside the call)
+or torch CUDA tensors of dtype complex128/float64 (device memory: used in place, results are torch
+tensors on the same device).  Shapes follow the reference's flattened views ``[batch][mesh][n_others]``.
+PyTorch is used only as the device-memory owner; all compute happens in libtqgpu.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+import warnings
+
+import numpy as np
+
+from . import _lib as L
+
+FERMION, BOSON = L.TQ_FERMION, L.TQ_BOSON
+
+
+class TriqsRuntimeError(RuntimeError):
+    """Raised where the reference throws triqs::runtime_error (c++/triqs/utility/exceptions.hpp:31-37)."""
+
+
+class TqError(RuntimeError):
+    pass
+
+
+# messages the reference prints to std::cerr (c++/triqs/gfs/transform/fourier_matsubara.cpp:109-110, 131-133, 208-210)
+WARNING_TEXT = {
+    L.TQ_WARN_NOISY_TAU: "WARNING: Direct Fourier cannot deduce the high-frequency moments of G(tau) due to noise or a coarse tau-grid. "
+                         "Please specify the high-frequency moments for higher accuracy.\n",
+    L.TQ_WARN_SHORT_TAU_MESH: "[Direct Fourier] WARNING: The imaginary time mesh is less than six times as long as the number of positive "
+                              "frequencies.\nThis can lead to substantial numerical inaccuracies at the boundary of the frequency mesh.\n",
+    L.TQ_WARN_TAIL_ERR: "WARNING: High frequency moments have an error greater than 1e-4.\n"
+                        " Please make sure you treat the constant offset analytically!\n",
+}
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _as_c128(x):
+    if _is_torch(x):
+        import torch
+        if x.dtype != torch.complex128:
+            x = x.to(torch.complex128)
+        return x.contiguous()
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def _as_f64(x):
+    if _is_torch(x):
+        import torch
+        return x.to(torch.float64).contiguous()
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return ctypes.c_void_p(x.data_ptr())
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+def _empty_like_kind(ref, shape, dtype=np.complex128):
+    if _is_torch(ref):
+        import torch
+        td = torch.complex128 if dtype == np.complex128 else torch.float64
+        return torch.empty(shape, dtype=td, device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+class Context:
+    """One per process/GPU: owns the stream, the plan caches and (optionally) the NCCL communicator."""
+
+    def __init__(self, device: int = 0, print_warnings: bool = True):
+        self._lib = L.load()  # raises if libtqgpu.so is missing -- no CPU fallback
+        h = ctypes.c_void_p()
+        st = self._lib.tq_create(device, ctypes.byref(h))
+        if st == L.TQ_ERR_NO_DEVICE:
+            raise TqError("tq_create: no CUDA device -- triqs_b200 never computes on the CPU")
+        if st != L.TQ_OK:
+            raise TqError(f"tq_create failed with status {st}")
+        self._h = h
+        self.device = device
+        self.print_warnings = print_warnings
+        self.last_warn = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, st):
+        if st == L.TQ_OK:
+            return
+        msg = self._lib.tq_last_error(self._h).decode(errors="replace")
+        if st == L.TQ_ERR_RUNTIME:
+            raise TriqsRuntimeError(msg)
+        raise TqError(f"status {st}: {msg}")
+
+    def _emit(self, warn):
+        self.last_warn = warn
+        if not self.print_warnings:
+            return
+        bits = int(np.bitwise_or.reduce(warn)) if len(warn) else 0
+        for b, text in WARNING_TEXT.items():
+            if bits & b:
+                sys.stderr.write(text)
+
+    def synchronize(self):
+        self._check(self._lib.tq_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.tq_stream(self._h)
+
+    def launch_count(self) -> int:
+        return int(self._lib.tq_launch_count(self._h))
+
+    # -- Matsubara transforms -------------------------------------------------------------------
+    def fourier_tau_to_iw(self, gt, beta, statistic, n_iw, moments=None, out=None):
+        """gt [batch, n_tau, n_others] -> gw [batch, n_w, n_others]  (tq_fourier_tau_to_iw)."""
+        gt = _as_c128(gt)
+        batch, n_tau, n_others = gt.shape
+        n_w = 2 * n_iw if statistic == FERMION else 2 * n_iw - 1
+        n_mom = 0
+        if moments is not None:
+            moments = _as_c128(moments)
+            n_mom = moments.shape[1]
+        gw = out if out is not None else _empty_like_kind(gt, (batch, n_w, n_others))
+        warn = (ctypes.c_int * batch)()
+        self._check(self._lib.tq_fourier_tau_to_iw(self._h, beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments), n_mom,
+                                                   _ptr(gw), warn))
+        self._emit(np.frombuffer(warn, dtype=np.int32))
+        return gw
+
+    def fourier_iw_to_tau(self, gw, beta, statistic, n_tau, moments=None, out=None, return_err=False):
+        """gw [batch, n_w, n_others] (full mesh) -> gt [batch, n_tau, n_others]  (tq_fourier_iw_to_tau)."""
+        gw = _as_c128(gw)
+        batch, n_w, n_others = gw.shape
+        if statistic == FERMION:
+            if n_w % 2:
+                raise TriqsRuntimeError("Fourier is only implemented for g(i omega_n) with full mesh (positive and negative frequencies)")
+            n_iw = n_w // 2
+        else:
+            if n_w % 2 == 0:
+                raise TriqsRuntimeError("Fourier is only implemented for g(i omega_n) with full mesh (positive and negative frequencies)")
+            n_iw = (n_w + 1) // 2
+        n_mom = 0
+        if moments is not None:
+            moments = _as_c128(moments)
+            n_mom = moments.shape[1]
+        gt = out if out is not None else _empty_like_kind(gw, (batch, n_tau, n_others))
+        warn = (ctypes.c_int * batch)()
+        err = (ctypes.c_double * batch)()
+        self._check(self._lib.tq_fourier_iw_to_tau(self._h, beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
+                                                   _ptr(gt), warn, err))
+        self._emit(np.frombuffer(warn, dtype=np.int32))
+        if return_err:
+            return gt, np.frombuffer(err, dtype=np.float64).copy()
+        return gt
+
+    # -- tail fit ----------------------------------------------------------------------------
+    def fit_tail(self, g, beta, statistic, known_moments=None, hermitian=False, inner_dim=1, tail_fraction=0.2, n_tail_max=30,
+                 expansion_order=None):
+        """g [batch, n_w, n_cols] -> (moments [batch, n_moments, n_cols], err [batch])  (tq_fit_tail)."""
+        g = _as_c128(g)
+        batch, n_w, n_cols = g.shape
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        n_known = 0
+        if known_moments is not None:
+            known_moments = _as_c128(known_moments)
+            n_known = known_moments.shape[1]
+            if known_moments.shape[2] != n_cols:
+                raise TriqsRuntimeError("known_moments shape incompatible with shape of data")
+        out = _empty_like_kind(g, (batch, max(L.TQ_MAX_MOMENTS, n_known), n_cols))
+        nm = ctypes.c_int(0)
+        err = (ctypes.c_double * batch)()
+        self._check(self._lib.tq_fit_tail(self._h, beta, statistic, n_iw, tail_fraction, n_tail_max,
+                                          -1 if expansion_order is None else int(expansion_order), int(bool(hermitian)), int(inner_dim), n_cols,
+                                          batch, _ptr(g), _ptr(known_moments), n_known, _ptr(out), ctypes.byref(nm), err))
+        n_moments = nm.value
+        flat = out.reshape(-1)[: batch * n_moments * n_cols].reshape(batch, n_moments, n_cols)
+        return flat, np.frombuffer(err, dtype=np.float64).copy()
+
+    def tail_fitter_setup(self, beta, statistic, n_iw, n_fixed=0, hermitian=False, tail_fraction=0.2, n_tail_max=30, expansion_order=None):
+        return tail_fitter_setup(beta, statistic, n_iw, n_fixed, hermitian, tail_fraction, n_tail_max, expansion_order)
+
+    # -- plain DFT / lattice -------------------------------------------------------------------
+    def fft_many(self, x, dims, sign, out=None):
+        """x [prod(dims), howmany]; unnormalised; sign=+1 is FFTW_BACKWARD  (tq_fft_many)."""
+        x = _as_c128(x)
+        total, howmany = x.shape
+        assert total == int(np.prod(dims))
+        y = out if out is not None else _empty_like_kind(x, x.shape)
+        d = (ctypes.c_int * len(dims))(*[int(v) for v in dims])
+        self._check(self._lib.tq_fft_many(self._h, len(dims), d, howmany, _ptr(x), _ptr(y), int(sign)))
+        return y
+
+    def fourier_lattice(self, x, dims, to_k: bool, out=None):
+        """x [d0*d1*d2, n_others]; to_k: cyclat -> brzone, else brzone -> cyclat  (tq_fourier_lattice)."""
+        x = _as_c128(x)
+        nk, n_others = x.shape
+        assert nk == int(np.prod(dims)) and len(dims) == 3
+        y = out if out is not None else _empty_like_kind(x, x.shape)
+        d = (ctypes.c_long * 3)(*[int(v) for v in dims])
+        self._check(self._lib.tq_fourier_lattice(self._h, d, int(bool(to_k)), n_others, _ptr(x), _ptr(y)))
+        return y
+
+    # -- inversion / Dyson ----------------------------------------------------------------------
+    def invert_in_place(self, a):
+        """a [n_pts, n, n] complex128 (C-contiguous), inverted in place  (tq_invert_batched)."""
+        if not _is_torch(a):
+            assert a.dtype == np.complex128 and a.flags.c_contiguous
+        n_pts, n, n2 = a.shape
+        assert n == n2
+        self._check(self._lib.tq_invert_batched(self._h, n, n_pts, _ptr(a)))
+        return a
+
+    def dyson_ksum(self, eps_k, sigma, beta, statistic, mu, weights=None, uniform_weight=None, all_reduce=False, out=None):
+        """eps_k [n_k, n, n], sigma [n_w, n, n] -> G_loc [n_w, n, n]  (tq_dyson_ksum)."""
+        eps_k = _as_c128(eps_k)
+        sigma = _as_c128(sigma)
+        n_k, n, _ = eps_k.shape
+        n_w = sigma.shape[0]
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        if weights is not None:
+            weights = _as_f64(weights)
+        if uniform_weight is None:
+            uniform_weight = 1.0 / max(n_k, 1)
+        g = out if out is not None else _empty_like_kind(sigma, sigma.shape)
+        self._check(self._lib.tq_dyson_ksum(self._h, n, n_k, n_iw, beta, statistic, mu, _ptr(eps_k), _ptr(weights), float(uniform_weight),
+                                            _ptr(sigma), _ptr(g), int(bool(all_reduce))))
+        return g
+
+    # -- interpolation ---------------------------------------------------------------------------
+    def interp_tau(self, table, beta, taus, out=None):
+        """table [n_tau, n_elem], taus [n_pts] -> [n_pts, n_elem]  (tq_interp_tau)."""
+        table = _as_c128(table)
+        taus = _as_f64(taus)
+        n_tau, n_elem = table.shape
+        n_pts = taus.shape[0]
+        y = out if out is not None else _empty_like_kind(table, (n_pts, n_elem))
+        self._check(self._lib.tq_interp_tau(self._h, beta, n_tau, n_elem, _ptr(table), n_pts, _ptr(taus), _ptr(y)))
+        return y
+
+    # -- multi GPU ---------------------------------------------------------------------------------
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        buf = (ctypes.c_ubyte * L.TQ_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.tq_comm_init(self._h, n_ranks, rank, buf))
+
+    def all_reduce_sum(self, t):
+        """in-place sum over ranks of a torch CUDA tensor (float64 or complex128)."""
+        import torch
+        assert _is_torch(t) and t.is_cuda and t.is_contiguous()
+        count = t.numel() * (2 if t.dtype == torch.complex128 else 1)
+        self._check(self._lib.tq_all_reduce_sum(self._h, ctypes.c_void_p(t.data_ptr()), count))
+        return t
+
+
+def comm_unique_id() -> bytes:
+    lib = L.load()
+    buf = (ctypes.c_ubyte * L.TQ_COMM_ID_BYTES)()
+    st = lib.tq_comm_unique_id(buf)
+    if st != L.TQ_OK:
+        raise TqError("tq_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf)
+
+
+def tail_fitter_setup(beta, statistic, n_iw, n_fixed=0, hermitian=False, tail_fraction=0.2, n_tail_max=30, expansion_order=None):
+    """Mesh-only part of the tail fit (host code, no GPU needed): fit indices, pseudo-inverse, singular values."""
+    lib = L.load()
+    n_idx = ctypes.c_int(0)
+    n_var = ctypes.c_int(0)
+    idx = (ctypes.c_long * (2 * n_tail_max))()
+    pinv = np.zeros(L.TQ_MAX_MOMENTS * 4 * n_tail_max, dtype=np.complex128)
+    sv = (ctypes.c_double * L.TQ_MAX_MOMENTS)()
+    err = ctypes.create_string_buffer(512)
+    st = lib.tq_tail_fitter_setup_host(beta, statistic, n_iw, tail_fraction, n_tail_max, -1 if expansion_order is None else expansion_order,
+                                       n_fixed, int(bool(hermitian)), ctypes.byref(n_idx), idx, ctypes.byref(n_var),
+                                       ctypes.c_void_p(pinv.ctypes.data), sv, err, 512)
+    if st == L.TQ_ERR_RUNTIME:
+        raise TriqsRuntimeError(err.value.decode())
+    if st != L.TQ_OK:
+        raise TqError(f"tq_tail_fitter_setup_host: status {st}")
+    rows = n_idx.value * (2 if hermitian else 1)
+    return {
+        "idx": np.array(idx[: n_idx.value], dtype=np.int64),
+        "n_var": n_var.value,
+        "pinv": pinv[: n_var.value * rows].reshape(n_var.value, rows).copy(),
+        "sv": np.array(sv[: n_var.value]),
+    }

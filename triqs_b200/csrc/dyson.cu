@@ -1,0 +1,225 @@
+// Batched orbital-sized complex matrix inversion and the fused lattice Dyson k-sum.
+//
+// Restates  invert_in_place            c++/triqs/gfs/functions/functions2.hpp:197-201
+//           _gf_invert_data_in_place   c++/triqs/gfs/gf/gf_expr.hpp:219-222
+//           SumkDiscrete.__call__      python/triqs/sumk/sumk_discrete.py:140-166
+// nda::inverse_in_place (LAPACK zgetrf + zgetri for n > 3) is external to the reference tree; here every
+// thread inverts one n x n matrix entirely in registers by Gauss-Jordan elimination with partial (row)
+// pivoting, fully unrolled, with predicated register swaps instead of indexed accesses.  In the k-sum the
+// inverse is consumed immediately: G(k, w) (214 GB at 64^3 x 2048 x 5x5) never exists in memory.
+#include "tq_common.cuh"
+#include "tq_linalg.cuh"
+
+#include <algorithm>
+
+// -------------------------------------------------------------------------------------------------
+// tq_invert_batched: a[n_pts][n][n] in place.  Coalesced staging through shared memory.
+// -------------------------------------------------------------------------------------------------
+template <int N> __global__ void __launch_bounds__(128) k_invert_batched(cd *a, long n_pts) {
+  constexpr int NN = N * N;
+  constexpr int STR = (NN % 2 == 0) ? NN + 1 : NN; // odd number of complex per matrix: conflict-free 16-byte accesses
+  extern __shared__ double2 sm[];                  // [128][STR]
+  const long base = (long)blockIdx.x * 128;
+  const int cnt = (int)min(128L, n_pts - base);
+  cd *g = a + (size_t)base * NN;
+  for (int i = threadIdx.x; i < cnt * NN; i += 128) {
+    int m = i / NN, e = i - m * NN;
+    sm[m * STR + e] = g[i];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    cd M[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) M[i][j] = sm[threadIdx.x * STR + i * N + j];
+    tq_invert_inplace<N>(M);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) sm[threadIdx.x * STR + i * N + j] = M[i][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt * NN; i += 128) {
+    int m = i / NN, e = i - m * NN;
+    g[i] = sm[m * STR + e];
+  }
+}
+
+extern "C" tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_complex *a) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!a || n < 1 || n_pts < 0) return tq_fail(ctx, TQ_ERR_INVALID, "tq_invert_batched: invalid argument");
+  if (n > TQ_MAX_MATRIX_DIM) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_invert_batched: n > " + std::to_string(TQ_MAX_MATRIX_DIM));
+  if (n_pts == 0) return TQ_OK;
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(cd) * (size_t)n_pts * n * n;
+  const bool dev = tq_is_device_ptr(a);
+  cd *d = (cd *)a;
+  if (!dev) {
+    TQ_TRY(tq_reserve(ctx, ctx->stage_in, bytes));
+    d = (cd *)ctx->stage_in.p;
+    TQ_CUDA(ctx, cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const long nb = (n_pts + 127) / 128;
+  if (nb > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_invert_batched: too many points");
+#define TQ_INV_CASE(NV)                                                                                                          \
+  case NV: {                                                                                                                     \
+    constexpr int NN = NV * NV, STR = (NN % 2 == 0) ? NN + 1 : NN;                                                               \
+    const size_t smem = sizeof(cd) * 128 * STR;                                                                                  \
+    auto k = k_invert_batched<NV>;                                                                                               \
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
+    k<<<(unsigned)nb, 128, smem, ctx->stream>>>(d, n_pts);                                                                       \
+  } break;
+  switch (n) {
+    TQ_INV_CASE(1)
+    TQ_INV_CASE(2)
+    TQ_INV_CASE(3)
+    TQ_INV_CASE(4)
+    TQ_INV_CASE(5)
+    TQ_INV_CASE(6)
+    TQ_INV_CASE(7)
+    TQ_INV_CASE(8)
+  }
+#undef TQ_INV_CASE
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  if (!dev) {
+    TQ_CUDA(ctx, cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return TQ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused k-sum.  CTA = 128 frequencies x one chunk of k-points; thread = one frequency.
+//   A(w) = (i w_n + mu) 1 - Sigma(w)  lives in shared memory ([element][thread], conflict free)
+//   per k: M = A - eps_k (eps_k read with warp-uniform loads), M <- M^-1 in registers, acc += weight * M
+//   partial[chunk][w][n][n] is reduced by a second tiny kernel in fixed order (deterministic result).
+// -------------------------------------------------------------------------------------------------
+template <int N> __global__ void __launch_bounds__(128) k_dyson_partial(const cd *__restrict__ eps, const double *__restrict__ weights,
+                                                                       double uniform_weight, const cd *__restrict__ sigma, int n_w, long n_k,
+                                                                       long k_per_chunk, double beta, int stat, int first, double mu,
+                                                                       cd *__restrict__ partial) {
+  constexpr int NN = N * N;
+  extern __shared__ double As_[]; // [2 NN][128]
+  double(*As)[128] = reinterpret_cast<double(*)[128]>(As_);
+  const int w = blockIdx.x * 128 + threadIdx.x;
+  const bool active = w < n_w;
+  const int wc = active ? w : n_w - 1;
+  {
+    const double om = M_PI * (double)(2 * (long)(first + wc) + stat) / beta; // matsubara.hpp:55
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        cd s = sigma[(size_t)wc * NN + i * N + j];
+        double re = -s.x, im = -s.y;
+        if (i == j) {
+          re += mu;
+          im += om;
+        }
+        As[2 * (i * N + j)][threadIdx.x] = re;
+        As[2 * (i * N + j) + 1][threadIdx.x] = im;
+      }
+  }
+  cd acc[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[i][j] = cmk(0, 0);
+  const long k0 = (long)blockIdx.y * k_per_chunk;
+  const long k1 = min(n_k, k0 + k_per_chunk);
+  for (long k = k0; k < k1; ++k) {
+    const cd *e = eps + (size_t)k * NN;
+    cd M[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        cd ev = __ldg(&e[i * N + j]);
+        M[i][j] = cmk(As[2 * (i * N + j)][threadIdx.x] - ev.x, As[2 * (i * N + j) + 1][threadIdx.x] - ev.y);
+      }
+    tq_invert_inplace<N>(M);
+    const double wk = weights ? __ldg(&weights[k]) : uniform_weight;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[i][j] = caxpy(wk, M[i][j], acc[i][j]);
+  }
+  if (active) {
+    cd *p = partial + ((size_t)blockIdx.y * n_w + w) * NN;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) p[i * N + j] = acc[i][j];
+  }
+}
+
+__global__ void k_dyson_reduce(const cd *__restrict__ partial, int n_chunks, long n_elem, cd *__restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elem) return;
+  cd s = cmk(0, 0);
+  for (int c = 0; c < n_chunks; ++c) s = cadd(s, partial[(size_t)c * n_elem + i]);
+  out[i] = s;
+}
+
+extern "C" tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, double beta, int statistic, double mu, const tq_complex *eps_k,
+                                   const double *weights, double uniform_weight, const tq_complex *sigma, tq_complex *out, int all_reduce) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!eps_k || !sigma || !out || n < 1 || n_k < 0 || n_iw < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_dyson_ksum: invalid argument");
+  if (n > TQ_MAX_MATRIX_DIM) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_dyson_ksum: n > " + std::to_string(TQ_MAX_MATRIX_DIM));
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long last = n_iw - 1;
+  const long first = -(last + (statistic == TQ_FERMION ? 1 : 0));
+  const long n_w = last - first + 1;
+  const long nn = (long)n * n;
+  const void *d_eps = nullptr, *d_sig = nullptr, *d_wts = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, eps_k, sizeof(cd) * (size_t)n_k * nn, ctx->stage_in, &d_eps));
+  TQ_TRY(tq_stage_in(ctx, sigma, sizeof(cd) * (size_t)n_w * nn, ctx->stage_in2, &d_sig));
+  if (weights) TQ_TRY(tq_stage_in(ctx, weights, sizeof(double) * (size_t)n_k, ctx->stage_in3, &d_wts));
+  TQ_TRY(tq_stage_out_begin(ctx, out, sizeof(cd) * (size_t)n_w * nn, ctx->stage_out, &d_out, &out_host));
+  const int w_tiles = (int)((n_w + 127) / 128);
+  // enough CTAs for ~4 waves of 4 CTAs/SM, but at least 64 k-points per chunk
+  long want_chunks = std::max<long>(1, (4L * 4 * ctx->sm_count + w_tiles - 1) / w_tiles);
+  long k_per_chunk = std::max<long>(64, (n_k + want_chunks - 1) / want_chunks);
+  int n_chunks = (int)std::max<long>(1, (n_k + k_per_chunk - 1) / k_per_chunk);
+  if (n_chunks > 65535) {
+    n_chunks = 65535;
+    k_per_chunk = (n_k + n_chunks - 1) / n_chunks;
+    n_chunks = (int)((n_k + k_per_chunk - 1) / k_per_chunk);
+  }
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, sizeof(cd) * (size_t)n_chunks * n_w * nn));
+  cd *d_part = (cd *)ctx->scratch.p;
+  dim3 grid(w_tiles, n_chunks);
+#define TQ_DYSON_CASE(NV)                                                                                                        \
+  case NV: {                                                                                                                     \
+    const size_t smem = sizeof(double) * 2 * NV * NV * 128;                                                                      \
+    auto k = k_dyson_partial<NV>;                                                                                                \
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
+    k<<<grid, 128, smem, ctx->stream>>>((const cd *)d_eps, (const double *)d_wts, uniform_weight, (const cd *)d_sig, (int)n_w, n_k,     \
+                                        k_per_chunk, beta, statistic, (int)first, mu, d_part);                                   \
+  } break;
+  switch (n) {
+    TQ_DYSON_CASE(1)
+    TQ_DYSON_CASE(2)
+    TQ_DYSON_CASE(3)
+    TQ_DYSON_CASE(4)
+    TQ_DYSON_CASE(5)
+    TQ_DYSON_CASE(6)
+    TQ_DYSON_CASE(7)
+    TQ_DYSON_CASE(8)
+  }
+#undef TQ_DYSON_CASE
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  const long n_elem = n_w * nn;
+  k_dyson_reduce<<<(unsigned)((n_elem + 255) / 256), 256, 0, ctx->stream>>>(d_part, n_chunks, n_elem, (cd *)d_out);
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  if (all_reduce) TQ_TRY(tq_all_reduce_sum(ctx, (double *)d_out, (size_t)2 * n_elem)); // sumk_discrete.py:163
+  TQ_TRY(tq_stage_out_finish(ctx, out, sizeof(cd) * (size_t)n_w * nn, d_out, out_host));
+  return TQ_OK;
+}

@@ -1,0 +1,756 @@
+// imtime <-> imfreq transforms, fused:  tail model subtraction + phase twist -> tile FFT -> correction + window gather.
+//
+// Restates (does not copy) c++/triqs/gfs/transform/fourier_matsubara.cpp:
+//   :39-92   fit_tail(gt)          -> k_moments_from_tau   (8-point one-sided differences x literal V_inv)
+//   :96-186  _fourier_impl(imfreq) -> matsubara_tile_kernel<IN_TAU, OUT_FREQ | OUT_SCRATCH>, <IN_SCRATCH, OUT_FREQ>
+//   :190-271 _fourier_impl(imtime) -> matsubara_tile_kernel<IN_FREQ, OUT_TAU | OUT_SCRATCH>, <IN_SCRATCH, OUT_TAU>
+// A transform whose columns fit one SM's shared memory runs as ONE kernel (HBM is read once and written
+// once); longer ones (L = 10^5) run as a two-kernel four-step FFT L = Na * Nb with an L2-resident scratch.
+#include "tq_fft.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+// -------------------------------------------------------------------------------------------------
+// device-side description of the meshes and the 3-pole tail model
+// -------------------------------------------------------------------------------------------------
+struct MatsubaraDev {
+  int L, n_w, first, last, stat, nhi, lo_shift;
+  double beta, fact_fwd, inv_beta;
+  double b[3], C[3];
+  int rev[3];
+  const cd *ph_hi_fwd; // (beta/L) exp(+i pi (h << lo_shift) / L)
+  const cd *ph_hi_inv; // exp(-i pi (h << lo_shift) / L)
+  const cd *ph_lo;     // exp(+i pi l / L)
+  const double *e_hi;  // [3][nhi]   exp(-|b_i| beta (h << lo_shift) / L)
+  const double *e_lo;  // [3][1 << lo_shift]
+  const double4 *wtab; // [n_w] (omega_n, 1/(b1^2+w^2), 1/(b2^2+w^2), 1/(b3^2+w^2))
+};
+
+struct BigTw {
+  const cd *hi; // exp(+2 pi i (h << shift) / L)
+  const cd *lo; // exp(+2 pi i l / L)
+  int shift;
+};
+
+struct TileArgs {
+  FftPlan P;
+  int TC, n_cols, skewmask, direct_tw;
+  int in_stride, out_stride; // global row = item + stride * local
+  int Na;                    // scratch layout [Nb][Na][n_cols]
+  const cd *in;
+  cd *out;
+  cd *scratch;
+  const cd *gt_ref;  // G(tau) input (for the trapezoid correction, forward only)
+  const cd *moments; // [batch][mom_rows][n_cols]; rows 1..3 are used
+  long in_gf_stride, out_gf_stride, scratch_gf_stride, mom_gf_stride, gt_gf_stride;
+  MatsubaraDev D;
+  BigTw btw;
+};
+
+enum { IN_TAU = 0, IN_FREQ = 1, IN_SCRATCH = 2 };
+enum { OUT_FREQ = 0, OUT_TAU = 1, OUT_SCRATCH = 2 };
+
+// h_i(tau_j): one{Fermion,Boson}(a, b_i, tau_j, beta) = a * h_i(tau_j)     fourier_matsubara.cpp:28-34
+TQ_D void row_model(const MatsubaraDev &D, int j, double h[3]) {
+  const int mask = (1 << D.lo_shift) - 1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int jj = D.rev[i] ? D.L - j : j;
+    h[i] = D.C[i] * __ldg(&D.e_hi[i * D.nhi + (jj >> D.lo_shift)]) * __ldg(&D.e_lo[(i << D.lo_shift) + (jj & mask)]);
+  }
+}
+TQ_D cd phase_fwd(const MatsubaraDev &D, int j) {
+  const int mask = (1 << D.lo_shift) - 1;
+  return cmul(__ldg(&D.ph_hi_fwd[j >> D.lo_shift]), __ldg(&D.ph_lo[j & mask]));
+}
+TQ_D cd phase_inv(const MatsubaraDev &D, int j) {
+  const int mask = (1 << D.lo_shift) - 1;
+  return cmul(__ldg(&D.ph_hi_inv[j >> D.lo_shift]), cconj(__ldg(&D.ph_lo[j & mask])));
+}
+TQ_D double4 load_w(const MatsubaraDev &D, int di) {
+  const double2 *p = reinterpret_cast<const double2 *>(D.wtab + di);
+  double2 a = __ldg(p), b = __ldg(p + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+// sum_i a_i / (i w - b_i) = -S2 - i w S1,  S1 = sum a_i r_i,  S2 = sum a_i b_i r_i,  r_i = 1/(b_i^2 + w^2)
+TQ_D cd tail_iw(const MatsubaraDev &D, double4 w, cd a1, cd a2, cd a3) {
+  double r1 = w.y, r2 = w.z, r3 = w.w;
+  cd S1 = caxpy(r3, a3, caxpy(r2, a2, cscale(r1, a1)));
+  cd S2 = caxpy(r3 * D.b[2], a3, caxpy(r2 * D.b[1], a2, cscale(r1 * D.b[0], a1)));
+  return cmk(fma(w.x, S1.y, -S2.x), -fma(w.x, S1.x, S2.y));
+}
+TQ_D cd bigtw(const BigTw &t, int m) { return cmul(__ldg(&t.hi[m >> t.shift]), __ldg(&t.lo[m & ((1 << t.shift) - 1)])); }
+
+// freq-space index k in [0, L) -> mesh data index, or -1 when k is outside the window  (:182, :254  "(iw.n + L) % L")
+TQ_D int freq_data_index(const MatsubaraDev &D, int k) {
+  int n = (k <= D.last) ? k : k - D.L;
+  return (n >= D.first && n <= D.last) ? n - D.first : -1;
+}
+
+template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) matsubara_tile_kernel(const TileArgs A) {
+  extern __shared__ double2 smem[];
+  const MatsubaraDev &D = A.D;
+  const int item = blockIdx.x, gf = blockIdx.z;
+  const int c0 = blockIdx.y * A.TC;
+  const int tc = min(A.TC, A.n_cols - c0);
+  const int N = A.P.N;
+  const int pitch = tc;
+  const int sk = A.skewmask;
+  cd *tile = smem;
+  cd *coef = smem + (size_t)fft_rows_alloc(N, sk) * pitch; // a1[tc], a2[tc], a3[tc], extra[tc]
+  const bool fermion = D.stat == TQ_FERMION;
+
+  // ---- per-column pole weights from the moments  (:151-169, :238-252)
+  if (IN != IN_SCRATCH || OUT != OUT_SCRATCH) {
+    const cd *mom = A.moments + (size_t)gf * A.mom_gf_stride;
+    for (int c = threadIdx.x; c < tc; c += NT) {
+      cd m1 = mom[(size_t)1 * A.n_cols + c0 + c], m2 = mom[(size_t)2 * A.n_cols + c0 + c], m3 = mom[(size_t)3 * A.n_cols + c0 + c];
+      cd a1, a2, a3;
+      if (fermion) {
+        a1 = csub(m1, m3);
+        a2 = cscale(0.5, cadd(m2, m3));
+        a3 = cscale(0.5, csub(m3, m2));
+      } else {
+        a1 = cscale(4.0 / 3.0, csub(m1, m3));
+        a2 = csub(m3, cscale(0.5, cadd(m1, m2)));
+        a3 = cadd(cadd(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
+      }
+      coef[c] = a1;
+      coef[tc + c] = a2;
+      coef[2 * tc + c] = a3;
+      if (OUT == OUT_FREQ) {
+        // trapezoid end-point correction  -0.5 fact (g_0 + m1 -/+ ... g_L)   (:181)
+        const cd *g = A.gt_ref + (size_t)gf * A.gt_gf_stride;
+        cd g0 = g[c0 + c], gL = g[(size_t)D.L * A.n_cols + c0 + c];
+        cd t = cadd(g0, m1);
+        t = fermion ? cadd(t, gL) : csub(t, gL);
+        coef[3 * tc + c] = cscale(-0.5 * D.fact_fwd, t);
+      } else {
+        coef[3 * tc + c] = m1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- load + pre-transform
+  const int ntile = N * tc;
+  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
+    int r, c;
+    if (tc == 1) { r = idx; c = 0; } else { r = idx / tc; c = idx - r * tc; }
+    cd x;
+    if (IN == IN_TAU) {
+      int j = item + A.in_stride * r;
+      cd g = A.in[(size_t)gf * A.in_gf_stride + (size_t)j * A.n_cols + c0 + c];
+      double h[3];
+      row_model(D, j, h);
+      x = caxpy(-h[2], coef[2 * tc + c], caxpy(-h[1], coef[tc + c], caxpy(-h[0], coef[c], g)));
+      x = fermion ? cmul(phase_fwd(D, j), x) : cscale(D.fact_fwd, x);
+    } else if (IN == IN_FREQ) {
+      int k = item + A.in_stride * r;
+      int di = freq_data_index(D, k);
+      if (di >= 0) {
+        cd g = A.in[(size_t)gf * A.in_gf_stride + (size_t)di * A.n_cols + c0 + c];
+        cd t = tail_iw(D, load_w(D, di), coef[c], coef[tc + c], coef[2 * tc + c]);
+        x = cscale(D.inv_beta, csub(g, t));
+      } else {
+        x = cmk(0.0, 0.0);
+      }
+    } else {
+      x = A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)item * A.Na + r) * A.n_cols + c0 + c];
+    }
+    tile[(size_t)fft_row(r, sk) * pitch + c] = x;
+  }
+  __syncthreads();
+
+  fft_tile<SGN>(A.P, tile, pitch, tc, A.direct_tw != 0, sk);
+
+  // ---- post-transform + store (applies the digit-reversal permutation)
+  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
+    int kk, c;
+    if (tc == 1) { kk = idx; c = 0; } else { kk = idx / tc; c = idx - kk * tc; }
+    if (OUT == OUT_FREQ) {
+      int k = item + A.out_stride * kk;
+      int di = freq_data_index(D, k);
+      if (di < 0) continue;
+      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
+      cd t = tail_iw(D, load_w(D, di), coef[c], coef[tc + c], coef[2 * tc + c]);
+      A.out[(size_t)gf * A.out_gf_stride + (size_t)di * A.n_cols + c0 + c] = cadd(cadd(v, coef[3 * tc + c]), t);
+    } else if (OUT == OUT_TAU) {
+      int j = item + A.out_stride * kk;
+      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
+      double h[3];
+      row_model(D, j, h);
+      if (fermion) v = cmul(v, phase_inv(D, j));
+      v = caxpy(h[2], coef[2 * tc + c], caxpy(h[1], coef[tc + c], caxpy(h[0], coef[c], v)));
+      cd *o = A.out + (size_t)gf * A.out_gf_stride;
+      o[(size_t)j * A.n_cols + c0 + c] = v;
+      if (j == 0) { // gt[L] = -/+ (gt[0] + m1)    (:267-268)
+        cd e = cadd(v, coef[3 * tc + c]);
+        o[(size_t)D.L * A.n_cols + c0 + c] = fermion ? cneg(e) : e;
+      }
+    } else {
+      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
+      cd w = bigtw(A.btw, item * kk);
+      if (SGN < 0) w = cconj(w);
+      A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)kk * A.Na + item) * A.n_cols + c0 + c] = cmul(v, w);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// moments of G(tau) from one-sided finite differences  (fourier_matsubara.cpp:39-92, noise check :100-114)
+// -------------------------------------------------------------------------------------------------
+__constant__ double c_vinv[2][8] = {
+   // rows 0 and 1 of the literal inverse Vandermonde matrix of fourier_matsubara.cpp:52-55 (only these are used, :89-90)
+   {8.000000000008853, -28.000000000055913, 56.000000000151815, -70.00000000021936, 56.00000000020795, -28.000000000115904,
+    8.00000000003683, -1.0000000000049232},
+   {-13.742857142879107, 62.10000000013776, -133.5333333337073, 172.75000000055635, -141.00000000052023, 71.43333333362274,
+    -20.600000000091182, 2.592857142869304}};
+
+__device__ double block_max(double v, double *sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (l == 0) sh[0] = r;
+  }
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_moments_from_tau(const cd *gt, long gf_stride, int n_tau, int n_cols, double beta, int stat, cd *mom4,
+                                                          int *warn) {
+  __shared__ double sh[32];
+  const int gf = blockIdx.x;
+  const cd *g = gt + (size_t)gf * gf_stride;
+  const int L = n_tau - 1;
+  const double delta = (beta - 0.0) / (n_tau - 1);
+  double m1 = 0.0, m2 = 0.0;
+  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    cd g0 = g[c], g1 = g[(size_t)1 * n_cols + c], g2 = g[(size_t)2 * n_cols + c];
+    cd gL = g[(size_t)L * n_cols + c], gL1 = g[(size_t)(L - 1) * n_cols + c], gL2 = g[(size_t)(L - 2) * n_cols + c];
+    cd d;
+    d = csub(g1, g0);
+    double a = hypot(d.x, d.y);
+    d = csub(gL1, gL);
+    a += hypot(d.x, d.y);
+    d = csub(g2, g0);
+    double b = hypot(d.x, d.y);
+    d = csub(gL2, gL);
+    b += hypot(d.x, d.y);
+    m1 = fmax(m1, a);
+    m2 = fmax(m2, b);
+  }
+  double der_1 = block_max(m1, sh) / delta;
+  double der_2 = 0.5 * block_max(m2, sh) / delta;
+  const bool noisy = (der_1 < 0.95 * der_2) || (der_1 > 1.05 * der_2);
+  if (threadIdx.x == 0 && warn) warn[gf] = noisy ? TQ_WARN_NOISY_TAU : 0;
+  cd *mo = mom4 + (size_t)gf * 4 * n_cols;
+  const double sign = (stat == TQ_FERMION) ? -1.0 : 1.0;
+  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    cd t1 = cmk(0, 0), t2 = cmk(0, 0), t3 = cmk(0, 0);
+    if (!noisy) {
+      cd g0 = g[c], gL = g[(size_t)L * n_cols + c];
+      cd gl0 = cmk(0, 0), gl1 = cmk(0, 0), gr0 = cmk(0, 0), gr1 = cmk(0, 0);
+#pragma unroll
+      for (int m = 1; m <= 8; ++m) {
+        double wr = double(m) / double(n_tau - 1);
+        double tau_m = 0.0 * (1 - wr) + beta * wr; // linear.hpp:154-160
+        cd dl = csub(g[(size_t)m * n_cols + c], g0);
+        cd dr = csub(gL, g[(size_t)(L - m) * n_cols + c]);
+        dl = cmk(dl.x / tau_m, dl.y / tau_m);
+        dr = cmk(dr.x / tau_m, dr.y / tau_m);
+        gl0 = caxpy(c_vinv[0][m - 1], dl, gl0);
+        gl1 = caxpy(c_vinv[1][m - 1], dl, gl1);
+        gr0 = caxpy(c_vinv[0][m - 1], dr, gr0);
+        gr1 = caxpy(c_vinv[1][m - 1], dr, gr1);
+      }
+      t1 = cneg(csub(g0, cscale(sign, gL)));
+      t2 = csub(gl0, cscale(sign, gr0));
+      t3 = cscale(-2.0 / delta, cadd(gl1, cscale(sign, gr1)));
+    }
+    mo[c] = cmk(0, 0);
+    mo[(size_t)n_cols + c] = t1;
+    mo[(size_t)2 * n_cols + c] = t2;
+    mo[(size_t)3 * n_cols + c] = t3;
+  }
+}
+
+// known moments -> dense [batch][4][n_cols] (zero padded) and max |0th moment|   (:116-122, :199-201)
+__global__ void k_prepare_known_moments(const cd *known, int n_known, int n_cols, long total_cols /* batch * n_cols */, cd *mom4,
+                                        unsigned long long *max_m0_bits) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double a0 = 0.0;
+  if (i < total_cols) {
+    long gf = i / n_cols;
+    int c = (int)(i - gf * n_cols);
+    const cd *k = known + (size_t)gf * n_known * n_cols;
+    cd *mo = mom4 + (size_t)gf * 4 * n_cols;
+    for (int r = 0; r < 4; ++r) mo[(size_t)r * n_cols + c] = (r < n_known) ? k[(size_t)r * n_cols + c] : cmk(0, 0);
+    cd m0 = k[c];
+    a0 = hypot(m0.x, m0.y);
+    if (!(a0 == a0)) a0 = INFINITY; // NaN fails the "< 1e-8" assertion
+  }
+  for (int o = 16; o > 0; o >>= 1) a0 = fmax(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+  if ((threadIdx.x & 31) == 0 && a0 > 0.0) atomicMax(max_m0_bits, (unsigned long long)__double_as_longlong(a0));
+}
+
+// -------------------------------------------------------------------------------------------------
+// host: plans
+// -------------------------------------------------------------------------------------------------
+struct MatsubaraPlan {
+  MatsubaraDev dev{};
+  BigTw btw{};
+  std::vector<void *> allocs;
+  ~MatsubaraPlan() {
+    for (void *p : allocs) cudaFree(p);
+  }
+};
+
+template <class T> static tq_status upload(tq_ctx *ctx, MatsubaraPlan &pl, const std::vector<T> &h, const T **d) {
+  void *p = nullptr;
+  TQ_CUDA(ctx, cudaMalloc(&p, sizeof(T) * std::max<size_t>(h.size(), 1)));
+  pl.allocs.push_back(p);
+  TQ_CUDA(ctx, cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+  *d = (const T *)p;
+  return TQ_OK;
+}
+
+static tq_status get_matsubara_plan(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, std::shared_ptr<MatsubaraPlan> *out) {
+  auto key = std::make_tuple(beta, stat, n_tau, n_iw);
+  auto it = ctx->matsubara_plans.find(key);
+  if (it != ctx->matsubara_plans.end()) {
+    *out = it->second;
+    return TQ_OK;
+  }
+  auto pl = std::make_shared<MatsubaraPlan>();
+  MatsubaraDev &D = pl->dev;
+  const long L = n_tau - 1;
+  D.L = (int)L;
+  D.stat = stat;
+  D.beta = beta;
+  D.fact_fwd = beta / L;  // fourier_matsubara.cpp:141
+  D.inv_beta = 1.0 / beta; // :229
+  D.last = (int)(n_iw - 1);                              // imfreq.hpp:58-60
+  D.first = -(D.last + (stat == TQ_FERMION ? 1 : 0));
+  D.n_w = D.last - D.first + 1;
+  D.lo_shift = 7;
+  const int LO = 1 << D.lo_shift;
+  D.nhi = (int)(L >> D.lo_shift) + 1;
+  if (stat == TQ_FERMION) {
+    D.b[0] = 0; D.b[1] = 1; D.b[2] = -1; // :152-154
+  } else {
+    D.b[0] = -0.5; D.b[1] = -1; D.b[2] = 1; // :163-165
+  }
+  const long double pi = 3.141592653589793238462643383279502884L;
+  std::vector<cd> ph_hi_f(D.nhi), ph_hi_i(D.nhi), ph_lo(LO);
+  for (int h = 0; h < D.nhi; ++h) {
+    long double ang = pi * (long double)((long)h << D.lo_shift) / (long double)L;
+    ph_hi_f[h] = cmk((double)((long double)D.fact_fwd * cosl(ang)), (double)((long double)D.fact_fwd * sinl(ang)));
+    ph_hi_i[h] = cmk((double)cosl(ang), (double)(-sinl(ang)));
+  }
+  for (int l = 0; l < LO; ++l) {
+    long double ang = pi * (long double)l / (long double)L;
+    ph_lo[l] = cmk((double)cosl(ang), (double)sinl(ang));
+  }
+  std::vector<double> e_hi(3 * (size_t)D.nhi), e_lo(3 * (size_t)LO);
+  for (int i = 0; i < 3; ++i) {
+    long double ab = fabsl((long double)D.b[i]);
+    D.rev[i] = D.b[i] < 0 ? 1 : 0;
+    long double eb = expl(-(long double)beta * ab);
+    if (stat == TQ_FERMION)
+      D.C[i] = (double)(-1.0L / (1.0L + eb)); // oneFermion, :28-30
+    else
+      D.C[i] = D.b[i] >= 0 ? (double)(1.0L / (eb - 1.0L)) : (double)(1.0L / (1.0L - eb)); // oneBoson, :32-34
+    for (int h = 0; h < D.nhi; ++h)
+      e_hi[(size_t)i * D.nhi + h] = (double)expl(-ab * (long double)beta * (long double)((long)h << D.lo_shift) / (long double)L);
+    for (int l = 0; l < LO; ++l) e_lo[(size_t)i * LO + l] = (double)expl(-ab * (long double)beta * (long double)l / (long double)L);
+  }
+  std::vector<double4> wtab(D.n_w);
+  for (int i = 0; i < D.n_w; ++i) {
+    long n = D.first + i;
+    double w = M_PI * (double)(2 * n + stat) / beta; // matsubara.hpp:55
+    double4 t;
+    t.x = w;
+    t.y = 1.0 / (D.b[0] * D.b[0] + w * w);
+    t.z = 1.0 / (D.b[1] * D.b[1] + w * w);
+    t.w = 1.0 / (D.b[2] * D.b[2] + w * w);
+    wtab[i] = t;
+  }
+  TQ_TRY(upload(ctx, *pl, ph_hi_f, &D.ph_hi_fwd));
+  TQ_TRY(upload(ctx, *pl, ph_hi_i, &D.ph_hi_inv));
+  TQ_TRY(upload(ctx, *pl, ph_lo, &D.ph_lo));
+  TQ_TRY(upload(ctx, *pl, e_hi, &D.e_hi));
+  TQ_TRY(upload(ctx, *pl, e_lo, &D.e_lo));
+  TQ_TRY(upload(ctx, *pl, wtab, &D.wtab));
+  // two-level table of exp(2 pi i m / L), m in [0, L), for the four-step twiddles
+  {
+    int shift = 9;
+    int nlo = 1 << shift, nhi = (int)(L >> shift) + 1;
+    std::vector<cd> hi(nhi), lo(nlo);
+    const long double two_pi = 2 * pi;
+    for (int h = 0; h < nhi; ++h) {
+      long double ang = two_pi * (long double)((long)h << shift) / (long double)L;
+      hi[h] = cmk((double)cosl(ang), (double)sinl(ang));
+    }
+    for (int l = 0; l < nlo; ++l) {
+      long double ang = two_pi * (long double)l / (long double)L;
+      lo[l] = cmk((double)cosl(ang), (double)sinl(ang));
+    }
+    pl->btw.shift = shift;
+    TQ_TRY(upload(ctx, *pl, hi, &pl->btw.hi));
+    TQ_TRY(upload(ctx, *pl, lo, &pl->btw.lo));
+  }
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->matsubara_plans[key] = pl;
+  *out = pl;
+  return TQ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host: tiling decisions and launches
+// -------------------------------------------------------------------------------------------------
+struct Tiling {
+  bool two_pass = false;
+  int Na = 1, Nb = 1; // L = Na * Nb (two_pass)
+  int tc = 1;
+  int skew = 0;
+};
+
+static size_t tile_bytes(int N, int tc, int skewmask) { return ((size_t)fft_rows_alloc(N, skewmask) * tc + 4 * (size_t)tc) * sizeof(cd); }
+
+static bool radix_ok(long N) {
+  FftPlan P;
+  return tq_fft_factorize((int)N, P);
+}
+
+static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Tiling *t) {
+  const size_t budget = (size_t)ctx->max_smem_optin;
+  const size_t half = budget / 2 - 1024; // two CTAs per SM
+  // single pass
+  if (tile_bytes((int)L, 1, 0) <= budget && radix_ok(L)) {
+    t->two_pass = false;
+    int tc_fit_half = (int)std::min<long>(n_cols, (long)(half / (sizeof(cd) * (L + 4))));
+    int tc_fit_full = (int)std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (L + 4))));
+    // prefer tiles that let two CTAs share an SM unless that would shrink the contiguous run below 128 B
+    int tc = (tc_fit_half >= 8 || tc_fit_half >= n_cols) ? tc_fit_half : tc_fit_full;
+    // enough CTAs to fill the machine: do not make tiles wider than needed when the batch is small
+    while (tc > 8 && batch * ((n_cols + tc - 1) / tc) < 2L * ctx->sm_count && tc > 1) tc = (tc + 1) / 2;
+    if (tc < 1) tc = 1;
+    t->tc = tc;
+    t->skew = (tc == 1 && tile_bytes((int)L, 1, ~0) <= budget) ? ~0 : 0;
+    return TQ_OK;
+  }
+  // two pass: most balanced factor pair with both lengths supported
+  long best = -1;
+  for (long a = 1; a * a <= L; ++a) {
+    if (L % a) continue;
+    long b = L / a; // b >= a
+    if (!radix_ok(a) || !radix_ok(b)) continue;
+    if (tile_bytes((int)b, 1, 0) > budget) continue;
+    best = a; // keeps the largest a <= sqrt(L), i.e. the most balanced pair
+  }
+  if (best < 0)
+    return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "Fourier: time mesh length " + std::to_string(L) + " cannot be tiled into shared memory (no factor pair)");
+  t->two_pass = true;
+  t->Nb = (int)best;      // first pass length (smaller tile)
+  t->Na = (int)(L / best); // second pass length
+  int tc = (int)std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (t->Na + 4))));
+  if (tc < 1) tc = 1;
+  t->tc = tc;
+  t->skew = 0;
+  return TQ_OK;
+}
+
+template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, const TileArgs &A, int n_items, long batch) {
+  const int tiles = (A.n_cols + A.TC - 1) / A.TC;
+  const size_t smem = tile_bytes(A.P.N, A.TC, A.skewmask);
+  dim3 grid(n_items, tiles, (unsigned)batch);
+  if (batch > 65535) return tq_fail(ctx, TQ_ERR_INVALID, "batch > 65535 per launch");
+  const bool big = smem > (size_t)ctx->max_smem_optin / 2 - 1024;
+  if (big) {
+    auto k = matsubara_tile_kernel<IN, OUT, SGN, 512, 1>;
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 512, smem, ctx->stream>>>(A);
+  } else {
+    auto k = matsubara_tile_kernel<IN, OUT, SGN, 256, 2>;
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, ctx->stream>>>(A);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  return TQ_OK;
+}
+
+// runs the transform for gfs [0, batch) whose device arrays start at d_in / d_out; moments are [batch][mom_rows][n_cols]
+template <int IN_KIND /* IN_TAU: forward, IN_FREQ: inverse */>
+static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long batch, const cd *d_in, cd *d_out, const cd *d_mom, int mom_rows) {
+  const MatsubaraDev &D = pl.dev;
+  const long L = D.L;
+  constexpr bool fwd = IN_KIND == IN_TAU;
+  constexpr int SGN = fwd ? 1 : -1;
+  Tiling t;
+  TQ_TRY(choose_tiling(ctx, L, n_cols, batch, &t));
+  TileArgs A{};
+  A.n_cols = (int)n_cols;
+  A.D = D;
+  A.btw = pl.btw;
+  A.moments = d_mom;
+  A.mom_gf_stride = (long)mom_rows * n_cols;
+  A.gt_ref = fwd ? d_in : nullptr;
+  A.gt_gf_stride = (L + 1) * n_cols;
+  const long in_rows = fwd ? L + 1 : D.n_w, out_rows = fwd ? D.n_w : L + 1;
+  A.in = d_in;
+  A.out = d_out;
+  A.in_gf_stride = in_rows * n_cols;
+  A.out_gf_stride = out_rows * n_cols;
+  const long maxb = 65535;
+  if (!t.two_pass) {
+    std::shared_ptr<FftPlanHost> fp;
+    TQ_TRY(tq_get_fft_plan(ctx, L, &fp));
+    A.P = fp->plan;
+    A.TC = t.tc;
+    A.skewmask = t.skew;
+    A.direct_tw = t.tc >= 8;
+    A.in_stride = 1;
+    A.out_stride = 1;
+    for (long b0 = 0; b0 < batch; b0 += maxb) {
+      long nb = std::min(maxb, batch - b0);
+      TileArgs B = A;
+      B.in = A.in + b0 * A.in_gf_stride;
+      B.out = A.out + b0 * A.out_gf_stride;
+      B.moments = A.moments + b0 * A.mom_gf_stride;
+      if (fwd) B.gt_ref = A.gt_ref + b0 * A.gt_gf_stride;
+      if (fwd)
+        TQ_TRY((launch_tile<IN_TAU, OUT_FREQ, SGN>(ctx, B, 1, nb)));
+      else
+        TQ_TRY((launch_tile<IN_FREQ, OUT_TAU, SGN>(ctx, B, 1, nb)));
+    }
+    return TQ_OK;
+  }
+  // four-step:  index_in = a + Na*b,  index_out = beta + Nb*alpha;  pass 1: length Nb over b for every a, times w_L^{a beta};
+  // pass 2: length Na over a for every beta.   scratch[gf][beta][a][col]
+  std::shared_ptr<FftPlanHost> fa, fb;
+  TQ_TRY(tq_get_fft_plan(ctx, t.Na, &fa));
+  TQ_TRY(tq_get_fft_plan(ctx, t.Nb, &fb));
+  // chunk the batch so that the scratch of one chunk stays L2 resident between the two kernels
+  size_t per_gf = (size_t)L * n_cols * sizeof(cd);
+  size_t l2_budget = 64ull << 20;
+  if (const char *e = getenv("TQ_TWOPASS_CHUNK_MB")) l2_budget = (size_t)atol(e) << 20;
+  long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
+  chunk = std::min<long>(chunk, std::min<long>(batch, maxb));
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));
+  A.scratch = (cd *)ctx->scratch.p;
+  A.scratch_gf_stride = L * n_cols;
+  A.Na = t.Na;
+  A.skewmask = 0;
+  A.direct_tw = t.tc >= 8;
+  for (long b0 = 0; b0 < batch; b0 += chunk) {
+    long nb = std::min(chunk, batch - b0);
+    TileArgs B = A;
+    B.in = A.in + b0 * A.in_gf_stride;
+    B.out = A.out + b0 * A.out_gf_stride;
+    B.moments = A.moments + b0 * A.mom_gf_stride;
+    if (fwd) B.gt_ref = A.gt_ref + b0 * A.gt_gf_stride;
+    // pass 1
+    B.P = fb->plan;
+    B.TC = (int)std::min<long>(n_cols, (long)((size_t)ctx->max_smem_optin / (sizeof(cd) * (t.Nb + 4))));
+    B.in_stride = t.Na;
+    B.out_stride = 0;
+    if (fwd)
+      TQ_TRY((launch_tile<IN_TAU, OUT_SCRATCH, SGN>(ctx, B, t.Na, nb)));
+    else
+      TQ_TRY((launch_tile<IN_FREQ, OUT_SCRATCH, SGN>(ctx, B, t.Na, nb)));
+    // pass 2
+    B.P = fa->plan;
+    B.TC = t.tc;
+    B.in_stride = 0;
+    B.out_stride = t.Nb;
+    if (fwd)
+      TQ_TRY((launch_tile<IN_SCRATCH, OUT_FREQ, SGN>(ctx, B, t.Nb, nb)));
+    else
+      TQ_TRY((launch_tile<IN_SCRATCH, OUT_TAU, SGN>(ctx, B, t.Nb, nb)));
+  }
+  return TQ_OK;
+}
+
+// tail_fit.cu
+tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
+                             int hermitian, int inner_dim, long n_cols, long batch, const cd *d_g, const cd *d_known, int n_known,
+                             cd *d_out_moments /* [batch][TQ_MAX_MOMENTS][n_cols] dense with n_moments rows */, int *n_moments,
+                             double *d_err /* device double[batch] */);
+
+struct StatusWords {
+  unsigned long long max_m0_bits;
+};
+
+extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                                          const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_tau_to_iw: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long L = n_tau - 1;
+  const long last = n_iw - 1;
+  // fourier_matsubara.cpp:127-129
+  if (L < 2 * (last + 1))
+    return tq_fail(ctx, TQ_ERR_RUNTIME,
+                   "Fourier: The time mesh mush be at least twice as long as the number of positive frequencies :\n gt.mesh().size() =  " +
+                      std::to_string(n_tau) + " gw.mesh().last_index()" + std::to_string(last));
+  const bool have_moments = moments != nullptr && n_moments > 0;
+  if (!have_moments && n_tau < 17) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_tau_to_iw: n_tau < 17 needs known moments");
+  std::shared_ptr<MatsubaraPlan> pl;
+  TQ_TRY(get_matsubara_plan(ctx, beta, statistic, n_tau, n_iw, &pl));
+  const long n_w = pl->dev.n_w;
+  const size_t in_bytes = sizeof(cd) * (size_t)batch * n_tau * n_others, out_bytes = sizeof(cd) * (size_t)batch * n_w * n_others;
+  const void *d_in = nullptr, *d_known = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, gt, in_bytes, ctx->stage_in, &d_in));
+  if (have_moments) TQ_TRY(tq_stage_in(ctx, moments, sizeof(cd) * (size_t)batch * n_moments * n_others, ctx->stage_in2, &d_known));
+  TQ_TRY(tq_stage_out_begin(ctx, gw, out_bytes, ctx->stage_out, &d_out, &out_host));
+  // small buffer: [batch][4][n_others] moments, int warn[batch], status words
+  const size_t mom_bytes = sizeof(cd) * (size_t)batch * 4 * n_others;
+  const size_t warn_off = (mom_bytes + 255) & ~size_t(255);
+  const size_t st_off = (warn_off + sizeof(int) * batch + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->small, st_off + sizeof(StatusWords)));
+  cd *d_mom = (cd *)ctx->small.p;
+  int *d_warn = (int *)((char *)ctx->small.p + warn_off);
+  StatusWords *d_st = (StatusWords *)((char *)ctx->small.p + st_off);
+  TQ_CUDA(ctx, cudaMemsetAsync(d_warn, 0, sizeof(int) * batch + 256 + sizeof(StatusWords), ctx->stream));
+  if (have_moments) {
+    long total = batch * n_others;
+    k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_others, total,
+                                                                                        d_mom, &d_st->max_m0_bits);
+  } else {
+    if (batch > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "batch too large");
+    k_moments_from_tau<<<(unsigned)batch, 256, 0, ctx->stream>>>((const cd *)d_in, n_tau * n_others, (int)n_tau, (int)n_others, beta, statistic,
+                                                                  d_mom, d_warn);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  TQ_TRY(run_transform<IN_TAU>(ctx, *pl, n_others, batch, (const cd *)d_in, (cd *)d_out, d_mom, 4));
+  // status read-back (one small copy; the reference's checks need the values on the host)
+  TQ_TRY(tq_reserve_pinned(ctx, sizeof(int) * batch + sizeof(StatusWords)));
+  int *h_warn = (int *)ctx->pinned;
+  StatusWords *h_st = (StatusWords *)((char *)ctx->pinned + sizeof(int) * batch);
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_warn, d_warn, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_st, d_st, sizeof(StatusWords), cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (have_moments) {
+    double a0;
+    memcpy(&a0, &h_st->max_m0_bits, sizeof(double));
+    if (!(a0 < 1e-8)) // :116-118
+      return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR: Direct Fourier implementation requires vanishing 0th moment\n  error is :" + std::to_string(a0));
+  }
+  const int mesh_warn = (L < 6 * (last + 1)) ? TQ_WARN_SHORT_TAU_MESH : 0; // :131-133
+  if (warn)
+    for (long b = 0; b < batch; ++b) warn[b] = h_warn[b] | mesh_warn;
+  TQ_TRY(tq_stage_out_finish(ctx, gw, out_bytes, d_out, out_host));
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                                          const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
+                                          double *tail_err) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_iw_to_tau: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long L = n_tau - 1;
+  const long last = n_iw - 1;
+  std::shared_ptr<MatsubaraPlan> pl;
+  TQ_TRY(get_matsubara_plan(ctx, beta, statistic, n_tau, n_iw, &pl));
+  const long n_w = pl->dev.n_w;
+  const size_t in_bytes = sizeof(cd) * (size_t)batch * n_w * n_others, out_bytes = sizeof(cd) * (size_t)batch * n_tau * n_others;
+  const void *d_in = nullptr, *d_known = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, gw, in_bytes, ctx->stage_in, &d_in));
+  const bool have_moments = moments != nullptr && n_moments > 0;
+  if (have_moments) TQ_TRY(tq_stage_in(ctx, moments, sizeof(cd) * (size_t)batch * n_moments * n_others, ctx->stage_in2, &d_known));
+  // small buffer: moments [batch][TQ_MAX_MOMENTS][n_others], err double[batch], status
+  const size_t mom_bytes = sizeof(cd) * (size_t)batch * TQ_MAX_MOMENTS * n_others;
+  const size_t err_off = (mom_bytes + 255) & ~size_t(255);
+  const size_t st_off = (err_off + sizeof(double) * batch + 255) & ~size_t(255);
+  const size_t zk_off = (st_off + sizeof(StatusWords) + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->small, zk_off + sizeof(cd) * (size_t)batch * n_others));
+  cd *d_mom = (cd *)ctx->small.p;
+  double *d_err = (double *)((char *)ctx->small.p + err_off);
+  StatusWords *d_st = (StatusWords *)((char *)ctx->small.p + st_off);
+  cd *d_zero_known = (cd *)((char *)ctx->small.p + zk_off);
+  TQ_CUDA(ctx, cudaMemsetAsync(d_err, 0, zk_off - err_off + sizeof(cd) * (size_t)batch * n_others, ctx->stream));
+  int mom_rows = 0;
+  bool fitted = false;
+  if (have_moments && n_moments >= 4) {
+    long total = batch * n_others;
+    k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_others, total,
+                                                                                        d_mom, &d_st->max_m0_bits);
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+    mom_rows = 4;
+  } else {
+    // :197  no moments -> make_zero_tail(gw, 1);  :203  fewer than 4 -> fit_tail(gw, known_moments)
+    const cd *kn = have_moments ? (const cd *)d_known : d_zero_known;
+    int nk = have_moments ? n_moments : 1;
+    if (have_moments) {
+      // the 0th-moment assertion (:199-201) is made on the user's moments before the fit
+      long total = batch * n_others;
+      TQ_TRY(tq_reserve(ctx, ctx->stage_in3, sizeof(cd) * (size_t)batch * 4 * n_others));
+      k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_others, total,
+                                                                                          (cd *)ctx->stage_in3.p, &d_st->max_m0_bits);
+      tq_count_launch(ctx);
+    }
+    tq_status st = tq_fit_tail_device(ctx, beta, statistic, n_iw, 0.2, 30, -1, 0, 1, n_others, batch, (const cd *)d_in, kn, nk, d_mom, &mom_rows,
+                                      d_err);
+    if (st != TQ_OK) return st;
+    fitted = true;
+    if (!(mom_rows > 3)) // :211
+      return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR: Inverse Fourier implementation requires at least a proper 3rd high-frequency moment\n");
+  }
+  if (L < 2 * (last + 1)) // :218-220
+    return tq_fail(ctx, TQ_ERR_RUNTIME,
+                   "Inverse Fourier: The time mesh mush be at least twice as long as the freq mesh :\n gt.mesh().size() =  " +
+                      std::to_string(n_tau) + " gw.mesh().last_index()" + std::to_string(last) + "\n");
+  TQ_TRY(tq_stage_out_begin(ctx, gt, out_bytes, ctx->stage_out, &d_out, &out_host));
+  TQ_TRY(run_transform<IN_FREQ>(ctx, *pl, n_others, batch, (const cd *)d_in, (cd *)d_out, d_mom, mom_rows));
+  TQ_TRY(tq_reserve_pinned(ctx, sizeof(double) * batch + sizeof(StatusWords)));
+  double *h_err = (double *)ctx->pinned;
+  StatusWords *h_st = (StatusWords *)((char *)ctx->pinned + sizeof(double) * batch);
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_st, d_st, sizeof(StatusWords), cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (have_moments) {
+    double a0;
+    memcpy(&a0, &h_st->max_m0_bits, sizeof(double));
+    if (!(a0 < 1e-8))
+      return tq_fail(ctx, TQ_ERR_RUNTIME,
+                     "ERROR: Inverse Fourier implementation requires vanishing 0th moment\n  error is :" + std::to_string(a0) + "\n");
+  }
+  int w_any = 0;
+  if (fitted) {
+    for (long b = 0; b < batch; ++b) {
+      double e = h_err[b];
+      if (!(e < 1e-2)) // :205-207
+        return tq_fail(ctx, TQ_ERR_RUNTIME,
+                       "ERROR: High frequency moments have an error greater than 1e-2.\n  Error = " + std::to_string(e) +
+                          "\n Please make sure you treat the constant offset analytically!\n");
+      if (warn) warn[b] = (e > 1e-4) ? TQ_WARN_TAIL_ERR : 0; // :208-210
+      w_any |= (e > 1e-4);
+    }
+  } else if (warn) {
+    for (long b = 0; b < batch; ++b) warn[b] = 0;
+  }
+  (void)w_any;
+  if (tail_err)
+    for (long b = 0; b < batch; ++b) tail_err[b] = fitted ? h_err[b] : 0.0;
+  TQ_TRY(tq_stage_out_finish(ctx, gt, out_bytes, d_out, out_host));
+  return TQ_OK;
+}

@@ -1,0 +1,156 @@
+// Plain batched multi-dimensional DFT (the _fourier_base seam) and the cyclat <-> brzone transforms.
+//
+// Restates c++/triqs/gfs/transform/fourier_common.cpp:25-45 (fftw_plan_many_dft, stride = howmany, dist = 1,
+// unnormalised, BACKWARD = e^{+i...}) and c++/triqs/gfs/transform/fourier_lattice.cpp:30-59.
+// The data is [prod(dims)][howmany] with the batch index innermost, so a transform along mesh axis d sees
+// the array as [outer][N_d][inner] with `inner` contiguous: a CTA stages a tile [N_d][TC] of TC adjacent
+// inner columns in shared memory (coalesced TC*16-byte runs), transforms it in place and writes it back.
+#include "tq_fft.cuh"
+
+#include <algorithm>
+
+struct PlainArgs {
+  FftPlan P;
+  const cd *in;
+  cd *out;
+  long inner;     // contiguous elements per (outer, n)
+  int TC, tiles;  // tiles = ceil(inner / TC)
+  int direct_tw;
+  double scale;   // applied on store (1 = none)
+};
+
+template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) plain_tile_kernel(const PlainArgs A) {
+  extern __shared__ double2 smem[];
+  const long o = blockIdx.x / A.tiles;
+  const int tile_id = blockIdx.x - (int)(o * A.tiles);
+  const long c0 = (long)tile_id * A.TC;
+  const int tc = (int)min((long)A.TC, A.inner - c0);
+  const int N = A.P.N;
+  cd *tile = smem;
+  const cd *src = A.in + (size_t)o * N * A.inner + c0;
+  cd *dst = A.out + (size_t)o * N * A.inner + c0;
+  const int ntile = N * tc;
+  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
+    int r = idx / tc, c = idx - r * tc;
+    tile[idx] = src[(size_t)r * A.inner + c];
+  }
+  __syncthreads();
+  fft_tile<SGN>(A.P, tile, tc, tc, A.direct_tw != 0, 0);
+  const bool scaled = A.scale != 1.0;
+  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
+    int k = idx / tc, c = idx - k * tc;
+    cd v = tile[(size_t)__ldg(&A.P.pos[k]) * tc + c];
+    if (scaled) v = cscale(A.scale, v);
+    dst[(size_t)k * A.inner + c] = v;
+  }
+}
+
+static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale) {
+  std::shared_ptr<FftPlanHost> fp;
+  TQ_TRY(tq_get_fft_plan(ctx, N, &fp));
+  const size_t budget = (size_t)ctx->max_smem_optin;
+  const size_t half = budget / 2 - 1024;
+  if (sizeof(cd) * (size_t)N > budget)
+    return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length " + std::to_string(N) + " does not fit one SM's shared memory");
+  long tc_half = (long)(half / (sizeof(cd) * N)), tc_full = (long)(budget / (sizeof(cd) * N));
+  long tcmax = tc_half >= 8 ? tc_half : tc_full;
+  tcmax = std::max<long>(1, std::min(tcmax, inner));
+  long tc = tcmax;
+  // prefer a tile width that divides the contiguous run and keeps 64-byte granularity
+  for (long t = tcmax; t >= std::max<long>(4, tcmax / 2); --t)
+    if (inner % t == 0 && t % 4 == 0) { tc = t; break; }
+  PlainArgs A{};
+  A.P = fp->plan;
+  A.in = in;
+  A.out = out;
+  A.inner = inner;
+  A.TC = (int)tc;
+  A.tiles = (int)((inner + tc - 1) / tc);
+  A.direct_tw = tc >= 8;
+  A.scale = scale;
+  const size_t smem = sizeof(cd) * (size_t)N * tc;
+  const long nblocks = outer * A.tiles;
+  if (nblocks > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: too many tiles");
+  const bool big = smem > half;
+#define TQ_LAUNCH_PLAIN(SGN, NT, MINB)                                                                                           \
+  do {                                                                                                                           \
+    auto k = plain_tile_kernel<SGN, NT, MINB>;                                                                                   \
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
+    k<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(A);                                                                          \
+  } while (0)
+  if (sign > 0) {
+    if (big) TQ_LAUNCH_PLAIN(1, 512, 1); else TQ_LAUNCH_PLAIN(1, 256, 2);
+  } else {
+    if (big) TQ_LAUNCH_PLAIN(-1, 512, 1); else TQ_LAUNCH_PLAIN(-1, 256, 2);
+  }
+#undef TQ_LAUNCH_PLAIN
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  return TQ_OK;
+}
+
+static tq_status fft_many_device(tq_ctx *ctx, int rank, const long *dims, long howmany, const cd *d_in, cd *d_out, int sign, double scale) {
+  long total = 1;
+  for (int d = 0; d < rank; ++d) total *= dims[d];
+  bool first = true;
+  int last_axis = -1;
+  for (int d = 0; d < rank; ++d)
+    if (dims[d] > 1) last_axis = d;
+  if (last_axis < 0) { // all lengths 1: identity (times scale)
+    if (d_in != d_out) TQ_CUDA(ctx, cudaMemcpyAsync(d_out, d_in, sizeof(cd) * (size_t)total * howmany, cudaMemcpyDeviceToDevice, ctx->stream));
+    return TQ_OK;
+  }
+  // innermost axis first (largest contiguous runs while the input is still cold)
+  for (int d = rank - 1; d >= 0; --d) {
+    if (dims[d] == 1) continue;
+    long outer = 1, inner = howmany;
+    for (int e = 0; e < d; ++e) outer *= dims[e];
+    for (int e = d + 1; e < rank; ++e) inner *= dims[e];
+    bool is_last = true;
+    for (int e = d - 1; e >= 0; --e)
+      if (dims[e] > 1) is_last = false;
+    TQ_TRY(launch_plain(ctx, outer, dims[d], inner, first ? d_in : d_out, d_out, sign, is_last ? scale : 1.0));
+    first = false;
+  }
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_fft_many(tq_ctx *ctx, int rank, const int *dims, long howmany, const tq_complex *in, tq_complex *out, int sign) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!in || !out || rank < 1 || rank > 3 || !dims || howmany < 1 || (sign != 1 && sign != -1))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  long ld[3] = {1, 1, 1}, total = 1;
+  for (int d = 0; d < rank; ++d) {
+    if (dims[d] < 1) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: dims must be >= 1");
+    ld[d] = dims[d];
+    total *= dims[d];
+  }
+  const size_t bytes = sizeof(cd) * (size_t)total * howmany;
+  const void *d_in = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, in, bytes, ctx->stage_in, &d_in));
+  TQ_TRY(tq_stage_out_begin(ctx, out, bytes, ctx->stage_out, &d_out, &out_host));
+  TQ_TRY(fft_many_device(ctx, rank, ld, howmany, (const cd *)d_in, (cd *)d_out, sign, 1.0));
+  TQ_TRY(tq_stage_out_finish(ctx, out, bytes, d_out, out_host));
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_fourier_lattice(tq_ctx *ctx, const long dims[3], int to_k, long n_others, const tq_complex *in, tq_complex *out) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!in || !out || !dims || n_others < 1 || dims[0] < 1 || dims[1] < 1 || dims[2] < 1)
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_lattice: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long nk = dims[0] * dims[1] * dims[2];
+  const size_t bytes = sizeof(cd) * (size_t)nk * n_others;
+  const void *d_in = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, in, bytes, ctx->stage_in, &d_in));
+  TQ_TRY(tq_stage_out_begin(ctx, out, bytes, ctx->stage_out, &d_out, &out_host));
+  // fourier_lattice.cpp:59 r -> k: FFTW_BACKWARD, no scale;  :51-55 k -> r: FFTW_FORWARD then /= N_k
+  TQ_TRY(fft_many_device(ctx, 3, dims, n_others, (const cd *)d_in, (cd *)d_out, to_k ? 1 : -1, to_k ? 1.0 : 1.0 / (double)nk));
+  TQ_TRY(tq_stage_out_finish(ctx, out, bytes, d_out, out_host));
+  return TQ_OK;
+}

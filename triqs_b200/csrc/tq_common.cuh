@@ -1,0 +1,95 @@
+// Shared declarations of libtqgpu: complex helpers, the context, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/tqgpu.h"
+
+#define TQ_HD __host__ __device__ __forceinline__
+#define TQ_D __device__ __forceinline__
+
+typedef double2 cd;
+
+TQ_HD cd cmk(double x, double y) { return make_double2(x, y); }
+TQ_HD cd cadd(cd a, cd b) { return cmk(a.x + b.x, a.y + b.y); }
+TQ_HD cd csub(cd a, cd b) { return cmk(a.x - b.x, a.y - b.y); }
+TQ_HD cd cneg(cd a) { return cmk(-a.x, -a.y); }
+TQ_HD cd cconj(cd a) { return cmk(a.x, -a.y); }
+TQ_HD cd cscale(double s, cd a) { return cmk(s * a.x, s * a.y); }
+TQ_HD cd cmul(cd a, cd b) { return cmk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+// a + b*c
+TQ_HD cd cfma(cd b, cd c, cd a) { return cmk(fma(b.x, c.x, fma(-b.y, c.y, a.x)), fma(b.x, c.y, fma(b.y, c.x, a.y))); }
+// a + s*b (s real)
+TQ_HD cd caxpy(double s, cd b, cd a) { return cmk(fma(s, b.x, a.x), fma(s, b.y, a.y)); }
+// multiply by +i / -i
+TQ_HD cd cmuli(cd a) { return cmk(-a.y, a.x); }
+TQ_HD cd cmulmi(cd a) { return cmk(a.y, -a.x); }
+TQ_HD double cabs2(cd a) { return fma(a.x, a.x, a.y * a.y); }
+
+// ---------------------------------------------------------------------------------------------
+
+struct DeviceBuffer {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct MatsubaraPlan;  // fourier_matsubara.cu
+struct FftPlanHost;    // tq_fft_plan.cu
+struct TailFitterPlan; // tail_fit.cu
+
+struct tq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  // grow-only scratch / staging
+  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small;
+  void *pinned = nullptr;
+  size_t pinned_cap = 0;
+  // caches (mesh-only data, like the reference's tail_fitter::_lss and FFTW plans)
+  std::map<std::tuple<long, int>, std::shared_ptr<FftPlanHost>> fft_plans;                        // (N, dummy)
+  std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
+  std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
+  // NCCL
+  void *nccl_comm = nullptr;
+  int n_ranks = 1, rank = 0;
+};
+
+tq_status tq_fail(tq_ctx *ctx, tq_status st, const std::string &msg);
+
+#define TQ_CUDA(ctx, call)                                                                                                       \
+  do {                                                                                                                           \
+    cudaError_t e__ = (call);                                                                                                    \
+    if (e__ != cudaSuccess)                                                                                                      \
+      return tq_fail(ctx, TQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " at " + __FILE__ + ":" +          \
+                                           std::to_string(__LINE__));                                                           \
+  } while (0)
+
+#define TQ_TRY(expr)                                                                                                             \
+  do {                                                                                                                           \
+    tq_status s__ = (expr);                                                                                                      \
+    if (s__ != TQ_OK) return s__;                                                                                                \
+  } while (0)
+
+tq_status tq_reserve(tq_ctx *ctx, DeviceBuffer &b, size_t bytes);
+tq_status tq_reserve_pinned(tq_ctx *ctx, size_t bytes);
+bool tq_is_device_ptr(const void *p);
+
+// Resolves a user pointer that may live on the host: returns a device pointer, staging through `stage` if needed.
+struct StagedIn {
+  const void *dev = nullptr;
+};
+tq_status tq_stage_in(tq_ctx *ctx, const void *user, size_t bytes, DeviceBuffer &stage, const void **dev);
+// Output: returns device pointer to write to; call tq_stage_out_finish afterwards to copy back when user ptr is host.
+tq_status tq_stage_out_begin(tq_ctx *ctx, void *user, size_t bytes, DeviceBuffer &stage, void **dev, bool *is_host);
+tq_status tq_stage_out_finish(tq_ctx *ctx, void *user, size_t bytes, void *dev, bool is_host);
+
+inline void tq_count_launch(tq_ctx *ctx, int n = 1) { ctx->launches += n; }

@@ -1,0 +1,269 @@
+// Context, error plumbing, staging buffers, memory helpers and the NCCL communicator of libtqgpu.
+#include "tq_common.cuh"
+#include "tq_fft.cuh"
+
+#include <cstring>
+#include <dlfcn.h>
+
+tq_status tq_fail(tq_ctx *ctx, tq_status st, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return st;
+}
+
+extern "C" const char *tq_version(void) { return "tqgpu 0.1 sm_100a"; }
+
+extern "C" tq_status tq_create(int device, tq_ctx **out) {
+  if (!out) return TQ_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) return TQ_ERR_NO_DEVICE; // never compute on the CPU
+  if (device < 0 || device >= n) return TQ_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return TQ_ERR_CUDA;
+  auto *ctx = new tq_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return TQ_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  *out = ctx;
+  return TQ_OK;
+}
+
+static void free_buf(DeviceBuffer &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+extern "C" tq_status tq_comm_destroy_internal(tq_ctx *ctx);
+
+extern "C" void tq_destroy(tq_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  tq_comm_destroy_internal(ctx);
+  ctx->fft_plans.clear();
+  ctx->matsubara_plans.clear();
+  ctx->tail_plans.clear();
+  free_buf(ctx->stage_in);
+  free_buf(ctx->stage_in2);
+  free_buf(ctx->stage_in3);
+  free_buf(ctx->stage_out);
+  free_buf(ctx->scratch);
+  free_buf(ctx->small);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *tq_last_error(const tq_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void *tq_stream(tq_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" uint64_t tq_launch_count(const tq_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" tq_status tq_synchronize(tq_ctx *ctx) {
+  if (!ctx) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TQ_OK;
+}
+
+tq_status tq_reserve(tq_ctx *ctx, DeviceBuffer &b, size_t bytes) {
+  if (bytes <= b.cap) return TQ_OK;
+  if (b.p) {
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TQ_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 8 + 256;
+  TQ_CUDA(ctx, cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  return TQ_OK;
+}
+
+tq_status tq_reserve_pinned(tq_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return TQ_OK;
+  if (ctx->pinned) {
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TQ_CUDA(ctx, cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+  }
+  TQ_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes + 256));
+  ctx->pinned_cap = bytes + 256;
+  return TQ_OK;
+}
+
+bool tq_is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+tq_status tq_stage_in(tq_ctx *ctx, const void *user, size_t bytes, DeviceBuffer &stage, const void **dev) {
+  if (!user) {
+    *dev = nullptr;
+    return TQ_OK;
+  }
+  if (tq_is_device_ptr(user)) {
+    *dev = user;
+    return TQ_OK;
+  }
+  TQ_TRY(tq_reserve(ctx, stage, bytes));
+  TQ_CUDA(ctx, cudaMemcpyAsync(stage.p, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = stage.p;
+  return TQ_OK;
+}
+
+tq_status tq_stage_out_begin(tq_ctx *ctx, void *user, size_t bytes, DeviceBuffer &stage, void **dev, bool *is_host) {
+  if (tq_is_device_ptr(user)) {
+    *dev = user;
+    *is_host = false;
+    return TQ_OK;
+  }
+  TQ_TRY(tq_reserve(ctx, stage, bytes));
+  *dev = stage.p;
+  *is_host = true;
+  return TQ_OK;
+}
+
+tq_status tq_stage_out_finish(tq_ctx *ctx, void *user, size_t bytes, void *dev, bool is_host) {
+  if (is_host) {
+    TQ_CUDA(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_device_alloc(tq_ctx *ctx, size_t bytes, void **dptr) {
+  if (!ctx || !dptr) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  TQ_CUDA(ctx, cudaMalloc(dptr, bytes));
+  return TQ_OK;
+}
+extern "C" tq_status tq_device_free(tq_ctx *ctx, void *dptr) {
+  if (!ctx) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  TQ_CUDA(ctx, cudaFree(dptr));
+  return TQ_OK;
+}
+extern "C" tq_status tq_memcpy_h2d(tq_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TQ_OK;
+}
+extern "C" tq_status tq_memcpy_d2h(tq_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded at run time (the torch-bundled libnccl.so.2 or the system one): the library has no
+// link-time dependency on it, single-GPU users never load it.
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_t_;
+typedef int (*fn_GetUniqueId)(ncclUniqueId_t *);
+typedef int (*fn_CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_t, int);
+typedef int (*fn_CommDestroy)(ncclComm_t_);
+typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, ncclComm_t_, cudaStream_t);
+typedef const char *(*fn_GetErrorString)(int);
+struct NcclApi {
+  void *handle = nullptr;
+  fn_GetUniqueId GetUniqueId = nullptr;
+  fn_CommInitRank CommInitRank = nullptr;
+  fn_CommDestroy CommDestroy = nullptr;
+  fn_AllReduce AllReduce = nullptr;
+  fn_GetErrorString GetErrorString = nullptr;
+  std::string load_error;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char *env = getenv("TQ_NCCL_LIB");
+  const char *cands[] = {env, "libnccl.so.2", "libnccl.so"};
+  for (const char *c : cands) {
+    if (!c) continue;
+    api.handle = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    api.load_error = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+    return api;
+  }
+  api.GetUniqueId = (fn_GetUniqueId)dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (fn_CommInitRank)dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (fn_CommDestroy)dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (fn_AllReduce)dlsym(api.handle, "ncclAllReduce");
+  api.GetErrorString = (fn_GetErrorString)dlsym(api.handle, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
+    api.load_error = "libnccl is missing symbols";
+    api.handle = nullptr;
+  }
+  return api;
+}
+} // namespace
+
+extern "C" tq_status tq_comm_unique_id(unsigned char id[TQ_COMM_ID_BYTES]) {
+  NcclApi &a = nccl();
+  if (!a.handle) return TQ_ERR_COMM;
+  ncclUniqueId_t u;
+  if (a.GetUniqueId(&u) != 0) return TQ_ERR_COMM;
+  static_assert(sizeof(u) == TQ_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  memcpy(id, &u, TQ_COMM_ID_BYTES);
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_comm_init(tq_ctx *ctx, int n_ranks, int rank, const unsigned char id[TQ_COMM_ID_BYTES]) {
+  if (!ctx || n_ranks < 1 || rank < 0 || rank >= n_ranks) return tq_fail(ctx, TQ_ERR_INVALID, "tq_comm_init: bad rank / n_ranks");
+  NcclApi &a = nccl();
+  if (!a.handle) return tq_fail(ctx, TQ_ERR_COMM, a.load_error);
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  tq_comm_destroy_internal(ctx);
+  ncclUniqueId_t u;
+  memcpy(&u, id, TQ_COMM_ID_BYTES);
+  ncclComm_t_ comm = nullptr;
+  int r = a.CommInitRank(&comm, n_ranks, u, rank);
+  if (r != 0) return tq_fail(ctx, TQ_ERR_COMM, std::string("ncclCommInitRank: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"));
+  ctx->nccl_comm = comm;
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_comm_destroy_internal(tq_ctx *ctx) {
+  if (ctx && ctx->nccl_comm) {
+    NcclApi &a = nccl();
+    if (a.handle) a.CommDestroy((ncclComm_t_)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->n_ranks = 1;
+    ctx->rank = 0;
+  }
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_all_reduce_sum(tq_ctx *ctx, double *data, size_t count) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!ctx->nccl_comm) {
+    if (ctx->n_ranks == 1) return TQ_OK; // single rank: the sum over ranks is the identity
+    return tq_fail(ctx, TQ_ERR_COMM, "tq_all_reduce_sum: communicator not initialised (call tq_comm_init)");
+  }
+  NcclApi &a = nccl();
+  // ncclDouble = 8, ncclSum = 0 (nccl.h)
+  int r = a.AllReduce(data, data, count, 8, 0, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
+  if (r != 0) return tq_fail(ctx, TQ_ERR_COMM, std::string("ncclAllReduce: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"));
+  return TQ_OK;
+}

@@ -1,0 +1,298 @@
+// In-shared-memory mixed-radix FFT engine (complex<double>).
+//
+// A CTA owns a tile s[n][c] (n in [0,N) transform axis, c in [0,TC) independent columns) in shared
+// memory and runs an IN-PLACE decimation-in-frequency transform over n for all columns:
+// pass p works on sub-blocks of length M_p (M_0 = N, M_{p+1} = M_p / R_p) and, for every q in
+// [0, M_p/R_p), replaces the R_p elements {base + q + r*M_p/R_p} by their R_p-point DFT times the
+// twiddles w_{M_p}^{q s}.  No butterfly reads what another one writes inside a pass, so one
+// __syncthreads per pass is enough and no ping-pong buffer is needed (that is what lets a
+// 10^4-point complex<double> column = 160 KB live in one SM's shared memory).
+// The result is left in mixed-radix digit-reversed order: X[k] sits at position fft_pos(plan, k);
+// the fused epilogues (frequency-window gather, tau post-twist, lattice store) apply that
+// permutation while they stream the result to HBM, so it costs no extra pass.
+//
+// Everything below is __host__ __device__ so the index math and butterflies are unit-tested on the
+// CPU build box (tests/hostsim), while the product only ever calls them from kernels.
+#pragma once
+#include "tq_common.cuh"
+
+#define TQ_MAX_PASSES 16
+#define TQ_MAX_GENERIC_RADIX 128
+
+struct FftPlan {
+  int N;
+  int npass;
+  int radix[TQ_MAX_PASSES];
+  int M[TQ_MAX_PASSES]; // sub-block length entering pass p
+  const cd *tw;         // tw[j] = exp(+2 pi i j / N), j in [0, N)
+  const int *pos;       // pos[k] = fft_pos(plan, k): where output k sits after the last pass
+};
+
+// position of output k after all passes: k = s_1 + R_1 s_2 + R_1 R_2 s_3 + ...,  pos = sum s_i * (M_i / R_i)
+TQ_HD int fft_pos(const FftPlan &P, int k) {
+  int pos = 0;
+#pragma unroll 1
+  for (int p = 0; p < P.npass; ++p) {
+    int R = P.radix[p];
+    int s = k % R;
+    k /= R;
+    pos += s * (P.M[p] / R);
+  }
+  return pos;
+}
+
+// optional skew of the row index (one pad row every 32) -- breaks the power-of-two/large strides of the
+// digit-reversed gather when TC == 1
+// (skewmask = ~0 enables it, 0 disables it; a run-time value keeps the number of kernel instantiations down)
+TQ_HD int fft_row(int n, int skewmask) { return n + ((n >> 5) & skewmask); }
+TQ_HD int fft_rows_alloc(int N, int skewmask) { return skewmask ? N + (N >> 5) + 1 : N; }
+
+// ---------------------------------------------------------------------------------------------
+// butterflies: y_s = sum_r a_r exp(SGN 2 pi i r s / R), in registers
+// ---------------------------------------------------------------------------------------------
+template <int SGN> TQ_HD cd mul_i_sgn(cd a) { return SGN > 0 ? cmuli(a) : cmulmi(a); }
+
+template <int SGN> TQ_HD void dft2(cd &a0, cd &a1) {
+  cd t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+template <int SGN> TQ_HD void dft3(cd &a0, cd &a1, cd &a2) {
+  const double S = 0.86602540378443864676; // sin(2 pi / 3)
+  cd t = cadd(a1, a2);
+  cd u = caxpy(-0.5, t, a0);
+  cd d = mul_i_sgn<SGN>(cscale(S, csub(a1, a2)));
+  a0 = cadd(a0, t);
+  a1 = cadd(u, d);
+  a2 = csub(u, d);
+}
+
+template <int SGN> TQ_HD void dft4(cd &a0, cd &a1, cd &a2, cd &a3) {
+  cd t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_i_sgn<SGN>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+
+template <int SGN> TQ_HD void dft5(cd &a0, cd &a1, cd &a2, cd &a3, cd &a4) {
+  const double C1 = 0.30901699437494742410;  // cos(2 pi/5)
+  const double C2 = -0.80901699437494742410; // cos(4 pi/5)
+  const double S1 = 0.95105651629515357212;  // sin(2 pi/5)
+  const double S2 = 0.58778525229247312917;  // sin(4 pi/5)
+  cd t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+  cd b1 = caxpy(C2, t2, caxpy(C1, t1, a0));
+  cd b2 = caxpy(C1, t2, caxpy(C2, t1, a0));
+  cd d1 = mul_i_sgn<SGN>(caxpy(S2, t4, cscale(S1, t3)));
+  cd d2 = mul_i_sgn<SGN>(caxpy(-S1, t4, cscale(S2, t3)));
+  a0 = cadd(a0, cadd(t1, t2));
+  a1 = cadd(b1, d1);
+  a4 = csub(b1, d1);
+  a2 = cadd(b2, d2);
+  a3 = csub(b2, d2);
+}
+
+template <int R, int SGN> struct Dft;
+template <int SGN> struct Dft<2, SGN> {
+  static TQ_HD void run(cd *a) { dft2<SGN>(a[0], a[1]); }
+};
+template <int SGN> struct Dft<3, SGN> {
+  static TQ_HD void run(cd *a) { dft3<SGN>(a[0], a[1], a[2]); }
+};
+template <int SGN> struct Dft<4, SGN> {
+  static TQ_HD void run(cd *a) { dft4<SGN>(a[0], a[1], a[2], a[3]); }
+};
+template <int SGN> struct Dft<5, SGN> {
+  static TQ_HD void run(cd *a) { dft5<SGN>(a[0], a[1], a[2], a[3], a[4]); }
+};
+// 8 = 2 x 4, decimation in frequency inside the registers
+template <int SGN> struct Dft<8, SGN> {
+  static TQ_HD void run(cd *a) {
+    const double H = 0.70710678118654752440;
+    cd u0 = cadd(a[0], a[4]), u1 = cadd(a[1], a[5]), u2 = cadd(a[2], a[6]), u3 = cadd(a[3], a[7]);
+    cd v0 = csub(a[0], a[4]), v1 = csub(a[1], a[5]), v2 = csub(a[2], a[6]), v3 = csub(a[3], a[7]);
+    // v_n *= w8^n, w8 = (1 + SGN i)/sqrt2
+    cd r1 = mul_i_sgn<SGN>(v1);
+    v1 = cscale(H, cadd(v1, r1));
+    v2 = mul_i_sgn<SGN>(v2);
+    cd r3 = mul_i_sgn<SGN>(v3);
+    v3 = cscale(H, csub(r3, v3));
+    dft4<SGN>(u0, u1, u2, u3);
+    dft4<SGN>(v0, v1, v2, v3);
+    a[0] = u0; a[2] = u1; a[4] = u2; a[6] = u3;
+    a[1] = v0; a[3] = v1; a[5] = v2; a[7] = v3;
+  }
+};
+// 10 = 2 x 5 by the prime-factor (Good-Thomas) map: n = (5 n1 + 2 n2) mod 10, k = (5 k1 + 6 k2) mod 10, no twiddles
+template <int SGN> struct Dft<10, SGN> {
+  static TQ_HD void run(cd *a) {
+    cd e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], e4 = a[8]; // n1 = 0
+    cd o0 = a[5], o1 = a[7], o2 = a[9], o3 = a[1], o4 = a[3]; // n1 = 1
+    dft5<SGN>(e0, e1, e2, e3, e4);
+    dft5<SGN>(o0, o1, o2, o3, o4);
+    a[0] = cadd(e0, o0); a[5] = csub(e0, o0);
+    a[6] = cadd(e1, o1); a[1] = csub(e1, o1);
+    a[2] = cadd(e2, o2); a[7] = csub(e2, o2);
+    a[8] = cadd(e3, o3); a[3] = csub(e3, o3);
+    a[4] = cadd(e4, o4); a[9] = csub(e4, o4);
+  }
+};
+// 16 = 4 x 4, decimation in frequency inside the registers
+template <int SGN> struct Dft<16, SGN> {
+  static TQ_HD void run(cd *a) {
+    const double H = 0.70710678118654752440;
+    const double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173; // cos, sin(pi/8)
+    cd b[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      cd x0 = a[n], x1 = a[n + 4], x2 = a[n + 8], x3 = a[n + 12];
+      dft4<SGN>(x0, x1, x2, x3);
+      b[n][0] = x0; b[n][1] = x1; b[n][2] = x2; b[n][3] = x3;
+    }
+    // b[n][s] *= w16^{n s}
+    const cd w1 = cmk(C1, SGN * S1), w2 = cmk(H, SGN * H), w3 = cmk(S1, SGN * C1);
+    b[1][1] = cmul(b[1][1], w1);
+    b[1][2] = cmul(b[1][2], w2);
+    b[1][3] = cmul(b[1][3], w3);
+    b[2][1] = cmul(b[2][1], w2);
+    b[2][2] = mul_i_sgn<SGN>(b[2][2]);                 // w16^4
+    b[2][3] = cmul(b[2][3], cmk(-H, SGN * H));         // w16^6
+    b[3][1] = cmul(b[3][1], w3);
+    b[3][2] = cmul(b[3][2], cmk(-H, SGN * H));         // w16^6
+    b[3][3] = cmul(b[3][3], cmk(-C1, -SGN * S1));      // w16^9
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      cd x0 = b[0][s], x1 = b[1][s], x2 = b[2][s], x3 = b[3][s];
+      dft4<SGN>(x0, x1, x2, x3);
+      a[s] = x0; a[s + 4] = x1; a[s + 8] = x2; a[s + 12] = x3;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// one pass over the tile.  Work item w -> (butterfly b = w / TC, column c = w % TC).
+//   DIRECT_TW = true : every twiddle w_M^{q s} is read from the master table (good when a warp shares
+//                      one butterfly, i.e. TC >= 32: the loads are broadcasts)
+//   DIRECT_TW = false: only w_M^{q} is read, the powers are built by a log-depth product chain
+// ---------------------------------------------------------------------------------------------
+template <int R, int SGN>
+TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__restrict__ tw, int tid, int nthreads, bool DIRECT_TW,
+                          int skewmask) {
+  const int Msub = M / R;
+  const int nb = N / R;
+  const int nwork = nb * TC;
+  const int twstride = N / M;
+  for (int w = tid; w < nwork; w += nthreads) {
+    int b, c;
+    if (TC == 1) { b = w; c = 0; } else { b = w / TC; c = w - b * TC; }
+    int blk = b / Msub;
+    int q = b - blk * Msub;
+    int base = blk * M + q;
+    cd a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
+    Dft<R, SGN>::run(a);
+    if (Msub > 1 && q != 0) {
+      if (DIRECT_TW) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          cd t = tw[(q * r) * twstride];
+          if (SGN < 0) t = cconj(t);
+          a[r] = cmul(a[r], t);
+        }
+      } else {
+        cd pw[R];
+        pw[1] = tw[q * twstride];
+        if (SGN < 0) pw[1] = cconj(pw[1]);
+#pragma unroll
+        for (int r = 2; r < R; ++r) pw[r] = (r & 1) ? cmul(pw[r - 1], pw[1]) : cmul(pw[r >> 1], pw[r >> 1]);
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] = cmul(a[r], pw[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[fft_row(base + r * Msub, skewmask) * pitch + c] = a[r];
+  }
+}
+
+// any radix (odd primes 7, 11, 13, 41, 101, ...): O(R^2) DFT per butterfly out of a thread-local array
+template <int SGN>
+TQ_HD void fft_pass_generic(cd *s, int pitch, int TC, int N, int M, int R, const cd *__restrict__ tw, int tid, int nthreads,
+                            int skewmask) {
+  const int Msub = M / R;
+  const int nb = N / R;
+  const int nwork = nb * TC;
+  const int twstride = N / M;
+  const int rstride = N / R; // w_R^j = tw[j * N / R]
+  for (int w = tid; w < nwork; w += nthreads) {
+    int b = w / TC, c = w - b * TC;
+    int blk = b / Msub;
+    int q = b - blk * Msub;
+    int base = blk * M + q;
+    cd a[TQ_MAX_GENERIC_RADIX];
+    for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
+    for (int k = 0; k < R; ++k) {
+      cd acc = a[0];
+      int j = 0;
+      for (int r = 1; r < R; ++r) {
+        j += k;
+        if (j >= R) j -= R;
+        cd t = tw[j * rstride];
+        if (SGN < 0) t = cconj(t);
+        acc = cfma(a[r], t, acc);
+      }
+      if (Msub > 1 && q != 0 && k != 0) {
+        cd t = tw[(q * k) * twstride];
+        if (SGN < 0) t = cconj(t);
+        acc = cmul(acc, t);
+      }
+      s[fft_row(base + k * Msub, skewmask) * pitch + c] = acc;
+    }
+  }
+}
+// NOTE: the generic pass writes s[base + k*Msub] while later k still need a[] -- a[] is a private copy,
+// and the R positions belong to this butterfly only, so in-place is safe.
+
+template <int SGN>
+TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, int tid, int nthreads, bool direct_tw, int skewmask) {
+  const int R = P.radix[p], M = P.M[p], N = P.N;
+  switch (R) {
+    case 2: fft_pass_fixed<2, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 3: fft_pass_fixed<3, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 4: fft_pass_fixed<4, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 5: fft_pass_fixed<5, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 8: fft_pass_fixed<8, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 10: fft_pass_fixed<10, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    case 16: fft_pass_fixed<16, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
+    default: fft_pass_generic<SGN>(s, pitch, TC, N, M, R, P.tw, tid, nthreads, skewmask); break;
+  }
+}
+
+#ifdef __CUDACC__
+// all passes, CTA-wide (every thread of the block must call it; tile must be complete and synced before)
+template <int SGN> __device__ void fft_tile(const FftPlan &P, cd *s, int pitch, int TC, bool direct_tw, int skewmask) {
+  for (int p = 0; p < P.npass; ++p) {
+    fft_pass<SGN>(P, p, s, pitch, TC, threadIdx.x, blockDim.x, direct_tw, skewmask);
+    __syncthreads();
+  }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// host side: factorisation + master twiddle table
+// ---------------------------------------------------------------------------------------------
+struct FftPlanHost {
+  FftPlan plan{};          // plan.tw / plan.pos are device pointers
+  std::vector<cd> tw_host; // host copy (tests / hostsim)
+  std::vector<int> pos_host;
+  bool supported = true;
+  ~FftPlanHost();
+};
+
+// fills radix[] / M[]; returns false if a prime factor exceeds TQ_MAX_GENERIC_RADIX
+bool tq_fft_factorize(int N, FftPlan &P);
+// exp(+2 pi i j / N) with long-double evaluation and octant symmetry
+void tq_fft_twiddles_host(int N, std::vector<cd> &tw);
+// cached plan with the table uploaded to the device
+tq_status tq_get_fft_plan(tq_ctx *ctx, long N, std::shared_ptr<FftPlanHost> *out);
