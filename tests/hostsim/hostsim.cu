@@ -18,12 +18,16 @@ extern "C" int hostsim_fft(int N, int TC, int sign, int direct_tw, int skew, dou
   cd *in = (cd *)data;
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < TC; ++c) s[(size_t)fft_row(n, sm) * TC + c] = in[(size_t)n * TC + c];
-  for (int p = 0; p < P.npass; ++p) {
-    if (sign > 0)
-      fft_pass<1>(P, p, s.data(), TC, TC, 0, 1, direct_tw != 0, sm);
-    else
-      fft_pass<-1>(P, p, s.data(), TC, TC, 0, 1, direct_tw != 0, sm);
-  }
+  // emulate a CTA of `nthreads` threads: passes are hazard free, so threads can run one after the other
+  const int nthreads = 7;
+  for (int p = 0; p < P.npass; ++p)
+    for (int tid = 0; tid < nthreads; ++tid) {
+      TileThread T = tile_thread(tid, nthreads, TC);
+      if (sign > 0)
+        fft_pass<1>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0, sm);
+      else
+        fft_pass<-1>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0, sm);
+    }
   for (int k = 0; k < N; ++k) {
     int pos = fft_pos(P, k);
     for (int c = 0; c < TC; ++c) in[(size_t)k * TC + c] = s[(size_t)fft_row(pos, sm) * TC + c];

@@ -36,7 +36,7 @@ struct BigTw {
 
 struct TileArgs {
   FftPlan P;
-  int TC, n_cols, skewmask, direct_tw;
+  int TC, n_cols, skewmask, direct_tw, smem_tw, rowtab;
   int in_stride, out_stride; // global row = item + stride * local
   int Na;                    // scratch layout [Nb][Na][n_cols]
   const cd *in;
@@ -89,6 +89,56 @@ TQ_D int freq_data_index(const MatsubaraDev &D, int k) {
   return (n >= D.first && n <= D.last) ? n - D.first : -1;
 }
 
+// Per-row factors.  Everything that depends only on the mesh row (not on the column) is evaluated once per
+// row into three double2 -- either into a shared-memory row table (tiles with several columns: the
+// table look-ups and the index math are amortised over the row) or inline (single-column tiles).
+//   input rows  : IN_TAU   {h0,h1} {h2,-} {phase}          IN_FREQ  {w,r1} {r2,r3} {data index,-}
+//   output rows : OUT_FREQ {w,r1} {r2,r3} {data index,pos}  OUT_TAU  {h0,h1} {h2,pos} {phase}   OUT_SCRATCH {twiddle} {pos,-} -
+template <int IN> TQ_D void in_row_entry(const TileArgs &A, int item, int r, cd e[3]) {
+  const MatsubaraDev &D = A.D;
+  if (IN == IN_TAU) {
+    const int j = item + A.in_stride * r;
+    double h[3];
+    row_model(D, j, h);
+    e[0] = cmk(h[0], h[1]);
+    e[1] = cmk(h[2], 0.0);
+    e[2] = D.stat == TQ_FERMION ? phase_fwd(D, j) : cmk(D.fact_fwd, 0.0);
+  } else if (IN == IN_FREQ) {
+    const int di = freq_data_index(D, item + A.in_stride * r);
+    double4 w = di >= 0 ? load_w(D, di) : make_double4(0, 0, 0, 0);
+    e[0] = cmk(w.x, w.y);
+    e[1] = cmk(w.z, w.w);
+    e[2] = cmk((double)di, 0.0);
+  }
+}
+template <int OUT, int SGN> TQ_D void out_row_entry(const TileArgs &A, int item, int kk, cd e[3]) {
+  const MatsubaraDev &D = A.D;
+  const double pos = (double)__ldg(&A.P.pos[kk]);
+  if (OUT == OUT_FREQ) {
+    const int di = freq_data_index(D, item + A.out_stride * kk);
+    double4 w = di >= 0 ? load_w(D, di) : make_double4(0, 0, 0, 0);
+    e[0] = cmk(w.x, w.y);
+    e[1] = cmk(w.z, w.w);
+    e[2] = cmk((double)di, pos);
+  } else if (OUT == OUT_TAU) {
+    const int j = item + A.out_stride * kk;
+    double h[3];
+    row_model(D, j, h);
+    e[0] = cmk(h[0], h[1]);
+    e[1] = cmk(h[2], pos);
+    e[2] = D.stat == TQ_FERMION ? phase_inv(D, j) : cmk(1.0, 0.0);
+  } else {
+    cd w = bigtw(A.btw, item * kk);
+    e[0] = SGN < 0 ? cconj(w) : w;
+    e[1] = cmk(pos, 0.0);
+    e[2] = cmk(0.0, 0.0);
+  }
+}
+// sum_i a_i / (i w - b_i) from a row entry {w,r1} {r2,r3}
+TQ_D cd tail_iw_e(const MatsubaraDev &D, cd e0, cd e1, cd a1, cd a2, cd a3) {
+  return tail_iw(D, make_double4(e0.x, e0.y, e1.x, e1.y), a1, a2, a3);
+}
+
 template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) matsubara_tile_kernel(const TileArgs A) {
   extern __shared__ double2 smem[];
   const MatsubaraDev &D = A.D;
@@ -99,11 +149,15 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
   const int pitch = tc;
   const int sk = A.skewmask;
   cd *tile = smem;
-  cd *coef = smem + (size_t)fft_rows_alloc(N, sk) * pitch; // a1[tc], a2[tc], a3[tc], extra[tc]
+  cd *coef = tile + (size_t)fft_rows_alloc(N, sk) * A.TC; // a1[tc], a2[tc], a3[tc], extra[tc]
+  cd *twS = coef + 4 * A.TC;                               // [N] copy of the twiddle table (if A.smem_tw)
+  cd *rowtab = twS + (A.smem_tw ? N : 0);                  // [N][3] per-row factors (if A.rowtab)
   const bool fermion = D.stat == TQ_FERMION;
+  const bool use_rt = A.rowtab != 0;
+  const TileThread T = tile_thread(threadIdx.x, NT, tc);
 
   // ---- per-column pole weights from the moments  (:151-169, :238-252)
-  if (IN != IN_SCRATCH || OUT != OUT_SCRATCH) {
+  {
     const cd *mom = A.moments + (size_t)gf * A.mom_gf_stride;
     for (int c = threadIdx.x; c < tc; c += NT) {
       cd m1 = mom[(size_t)1 * A.n_cols + c0 + c], m2 = mom[(size_t)2 * A.n_cols + c0 + c], m3 = mom[(size_t)3 * A.n_cols + c0 + c];
@@ -131,70 +185,107 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
         coef[3 * tc + c] = m1;
       }
     }
+    if (A.smem_tw)
+      for (int i = threadIdx.x; i < N; i += NT) twS[i] = __ldg(&A.P.tw[i]);
+    if (use_rt && IN != IN_SCRATCH)
+      for (int r = threadIdx.x; r < N; r += NT) in_row_entry<IN>(A, item, r, rowtab + 3 * r);
     __syncthreads();
   }
 
-  // ---- load + pre-transform
-  const int ntile = N * tc;
-  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
-    int r, c;
-    if (tc == 1) { r = idx; c = 0; } else { r = idx / tc; c = idx - r * tc; }
-    cd x;
-    if (IN == IN_TAU) {
-      int j = item + A.in_stride * r;
-      cd g = A.in[(size_t)gf * A.in_gf_stride + (size_t)j * A.n_cols + c0 + c];
-      double h[3];
-      row_model(D, j, h);
-      x = caxpy(-h[2], coef[2 * tc + c], caxpy(-h[1], coef[tc + c], caxpy(-h[0], coef[c], g)));
-      x = fermion ? cmul(phase_fwd(D, j), x) : cscale(D.fact_fwd, x);
-    } else if (IN == IN_FREQ) {
-      int k = item + A.in_stride * r;
-      int di = freq_data_index(D, k);
-      if (di >= 0) {
-        cd g = A.in[(size_t)gf * A.in_gf_stride + (size_t)di * A.n_cols + c0 + c];
-        cd t = tail_iw(D, load_w(D, di), coef[c], coef[tc + c], coef[2 * tc + c]);
-        x = cscale(D.inv_beta, csub(g, t));
-      } else {
-        x = cmk(0.0, 0.0);
+  // ---- load + pre-transform.  LU independent 16-byte loads per thread are issued before any is consumed:
+  // with 1-2 CTAs per SM that is what keeps enough bytes in flight to cover the HBM latency.
+  constexpr int LU = 8;
+  if (T.nbt > 0) {
+    for (int c = T.ct; c < tc; c += T.nct) {
+      const cd a1 = coef[c], a2 = coef[tc + c], a3 = coef[2 * tc + c];
+      for (int r0 = T.bt; r0 < N; r0 += T.nbt * LU) {
+        cd g[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+          const int r = r0 + u * T.nbt;
+          g[u] = cmk(0.0, 0.0);
+          if (r < N) {
+            if (IN == IN_TAU) {
+              const int j = item + A.in_stride * r;
+              g[u] = A.in[(size_t)gf * A.in_gf_stride + (size_t)j * A.n_cols + c0 + c];
+            } else if (IN == IN_FREQ) {
+              const int di = freq_data_index(D, item + A.in_stride * r);
+              if (di >= 0) g[u] = A.in[(size_t)gf * A.in_gf_stride + (size_t)di * A.n_cols + c0 + c];
+            } else {
+              g[u] = A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)item * A.Na + r) * A.n_cols + c0 + c];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+          const int r = r0 + u * T.nbt;
+          if (r >= N) continue;
+          cd x = g[u];
+          if (IN != IN_SCRATCH) {
+            cd e[3];
+            if (use_rt) {
+              e[0] = rowtab[3 * r];
+              e[1] = rowtab[3 * r + 1];
+              e[2] = rowtab[3 * r + 2];
+            } else {
+              in_row_entry<IN>(A, item, r, e);
+            }
+            if (IN == IN_TAU) {
+              x = caxpy(-e[1].x, a3, caxpy(-e[0].y, a2, caxpy(-e[0].x, a1, x)));
+              x = fermion ? cmul(e[2], x) : cscale(e[2].x, x);
+            } else if (e[2].x >= 0.0) {
+              x = cscale(D.inv_beta, csub(x, tail_iw_e(D, e[0], e[1], a1, a2, a3)));
+            }
+          }
+          tile[(size_t)fft_row(r, sk) * pitch + c] = x;
+        }
       }
-    } else {
-      x = A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)item * A.Na + r) * A.n_cols + c0 + c];
     }
-    tile[(size_t)fft_row(r, sk) * pitch + c] = x;
   }
   __syncthreads();
 
-  fft_tile<SGN>(A.P, tile, pitch, tc, A.direct_tw != 0, sk);
+  // output-row factors overwrite the input-row table (no longer needed); the passes below do not touch it
+  if (use_rt)
+    for (int kk = threadIdx.x; kk < N; kk += NT) out_row_entry<OUT, SGN>(A, item, kk, rowtab + 3 * kk);
+
+  fft_tile<SGN>(A.P, tile, pitch, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0, sk); // ends with __syncthreads()
+  if (A.P.npass == 0) __syncthreads();
 
   // ---- post-transform + store (applies the digit-reversal permutation)
-  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
-    int kk, c;
-    if (tc == 1) { kk = idx; c = 0; } else { kk = idx / tc; c = idx - kk * tc; }
-    if (OUT == OUT_FREQ) {
-      int k = item + A.out_stride * kk;
-      int di = freq_data_index(D, k);
-      if (di < 0) continue;
-      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
-      cd t = tail_iw(D, load_w(D, di), coef[c], coef[tc + c], coef[2 * tc + c]);
-      A.out[(size_t)gf * A.out_gf_stride + (size_t)di * A.n_cols + c0 + c] = cadd(cadd(v, coef[3 * tc + c]), t);
-    } else if (OUT == OUT_TAU) {
-      int j = item + A.out_stride * kk;
-      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
-      double h[3];
-      row_model(D, j, h);
-      if (fermion) v = cmul(v, phase_inv(D, j));
-      v = caxpy(h[2], coef[2 * tc + c], caxpy(h[1], coef[tc + c], caxpy(h[0], coef[c], v)));
-      cd *o = A.out + (size_t)gf * A.out_gf_stride;
-      o[(size_t)j * A.n_cols + c0 + c] = v;
-      if (j == 0) { // gt[L] = -/+ (gt[0] + m1)    (:267-268)
-        cd e = cadd(v, coef[3 * tc + c]);
-        o[(size_t)D.L * A.n_cols + c0 + c] = fermion ? cneg(e) : e;
+  if (T.nbt > 0) {
+    for (int c = T.ct; c < tc; c += T.nct) {
+      const cd a1 = coef[c], a2 = coef[tc + c], a3 = coef[2 * tc + c], ex = coef[3 * tc + c];
+      for (int kk = T.bt; kk < N; kk += T.nbt) {
+        cd e[3];
+        if (use_rt) {
+          e[0] = rowtab[3 * kk];
+          e[1] = rowtab[3 * kk + 1];
+          e[2] = rowtab[3 * kk + 2];
+        } else {
+          out_row_entry<OUT, SGN>(A, item, kk, e);
+        }
+        if (OUT == OUT_FREQ) {
+          const int di = (int)e[2].x;
+          if (di < 0) continue;
+          cd v = tile[(size_t)fft_row((int)e[2].y, sk) * pitch + c];
+          cd t = tail_iw_e(D, e[0], e[1], a1, a2, a3);
+          A.out[(size_t)gf * A.out_gf_stride + (size_t)di * A.n_cols + c0 + c] = cadd(cadd(v, ex), t);
+        } else if (OUT == OUT_TAU) {
+          const int j = item + A.out_stride * kk;
+          cd v = tile[(size_t)fft_row((int)e[1].y, sk) * pitch + c];
+          if (fermion) v = cmul(v, e[2]);
+          v = caxpy(e[1].x, a3, caxpy(e[0].y, a2, caxpy(e[0].x, a1, v)));
+          cd *o = A.out + (size_t)gf * A.out_gf_stride;
+          o[(size_t)j * A.n_cols + c0 + c] = v;
+          if (j == 0) { // gt[L] = -/+ (gt[0] + m1)    (:267-268)
+            cd t = cadd(v, ex);
+            o[(size_t)D.L * A.n_cols + c0 + c] = fermion ? cneg(t) : t;
+          }
+        } else {
+          cd v = tile[(size_t)fft_row((int)e[1].x, sk) * pitch + c];
+          A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)kk * A.Na + item) * A.n_cols + c0 + c] = cmul(v, e[0]);
+        }
       }
-    } else {
-      cd v = tile[(size_t)fft_row(__ldg(&A.P.pos[kk]), sk) * pitch + c];
-      cd w = bigtw(A.btw, item * kk);
-      if (SGN < 0) w = cconj(w);
-      A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)kk * A.Na + item) * A.n_cols + c0 + c] = cmul(v, w);
     }
   }
 }
@@ -424,11 +515,25 @@ struct Tiling {
   int skew = 0;
 };
 
-static size_t tile_bytes(int N, int tc, int skewmask) { return ((size_t)fft_rows_alloc(N, skewmask) * tc + 4 * (size_t)tc) * sizeof(cd); }
+// tiles with at least this many columns keep a shared-memory copy of the twiddles and a per-row factor table
+static bool tile_uses_tables(int tc) { return tc >= 4; }
+static size_t tile_bytes(int N, int tc, int skewmask) {
+  size_t n = (size_t)fft_rows_alloc(N, skewmask) * tc + 4 * (size_t)tc;
+  if (tile_uses_tables(tc)) n += 4 * (size_t)N; // twiddles [N] + row table [N][3]
+  return n * sizeof(cd);
+}
 
 static bool radix_ok(long N) {
   FftPlan P;
   return tq_fft_factorize((int)N, P);
+}
+
+// widest column tile (<= n_cols) whose working set fits the opt-in shared memory
+static int pick_tc(tq_ctx *ctx, int N, long n_cols, size_t budget = 0) {
+  if (!budget) budget = (size_t)ctx->max_smem_optin;
+  long tc = std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (N + 4))));
+  while (tc > 1 && tile_bytes(N, (int)tc, 0) > budget) --tc;
+  return (int)std::max<long>(tc, 1);
 }
 
 static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Tiling *t) {
@@ -437,8 +542,8 @@ static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Til
   // single pass
   if (tile_bytes((int)L, 1, 0) <= budget && radix_ok(L)) {
     t->two_pass = false;
-    int tc_fit_half = (int)std::min<long>(n_cols, (long)(half / (sizeof(cd) * (L + 4))));
-    int tc_fit_full = (int)std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (L + 4))));
+    int tc_fit_half = tile_bytes((int)L, 1, 0) <= half ? pick_tc(ctx, (int)L, n_cols, half) : 0;
+    int tc_fit_full = pick_tc(ctx, (int)L, n_cols);
     // prefer tiles that let two CTAs share an SM unless that would shrink the contiguous run below 128 B
     int tc = (tc_fit_half >= 8 || tc_fit_half >= n_cols) ? tc_fit_half : tc_fit_full;
     // enough CTAs to fill the machine: do not make tiles wider than needed when the batch is small
@@ -462,9 +567,7 @@ static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Til
   t->two_pass = true;
   t->Nb = (int)best;      // first pass length (smaller tile)
   t->Na = (int)(L / best); // second pass length
-  int tc = (int)std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (t->Na + 4))));
-  if (tc < 1) tc = 1;
-  t->tc = tc;
+  t->tc = pick_tc(ctx, t->Na, n_cols);
   t->skew = 0;
   return TQ_OK;
 }
@@ -518,7 +621,7 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
     A.P = fp->plan;
     A.TC = t.tc;
     A.skewmask = t.skew;
-    A.direct_tw = t.tc >= 8;
+    A.direct_tw = A.smem_tw = A.rowtab = tile_uses_tables(t.tc);
     A.in_stride = 1;
     A.out_stride = 1;
     for (long b0 = 0; b0 < batch; b0 += maxb) {
@@ -551,7 +654,6 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   A.scratch_gf_stride = L * n_cols;
   A.Na = t.Na;
   A.skewmask = 0;
-  A.direct_tw = t.tc >= 8;
   for (long b0 = 0; b0 < batch; b0 += chunk) {
     long nb = std::min(chunk, batch - b0);
     TileArgs B = A;
@@ -561,7 +663,8 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
     if (fwd) B.gt_ref = A.gt_ref + b0 * A.gt_gf_stride;
     // pass 1
     B.P = fb->plan;
-    B.TC = (int)std::min<long>(n_cols, (long)((size_t)ctx->max_smem_optin / (sizeof(cd) * (t.Nb + 4))));
+    B.TC = pick_tc(ctx, t.Nb, n_cols);
+    B.direct_tw = B.smem_tw = B.rowtab = tile_uses_tables(B.TC);
     B.in_stride = t.Na;
     B.out_stride = 0;
     if (fwd)
@@ -571,6 +674,7 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
     // pass 2
     B.P = fa->plan;
     B.TC = t.tc;
+    B.direct_tw = B.smem_tw = B.rowtab = tile_uses_tables(B.TC);
     B.in_stride = 0;
     B.out_stride = t.Nb;
     if (fwd)

@@ -15,7 +15,7 @@ struct PlainArgs {
   cd *out;
   long inner;     // contiguous elements per (outer, n)
   int TC, tiles;  // tiles = ceil(inner / TC)
-  int direct_tw;
+  int direct_tw, smem_tw;
   double scale;   // applied on store (1 = none)
 };
 
@@ -27,21 +27,46 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
   const int tc = (int)min((long)A.TC, A.inner - c0);
   const int N = A.P.N;
   cd *tile = smem;
+  cd *twS = tile + (size_t)N * A.TC;                       // [N] twiddles (if A.smem_tw)
+  int *posS = reinterpret_cast<int *>(twS + (A.smem_tw ? N : 0)); // [N] output positions (if A.smem_tw)
   const cd *src = A.in + (size_t)o * N * A.inner + c0;
   cd *dst = A.out + (size_t)o * N * A.inner + c0;
-  const int ntile = N * tc;
-  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
-    int r = idx / tc, c = idx - r * tc;
-    tile[idx] = src[(size_t)r * A.inner + c];
+  const TileThread T = tile_thread(threadIdx.x, NT, tc);
+  if (A.smem_tw)
+    for (int i = threadIdx.x; i < N; i += NT) {
+      twS[i] = __ldg(&A.P.tw[i]);
+      posS[i] = __ldg(&A.P.pos[i]);
+    }
+  constexpr int LU = 8; // independent loads in flight per thread
+  if (T.nbt > 0) {
+    for (int c = T.ct; c < tc; c += T.nct) {
+      for (int r0 = T.bt; r0 < N; r0 += T.nbt * LU) {
+        cd g[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+          const int r = r0 + u * T.nbt;
+          if (r < N) g[u] = src[(size_t)r * A.inner + c];
+        }
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+          const int r = r0 + u * T.nbt;
+          if (r < N) tile[(size_t)r * tc + c] = g[u];
+        }
+      }
+    }
   }
   __syncthreads();
-  fft_tile<SGN>(A.P, tile, tc, tc, A.direct_tw != 0, 0);
+  fft_tile<SGN>(A.P, tile, tc, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0, 0);
   const bool scaled = A.scale != 1.0;
-  for (int idx = threadIdx.x; idx < ntile; idx += NT) {
-    int k = idx / tc, c = idx - k * tc;
-    cd v = tile[(size_t)__ldg(&A.P.pos[k]) * tc + c];
-    if (scaled) v = cscale(A.scale, v);
-    dst[(size_t)k * A.inner + c] = v;
+  if (T.nbt > 0) {
+    for (int c = T.ct; c < tc; c += T.nct) {
+      for (int k = T.bt; k < N; k += T.nbt) {
+        const int pos = A.smem_tw ? posS[k] : __ldg(&A.P.pos[k]);
+        cd v = tile[(size_t)pos * tc + c];
+        if (scaled) v = cscale(A.scale, v);
+        dst[(size_t)k * A.inner + c] = v;
+      }
+    }
   }
 }
 
@@ -52,7 +77,11 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   const size_t half = budget / 2 - 1024;
   if (sizeof(cd) * (size_t)N > budget)
     return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length " + std::to_string(N) + " does not fit one SM's shared memory");
+  // per row: tc columns + (twiddle + position when tabulated in shared memory)
+  auto fits = [&](long tc, size_t lim) { return sizeof(cd) * (size_t)N * tc + (tc >= 4 ? (sizeof(cd) + sizeof(int)) * (size_t)N : 0) <= lim; };
   long tc_half = (long)(half / (sizeof(cd) * N)), tc_full = (long)(budget / (sizeof(cd) * N));
+  while (tc_half > 0 && !fits(tc_half, half)) --tc_half;
+  while (tc_full > 1 && !fits(tc_full, budget)) --tc_full;
   long tcmax = tc_half >= 8 ? tc_half : tc_full;
   tcmax = std::max<long>(1, std::min(tcmax, inner));
   long tc = tcmax;
@@ -66,9 +95,9 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   A.inner = inner;
   A.TC = (int)tc;
   A.tiles = (int)((inner + tc - 1) / tc);
-  A.direct_tw = tc >= 8;
+  A.direct_tw = A.smem_tw = tc >= 4;
   A.scale = scale;
-  const size_t smem = sizeof(cd) * (size_t)N * tc;
+  const size_t smem = sizeof(cd) * (size_t)N * tc + (A.smem_tw ? (sizeof(cd) + sizeof(int)) * (size_t)N : 0);
   const long nblocks = outer * A.tiles;
   if (nblocks > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: too many tiles");
   const bool big = smem > half;

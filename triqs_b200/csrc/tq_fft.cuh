@@ -171,109 +171,141 @@ template <int SGN> struct Dft<16, SGN> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// one pass over the tile.  Work item w -> (butterfly b = w / TC, column c = w % TC).
-//   DIRECT_TW = true : every twiddle w_M^{q s} is read from the master table (good when a warp shares
-//                      one butterfly, i.e. TC >= 32: the loads are broadcasts)
-//   DIRECT_TW = false: only w_M^{q} is read, the powers are built by a log-depth product chain
+// Thread layout inside a CTA: a thread owns a fixed column lane `ct` (of `nct` column lanes) and a
+// butterfly/row lane `bt` (of `nbt`): no integer division in any inner loop, adjacent threads touch
+// adjacent columns (coalesced global rows, conflict-free shared rows).
 // ---------------------------------------------------------------------------------------------
+struct TileThread {
+  int ct, nct, bt, nbt;
+};
+TQ_HD TileThread tile_thread(int tid, int nthreads, int TC) {
+  TileThread t;
+  t.nct = TC < nthreads ? TC : nthreads;
+  t.nbt = nthreads / t.nct;
+  t.bt = tid / t.nct;
+  t.ct = tid - t.bt * t.nct;
+  if (t.bt >= t.nbt) { // left-over threads (nthreads not a multiple of TC) idle
+    t.bt = 0;
+    t.nbt = 0;
+  }
+  return t;
+}
+
+// n / d for n * d < 2^32 with m = ceil(2^32 / d) (m = 0 encodes d = 1)
+TQ_HD unsigned fastdiv_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d); }
+TQ_HD int fastdiv(int n, unsigned m) {
+#ifdef __CUDA_ARCH__
+  return m ? (int)__umulhi((unsigned)n, m) : n;
+#else
+  return m ? (int)(((unsigned long long)(unsigned)n * m) >> 32) : n;
+#endif
+}
+
+// one pass over the tile.
+//   direct_tw = true : every twiddle w_M^{q s} is read from the table `tw` (a shared-memory copy when a
+//                      warp shares a butterfly, i.e. many columns: the loads are broadcasts)
+//   direct_tw = false: only w_M^{q} is read, the powers are built by a log-depth product chain (TC == 1)
 template <int R, int SGN>
-TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__restrict__ tw, int tid, int nthreads, bool DIRECT_TW,
-                          int skewmask) {
+TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__restrict__ tw, TileThread T, bool direct_tw, int skewmask) {
   const int Msub = M / R;
   const int nb = N / R;
-  const int nwork = nb * TC;
   const int twstride = N / M;
-  for (int w = tid; w < nwork; w += nthreads) {
-    int b, c;
-    if (TC == 1) { b = w; c = 0; } else { b = w / TC; c = w - b * TC; }
-    int blk = b / Msub;
-    int q = b - blk * Msub;
-    int base = blk * M + q;
-    cd a[R];
+  const unsigned magic = fastdiv_magic((unsigned)Msub);
+  if (T.nbt == 0) return;
+  for (int c = T.ct; c < TC; c += T.nct) {
+    for (int b = T.bt; b < nb; b += T.nbt) {
+      int blk = fastdiv(b, magic);
+      int q = b - blk * Msub;
+      int base = blk * M + q;
+      cd a[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
-    Dft<R, SGN>::run(a);
-    if (Msub > 1 && q != 0) {
-      if (DIRECT_TW) {
+      for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
+      Dft<R, SGN>::run(a);
+      if (Msub > 1 && q != 0) {
+        if (direct_tw) {
 #pragma unroll
-        for (int r = 1; r < R; ++r) {
-          cd t = tw[(q * r) * twstride];
-          if (SGN < 0) t = cconj(t);
-          a[r] = cmul(a[r], t);
+          for (int r = 1; r < R; ++r) {
+            cd t = tw[(q * r) * twstride];
+            if (SGN < 0) t = cconj(t);
+            a[r] = cmul(a[r], t);
+          }
+        } else {
+          cd pw[R];
+          pw[1] = tw[q * twstride];
+          if (SGN < 0) pw[1] = cconj(pw[1]);
+#pragma unroll
+          for (int r = 2; r < R; ++r) pw[r] = (r & 1) ? cmul(pw[r - 1], pw[1]) : cmul(pw[r >> 1], pw[r >> 1]);
+#pragma unroll
+          for (int r = 1; r < R; ++r) a[r] = cmul(a[r], pw[r]);
         }
-      } else {
-        cd pw[R];
-        pw[1] = tw[q * twstride];
-        if (SGN < 0) pw[1] = cconj(pw[1]);
-#pragma unroll
-        for (int r = 2; r < R; ++r) pw[r] = (r & 1) ? cmul(pw[r - 1], pw[1]) : cmul(pw[r >> 1], pw[r >> 1]);
-#pragma unroll
-        for (int r = 1; r < R; ++r) a[r] = cmul(a[r], pw[r]);
       }
-    }
 #pragma unroll
-    for (int r = 0; r < R; ++r) s[fft_row(base + r * Msub, skewmask) * pitch + c] = a[r];
+      for (int r = 0; r < R; ++r) s[fft_row(base + r * Msub, skewmask) * pitch + c] = a[r];
+    }
   }
 }
 
-// any radix (odd primes 7, 11, 13, 41, 101, ...): O(R^2) DFT per butterfly out of a thread-local array
+// any radix (odd primes 7, 11, 13, 41, 101, ...): O(R^2) DFT per butterfly out of a thread-local array.
+// The R positions belong to this butterfly only and a[] is a private copy, so in-place is safe.
 template <int SGN>
-TQ_HD void fft_pass_generic(cd *s, int pitch, int TC, int N, int M, int R, const cd *__restrict__ tw, int tid, int nthreads,
-                            int skewmask) {
+TQ_HD void fft_pass_generic(cd *s, int pitch, int TC, int N, int M, int R, const cd *__restrict__ tw, TileThread T, int skewmask) {
   const int Msub = M / R;
   const int nb = N / R;
-  const int nwork = nb * TC;
   const int twstride = N / M;
   const int rstride = N / R; // w_R^j = tw[j * N / R]
-  for (int w = tid; w < nwork; w += nthreads) {
-    int b = w / TC, c = w - b * TC;
-    int blk = b / Msub;
-    int q = b - blk * Msub;
-    int base = blk * M + q;
-    cd a[TQ_MAX_GENERIC_RADIX];
-    for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
-    for (int k = 0; k < R; ++k) {
-      cd acc = a[0];
-      int j = 0;
-      for (int r = 1; r < R; ++r) {
-        j += k;
-        if (j >= R) j -= R;
-        cd t = tw[j * rstride];
-        if (SGN < 0) t = cconj(t);
-        acc = cfma(a[r], t, acc);
+  const unsigned magic = fastdiv_magic((unsigned)Msub);
+  if (T.nbt == 0) return;
+  for (int c = T.ct; c < TC; c += T.nct) {
+    for (int b = T.bt; b < nb; b += T.nbt) {
+      int blk = fastdiv(b, magic);
+      int q = b - blk * Msub;
+      int base = blk * M + q;
+      cd a[TQ_MAX_GENERIC_RADIX];
+      for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
+      for (int k = 0; k < R; ++k) {
+        cd acc = a[0];
+        int j = 0;
+        for (int r = 1; r < R; ++r) {
+          j += k;
+          if (j >= R) j -= R;
+          cd t = tw[j * rstride];
+          if (SGN < 0) t = cconj(t);
+          acc = cfma(a[r], t, acc);
+        }
+        if (Msub > 1 && q != 0 && k != 0) {
+          cd t = tw[(q * k) * twstride];
+          if (SGN < 0) t = cconj(t);
+          acc = cmul(acc, t);
+        }
+        s[fft_row(base + k * Msub, skewmask) * pitch + c] = acc;
       }
-      if (Msub > 1 && q != 0 && k != 0) {
-        cd t = tw[(q * k) * twstride];
-        if (SGN < 0) t = cconj(t);
-        acc = cmul(acc, t);
-      }
-      s[fft_row(base + k * Msub, skewmask) * pitch + c] = acc;
     }
   }
 }
-// NOTE: the generic pass writes s[base + k*Msub] while later k still need a[] -- a[] is a private copy,
-// and the R positions belong to this butterfly only, so in-place is safe.
 
 template <int SGN>
-TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, int tid, int nthreads, bool direct_tw, int skewmask) {
+TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, const cd *__restrict__ tw, TileThread T, bool direct_tw,
+                    int skewmask) {
   const int R = P.radix[p], M = P.M[p], N = P.N;
   switch (R) {
-    case 2: fft_pass_fixed<2, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 3: fft_pass_fixed<3, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 4: fft_pass_fixed<4, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 5: fft_pass_fixed<5, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 8: fft_pass_fixed<8, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 10: fft_pass_fixed<10, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    case 16: fft_pass_fixed<16, SGN>(s, pitch, TC, N, M, P.tw, tid, nthreads, direct_tw, skewmask); break;
-    default: fft_pass_generic<SGN>(s, pitch, TC, N, M, R, P.tw, tid, nthreads, skewmask); break;
+    case 2: fft_pass_fixed<2, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 3: fft_pass_fixed<3, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 4: fft_pass_fixed<4, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 5: fft_pass_fixed<5, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 8: fft_pass_fixed<8, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 10: fft_pass_fixed<10, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 16: fft_pass_fixed<16, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    default: fft_pass_generic<SGN>(s, pitch, TC, N, M, R, tw, T, skewmask); break;
   }
 }
 
 #ifdef __CUDACC__
-// all passes, CTA-wide (every thread of the block must call it; tile must be complete and synced before)
-template <int SGN> __device__ void fft_tile(const FftPlan &P, cd *s, int pitch, int TC, bool direct_tw, int skewmask) {
+// all passes, CTA-wide (every thread of the block must call it; tile must be complete and synced before).
+// `tw` is the twiddle table the passes read: the plan's global table or a shared-memory copy of it.
+template <int SGN> __device__ void fft_tile(const FftPlan &P, cd *s, int pitch, int TC, const cd *tw, bool direct_tw, int skewmask) {
+  const TileThread T = tile_thread(threadIdx.x, blockDim.x, TC);
   for (int p = 0; p < P.npass; ++p) {
-    fft_pass<SGN>(P, p, s, pitch, TC, threadIdx.x, blockDim.x, direct_tw, skewmask);
+    fft_pass<SGN>(P, p, s, pitch, TC, tw, T, direct_tw, skewmask);
     __syncthreads();
   }
 }
