@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native TRIQS Green's-function hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--replicas R] [--no-extras]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Headline workload = BASELINE.json configs[1]: BlockGf of 2 spin blocks x 5x5 orbitals, beta = 100,
+n_tau = 100001 (FFT length L = 10^5), n_iw = 10000, one step = imtime -> imfreq (tau-derivative tail
+estimate) followed by imfreq -> imtime (least-squares tail fit) for R independent BlockGfs per GPU
+(R = 16: 1.28 GB of G(tau) per step, larger than the 126 MB L2, so no L2 flush is needed between steps).
+Metric: Gf points per second (one point = one mesh point of an OUTPUT gf with its whole 5x5 target).
+
+Prints ONE JSON line (contract in the task statement): value (device resident), e2e (host buffers through
+the C ABI), roofline of the dominant kernel, cpu_baseline (oracle, 1 core, bounded sample), clocks, ...
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BETA, N_TAU, N_IW, NORB, NBLOCK = 100.0, 100001, 10000, 5, 2
+N_W = 2 * N_IW
+NCOL = NORB * NORB
+POINTS_PER_BLOCKGF = NBLOCK * (N_W + N_TAU)                       # output points of one round trip
+ALG_BYTES_PER_BLOCK = 16.0 * NCOL * 2 * (N_TAU + N_W)             # 96.0008 MB per block per round trip
+METRIC = "Gf points/sec (FFT+tail fit round trip imtime<->imfreq, BlockGf 2x5x5, n_tau=100001, n_iw=10000)"
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic input (untimed): G_b(iw) = (iw - H_b)^-1, H_b random Hermitian with spectrum in [-2, 2], seed 2001 + b
+# ---------------------------------------------------------------------------------------------
+def block_hamiltonian(b):
+    rng = np.random.default_rng(2001 + b)
+    a = rng.normal(size=(NORB, NORB)) + 1j * rng.normal(size=(NORB, NORB))
+    h = a + a.conj().T
+    w, v = np.linalg.eigh(h)
+    w = -2 + 4 * (w - w.min()) / (w.max() - w.min())
+    return w, v
+
+
+def block_gtau(b, n_tau=N_TAU, beta=BETA):
+    w, v = block_hamiltonian(b)
+    tau = beta * (np.arange(n_tau) / (n_tau - 1))
+    f = np.where(w[None, :] > 0, -np.exp(-w[None, :] * tau[:, None]) / (1 + np.exp(-beta * np.abs(w[None, :]))),
+                 -np.exp(-w[None, :] * (tau[:, None] - beta)) / (1 + np.exp(-beta * np.abs(w[None, :]))))
+    g = np.einsum("ik,tk,jk->tij", v, f, v.conj())
+    return np.ascontiguousarray(g.reshape(n_tau, NCOL))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the restated reference algorithm (oracle/) on the host cores
+# ---------------------------------------------------------------------------------------------
+def _oracle_round_trip(b):
+    from oracle import triqs_oracle as O
+    gt = block_gtau(b % NBLOCK)
+    t0 = time.perf_counter()
+    gw = O.fourier_tau_to_iw(gt, BETA, O.FERMION, N_IW)
+    gt2 = O.fourier_iw_to_tau(gw, BETA, O.FERMION, N_TAU)
+    dt = time.perf_counter() - t0
+    return dt, float(np.max(np.abs(gt2 - gt)))
+
+
+def cpu_baseline_single_core(budget_s=12.0):
+    """oracle port, one core: blocks are processed sequentially like the reference (block/map.hpp:35-40)."""
+    n, t = 0, 0.0
+    while t < budget_s and n < 64:
+        dt, _ = _oracle_round_trip(n)
+        t += dt
+        n += 1
+    pts = n * (N_W + N_TAU)
+    return {"value": pts / t, "unit": "Gf points/s", "cores": 1, "kind": "port",
+            "sample": f"{n} blocks (5x5, L=1e5) imtime->imfreq->imtime with the NumPy/pocketfft oracle, {t:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be built here) on all host
+    cores, one worker per core over independent blocks -- the only parallelism the reference has (MPI ranks / blocks)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    per_step = workers  # blocks per step: one per worker
+    with mp.Pool(workers) as pool:
+        for _ in range(max(args.warmup, 1) if args.warmup > 0 else 0):
+            pool.map(_oracle_round_trip, range(per_step))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_oracle_round_trip, range(per_step))
+        dt = time.perf_counter() - t0
+    pts = args.steps * per_step * (N_W + N_TAU)
+    val = pts / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gf points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1] BlockGf 2x(5x5) beta=100 n_tau=100001 n_iw=10000 round trip",
+                       "sample": f"{per_step} blocks per step ({workers} worker processes)"},
+            "cpu_baseline": {"value": val, "unit": "Gf points/s", "cores": workers, "kind": "port",
+                             "sample": f"{args.steps} steps x {per_step} blocks, NumPy/pocketfft restatement of fourier_matsubara.cpp"},
+            "e2e": {"value": val, "unit": "Gf points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    import triqs_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = triqs_b200.Context(local, print_warnings=False)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    F = triqs_b200.FERMION
+    R = args.replicas
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # inputs: R BlockGfs = 2R blocks; replicas differ by a scale so that no two gfs are bit-identical
+    blocks = [torch.from_numpy(block_gtau(b)) for b in range(NBLOCK)]
+    host_gt = torch.empty((NBLOCK * R, N_TAU, NCOL), dtype=torch.complex128).pin_memory()
+    for i in range(NBLOCK * R):
+        host_gt[i] = blocks[i % NBLOCK] * (1.0 + 0.01 * (i // NBLOCK))
+    gt = host_gt.to(dev)
+    gw = torch.empty((NBLOCK * R, N_W, NCOL), dtype=torch.complex128, device=dev)
+    gt2 = torch.empty_like(gt)
+
+    def step():
+        ctx.fourier_tau_to_iw(gt, BETA, F, N_IW, out=gw)
+        ctx.fourier_iw_to_tau(gw, BETA, F, N_TAU, out=gt2)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    l0 = ctx.launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = cs.summary()
+    pts_step = world * R * POINTS_PER_BLOCKGF
+    value = pts_step * args.steps / (ms * 1e-3)
+
+    # correctness of what was timed (cheap, untimed): round trip returns the input
+    rt_err = float((gt2[:NBLOCK] - gt[:NBLOCK]).abs().max().item())
+
+    # per-kernel durations, same steps again with CUDA events around every launch
+    ctx.profile_enable(True)
+    timed(step, args.steps)
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    # algorithmic HBM bytes each kernel is responsible for, per block (DESIGN.md "Roofline accounting")
+    alg = {"tau2iw_pass1": 16.0 * NCOL * N_TAU, "tau2iw_pass2": 16.0 * NCOL * N_W, "iw2tau_pass1": 16.0 * NCOL * N_W,
+           "iw2tau_pass2": 16.0 * NCOL * N_TAU}
+    dom = max((k for k in prof if k in alg), key=lambda k: prof[k]["ms"], default=None)
+    roofline = None
+    if dom:
+        launches_k = prof[dom]["launches"]
+        blocks_per_launch = NBLOCK * R * args.steps / launches_k
+        dur_ms = prof[dom]["ms"] / launches_k
+        achieved = alg[dom] * blocks_per_launch / (dur_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": dur_ms, "alg_bytes_per_launch": alg[dom] * blocks_per_launch,
+                    "step_achieved_gbs": world * R * NBLOCK * ALG_BYTES_PER_BLOCK / (ms / args.steps * 1e-3) / 1e9 / world,
+                    "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
+
+    # end to end through the C ABI with HOST buffers (pinned): H2D of the inputs and D2H of the results inside the timed region
+    host_gw = torch.empty((NBLOCK * R, N_W, NCOL), dtype=torch.complex128).pin_memory()
+    host_gt2 = torch.empty((NBLOCK * R, N_TAU, NCOL), dtype=torch.complex128).pin_memory()
+    h_gt, h_gw, h_gt2 = host_gt.numpy(), host_gw.numpy(), host_gt2.numpy()
+
+    def e2e_step():
+        ctx.fourier_tau_to_iw(h_gt, BETA, F, N_IW, out=h_gw)
+        ctx.fourier_iw_to_tau(h_gw, BETA, F, N_TAU, out=h_gt2)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = pts_step * e2e_steps / float(dt.item())
+    e2e_err = float(np.max(np.abs(h_gt2[:NBLOCK] - h_gt[:NBLOCK])))
+    e2e = {"value": e2e_val, "unit": "Gf points/s", "h2d_bytes_per_step": int(h_gt.nbytes + h_gw.nbytes),
+           "d2h_bytes_per_step": int(h_gw.nbytes + h_gt2.nbytes), "steps": e2e_steps, "round_trip_max_abs_err": e2e_err}
+
+    extras = {}
+    if not args.no_extras:
+        del gt2, host_gw, host_gt2
+        extras = run_extras(ctx, stream, dev, world, rank, timed_fn=timed)
+
+    if rank == 0:
+        cpu = cpu_baseline_single_core()
+        line = {"metric": METRIC, "value": value, "unit": "Gf points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "configs[1] BlockGf 2x(5x5) beta=100 n_tau=100001 n_iw=10000 imtime<->imfreq round trip",
+                           "blockgfs_per_gpu_per_step": R, "input_bytes_per_gpu_per_step": int(gt.numel() * 16),
+                           "l2": "inputs (1.28 GB/step/GPU) exceed the 126 MB L2; no flush between steps",
+                           "parallelism": f"independent BlockGfs sharded over {world} GPU(s), no collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "round_trip_max_abs_err": rt_err, "extras": extras}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(ctx, stream, dev, world, rank, timed_fn):
+    """The other BASELINE.json configs, short, device resident (not the headline; reported for the record)."""
+    import torch
+    import torch.distributed as dist
+
+    import triqs_b200
+    F = triqs_b200.FERMION
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def guard(name, fn):
+        try:
+            fn()
+        except Exception as e:  # an extra must never take the headline down
+            out[name] = {"error": repr(e)[:200]}
+
+    def c1():
+        B = 8192
+        gt = torch.cumsum(torch.randn(B, 10001, 1, dtype=torch.float64, device=dev, generator=g), dim=1).to(torch.complex128) * 1e-3
+        gw = torch.empty(B, 2050, 1, dtype=torch.complex128, device=dev)
+        ms = timed_fn(lambda: ctx.fourier_tau_to_iw(gt, 10.0, F, 1025, out=gw), 5) / 5
+        fit = lambda: ctx.fit_tail(gw.reshape(B, 2050, 1), 10.0, F, hermitian=True, inner_dim=1)
+        ms_fit = timed_fn(fit, 3) / 3
+        out["c1_tau2iw_fit_hermitian_tail_B8192"] = {"ms": ms + ms_fit, "ms_transform": ms, "ms_fit": ms_fit,
+                                                     "points_per_s": world * B * 2050 / ((ms + ms_fit) * 1e-3),
+                                                     "GBps_per_gpu": B * 192816.0 / ((ms + ms_fit) * 1e-3) / 1e9}
+
+    def c3():
+        nk, no = 65536, 9216
+        x = torch.randn(nk, no, dtype=torch.float64, device=dev, generator=g).to(torch.complex128)
+        y = torch.empty_like(x)
+        ms = timed_fn(lambda: ctx.fourier_lattice(x, (256, 256, 1), True, out=y), 3) / 3
+        out["c3_lattice_256x256_x1024iw_3x3"] = {"ms": ms, "points_per_s": world * nk * 1024 / (ms * 1e-3),
+                                                  "GBps_per_gpu": 2.0 * nk * no * 16 / (ms * 1e-3) / 1e9}
+
+    def c4():
+        nk_tot, nw, n = 64 ** 3, 2048, 5
+        lo = rank * (nk_tot // world) + min(rank, nk_tot % world)
+        hi = lo + nk_tot // world + (1 if rank < nk_tot % world else 0)
+        eps = torch.randn(hi - lo, n, n, dtype=torch.complex128, device=dev, generator=g) * 0.3
+        eps = (eps + eps.conj().transpose(1, 2)).contiguous()
+        gs = torch.Generator(device=dev).manual_seed(4002)
+        sig = torch.randn(nw, n, n, dtype=torch.complex128, device=dev, generator=gs) * 0.1
+        gl = torch.empty_like(sig)
+        use_comm = False
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt = torch.tensor(list(triqs_b200.comm_unique_id()), dtype=torch.uint8, device=dev)
+            dist.broadcast(idt, 0)
+            ctx.comm_init(world, rank, bytes(idt.cpu().tolist()))
+            use_comm = True
+        ms = timed_fn(lambda: ctx.dyson_ksum(eps, sig, 10.0, F, 0.1, uniform_weight=1.0 / nk_tot, all_reduce=use_comm, out=gl), 2) / 2
+        out["c4_dyson_ksum_64^3_x2048iw_5x5"] = {"ms": ms, "inversions_per_s": nk_tot * nw / (ms * 1e-3),
+                                                 "materialised_equiv_GBps": nk_tot * nw * 400.0 / (ms * 1e-3) / 1e9,
+                                                 "all_reduce": use_comm, "k_points_this_rank": hi - lo}
+
+    def c5():
+        npts = 25_000_000
+        table = torch.randn(8192, 25, dtype=torch.complex128, device=dev, generator=g)
+        taus = torch.rand(npts, dtype=torch.float64, device=dev, generator=g) * 10.0
+        o = torch.empty(npts, 25, dtype=torch.complex128, device=dev)
+        ms = timed_fn(lambda: ctx.interp_tau(table, 10.0, taus, out=o), 3) / 3
+        out["c5_interp_2.5e7pts_5x5_block"] = {"ms": ms, "points_per_s": world * npts / (ms * 1e-3), "GBps_per_gpu": npts * 408.0 / (ms * 1e-3) / 1e9}
+
+    for name, fn in (("c1", c1), ("c3", c3), ("c4", c4), ("c5", c5)):
+        guard(name, fn)
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--replicas", type=int, default=16, help="BlockGfs per GPU per step")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

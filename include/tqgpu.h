@@ -66,6 +66,11 @@ tq_status tq_synchronize(tq_ctx *ctx);
 uint64_t tq_launch_count(const tq_ctx *ctx);
 /* library build id string ("tqgpu <version> sm_100a") */
 const char *tq_version(void);
+/* Per-kernel timing for benchmarks: while enabled, every kernel launch of this context is bracketed by CUDA
+ * events on the context's stream.  tq_profile_report synchronises, writes a JSON object
+ * {"kernel tag": {"launches": n, "ms": total}, ...} into buf (truncated to len) and clears the records. */
+tq_status tq_profile_enable(tq_ctx *ctx, int on);
+tq_status tq_profile_report(tq_ctx *ctx, char *buf, size_t len);
 
 /* ---- Matsubara transforms ------------------------------------------------------------------ */
 

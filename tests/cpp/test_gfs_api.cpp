@@ -1,0 +1,169 @@
+// C++ host-side test of the drop-in API (triqs_b200/cpp/triqs_b200/gfs.hpp) -- reads like the reference's own tests:
+//   test/c++/gfs/fourier_matsubara.cpp:23-114, fourier_block.cpp:24-99, g_r_k.cpp:28-62, meshes/eval.cpp:62-89,
+//   fit_tail_matsubara.cpp:27-72, and test/python/base/tail_issues.py:74-102 (fit_hermitian_tail).
+// Needs a GPU; built by __graft_entry__.build() and run by tests/test_gpu_cpp_api.py.
+#include <triqs_b200/gfs.hpp>
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace triqs_b200;
+
+static int failures = 0;
+#define EXPECT(cond)                                                                                                             \
+  do {                                                                                                                           \
+    if (!(cond)) {                                                                                                               \
+      std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond);                                                              \
+      ++failures;                                                                                                                \
+    }                                                                                                                            \
+  } while (0)
+
+template <typename G> double max_diff(G const &a, G const &b) {
+  double m = 0;
+  for (size_t i = 0; i < a.data().size(); ++i) m = std::max(m, std::abs(a.data()[i] - b.data()[i]));
+  return m;
+}
+
+static double one_pole(double En, double t, double beta, double s) {
+  if (En > 0) return -std::exp(-En * t) / (1 - s * std::exp(-En * beta));
+  return s * std::exp(En * (beta - t)) / (1 - s * std::exp(En * beta));
+}
+
+template <typename T> void test_fourier(statistic_enum statistic, std::vector<long> shape) {
+  double precision = 1e-8, beta = 10, E = -1;
+  long N_iw = 1000, N_tau = 10000;
+  auto Gw1 = gf<mesh::imfreq, T>{{beta, statistic, N_iw}, shape};
+  long no = Gw1.n_others();
+  for (long i = 0; i < Gw1.mesh().size(); ++i) {
+    dcomplex iw = Gw1.mesh()[i];
+    for (long c = 0; c < no; ++c) Gw1[i][c] = 1.0 / (iw - E) + 1.0 / (iw + 2 * E) - 4.5 / (iw - 1.25 * E);
+  }
+  auto Gt1 = gf<mesh::imtime, T>{{beta, statistic, N_tau}, shape};
+  set_from_fourier(Gt1, Gw1);
+  auto Gw1b = gf<mesh::imfreq, T>{{beta, statistic, N_iw}, shape};
+  set_from_fourier(Gw1b, Gt1);
+  EXPECT(max_diff(Gw1, Gw1b) < precision);
+  auto Gt1_exact = Gt1;
+  double s = (statistic == Fermion ? -1 : 1);
+  for (long i = 0; i < Gt1.mesh().size(); ++i) {
+    double t = Gt1.mesh()[i];
+    for (long c = 0; c < no; ++c) Gt1_exact[i][c] = one_pole(E, t, beta, s) + one_pole(-2 * E, t, beta, s) - 4.5 * one_pole(1.25 * E, t, beta, s);
+  }
+  EXPECT(max_diff(Gt1, Gt1_exact) < precision);
+  // tail from fit_tail passed explicitly
+  auto [tail, err] = fit_tail(Gw1);
+  auto Gt1_tail = gf<mesh::imtime, T>{{beta, statistic, N_tau}, shape};
+  set_from_fourier(Gt1_tail, Gw1, tail);
+  EXPECT(max_diff(Gt1_tail, Gt1_exact) < precision);
+  // only 0th and 1st moment
+  auto known_moments = make_zero_tail(Gt1, 2);
+  for (long c = 0; c < no; ++c) known_moments(1, c) = -2.5;
+  auto Gt1_km = gf<mesh::imtime, T>{{beta, statistic, N_tau}, shape};
+  set_from_fourier(Gt1_km, Gw1, known_moments);
+  EXPECT(max_diff(Gt1_km, Gt1_exact) < precision);
+  // factories
+  auto Gt2 = make_gf_from_fourier(Gw1, N_tau);
+  auto Gw2b = make_gf_from_fourier(Gt2, N_iw);
+  EXPECT(max_diff(Gt2, Gt1) < precision);
+  EXPECT(max_diff(Gw2b, Gw1) < precision);
+  // repeated transforms
+  for (int i = 0; i < 10; ++i) {
+    set_from_fourier(Gt1, Gw1b);
+    set_from_fourier(Gw1b, Gt1);
+  }
+  EXPECT(max_diff(Gw1, Gw1b) < precision);
+}
+
+void test_errors() {
+  bool thrown = false;
+  try {
+    auto gt = gf<mesh::imtime, scalar_valued>{{1.0, Fermion, 101}};
+    auto gw = make_gf_from_fourier(gt, 60); // time mesh too short
+  } catch (runtime_error const &e) { thrown = std::string(e.what()).find("at least twice as long") != std::string::npos; }
+  EXPECT(thrown);
+}
+
+void test_block() { // fourier_block.cpp: beta = 1, N_iw = 1000, N_tau = 6001
+  double beta = 1;
+  long N_iw = 1000, N_tau = 6001;
+  std::vector<gf<mesh::imfreq, matrix_valued>> blocks;
+  for (int b = 0; b < 2; ++b) {
+    gf<mesh::imfreq, matrix_valued> g{{beta, Fermion, N_iw}, {2, 2}};
+    for (long i = 0; i < g.mesh().size(); ++i) {
+      dcomplex iw = g.mesh()[i];
+      g[i][0] = 1.0 / (iw - (1.0 + b));
+      g[i][3] = 1.0 / (iw + 0.5);
+    }
+    blocks.push_back(g);
+  }
+  block_gf<mesh::imfreq, matrix_valued> bgw{{"up", "down"}, blocks};
+  auto bgt = make_gf_from_fourier(bgw, N_tau);
+  auto bgw2 = make_gf_from_fourier(bgt, N_iw);
+  for (int b = 0; b < 2; ++b) EXPECT(max_diff(bgw[b], bgw2[b]) < 1e-7);
+}
+
+void test_hermitian_tail() { // tail_issues.py:74-102
+  for (double eps : {0.001, 0.1, 1.0, 10.0}) {
+    long Nw = std::max(25L, long(eps * 60));
+    gf<mesh::imfreq, matrix_valued> g{{1.0, Fermion, Nw}, {2, 2}};
+    dcomplex H[2][2] = {{eps * 1.0, eps * dcomplex(0, 0.1)}, {eps * dcomplex(0, -0.1), eps * 2.0}};
+    for (long i = 0; i < g.mesh().size(); ++i) {
+      dcomplex iw = g.mesh()[i];
+      dcomplex a = iw - H[0][0], b = -H[0][1], c = -H[1][0], d = iw - H[1][1];
+      dcomplex det = a * d - b * c;
+      g[i][0] = d / det; g[i][1] = -b / det; g[i][2] = -c / det; g[i][3] = a / det;
+    }
+    auto [tail, err] = fit_hermitian_tail(g);
+    // moments 1..3 = H^0, H^1, H^2
+    dcomplex H2[4] = {H[0][0] * H[0][0] + H[0][1] * H[1][0], H[0][0] * H[0][1] + H[0][1] * H[1][1], H[1][0] * H[0][0] + H[1][1] * H[1][0],
+                      H[1][0] * H[0][1] + H[1][1] * H[1][1]};
+    dcomplex ex[3][4] = {{1, 0, 0, 1}, {H[0][0], H[0][1], H[1][0], H[1][1]}, {H2[0], H2[1], H2[2], H2[3]}};
+    for (int n = 0; n < 3; ++n) {
+      double num = 0, den = 0;
+      for (int c = 0; c < 4; ++c) { num = std::max(num, std::abs(ex[n][c] - tail(1 + n, c))); den = std::max(den, std::abs(ex[n][c])); }
+      EXPECT(num / den < 1e-4);
+    }
+  }
+}
+
+void test_lattice() { // g_r_k.cpp:52-58
+  long N = 10;
+  gf<mesh::brzone, scalar_valued> gk{{N, N, 1}};
+  for (long i = 0; i < N; ++i)
+    for (long j = 0; j < N; ++j) gk[i * N + j][0] = -2 * (std::cos(2 * M_PI * i / N) + std::cos(2 * M_PI * j / N));
+  auto gr = make_gf_from_fourier(gk);
+  EXPECT(std::abs(gr[1 * N + 0][0] + 1.0) < 1e-13);
+  EXPECT(std::abs(gr[(N - 1) * N + 0][0] + 1.0) < 1e-13);
+  EXPECT(std::abs(gr[0 * N + 1][0] + 1.0) < 1e-13);
+  EXPECT(std::abs(gr[0 * N + N - 1][0] + 1.0) < 1e-13);
+  EXPECT(std::abs(gr[0][0]) < 1e-13);
+  auto gk2 = make_gf_from_fourier(gr);
+  EXPECT(max_diff(gk, gk2) < 1e-12);
+}
+
+void test_eval_and_inverse() { // meshes/eval.cpp:62-89, gf_inverse.cpp
+  gf<mesh::imtime, scalar_valued> g{{10.0, Fermion, 5}};
+  double v[5] = {1, 10, 100, 1000, 1e4};
+  for (int i = 0; i < 5; ++i) g[i][0] = v[i];
+  EXPECT(std::abs(g(2.0)[0] - (0.2 * 1 + 0.8 * 10)) < 1e-13);
+  EXPECT(std::abs(g(3.5)[0] - (0.6 * 10 + 0.4 * 100)) < 1e-12);
+  gf<mesh::imfreq, matrix_valued> m{{10.0, Fermion, 20}, {1, 1}};
+  for (long i = 0; i < m.mesh().size(); ++i) m[i][0] = m.mesh()[i] - 0.3;
+  auto mi = inverse(m);
+  for (long i = 0; i < m.mesh().size(); ++i) EXPECT(std::abs(mi[i][0] - 1.0 / (m.mesh()[i] - 0.3)) < 1e-14);
+}
+
+int main() {
+  test_fourier<scalar_valued>(Fermion, {});
+  test_fourier<matrix_valued>(Fermion, {2, 2});
+  test_fourier<tensor_valued<3>>(Fermion, {2, 2, 2});
+  test_fourier<scalar_valued>(Boson, {});
+  test_fourier<matrix_valued>(Boson, {2, 2});
+  test_errors();
+  test_block();
+  test_hermitian_tail();
+  test_lattice();
+  test_eval_and_inverse();
+  std::printf(failures ? "%d FAILURES\n" : "ALL C++ API TESTS PASSED\n", failures);
+  return failures ? 1 : 0;
+}

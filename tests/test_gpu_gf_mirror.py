@@ -1,0 +1,83 @@
+"""The Python mirror of the reference API (triqs_b200.gf) on the GPU: same call shapes as python/triqs/gf."""
+import numpy as np
+import pytest
+
+from oracle import triqs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _gw(beta, n_iw, n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    H = 0.5 * (a + a.conj().T)
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    return np.linalg.inv(iw[:, None, None] * np.eye(n)[None] - H[None]), H
+
+
+def test_gf_round_trip_blockgf_and_tail():
+    from triqs_b200 import gf as G
+    beta, n_iw = 10.0, 300
+    blocks = []
+    for b in range(2):
+        d, H = _gw(beta, n_iw, 2, b)
+        blocks.append(G.Gf(G.MeshImFreq(beta, O.FERMION, n_iw), (2, 2), d))
+    bg = G.BlockGf(["up", "down"], blocks)
+    bgt = G.make_gf_from_fourier(bg)              # default n_tau = 6 n_iw + 1
+    assert bgt["up"].mesh.n_tau == 6 * n_iw + 1
+    bgw = G.make_gf_from_fourier(bgt, n_iw)
+    for b in range(2):
+        ref_t = O.fourier_iw_to_tau(blocks[b].flat(), beta, O.FERMION, 6 * n_iw + 1)
+        assert np.max(np.abs(bgt[b].flat() - ref_t)) / np.max(np.abs(ref_t)) < 1e-11
+        assert np.max(np.abs(bgw[b].data - blocks[b].data)) < 1e-8
+    tail, err = G.fit_hermitian_tail(blocks[0])
+    assert tail.shape[1:] == (2, 2) and err < 1e-8
+    assert np.max(np.abs(tail[1] - np.eye(2))) < 1e-6
+    tails, max_err = G.fit_hermitian_tail(bg)
+    assert len(tails) == 2 and max_err < 1e-8
+    # single gf, known moments
+    km = G.make_zero_tail(blocks[0], 2)
+    km[1] = np.eye(2)
+    gt = G.make_gf_from_fourier(blocks[0], 2001, km)
+    ref = O.fourier_iw_to_tau(blocks[0].flat(), beta, O.FERMION, 2001, km.reshape(2, 4))
+    assert np.max(np.abs(gt.flat() - ref)) / np.max(np.abs(ref)) < 1e-11
+
+
+def test_gf_call_inverse_and_lattice():
+    from triqs_b200 import gf as G
+    d, H = _gw(10.0, 50, 3, 3)
+    g = G.Gf(G.MeshImFreq(10.0, O.FERMION, 50), (3, 3), d)
+    gi = G.inverse(g)
+    iw = g.mesh.values()
+    assert np.max(np.abs(gi.data - (iw[:, None, None] * np.eye(3)[None] - H[None]))) < 1e-12
+    gt = G.make_gf_from_fourier(g, 601)
+    v = gt(np.array([0.0, 1.234, 10.0]))
+    ref = O.interp_tau(gt.flat(), 10.0, np.array([0.0, 1.234, 10.0])).reshape(3, 3, 3)
+    assert np.array_equal(v, ref)
+    assert np.array_equal(gt(1.234), ref[1])
+    rng = np.random.default_rng(0)
+    gr = G.Gf(G.MeshCycLat((6, 5, 4)), (2,), rng.normal(size=(120, 2)) + 1j * rng.normal(size=(120, 2)))
+    gk = G.make_gf_from_fourier(gr)
+    assert isinstance(gk.mesh, G.MeshBrZone)
+    assert np.max(np.abs(gk.flat() - O.fourier_lattice_r_to_k(gr.flat(), (6, 5, 4)))) < 1e-12
+    back = G.make_gf_from_fourier(gk)
+    assert np.max(np.abs(back.data - gr.data)) < 1e-13
+
+
+def test_dyson_k_sum_sharded_on_one_gpu():
+    """ranks emulated sequentially on one GPU: partial sums with the 1/N_k(total) weight add up to the whole."""
+    import triqs_b200
+    from triqs_b200 import gf as G
+    ctx = triqs_b200.Context(0, print_warnings=False)
+    rng = np.random.default_rng(4)
+    eps = rng.normal(size=(101, 5, 5)) + 1j * rng.normal(size=(101, 5, 5))
+    eps = eps + eps.conj().transpose(0, 2, 1)
+    iw = O.imfreq_values(10.0, O.FERMION, 40)
+    sig = np.stack([0.2 * np.eye(5) / (w + 0.3) for w in iw])
+    sigma = G.Gf(G.MeshImFreq(10.0, O.FERMION, 40), (5, 5), sig)
+    ref = O.dyson_ksum(eps, sig, 10.0, O.FERMION, 0.2)
+    parts = []
+    for r in range(4):
+        parts.append(G.dyson_k_sum(ctx, eps, sigma, 0.2, rank=r, n_ranks=4, reduce_fn=lambda p: p).data)
+    assert np.max(np.abs(sum(parts) - ref)) / np.max(np.abs(ref)) < 1e-12
+    ctx.close()

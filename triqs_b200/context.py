@@ -128,6 +128,16 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.tq_launch_count(self._h))
 
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.tq_profile_enable(self._h, int(on)))
+
+    def profile_report(self) -> dict:
+        """per-kernel {"tag": {"launches": n, "ms": total}} since the last report (CUDA events on the ctx stream)."""
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._check(self._lib.tq_profile_report(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     # -- Matsubara transforms -------------------------------------------------------------------
     def fourier_tau_to_iw(self, gt, beta, statistic, n_iw, moments=None, out=None):
         """gt [batch, n_tau, n_others] -> gw [batch, n_w, n_others]  (tq_fourier_tau_to_iw)."""

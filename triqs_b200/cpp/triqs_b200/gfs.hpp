@@ -1,0 +1,431 @@
+// Header-only C++ host mirror of the slice of the TRIQS gf API that sits on the GPU hot path.
+//
+// Same names, argument meaning and error behaviour as the reference (TRIQS 3.3.1) for
+//   gf<mesh, target>, block_gf                      c++/triqs/gfs/gf/gf.hpp:86-375, block/block_gf.hpp:104-295
+//   mesh::imtime / imfreq / brzone / cyclat         c++/triqs/mesh/{imtime,imfreq,brzone,cyclat}.hpp
+//   make_adjoint_mesh                               c++/triqs/mesh/adjoint.hpp:31-57
+//   make_gf_from_fourier / fourier                  c++/triqs/gfs/transform/fourier.hpp:93-276
+//   fit_tail / fit_hermitian_tail / make_zero_tail  c++/triqs/gfs/functions/functions2.hpp:50-162
+//   inverse / invert_in_place                       c++/triqs/gfs/functions/functions2.hpp:197-209
+//   g(tau) evaluation                               c++/triqs/gfs/evaluator.hpp:31-44
+// but every numerical operation is a call into the C ABI of libtqgpu.so (include/tqgpu.h): this header contains
+// no arithmetic of its own and there is no CPU path.  Data layout is the reference's: C-order
+// [mesh..., target...] std::complex<double>, so arrays can be handed over from nda views without a copy.
+#pragma once
+#include <array>
+#include <cmath>
+#include <complex>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "tqgpu.h"
+
+namespace triqs_b200 {
+
+  using dcomplex = std::complex<double>;
+
+  // triqs::runtime_error  (c++/triqs/utility/exceptions.hpp:31-37)
+  struct runtime_error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+
+  enum statistic_enum { Boson = 0, Fermion = 1 }; // c++/triqs/mesh/domains/matsubara.hpp
+
+  // one context per thread (the reference is single threaded)
+  inline tq_ctx *context() {
+    struct holder {
+      tq_ctx *c = nullptr;
+      holder() {
+        tq_status st = tq_create(0, &c);
+        if (st != TQ_OK) throw runtime_error("triqs_b200: no CUDA device / tq_create failed (there is no CPU fallback)");
+      }
+      ~holder() { tq_destroy(c); }
+    };
+    thread_local holder h;
+    return h.c;
+  }
+
+  inline void check(tq_status st) {
+    if (st == TQ_OK) return;
+    std::string msg = tq_last_error(context());
+    throw runtime_error(msg.empty() ? "triqs_b200: status " + std::to_string(int(st)) : msg);
+  }
+
+  // the reference prints these to std::cerr (fourier_matsubara.cpp:109-110, 131-133, 208-210)
+  inline void print_warnings(int bits) {
+    if (bits & TQ_WARN_NOISY_TAU)
+      std::cerr << "WARNING: Direct Fourier cannot deduce the high-frequency moments of G(tau) due to noise or a coarse tau-grid. "
+                   "Please specify the high-frequency moments for higher accuracy.\n";
+    if (bits & TQ_WARN_SHORT_TAU_MESH)
+      std::cerr << "[Direct Fourier] WARNING: The imaginary time mesh is less than six times as long as the number of positive frequencies.\n"
+                << "This can lead to substantial numerical inaccuracies at the boundary of the frequency mesh.\n";
+    if (bits & TQ_WARN_TAIL_ERR)
+      std::cerr << "WARNING: High frequency moments have an error greater than 1e-4.\n Please make sure you treat the constant offset analytically!\n";
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // meshes
+  // ------------------------------------------------------------------------------------------------
+  namespace mesh {
+    class imtime { // c++/triqs/mesh/imtime.hpp:36-122, bases/linear.hpp:47-55
+      double _beta = 1;
+      statistic_enum _stat = Fermion;
+      long _n = 2;
+
+      public:
+      imtime() = default;
+      imtime(double beta, statistic_enum s, long n_tau) : _beta(beta), _stat(s), _n(n_tau) {}
+      double beta() const { return _beta; }
+      statistic_enum statistic() const { return _stat; }
+      long size() const { return _n; }
+      double delta() const { return (_beta - 0.0) / (_n - 1); }
+      double to_value(long i) const { // linear.hpp:154-160
+        double wr = double(i) / (_n - 1);
+        return 0.0 * (1 - wr) + _beta * wr;
+      }
+      double operator[](long i) const { return to_value(i); }
+      bool operator==(imtime const &m) const { return _beta == m._beta && _stat == m._stat && _n == m._n; }
+    };
+
+    class imfreq { // c++/triqs/mesh/imfreq.hpp:43-304
+      double _beta = 1;
+      statistic_enum _stat = Fermion;
+      long _n_iw = 0;
+
+      public:
+      imfreq() = default;
+      imfreq(double beta, statistic_enum s, long n_iw = 1025) : _beta(beta), _stat(s), _n_iw(n_iw) {}
+      double beta() const { return _beta; }
+      statistic_enum statistic() const { return _stat; }
+      long n_iw() const { return _n_iw; }
+      long last_index() const { return _n_iw - 1; }
+      long first_index() const { return -(last_index() + (_stat == Fermion ? 1 : 0)); }
+      long size() const { return last_index() - first_index() + 1; }
+      bool positive_only() const { return false; }
+      dcomplex to_value(long n) const { return {0, M_PI * double(2 * n + _stat) / _beta}; } // matsubara.hpp:55
+      dcomplex operator[](long data_index) const { return to_value(first_index() + data_index); }
+      dcomplex w_max() const { return to_value(last_index()); }
+      long to_data_index(long n) const { return n - first_index(); }
+      bool operator==(imfreq const &m) const { return _beta == m._beta && _stat == m._stat && _n_iw == m._n_iw; }
+    };
+
+    struct lattice_mesh_base { // 3-index periodic meshes, data index i0*d1*d2 + i1*d2 + i2 (brzone.hpp:187-190)
+      std::array<long, 3> _dims{1, 1, 1};
+      std::array<long, 3> dims() const { return _dims; }
+      long size() const { return _dims[0] * _dims[1] * _dims[2]; }
+    };
+    struct cyclat : lattice_mesh_base {
+      cyclat() = default;
+      cyclat(long d0, long d1 = 1, long d2 = 1) { _dims = {d0, d1, d2}; }
+      bool operator==(cyclat const &m) const { return _dims == m._dims; }
+    };
+    struct brzone : lattice_mesh_base {
+      brzone() = default;
+      brzone(long d0, long d1 = 1, long d2 = 1) { _dims = {d0, d1, d2}; }
+      bool operator==(brzone const &m) const { return _dims == m._dims; }
+    };
+
+    // c++/triqs/mesh/adjoint.hpp:31-57
+    inline imfreq make_adjoint_mesh(imtime const &m, long n_iw = -1) {
+      if (n_iw == -1) n_iw = (m.size() - 1) / 6;
+      return {m.beta(), m.statistic(), n_iw};
+    }
+    inline imtime make_adjoint_mesh(imfreq const &m, long n_tau = -1) {
+      if (n_tau == -1) n_tau = 6 * (m.last_index() + 1) + 1;
+      return {m.beta(), m.statistic(), n_tau};
+    }
+    inline brzone make_adjoint_mesh(cyclat const &m) { return brzone{m._dims[0], m._dims[1], m._dims[2]}; }
+    inline cyclat make_adjoint_mesh(brzone const &m) { return cyclat{m._dims[0], m._dims[1], m._dims[2]}; }
+  } // namespace mesh
+
+  // ------------------------------------------------------------------------------------------------
+  // gf<mesh, target>
+  // ------------------------------------------------------------------------------------------------
+  struct scalar_valued {
+    static constexpr int rank = 0;
+  };
+  struct matrix_valued {
+    static constexpr int rank = 2;
+  };
+  template <int R> struct tensor_valued {
+    static constexpr int rank = R;
+  };
+
+  // moments / small dense arrays: C-order [n_rows, target...] flattened to [n_rows][n_others]
+  struct moment_array {
+    long n_rows = 0, n_others = 0;
+    std::vector<dcomplex> v;
+    moment_array() = default;
+    moment_array(long r, long c) : n_rows(r), n_others(c), v(size_t(r * c), dcomplex{0, 0}) {}
+    dcomplex &operator()(long r, long c) { return v[size_t(r * n_others + c)]; }
+    dcomplex const &operator()(long r, long c) const { return v[size_t(r * n_others + c)]; }
+    bool is_empty() const { return v.empty(); }
+  };
+
+  template <typename Mesh, typename Target = matrix_valued> class gf {
+    Mesh _mesh;
+    std::vector<long> _tshape; // target shape (empty for scalar_valued)
+    std::vector<dcomplex> _data;
+
+    public:
+    using mesh_t = Mesh;
+    using target_t = Target;
+    gf() = default;
+    gf(Mesh m, std::vector<long> target_shape = {}) : _mesh(std::move(m)), _tshape(std::move(target_shape)) {
+      if ((int)_tshape.size() != Target::rank) throw runtime_error("gf: target shape does not match the target rank");
+      _data.assign(size_t(_mesh.size() * n_others()), dcomplex{0, 0});
+    }
+    Mesh const &mesh() const { return _mesh; }
+    std::vector<long> const &target_shape() const { return _tshape; }
+    long n_others() const {
+      long n = 1;
+      for (long s : _tshape) n *= s;
+      return n;
+    }
+    // inner matrix dimension for the hermitian fit (functions2.hpp:96-106)
+    long inner_matrix_dim() const {
+      if (Target::rank == 0) return 1;
+      if (Target::rank == 2 && _tshape[0] == _tshape[1]) return _tshape[0];
+      throw runtime_error("Incompatible target_shape for fit_hermitian_tail");
+    }
+    std::vector<dcomplex> &data() { return _data; }
+    std::vector<dcomplex> const &data() const { return _data; }
+    // value of the target at mesh data index i (pointer to n_others contiguous entries, C order)
+    dcomplex *operator[](long i) { return _data.data() + size_t(i * n_others()); }
+    dcomplex const *operator[](long i) const { return _data.data() + size_t(i * n_others()); }
+    // off-mesh evaluation g(tau): linear interpolation on the device (evaluator.hpp:35-43)
+    std::vector<dcomplex> operator()(double x) const;
+  };
+
+  template <typename Mesh, typename Target = matrix_valued> class block_gf { // block/block_gf.hpp:104-295
+    std::vector<std::string> _names;
+    std::vector<gf<Mesh, Target>> _blocks;
+
+    public:
+    block_gf() = default;
+    block_gf(std::vector<std::string> names, std::vector<gf<Mesh, Target>> blocks) : _names(std::move(names)), _blocks(std::move(blocks)) {
+      if (_names.size() != _blocks.size()) throw runtime_error("block_gf: names and blocks differ in size");
+    }
+    long size() const { return (long)_blocks.size(); }
+    std::vector<std::string> const &block_names() const { return _names; }
+    gf<Mesh, Target> &operator[](long i) { return _blocks[size_t(i)]; }
+    gf<Mesh, Target> const &operator[](long i) const { return _blocks[size_t(i)]; }
+  };
+
+  template <typename G> moment_array make_zero_tail(G const &g, int n_moments = 10) { // functions2.hpp:154-162
+    return moment_array(n_moments, g.n_others());
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // Fourier  (fourier.hpp:93-276)
+  // ------------------------------------------------------------------------------------------------
+  namespace detail {
+    inline const tq_complex *cptr(std::vector<dcomplex> const &v) { return reinterpret_cast<const tq_complex *>(v.data()); }
+    inline tq_complex *ptr(std::vector<dcomplex> &v) { return reinterpret_cast<tq_complex *>(v.data()); }
+
+    // same-shape blocks go to the device as ONE batched call; otherwise block by block like map_block_gf (block/map.hpp:35-40)
+    template <typename G> bool same_shape(std::vector<G const *> const &gs) {
+      for (auto *g : gs)
+        if (!(g->mesh() == gs[0]->mesh()) || g->target_shape() != gs[0]->target_shape()) return false;
+      return true;
+    }
+  } // namespace detail
+
+  // g_out() = fourier(g_in[, known_moments]) on an existing gf (the lazy assignment of fourier.hpp:257-276)
+  template <typename T>
+  void set_from_fourier(gf<mesh::imfreq, T> &gw, gf<mesh::imtime, T> const &gt, moment_array const &known_moments = {}) {
+    if (gw.target_shape() != gt.target_shape()) throw runtime_error("fourier: target shapes differ");
+    int warn = 0;
+    check(tq_fourier_tau_to_iw(context(), gt.mesh().beta(), gt.mesh().statistic(), gt.mesh().size(), gw.mesh().n_iw(), gt.n_others(), 1,
+                               detail::cptr(gt.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                               (int)known_moments.n_rows, detail::ptr(gw.data()), &warn));
+    print_warnings(warn);
+  }
+  template <typename T>
+  void set_from_fourier(gf<mesh::imtime, T> &gt, gf<mesh::imfreq, T> const &gw, moment_array const &known_moments = {}) {
+    if (gw.target_shape() != gt.target_shape()) throw runtime_error("fourier: target shapes differ");
+    int warn = 0;
+    check(tq_fourier_iw_to_tau(context(), gw.mesh().beta(), gw.mesh().statistic(), gw.mesh().n_iw(), gt.mesh().size(), gw.n_others(), 1,
+                               detail::cptr(gw.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                               (int)known_moments.n_rows, detail::ptr(gt.data()), &warn, nullptr));
+    print_warnings(warn);
+  }
+  template <typename T> void set_from_fourier(gf<mesh::brzone, T> &gk, gf<mesh::cyclat, T> const &gr) {
+    auto d = gr.mesh().dims();
+    long dims[3] = {d[0], d[1], d[2]};
+    check(tq_fourier_lattice(context(), dims, 1, gr.n_others(), detail::cptr(gr.data()), detail::ptr(gk.data())));
+  }
+  template <typename T> void set_from_fourier(gf<mesh::cyclat, T> &gr, gf<mesh::brzone, T> const &gk) {
+    auto d = gk.mesh().dims();
+    long dims[3] = {d[0], d[1], d[2]};
+    check(tq_fourier_lattice(context(), dims, 0, gk.n_others(), detail::cptr(gk.data()), detail::ptr(gr.data())));
+  }
+
+  // factories  (fourier.hpp:122-144, 238-245)
+  template <typename T>
+  gf<mesh::imfreq, T> make_gf_from_fourier(gf<mesh::imtime, T> const &gt, long n_iw = -1, moment_array const &known_moments = {}) {
+    gf<mesh::imfreq, T> gw{mesh::make_adjoint_mesh(gt.mesh(), n_iw), gt.target_shape()};
+    set_from_fourier(gw, gt, known_moments);
+    return gw;
+  }
+  template <typename T>
+  gf<mesh::imtime, T> make_gf_from_fourier(gf<mesh::imfreq, T> const &gw, long n_tau = -1, moment_array const &known_moments = {}) {
+    gf<mesh::imtime, T> gt{mesh::make_adjoint_mesh(gw.mesh(), n_tau), gw.target_shape()};
+    set_from_fourier(gt, gw, known_moments);
+    return gt;
+  }
+  template <typename T> gf<mesh::brzone, T> make_gf_from_fourier(gf<mesh::cyclat, T> const &gr) {
+    gf<mesh::brzone, T> gk{mesh::make_adjoint_mesh(gr.mesh()), gr.target_shape()};
+    set_from_fourier(gk, gr);
+    return gk;
+  }
+  template <typename T> gf<mesh::cyclat, T> make_gf_from_fourier(gf<mesh::brzone, T> const &gk) {
+    gf<mesh::cyclat, T> gr{mesh::make_adjoint_mesh(gk.mesh()), gk.target_shape()};
+    set_from_fourier(gr, gk);
+    return gr;
+  }
+
+  // block_gf: all blocks of equal shape are transformed by one batched launch  (fourier.hpp:189-230)
+  template <typename T> block_gf<mesh::imfreq, T> make_gf_from_fourier(block_gf<mesh::imtime, T> const &bgt, long n_iw = -1) {
+    std::vector<gf<mesh::imfreq, T>> out;
+    std::vector<gf<mesh::imtime, T> const *> gs;
+    for (long b = 0; b < bgt.size(); ++b) gs.push_back(&bgt[b]);
+    if (bgt.size() > 1 && detail::same_shape(gs)) {
+      auto const &g0 = bgt[0];
+      auto mw = mesh::make_adjoint_mesh(g0.mesh(), n_iw);
+      long nb = bgt.size(), no = g0.n_others();
+      std::vector<dcomplex> in(size_t(nb * g0.mesh().size() * no)), res(size_t(nb * mw.size() * no));
+      for (long b = 0; b < nb; ++b) std::copy(bgt[b].data().begin(), bgt[b].data().end(), in.begin() + size_t(b * g0.mesh().size() * no));
+      std::vector<int> warn(size_t(nb), 0);
+      check(tq_fourier_tau_to_iw(context(), g0.mesh().beta(), g0.mesh().statistic(), g0.mesh().size(), mw.n_iw(), no, nb, detail::cptr(in),
+                                 nullptr, 0, detail::ptr(res), warn.data()));
+      int w = 0;
+      for (int x : warn) w |= x;
+      print_warnings(w);
+      for (long b = 0; b < nb; ++b) {
+        gf<mesh::imfreq, T> g{mw, g0.target_shape()};
+        std::copy(res.begin() + size_t(b * mw.size() * no), res.begin() + size_t((b + 1) * mw.size() * no), g.data().begin());
+        out.push_back(std::move(g));
+      }
+    } else {
+      for (long b = 0; b < bgt.size(); ++b) out.push_back(make_gf_from_fourier(bgt[b], n_iw));
+    }
+    return {bgt.block_names(), std::move(out)};
+  }
+  template <typename T> block_gf<mesh::imtime, T> make_gf_from_fourier(block_gf<mesh::imfreq, T> const &bgw, long n_tau = -1) {
+    std::vector<gf<mesh::imtime, T>> out;
+    std::vector<gf<mesh::imfreq, T> const *> gs;
+    for (long b = 0; b < bgw.size(); ++b) gs.push_back(&bgw[b]);
+    if (bgw.size() > 1 && detail::same_shape(gs)) {
+      auto const &g0 = bgw[0];
+      auto mt = mesh::make_adjoint_mesh(g0.mesh(), n_tau);
+      long nb = bgw.size(), no = g0.n_others();
+      std::vector<dcomplex> in(size_t(nb * g0.mesh().size() * no)), res(size_t(nb * mt.size() * no));
+      for (long b = 0; b < nb; ++b) std::copy(bgw[b].data().begin(), bgw[b].data().end(), in.begin() + size_t(b * g0.mesh().size() * no));
+      std::vector<int> warn(size_t(nb), 0);
+      check(tq_fourier_iw_to_tau(context(), g0.mesh().beta(), g0.mesh().statistic(), g0.mesh().n_iw(), mt.size(), no, nb, detail::cptr(in),
+                                 nullptr, 0, detail::ptr(res), warn.data(), nullptr));
+      int w = 0;
+      for (int x : warn) w |= x;
+      print_warnings(w);
+      for (long b = 0; b < nb; ++b) {
+        gf<mesh::imtime, T> g{mt, g0.target_shape()};
+        std::copy(res.begin() + size_t(b * mt.size() * no), res.begin() + size_t((b + 1) * mt.size() * no), g.data().begin());
+        out.push_back(std::move(g));
+      }
+    } else {
+      for (long b = 0; b < bgw.size(); ++b) out.push_back(make_gf_from_fourier(bgw[b], n_tau));
+    }
+    return {bgw.block_names(), std::move(out)};
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // tail fits  (functions2.hpp:50-134)
+  // ------------------------------------------------------------------------------------------------
+  struct tail_fit_parameters { // tail_fitter.hpp:302-321 (mesh.set_tail_fit_parameters)
+    double tail_fraction = 0.2;
+    int n_tail_max = 30;
+    int expansion_order = -1; // adaptive
+  };
+
+  namespace detail {
+    template <typename T>
+    std::pair<moment_array, double> fit_impl(gf<mesh::imfreq, T> const &g, moment_array const &known, bool herm, tail_fit_parameters p) {
+      if (!known.is_empty() && known.n_others != g.n_others()) throw runtime_error("known_moments shape incompatible with shape of data");
+      moment_array out(std::max<long>(TQ_MAX_MOMENTS, known.n_rows), g.n_others());
+      int nm = 0;
+      double err = 0;
+      check(tq_fit_tail(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), p.tail_fraction, p.n_tail_max, p.expansion_order,
+                        herm ? 1 : 0, herm ? (int)g.inner_matrix_dim() : 1, g.n_others(), 1, cptr(g.data()),
+                        known.is_empty() ? nullptr : cptr(known.v), (int)known.n_rows, ptr(out.v), &nm, &err));
+      out.n_rows = nm;
+      out.v.resize(size_t(nm * g.n_others()));
+      return {std::move(out), err};
+    }
+  } // namespace detail
+
+  template <typename T>
+  std::pair<moment_array, double> fit_tail(gf<mesh::imfreq, T> const &g, moment_array const &known_moments = {}, tail_fit_parameters p = {}) {
+    return detail::fit_impl(g, known_moments, false, p);
+  }
+  template <typename T>
+  std::pair<moment_array, double> fit_hermitian_tail(gf<mesh::imfreq, T> const &g, moment_array const &known_moments = {},
+                                                     tail_fit_parameters p = {}) {
+    return detail::fit_impl(g, known_moments, true, p);
+  }
+  // block overloads return the maximum error (functions2.hpp:66-78, 121-134)
+  template <typename T>
+  std::pair<std::vector<moment_array>, double> fit_hermitian_tail(block_gf<mesh::imfreq, T> const &bg, tail_fit_parameters p = {}) {
+    std::vector<moment_array> tails;
+    double max_err = 0;
+    for (long b = 0; b < bg.size(); ++b) {
+      auto [t, e] = fit_hermitian_tail(bg[b], {}, p);
+      tails.push_back(std::move(t));
+      max_err = std::max(max_err, e);
+    }
+    return {std::move(tails), max_err};
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // inverse  (functions2.hpp:197-209)
+  // ------------------------------------------------------------------------------------------------
+  template <typename M> void invert_in_place(gf<M, matrix_valued> &g) {
+    auto const &ts = g.target_shape();
+    if (ts[0] != ts[1]) throw runtime_error("invert_in_place: target is not square");
+    check(tq_invert_batched(context(), (int)ts[0], g.mesh().size(), detail::ptr(g.data())));
+  }
+  template <typename M> gf<M, matrix_valued> inverse(gf<M, matrix_valued> const &g) {
+    auto r = g;
+    invert_in_place(r);
+    return r;
+  }
+
+  // G_loc(iw) = sum_k w_k [(iw + mu) - eps_k - Sigma(iw)]^-1   (python/triqs/sumk/sumk_discrete.py:140-166)
+  inline gf<mesh::imfreq, matrix_valued> dyson_k_sum(gf<mesh::brzone, matrix_valued> const &eps_k, gf<mesh::imfreq, matrix_valued> const &sigma,
+                                                     double mu, bool all_reduce = false) {
+    gf<mesh::imfreq, matrix_valued> out{sigma.mesh(), sigma.target_shape()};
+    long n = sigma.target_shape()[0];
+    check(tq_dyson_ksum(context(), (int)n, eps_k.mesh().size(), sigma.mesh().n_iw(), sigma.mesh().beta(), sigma.mesh().statistic(), mu,
+                        detail::cptr(eps_k.data()), nullptr, 1.0 / double(eps_k.mesh().size()), detail::cptr(sigma.data()),
+                        detail::ptr(out.data()), all_reduce ? 1 : 0));
+    return out;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // evaluation  (evaluator.hpp:35-43; batched form for many points)
+  // ------------------------------------------------------------------------------------------------
+  template <typename T> std::vector<dcomplex> evaluate(gf<mesh::imtime, T> const &g, std::vector<double> const &taus) {
+    std::vector<dcomplex> out(size_t(taus.size() * g.n_others()));
+    check(tq_interp_tau(context(), g.mesh().beta(), g.mesh().size(), g.n_others(), detail::cptr(g.data()), (long)taus.size(), taus.data(),
+                        detail::ptr(out)));
+    return out;
+  }
+  template <typename Mesh, typename Target> std::vector<dcomplex> gf<Mesh, Target>::operator()(double x) const {
+    static_assert(std::is_same<Mesh, mesh::imtime>::value, "g(x) is implemented for imtime gfs");
+    return evaluate(*this, std::vector<double>{x});
+  }
+
+} // namespace triqs_b200

@@ -70,6 +70,7 @@ extern "C" tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_comple
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
     k<<<(unsigned)nb, 128, smem, ctx->stream>>>(d, n_pts);                                                                       \
   } break;
+  KernelScope ks(ctx, "invert_batched");
   switch (n) {
     TQ_INV_CASE(1)
     TQ_INV_CASE(2)
@@ -202,6 +203,8 @@ extern "C" tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, doub
     k<<<grid, 128, smem, ctx->stream>>>((const cd *)d_eps, (const double *)d_wts, uniform_weight, (const cd *)d_sig, (int)n_w, n_k,     \
                                         k_per_chunk, beta, statistic, (int)first, mu, d_part);                                   \
   } break;
+  {
+  KernelScope ks(ctx, "dyson_partial");
   switch (n) {
     TQ_DYSON_CASE(1)
     TQ_DYSON_CASE(2)
@@ -212,11 +215,15 @@ extern "C" tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, doub
     TQ_DYSON_CASE(7)
     TQ_DYSON_CASE(8)
   }
+  }
 #undef TQ_DYSON_CASE
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
   const long n_elem = n_w * nn;
-  k_dyson_reduce<<<(unsigned)((n_elem + 255) / 256), 256, 0, ctx->stream>>>(d_part, n_chunks, n_elem, (cd *)d_out);
+  {
+    KernelScope ks(ctx, "dyson_reduce");
+    k_dyson_reduce<<<(unsigned)((n_elem + 255) / 256), 256, 0, ctx->stream>>>(d_part, n_chunks, n_elem, (cd *)d_out);
+  }
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
   if (all_reduce) TQ_TRY(tq_all_reduce_sum(ctx, (double *)d_out, (size_t)2 * n_elem)); // sumk_discrete.py:163

@@ -529,8 +529,23 @@ static bool radix_ok(long N) {
 }
 
 // widest column tile (<= n_cols) whose working set fits the opt-in shared memory
+// TQ_TILE_BYTES (tuning knob): preferred shared-memory footprint of one tile; smaller tiles -> more CTAs per SM
+static size_t tile_target_bytes(tq_ctx *ctx) {
+  static long env = -1;
+  if (env < 0) {
+    const char *e = getenv("TQ_TILE_BYTES");
+    env = e ? atol(e) : 0;
+  }
+  return env > 0 ? std::min<size_t>((size_t)env, (size_t)ctx->max_smem_optin) : (size_t)ctx->max_smem_optin / 2 - 1024;
+}
+
 static int pick_tc(tq_ctx *ctx, int N, long n_cols, size_t budget = 0) {
-  if (!budget) budget = (size_t)ctx->max_smem_optin;
+  if (!budget) {
+    // prefer the target footprint if that still leaves >= 8 columns (128 contiguous bytes) per row
+    budget = (size_t)ctx->max_smem_optin;
+    const size_t tgt = tile_target_bytes(ctx);
+    if (tile_bytes(N, (int)std::min<long>(8, n_cols), 0) <= tgt) budget = tgt;
+  }
   long tc = std::min<long>(n_cols, (long)(budget / (sizeof(cd) * (N + 4))));
   while (tc > 1 && tile_bytes(N, (int)tc, 0) > budget) --tc;
   return (int)std::max<long>(tc, 1);
@@ -538,7 +553,7 @@ static int pick_tc(tq_ctx *ctx, int N, long n_cols, size_t budget = 0) {
 
 static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Tiling *t) {
   const size_t budget = (size_t)ctx->max_smem_optin;
-  const size_t half = budget / 2 - 1024; // two CTAs per SM
+  const size_t half = tile_target_bytes(ctx);
   // single pass
   if (tile_bytes((int)L, 1, 0) <= budget && radix_ok(L)) {
     t->two_pass = false;
@@ -578,6 +593,8 @@ template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, co
   dim3 grid(n_items, tiles, (unsigned)batch);
   if (batch > 65535) return tq_fail(ctx, TQ_ERR_INVALID, "batch > 65535 per launch");
   const bool big = smem > (size_t)ctx->max_smem_optin / 2 - 1024;
+  static const char *tags[3][3] = {{"tau2iw_single", "", "tau2iw_pass1"}, {"", "iw2tau_single", "iw2tau_pass1"}, {"tau2iw_pass2", "iw2tau_pass2", ""}};
+  KernelScope ks(ctx, tags[IN][OUT]);
   if (big) {
     auto k = matsubara_tile_kernel<IN, OUT, SGN, 512, 1>;
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -731,10 +748,12 @@ extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statisti
   TQ_CUDA(ctx, cudaMemsetAsync(d_warn, 0, sizeof(int) * batch + 256 + sizeof(StatusWords), ctx->stream));
   if (have_moments) {
     long total = batch * n_others;
+    KernelScope ks(ctx, "prepare_known_moments");
     k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_others, total,
                                                                                         d_mom, &d_st->max_m0_bits);
   } else {
     if (batch > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "batch too large");
+    KernelScope ks(ctx, "moments_from_tau");
     k_moments_from_tau<<<(unsigned)batch, 256, 0, ctx->stream>>>((const cd *)d_in, n_tau * n_others, (int)n_tau, (int)n_others, beta, statistic,
                                                                   d_mom, d_warn);
   }

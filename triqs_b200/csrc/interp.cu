@@ -44,6 +44,7 @@ extern "C" tq_status tq_interp_tau(tq_ctx *ctx, double beta, long n_tau, long n_
   const long total = n_pts * n_elem;
   long nb = (total + 255) / 256;
   nb = std::min<long>(nb, (long)ctx->sm_count * 8 * 64);
+  KernelScope ks(ctx, "interp_tau");
   k_interp_tau<<<(unsigned)nb, 256, 0, ctx->stream>>>((const cd *)d_tab, n_tau, (int)n_elem, 0.0, delta_inv, (const double *)d_tau, n_pts,
                                                       (cd *)d_out);
   tq_count_launch(ctx);

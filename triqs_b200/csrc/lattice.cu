@@ -74,7 +74,8 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   std::shared_ptr<FftPlanHost> fp;
   TQ_TRY(tq_get_fft_plan(ctx, N, &fp));
   const size_t budget = (size_t)ctx->max_smem_optin;
-  const size_t half = budget / 2 - 1024;
+  size_t half = budget / 2 - 1024;
+  if (const char *e = getenv("TQ_TILE_BYTES")) half = std::min<size_t>((size_t)atol(e), budget);
   if (sizeof(cd) * (size_t)N > budget)
     return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length " + std::to_string(N) + " does not fit one SM's shared memory");
   // per row: tc columns + (twiddle + position when tabulated in shared memory)
@@ -100,13 +101,14 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   const size_t smem = sizeof(cd) * (size_t)N * tc + (A.smem_tw ? (sizeof(cd) + sizeof(int)) * (size_t)N : 0);
   const long nblocks = outer * A.tiles;
   if (nblocks > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: too many tiles");
-  const bool big = smem > half;
+  const bool big = smem > budget / 2 - 1024;
 #define TQ_LAUNCH_PLAIN(SGN, NT, MINB)                                                                                           \
   do {                                                                                                                           \
     auto k = plain_tile_kernel<SGN, NT, MINB>;                                                                                   \
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
     k<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(A);                                                                          \
   } while (0)
+  KernelScope ks(ctx, "fft_axis");
   if (sign > 0) {
     if (big) TQ_LAUNCH_PLAIN(1, 512, 1); else TQ_LAUNCH_PLAIN(1, 256, 2);
   } else {

@@ -381,6 +381,7 @@ tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw,
   A.err = d_err;
   A.total = batch * n_cols;
   *n_moments = S.n_var + n_known;
+  KernelScope ks(ctx, "fit_tail");
   k_fit_tail<<<(unsigned)((A.total + 127) / 128), 128, 0, ctx->stream>>>(A);
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());

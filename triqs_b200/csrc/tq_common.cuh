@@ -58,6 +58,13 @@ struct tq_ctx {
   std::map<std::tuple<long, int>, std::shared_ptr<FftPlanHost>> fft_plans;                        // (N, dummy)
   std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
   std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
+  // per-kernel event timing (tq_profile_enable)
+  bool profiling = false;
+  struct ProfRec {
+    const char *tag;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRec> prof;
   // NCCL
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -93,3 +100,20 @@ tq_status tq_stage_out_begin(tq_ctx *ctx, void *user, size_t bytes, DeviceBuffer
 tq_status tq_stage_out_finish(tq_ctx *ctx, void *user, size_t bytes, void *dev, bool is_host);
 
 inline void tq_count_launch(tq_ctx *ctx, int n = 1) { ctx->launches += n; }
+
+// brackets one kernel launch with events when profiling is on:  { KernelScope ks(ctx, "tag"); kernel<<<...>>>(...); }
+struct KernelScope {
+  tq_ctx *ctx;
+  cudaEvent_t e1 = nullptr;
+  KernelScope(tq_ctx *c, const char *tag) : ctx(c) {
+    if (!ctx->profiling) return;
+    cudaEvent_t e0;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    ctx->prof.push_back({tag, e0, e1});
+  }
+  ~KernelScope() {
+    if (e1) cudaEventRecord(e1, ctx->stream);
+  }
+};

@@ -63,6 +63,40 @@ extern "C" const char *tq_last_error(const tq_ctx *ctx) { return ctx ? ctx->err.
 extern "C" void *tq_stream(tq_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" uint64_t tq_launch_count(const tq_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" tq_status tq_profile_enable(tq_ctx *ctx, int on) {
+  if (!ctx) return TQ_ERR_INVALID;
+  ctx->profiling = on != 0;
+  return TQ_OK;
+}
+
+extern "C" tq_status tq_profile_report(tq_ctx *ctx, char *buf, size_t len) {
+  if (!ctx || !buf || len < 3) return TQ_ERR_INVALID;
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto &r : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto &a = agg[r.tag];
+    a.first += 1;
+    a.second += ms;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto &kv : agg) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  strncpy(buf, out.c_str(), len - 1);
+  buf[len - 1] = 0;
+  return TQ_OK;
+}
+
 extern "C" tq_status tq_synchronize(tq_ctx *ctx) {
   if (!ctx) return TQ_ERR_INVALID;
   TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

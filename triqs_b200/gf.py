@@ -1,0 +1,281 @@
+"""Python host mirror of the reference's gf surface for the hot path (names follow python/triqs/gf).
+
+    MeshImTime, MeshImFreq, MeshBrZone, MeshCycLat        python/triqs/gf/meshes.py (C++: c++/triqs/mesh/*.hpp)
+    Gf, BlockGf                                           python/triqs/gf/gf.py, block_gf.py
+    make_gf_from_fourier, fit_tail, fit_hermitian_tail    python/triqs/gf/gf_fnt_desc.py:24-44,129-170, gf_factories_desc.py:46-124
+    make_zero_tail, inverse, Gf.invert, Gf.__call__       python/triqs/gf/gf.py:598-611; c++/triqs/gfs/evaluator.hpp:31-44
+    SumkDiscrete-style k-sum with MPI-like slicing        python/triqs/sumk/sumk_discrete.py:140-166, utility/mpi_mpi4py.py:96-109
+
+Only containers and argument plumbing live here; every number is computed by libtqgpu.so through
+``triqs_b200.context.Context``.  ``Gf.data`` is a NumPy array (host) or a torch CUDA tensor (device resident).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .context import BOSON, FERMION, Context, TriqsRuntimeError, _is_torch
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---------------------------------------------------------------------------------------------
+# meshes
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class MeshImTime:
+    beta: float
+    statistic: int  # FERMION / BOSON
+    n_tau: int
+
+    def __len__(self):
+        return self.n_tau
+
+    @property
+    def delta(self):
+        return (self.beta - 0.0) / (self.n_tau - 1)
+
+    def values(self):
+        """c++/triqs/mesh/bases/linear.hpp:154-160"""
+        wr = np.arange(self.n_tau, dtype=np.float64) / (self.n_tau - 1)
+        return 0.0 * (1 - wr) + self.beta * wr
+
+
+@dataclass(frozen=True)
+class MeshImFreq:
+    beta: float
+    statistic: int
+    n_iw: int = 1025  # c++/triqs/mesh/imfreq.hpp:77
+
+    @property
+    def last_index(self):
+        return self.n_iw - 1
+
+    @property
+    def first_index(self):
+        return -(self.last_index + (1 if self.statistic == FERMION else 0))
+
+    def __len__(self):
+        return self.last_index - self.first_index + 1
+
+    def values(self):
+        """c++/triqs/mesh/domains/matsubara.hpp:55"""
+        n = np.arange(self.first_index, self.last_index + 1, dtype=np.int64)
+        return 1j * (math.pi * (2 * n + self.statistic).astype(np.float64) / self.beta)
+
+
+@dataclass(frozen=True)
+class MeshCycLat:
+    dims: tuple
+
+    def __len__(self):
+        return int(np.prod(self.dims))
+
+
+@dataclass(frozen=True)
+class MeshBrZone:
+    dims: tuple
+
+    def __len__(self):
+        return int(np.prod(self.dims))
+
+
+def make_adjoint_mesh(m, n=-1):
+    """c++/triqs/mesh/adjoint.hpp:31-57"""
+    if isinstance(m, MeshImTime):
+        return MeshImFreq(m.beta, m.statistic, (m.n_tau - 1) // 6 if n == -1 else n)
+    if isinstance(m, MeshImFreq):
+        return MeshImTime(m.beta, m.statistic, 6 * (m.last_index + 1) + 1 if n == -1 else n)
+    if isinstance(m, MeshCycLat):
+        return MeshBrZone(m.dims)
+    if isinstance(m, MeshBrZone):
+        return MeshCycLat(m.dims)
+    raise TypeError(m)
+
+
+# ---------------------------------------------------------------------------------------------
+# containers
+# ---------------------------------------------------------------------------------------------
+class Gf:
+    """mesh + data[mesh, target...] (C order, complex128) -- c++/triqs/gfs/gf/gf.hpp:86-375."""
+
+    def __init__(self, mesh, target_shape=(), data=None, ctx: Context | None = None):
+        self.mesh = mesh
+        self.target_shape = tuple(target_shape)
+        shape = (len(mesh),) + self.target_shape
+        if data is None:
+            data = np.zeros(shape, dtype=np.complex128)
+        elif tuple(data.shape) != shape:
+            raise TriqsRuntimeError(f"Gf: data shape {tuple(data.shape)} does not match mesh/target {shape}")
+        self.data = data
+        self._ctx = ctx
+
+    @property
+    def ctx(self) -> Context:
+        return self._ctx or default_context()
+
+    @property
+    def n_others(self):
+        return int(np.prod(self.target_shape)) if self.target_shape else 1
+
+    def flat(self):
+        """flatten_gf_2d<0> (c++/triqs/gfs/gf/flatten.hpp:61-64): a view, no copy -- the layout is already [mesh, n_others]."""
+        return self.data.reshape(len(self.mesh), self.n_others)
+
+    def copy(self):
+        d = self.data.clone() if _is_torch(self.data) else self.data.copy()
+        return Gf(self.mesh, self.target_shape, d, self._ctx)
+
+    def invert(self):
+        """python/triqs/gf/gf.py:598-611 -> _gf_invert_data_in_place"""
+        n = self.target_shape[0]
+        if len(self.target_shape) != 2 or self.target_shape[1] != n:
+            raise TriqsRuntimeError("invert: matrix_valued square target required")
+        self.ctx.invert_in_place(self.data.reshape(-1, n, n))
+        return self
+
+    def __call__(self, tau):
+        """off-mesh evaluation on an imtime mesh (c++/triqs/gfs/evaluator.hpp:35-43); accepts a scalar or an array of tau."""
+        if not isinstance(self.mesh, MeshImTime):
+            raise TriqsRuntimeError("Gf.__call__ is implemented for imtime meshes")
+        scalar = np.isscalar(tau)
+        taus = np.atleast_1d(np.asarray(tau, dtype=np.float64)) if not _is_torch(tau) else tau
+        out = self.ctx.interp_tau(self.flat(), self.mesh.beta, taus)
+        out = out.reshape((out.shape[0],) + self.target_shape)
+        return out[0] if scalar else out
+
+
+class BlockGf:
+    """named list of Gf -- c++/triqs/gfs/block/block_gf.hpp:104-295, python/triqs/gf/block_gf.py."""
+
+    def __init__(self, name_list, block_list):
+        if len(name_list) != len(block_list):
+            raise TriqsRuntimeError("BlockGf: names and blocks differ in length")
+        self.names = list(name_list)
+        self.blocks = list(block_list)
+
+    def __iter__(self):
+        return iter(zip(self.names, self.blocks))
+
+    def __getitem__(self, key):
+        return self.blocks[self.names.index(key)] if isinstance(key, str) else self.blocks[key]
+
+    def __len__(self):
+        return len(self.blocks)
+
+
+def make_zero_tail(g: Gf, n_moments=10):
+    """c++/triqs/gfs/functions/functions2.hpp:154-162"""
+    return np.zeros((n_moments,) + g.target_shape, dtype=np.complex128)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fourier
+# ---------------------------------------------------------------------------------------------
+def _stack(blocks):
+    d0 = blocks[0].flat()
+    if _is_torch(d0):
+        import torch
+        return torch.stack([b.flat() for b in blocks])
+    return np.stack([b.flat() for b in blocks])
+
+
+def make_gf_from_fourier(g, n=-1, known_moments=None):
+    """fourier.hpp:93-245: imtime <-> imfreq and cyclat <-> brzone; a BlockGf of equally shaped blocks is ONE batched launch."""
+    if isinstance(g, BlockGf):
+        same = all(b.mesh == g.blocks[0].mesh and b.target_shape == g.blocks[0].target_shape for b in g.blocks)
+        if not same or known_moments is not None:
+            kms = known_moments if known_moments is not None else [None] * len(g)
+            return BlockGf(g.names, [make_gf_from_fourier(b, n, km) for b, km in zip(g.blocks, kms)])
+        b0 = g.blocks[0]
+        out = _transform(b0.ctx, b0.mesh, _stack(g.blocks), n, None)
+        mo = make_adjoint_mesh(b0.mesh, n)
+        return BlockGf(g.names, [Gf(mo, b0.target_shape, out[i].reshape((len(mo),) + b0.target_shape), b0._ctx) for i in range(len(g))])
+    km = None
+    if known_moments is not None:
+        km = known_moments.reshape(1, known_moments.shape[0], g.n_others)
+    out = _transform(g.ctx, g.mesh, g.flat()[None], n, km)
+    mo = make_adjoint_mesh(g.mesh, n)
+    return Gf(mo, g.target_shape, out[0].reshape((len(mo),) + g.target_shape), g._ctx)
+
+
+def _transform(ctx, mesh, data3, n, km):
+    if isinstance(mesh, MeshImTime):
+        mo = make_adjoint_mesh(mesh, n)
+        return ctx.fourier_tau_to_iw(data3, mesh.beta, mesh.statistic, mo.n_iw, moments=km)
+    if isinstance(mesh, MeshImFreq):
+        mo = make_adjoint_mesh(mesh, n)
+        return ctx.fourier_iw_to_tau(data3, mesh.beta, mesh.statistic, mo.n_tau, moments=km)
+    if isinstance(mesh, (MeshCycLat, MeshBrZone)):
+        outs = [ctx.fourier_lattice(d, tuple(mesh.dims), to_k=isinstance(mesh, MeshCycLat)) for d in data3]
+        if _is_torch(outs[0]):
+            import torch
+            return torch.stack(outs)
+        return np.stack(outs)
+    raise TypeError(mesh)
+
+
+def fit_tail(g: Gf, known_moments=None, hermitian=False, **fit_params):
+    """functions2.hpp:50-56 (and :94-110 with hermitian=True): returns (tail[n_moments, target...], err)."""
+    if not isinstance(g.mesh, MeshImFreq):
+        raise TriqsRuntimeError("fit_tail needs an imfreq gf")
+    inner = 1
+    if hermitian:
+        if len(g.target_shape) == 0:
+            inner = 1
+        elif len(g.target_shape) == 2 and g.target_shape[0] == g.target_shape[1]:
+            inner = g.target_shape[0]
+        else:
+            raise TriqsRuntimeError("Incompatible target_shape for fit_hermitian_tail")  # functions2.hpp:105
+    km = None if known_moments is None else known_moments.reshape(1, known_moments.shape[0], g.n_others)
+    mom, err = g.ctx.fit_tail(g.flat()[None], g.mesh.beta, g.mesh.statistic, known_moments=km, hermitian=hermitian, inner_dim=inner,
+                              **fit_params)
+    return mom[0].reshape((mom.shape[1],) + g.target_shape), float(err[0])
+
+
+def fit_hermitian_tail(g, known_moments=None, **fit_params):
+    if isinstance(g, BlockGf):  # functions2.hpp:121-134: list of tails, maximum error
+        res = [fit_tail(b, None if known_moments is None else known_moments[i], hermitian=True, **fit_params) for i, b in enumerate(g.blocks)]
+        return [r[0] for r in res], max(r[1] for r in res)
+    return fit_tail(g, known_moments, hermitian=True, **fit_params)
+
+
+def inverse(g: Gf) -> Gf:
+    """functions2.hpp:203-209"""
+    return g.copy().invert()
+
+
+# ---------------------------------------------------------------------------------------------
+# lattice Dyson k-sum, sharded like SumkDiscrete (sumk_discrete.py:140-166)
+# ---------------------------------------------------------------------------------------------
+def slice_bounds(n: int, size: int, rank: int):
+    """mpi.slice_array bounds (python/triqs/utility/mpi_mpi4py.py:96-109): the first n % size ranks get one extra."""
+    q, r = divmod(n, size)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def dyson_k_sum(ctx: Context, eps_k, sigma: Gf, mu: float, weights=None, rank: int = 0, n_ranks: int = 1, reduce_fn=None):
+    """G_loc = sum_k w_k [(iw + mu) - eps_k - Sigma]^-1 with k-points sliced over ranks.
+
+    ``reduce_fn(partial)`` sums the per-rank partial over ranks: None -> the library's NCCL all-reduce (needs
+    ctx.comm_init and a device-resident sigma), or e.g. a torch.distributed all_reduce (gloo on CPU tests)."""
+    n_k = eps_k.shape[0]
+    lo, hi = slice_bounds(n_k, n_ranks, rank)
+    w = None if weights is None else weights[lo:hi]
+    n = sigma.target_shape[0]
+    use_lib = reduce_fn is None and n_ranks > 1
+    part = ctx.dyson_ksum(eps_k[lo:hi], sigma.data.reshape(-1, n, n), sigma.mesh.beta, sigma.mesh.statistic, mu, weights=w,
+                          uniform_weight=1.0 / n_k, all_reduce=use_lib)
+    if reduce_fn is not None and n_ranks > 1:
+        part = reduce_fn(part)
+    return Gf(sigma.mesh, sigma.target_shape, part.reshape((len(sigma.mesh),) + sigma.target_shape), ctx)
