@@ -23,10 +23,11 @@ extern "C" int hostsim_fft(int N, int TC, int sign, int direct_tw, int skew, dou
   for (int p = 0; p < P.npass; ++p)
     for (int tid = 0; tid < nthreads; ++tid) {
       TileThread T = tile_thread(tid, nthreads, TC);
-      if (sign > 0)
-        fft_pass<1>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0, sm);
-      else
-        fft_pass<-1>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0, sm);
+      if (sign > 0) {
+        if (skew) fft_pass<1, true>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0); else fft_pass<1, false>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0);
+      } else {
+        if (skew) fft_pass<-1, true>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0); else fft_pass<-1, false>(P, p, s.data(), TC, TC, P.tw, T, direct_tw != 0);
+      }
     }
   for (int k = 0; k < N; ++k) {
     int pos = fft_pos(P, k);

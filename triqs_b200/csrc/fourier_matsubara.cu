@@ -47,6 +47,7 @@ struct TileArgs {
   long in_gf_stride, out_gf_stride, scratch_gf_stride, mom_gf_stride, gt_gf_stride;
   MatsubaraDev D;
   BigTw btw;
+  long long *dbg; // developer phase timing (TQ_PHASE_DEBUG): 6 clock64 stamps per CTA, or nullptr
 };
 
 enum { IN_TAU = 0, IN_FREQ = 1, IN_SCRATCH = 2 };
@@ -139,7 +140,8 @@ TQ_D cd tail_iw_e(const MatsubaraDev &D, cd e0, cd e1, cd a1, cd a2, cd a3) {
   return tail_iw(D, make_double4(e0.x, e0.y, e1.x, e1.y), a1, a2, a3);
 }
 
-template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) matsubara_tile_kernel(const TileArgs A) {
+template <int IN, int OUT, int SGN, bool SKEW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) matsubara_tile_kernel(const TileArgs A) {
   extern __shared__ double2 smem[];
   const MatsubaraDev &D = A.D;
   const int item = blockIdx.x, gf = blockIdx.z;
@@ -147,20 +149,25 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
   const int tc = min(A.TC, A.n_cols - c0);
   const int N = A.P.N;
   const int pitch = tc;
-  const int sk = A.skewmask;
+  constexpr int sk = SKEW ? ~0 : 0;
   cd *tile = smem;
-  cd *coef = tile + (size_t)fft_rows_alloc(N, sk) * A.TC; // a1[tc], a2[tc], a3[tc], extra[tc]
-  cd *twS = coef + 4 * A.TC;                               // [N] copy of the twiddle table (if A.smem_tw)
-  cd *rowtab = twS + (A.smem_tw ? N : 0);                  // [N][3] per-row factors (if A.rowtab)
+  cd *coef = tile + fft_rows_alloc(N, sk) * A.TC; // a1[tc], a2[tc], a3[tc], extra[tc]
+  cd *twS = coef + 4 * A.TC;                      // [N] copy of the twiddle table (if A.smem_tw)
+  cd *rowtab = twS + (A.smem_tw ? N : 0);         // [N][3] per-row factors (if A.rowtab)
   const bool fermion = D.stat == TQ_FERMION;
   const bool use_rt = A.rowtab != 0;
   const TileThread T = tile_thread(threadIdx.x, NT, tc);
+  const int n_cols = A.n_cols;
+  long long *dbg = A.dbg ? A.dbg + 6 * ((size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)) : nullptr;
+#define TQ_STAMP(i)                                                                                                              \
+  if (dbg && threadIdx.x == 0) dbg[i] = clock64();
+  TQ_STAMP(0)
 
   // ---- per-column pole weights from the moments  (:151-169, :238-252)
   {
     const cd *mom = A.moments + (size_t)gf * A.mom_gf_stride;
     for (int c = threadIdx.x; c < tc; c += NT) {
-      cd m1 = mom[(size_t)1 * A.n_cols + c0 + c], m2 = mom[(size_t)2 * A.n_cols + c0 + c], m3 = mom[(size_t)3 * A.n_cols + c0 + c];
+      cd m1 = mom[(size_t)1 * n_cols + c0 + c], m2 = mom[(size_t)2 * n_cols + c0 + c], m3 = mom[(size_t)3 * n_cols + c0 + c];
       cd a1, a2, a3;
       if (fermion) {
         a1 = csub(m1, m3);
@@ -177,7 +184,7 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
       if (OUT == OUT_FREQ) {
         // trapezoid end-point correction  -0.5 fact (g_0 + m1 -/+ ... g_L)   (:181)
         const cd *g = A.gt_ref + (size_t)gf * A.gt_gf_stride;
-        cd g0 = g[c0 + c], gL = g[(size_t)D.L * A.n_cols + c0 + c];
+        cd g0 = g[c0 + c], gL = g[(size_t)D.L * n_cols + c0 + c];
         cd t = cadd(g0, m1);
         t = fermion ? cadd(t, gL) : csub(t, gL);
         coef[3 * tc + c] = cscale(-0.5 * D.fact_fwd, t);
@@ -191,6 +198,7 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
       for (int r = threadIdx.x; r < N; r += NT) in_row_entry<IN>(A, item, r, rowtab + 3 * r);
     __syncthreads();
   }
+  TQ_STAMP(1)
 
   // ---- load + pre-transform.  LU independent 16-byte loads per thread are issued before any is consumed:
   // with 1-2 CTAs per SM that is what keeps enough bytes in flight to cover the HBM latency.
@@ -198,6 +206,19 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
   if (T.nbt > 0) {
     for (int c = T.ct; c < tc; c += T.nct) {
       const cd a1 = coef[c], a2 = coef[tc + c], a3 = coef[2 * tc + c];
+      // global row pointer of local row r:  base + r * gstep   (IN_TAU: row j = item + in_stride r; IN_SCRATCH: row r)
+      const cd *gbase;
+      size_t gstep;
+      if (IN == IN_TAU) {
+        gbase = A.in + (size_t)gf * A.in_gf_stride + (size_t)item * n_cols + c0 + c;
+        gstep = (size_t)A.in_stride * n_cols;
+      } else if (IN == IN_FREQ) {
+        gbase = A.in + (size_t)gf * A.in_gf_stride + c0 + c;
+        gstep = (size_t)n_cols;
+      } else {
+        gbase = A.scratch + (size_t)gf * A.scratch_gf_stride + (size_t)item * A.Na * n_cols + c0 + c;
+        gstep = (size_t)n_cols;
+      }
       for (int r0 = T.bt; r0 < N; r0 += T.nbt * LU) {
         cd g[LU];
 #pragma unroll
@@ -205,14 +226,11 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
           const int r = r0 + u * T.nbt;
           g[u] = cmk(0.0, 0.0);
           if (r < N) {
-            if (IN == IN_TAU) {
-              const int j = item + A.in_stride * r;
-              g[u] = A.in[(size_t)gf * A.in_gf_stride + (size_t)j * A.n_cols + c0 + c];
-            } else if (IN == IN_FREQ) {
+            if (IN == IN_FREQ) {
               const int di = freq_data_index(D, item + A.in_stride * r);
-              if (di >= 0) g[u] = A.in[(size_t)gf * A.in_gf_stride + (size_t)di * A.n_cols + c0 + c];
+              if (di >= 0) g[u] = gbase[(size_t)di * gstep];
             } else {
-              g[u] = A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)item * A.Na + r) * A.n_cols + c0 + c];
+              g[u] = gbase[(size_t)r * gstep];
             }
           }
         }
@@ -224,9 +242,10 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
           if (IN != IN_SCRATCH) {
             cd e[3];
             if (use_rt) {
-              e[0] = rowtab[3 * r];
-              e[1] = rowtab[3 * r + 1];
-              e[2] = rowtab[3 * r + 2];
+              const cd *rt = rowtab + 3 * r;
+              e[0] = rt[0];
+              e[1] = rt[1];
+              e[2] = rt[2];
             } else {
               in_row_entry<IN>(A, item, r, e);
             }
@@ -237,57 +256,68 @@ template <int IN, int OUT, int SGN, int NT, int MINB> __global__ void __launch_b
               x = cscale(D.inv_beta, csub(x, tail_iw_e(D, e[0], e[1], a1, a2, a3)));
             }
           }
-          tile[(size_t)fft_row(r, sk) * pitch + c] = x;
+          tile[fft_row(r, sk) * pitch + c] = x;
         }
       }
     }
   }
   __syncthreads();
+  TQ_STAMP(2)
 
   // output-row factors overwrite the input-row table (no longer needed); the passes below do not touch it
   if (use_rt)
     for (int kk = threadIdx.x; kk < N; kk += NT) out_row_entry<OUT, SGN>(A, item, kk, rowtab + 3 * kk);
 
-  fft_tile<SGN>(A.P, tile, pitch, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0, sk); // ends with __syncthreads()
+  fft_tile<SGN, SKEW>(A.P, tile, pitch, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0); // ends with __syncthreads()
   if (A.P.npass == 0) __syncthreads();
+  TQ_STAMP(3)
 
   // ---- post-transform + store (applies the digit-reversal permutation)
   if (T.nbt > 0) {
     for (int c = T.ct; c < tc; c += T.nct) {
       const cd a1 = coef[c], a2 = coef[tc + c], a3 = coef[2 * tc + c], ex = coef[3 * tc + c];
+      cd *obase;
+      if (OUT == OUT_SCRATCH)
+        obase = A.scratch + (size_t)gf * A.scratch_gf_stride + (size_t)item * n_cols + c0 + c; // + kk * Na * n_cols
+      else
+        obase = A.out + (size_t)gf * A.out_gf_stride + c0 + c;
+      const size_t sstep = (size_t)A.Na * n_cols;
       for (int kk = T.bt; kk < N; kk += T.nbt) {
         cd e[3];
         if (use_rt) {
-          e[0] = rowtab[3 * kk];
-          e[1] = rowtab[3 * kk + 1];
-          e[2] = rowtab[3 * kk + 2];
+          const cd *rt = rowtab + 3 * kk;
+          e[0] = rt[0];
+          e[1] = rt[1];
+          e[2] = rt[2];
         } else {
           out_row_entry<OUT, SGN>(A, item, kk, e);
         }
         if (OUT == OUT_FREQ) {
           const int di = (int)e[2].x;
           if (di < 0) continue;
-          cd v = tile[(size_t)fft_row((int)e[2].y, sk) * pitch + c];
+          cd v = tile[fft_row((int)e[2].y, sk) * pitch + c];
           cd t = tail_iw_e(D, e[0], e[1], a1, a2, a3);
-          A.out[(size_t)gf * A.out_gf_stride + (size_t)di * A.n_cols + c0 + c] = cadd(cadd(v, ex), t);
+          obase[(size_t)di * n_cols] = cadd(cadd(v, ex), t);
         } else if (OUT == OUT_TAU) {
           const int j = item + A.out_stride * kk;
-          cd v = tile[(size_t)fft_row((int)e[1].y, sk) * pitch + c];
+          cd v = tile[fft_row((int)e[1].y, sk) * pitch + c];
           if (fermion) v = cmul(v, e[2]);
           v = caxpy(e[1].x, a3, caxpy(e[0].y, a2, caxpy(e[0].x, a1, v)));
-          cd *o = A.out + (size_t)gf * A.out_gf_stride;
-          o[(size_t)j * A.n_cols + c0 + c] = v;
+          obase[(size_t)j * n_cols] = v;
           if (j == 0) { // gt[L] = -/+ (gt[0] + m1)    (:267-268)
             cd t = cadd(v, ex);
-            o[(size_t)D.L * A.n_cols + c0 + c] = fermion ? cneg(t) : t;
+            obase[(size_t)D.L * n_cols] = fermion ? cneg(t) : t;
           }
         } else {
-          cd v = tile[(size_t)fft_row((int)e[1].x, sk) * pitch + c];
-          A.scratch[(size_t)gf * A.scratch_gf_stride + ((size_t)kk * A.Na + item) * A.n_cols + c0 + c] = cmul(v, e[0]);
+          cd v = tile[fft_row((int)e[1].x, sk) * pitch + c];
+          obase[(size_t)kk * sstep] = cmul(v, e[0]);
         }
       }
     }
   }
+  __syncthreads();
+  TQ_STAMP(4)
+#undef TQ_STAMP
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -587,7 +617,7 @@ static tq_status choose_tiling(tq_ctx *ctx, long L, long n_cols, long batch, Til
   return TQ_OK;
 }
 
-template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, const TileArgs &A, int n_items, long batch) {
+template <int IN, int OUT, int SGN, bool SKEW> static tq_status launch_tile_impl(tq_ctx *ctx, const TileArgs &A, int n_items, long batch) {
   const int tiles = (A.n_cols + A.TC - 1) / A.TC;
   const size_t smem = tile_bytes(A.P.N, A.TC, A.skewmask);
   dim3 grid(n_items, tiles, (unsigned)batch);
@@ -595,18 +625,51 @@ template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, co
   const bool big = smem > (size_t)ctx->max_smem_optin / 2 - 1024;
   static const char *tags[3][3] = {{"tau2iw_single", "", "tau2iw_pass1"}, {"", "iw2tau_single", "iw2tau_pass1"}, {"tau2iw_pass2", "iw2tau_pass2", ""}};
   KernelScope ks(ctx, tags[IN][OUT]);
+  TileArgs Ad = A;
+  static const bool phase_debug = getenv("TQ_PHASE_DEBUG") != nullptr;
+  const size_t nblk = (size_t)n_items * tiles * batch;
+  if (phase_debug) {
+    TQ_CUDA(ctx, cudaMallocManaged(&Ad.dbg, sizeof(long long) * 6 * nblk));
+    TQ_CUDA(ctx, cudaMemset(Ad.dbg, 0, sizeof(long long) * 6 * nblk));
+  }
+  const TileArgs &A2 = Ad;
   if (big) {
-    auto k = matsubara_tile_kernel<IN, OUT, SGN, 512, 1>;
+    auto k = matsubara_tile_kernel<IN, OUT, SGN, SKEW, 512, 1>;
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 512, smem, ctx->stream>>>(A);
+    k<<<grid, 512, smem, ctx->stream>>>(A2);
   } else {
-    auto k = matsubara_tile_kernel<IN, OUT, SGN, 256, 2>;
+    auto k = matsubara_tile_kernel<IN, OUT, SGN, SKEW, 256, 2>;
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(A);
+    k<<<grid, 256, smem, ctx->stream>>>(A2);
   }
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
+  if (phase_debug) {
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ph[4] = {0, 0, 0, 0};
+    long long tmin = -1, tmax = 0;
+    for (size_t i = 0; i < nblk; ++i) {
+      long long *d = Ad.dbg + 6 * i;
+      for (int j = 0; j < 4; ++j) ph[j] += double(d[j + 1] - d[j]);
+      if (tmin < 0 || d[0] < tmin) tmin = d[0];
+      if (d[4] > tmax) tmax = d[4];
+    }
+    fprintf(stderr, "[phase] %-14s N=%d tc=%d ctas=%zu smem=%zu  avg cycles: prologue %.0f load %.0f fft %.0f store %.0f  (sum %.0f)  span(first..last, one SM clock) %lld\n",
+            tags[IN][OUT], A.P.N, A.TC, nblk, smem, ph[0] / nblk, ph[1] / nblk, ph[2] / nblk, ph[3] / nblk,
+            (ph[0] + ph[1] + ph[2] + ph[3]) / nblk, tmax - tmin);
+    cudaFree(Ad.dbg);
+  }
   return TQ_OK;
+}
+// the skewed tile layout exists only for the single-pass, single-column kernels
+template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, const TileArgs &A, int n_items, long batch) {
+  if (A.skewmask) {
+    if constexpr ((IN == IN_TAU && OUT == OUT_FREQ) || (IN == IN_FREQ && OUT == OUT_TAU))
+      return launch_tile_impl<IN, OUT, SGN, true>(ctx, A, n_items, batch);
+    else
+      return tq_fail(ctx, TQ_ERR_INVALID, "internal: skewed tile in a two-pass kernel");
+  }
+  return launch_tile_impl<IN, OUT, SGN, false>(ctx, A, n_items, batch);
 }
 
 // runs the transform for gfs [0, batch) whose device arrays start at d_in / d_out; moments are [batch][mom_rows][n_cols]

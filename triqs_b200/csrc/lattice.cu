@@ -40,29 +40,31 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
   constexpr int LU = 8; // independent loads in flight per thread
   if (T.nbt > 0) {
     for (int c = T.ct; c < tc; c += T.nct) {
+      const cd *gp = src + c;
+      cd *tp = tile + c;
       for (int r0 = T.bt; r0 < N; r0 += T.nbt * LU) {
         cd g[LU];
 #pragma unroll
         for (int u = 0; u < LU; ++u) {
           const int r = r0 + u * T.nbt;
-          if (r < N) g[u] = src[(size_t)r * A.inner + c];
+          if (r < N) g[u] = gp[(size_t)r * A.inner];
         }
 #pragma unroll
         for (int u = 0; u < LU; ++u) {
           const int r = r0 + u * T.nbt;
-          if (r < N) tile[(size_t)r * tc + c] = g[u];
+          if (r < N) tp[r * tc] = g[u];
         }
       }
     }
   }
   __syncthreads();
-  fft_tile<SGN>(A.P, tile, tc, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0, 0);
+  fft_tile<SGN, false>(A.P, tile, tc, tc, A.smem_tw ? twS : A.P.tw, A.direct_tw != 0);
   const bool scaled = A.scale != 1.0;
   if (T.nbt > 0) {
     for (int c = T.ct; c < tc; c += T.nct) {
       for (int k = T.bt; k < N; k += T.nbt) {
         const int pos = A.smem_tw ? posS[k] : __ldg(&A.P.pos[k]);
-        cd v = tile[(size_t)pos * tc + c];
+        cd v = tile[pos * tc + c];
         if (scaled) v = cscale(A.scale, v);
         dst[(size_t)k * A.inner + c] = v;
       }

@@ -205,33 +205,36 @@ TQ_HD int fastdiv(int n, unsigned m) {
 //   direct_tw = true : every twiddle w_M^{q s} is read from the table `tw` (a shared-memory copy when a
 //                      warp shares a butterfly, i.e. many columns: the loads are broadcasts)
 //   direct_tw = false: only w_M^{q} is read, the powers are built by a log-depth product chain (TC == 1)
-template <int R, int SGN>
-TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__restrict__ tw, TileThread T, bool direct_tw, int skewmask) {
+template <int R, int SGN, bool SKEW>
+TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__restrict__ tw, TileThread T, bool direct_tw) {
   const int Msub = M / R;
   const int nb = N / R;
   const int twstride = N / M;
   const unsigned magic = fastdiv_magic((unsigned)Msub);
+  const int st = Msub * pitch; // distance between the legs of a butterfly (elements), un-skewed tiles
   if (T.nbt == 0) return;
   for (int c = T.ct; c < TC; c += T.nct) {
     for (int b = T.bt; b < nb; b += T.nbt) {
-      int blk = fastdiv(b, magic);
-      int q = b - blk * Msub;
-      int base = blk * M + q;
+      const int blk = fastdiv(b, magic);
+      const int q = b - blk * Msub;
+      const int base = blk * M + q;
+      cd *p = s + (base * pitch + c);
       cd a[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) a[r] = s[fft_row(base + r * Msub, skewmask) * pitch + c];
+      for (int r = 0; r < R; ++r) a[r] = SKEW ? s[fft_row(base + r * Msub, ~0) * pitch + c] : p[r * st];
       Dft<R, SGN>::run(a);
       if (Msub > 1 && q != 0) {
+        const int qt = q * twstride;
         if (direct_tw) {
 #pragma unroll
           for (int r = 1; r < R; ++r) {
-            cd t = tw[(q * r) * twstride];
+            cd t = tw[qt * r];
             if (SGN < 0) t = cconj(t);
             a[r] = cmul(a[r], t);
           }
         } else {
           cd pw[R];
-          pw[1] = tw[q * twstride];
+          pw[1] = tw[qt];
           if (SGN < 0) pw[1] = cconj(pw[1]);
 #pragma unroll
           for (int r = 2; r < R; ++r) pw[r] = (r & 1) ? cmul(pw[r - 1], pw[1]) : cmul(pw[r >> 1], pw[r >> 1]);
@@ -240,7 +243,12 @@ TQ_HD void fft_pass_fixed(cd *s, int pitch, int TC, int N, int M, const cd *__re
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) s[fft_row(base + r * Msub, skewmask) * pitch + c] = a[r];
+      for (int r = 0; r < R; ++r) {
+        if (SKEW)
+          s[fft_row(base + r * Msub, ~0) * pitch + c] = a[r];
+        else
+          p[r * st] = a[r];
+      }
     }
   }
 }
@@ -283,18 +291,18 @@ TQ_HD void fft_pass_generic(cd *s, int pitch, int TC, int N, int M, int R, const
   }
 }
 
-template <int SGN>
-TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, const cd *__restrict__ tw, TileThread T, bool direct_tw,
-                    int skewmask) {
+template <int SGN, bool SKEW>
+TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, const cd *__restrict__ tw, TileThread T, bool direct_tw) {
+  const int skewmask = SKEW ? ~0 : 0;
   const int R = P.radix[p], M = P.M[p], N = P.N;
   switch (R) {
-    case 2: fft_pass_fixed<2, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 3: fft_pass_fixed<3, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 4: fft_pass_fixed<4, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 5: fft_pass_fixed<5, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 8: fft_pass_fixed<8, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 10: fft_pass_fixed<10, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
-    case 16: fft_pass_fixed<16, SGN>(s, pitch, TC, N, M, tw, T, direct_tw, skewmask); break;
+    case 2: fft_pass_fixed<2, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 3: fft_pass_fixed<3, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 4: fft_pass_fixed<4, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 5: fft_pass_fixed<5, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 8: fft_pass_fixed<8, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 10: fft_pass_fixed<10, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
+    case 16: fft_pass_fixed<16, SGN, SKEW>(s, pitch, TC, N, M, tw, T, direct_tw); break;
     default: fft_pass_generic<SGN>(s, pitch, TC, N, M, R, tw, T, skewmask); break;
   }
 }
@@ -302,10 +310,10 @@ TQ_HD void fft_pass(const FftPlan &P, int p, cd *s, int pitch, int TC, const cd 
 #ifdef __CUDACC__
 // all passes, CTA-wide (every thread of the block must call it; tile must be complete and synced before).
 // `tw` is the twiddle table the passes read: the plan's global table or a shared-memory copy of it.
-template <int SGN> __device__ void fft_tile(const FftPlan &P, cd *s, int pitch, int TC, const cd *tw, bool direct_tw, int skewmask) {
+template <int SGN, bool SKEW> __device__ void fft_tile(const FftPlan &P, cd *s, int pitch, int TC, const cd *tw, bool direct_tw) {
   const TileThread T = tile_thread(threadIdx.x, blockDim.x, TC);
   for (int p = 0; p < P.npass; ++p) {
-    fft_pass<SGN>(P, p, s, pitch, TC, tw, T, direct_tw, skewmask);
+    fft_pass<SGN, SKEW>(P, p, s, pitch, TC, tw, T, direct_tw);
     __syncthreads();
   }
 }
