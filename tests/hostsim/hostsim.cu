@@ -36,6 +36,46 @@ extern "C" int hostsim_fft(int N, int TC, int sign, int direct_tw, int skew, dou
   return P.npass;
 }
 
+#include "../../triqs_b200/csrc/tq_fft2.cuh"
+struct PostCollect {
+  cd *out;
+  int tcw, c;
+  TQ_HD void begin(int cc) { c = cc; }
+  TQ_HD void store(int k, cd v) { out[(size_t)k * tcw + c] = v; }
+};
+template <int N, int RA, int RB> static void run_fft2(int tcw, int sign, cd *data) {
+  std::vector<cd> tw;
+  tq_fft_twiddles_host(N, tw);
+  const int pitch = tcw + 2; // padded rows, like a partially filled TMA box
+  std::vector<cd> s((size_t)N * pitch);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < tcw; ++c) s[(size_t)n * pitch + c] = data[(size_t)n * tcw + c];
+  const int nthreads = 37;
+  PreIdentity pre;
+  PostCollect post{data, tcw, 0};
+  for (int tid = 0; tid < nthreads; ++tid) {
+    if (sign > 0) fft2_pass_a<N, RA, RB, 1>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
+    else fft2_pass_a<N, RA, RB, -1>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
+  }
+  for (int tid = 0; tid < nthreads; ++tid) {
+    if (sign > 0) fft2_pass_b<N, RA, RB, 1>(s.data(), pitch, tcw, tid, nthreads, post);
+    else fft2_pass_b<N, RA, RB, -1>(s.data(), pitch, tcw, tid, nthreads, post);
+  }
+}
+// compile-time two-pass tile FFT of the pipelined kernels (tq_fft2.cuh)
+extern "C" int hostsim_fft2(int N, int RA, int tcw, int sign, double *data /* [N][tcw] complex, in place */) {
+  cd *d = (cd *)data;
+  if (N == 250 && RA == 10) run_fft2<250, 10, 25>(tcw, sign, d);
+  else if (N == 400 && RA == 20) run_fft2<400, 20, 20>(tcw, sign, d);
+  else if (N == 256 && RA == 16) run_fft2<256, 16, 16>(tcw, sign, d);
+  else if (N == 100 && RA == 10) run_fft2<100, 10, 10>(tcw, sign, d);
+  else if (N == 500 && RA == 20) run_fft2<500, 20, 25>(tcw, sign, d);
+  else if (N == 625 && RA == 25) run_fft2<625, 25, 25>(tcw, sign, d);
+  else if (N == 128 && RA == 8) run_fft2<128, 8, 16>(tcw, sign, d);
+  else return -1;
+  return 0;
+}
+
 extern "C" int hostsim_radices(int N, int *radix) {
   FftPlan P;
   if (!tq_fft_factorize(N, P)) return -1;

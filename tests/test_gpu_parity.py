@@ -157,6 +157,32 @@ def test_c2_blockgf_round_trip(ctx):
     assert np.all(err < 1e-4)
 
 
+@pytest.mark.parametrize("stat,ncols,n_iw", [(F, 1, 10000), (B, 4, 10000), (F, 30, 7000), (B, 3, 1025), (F, 7, 50000), (F, 16, 10000)])
+def test_long_mesh_pipelined_variants(ctx, stat, ncols, n_iw):
+    """L = 10^5 goes through the TMA-pipelined four-step kernels (fourier_pipe.cu): both statistics, ragged column
+    tiles, windows that do not align with the four-step factors, batch > 1."""
+    beta, n_tau = 40.0, 100001
+    rng = np.random.default_rng(ncols * 1000 + n_iw)
+    iw = O.imfreq_values(beta, stat, n_iw)
+    gws = []
+    for b in range(2):
+        E = rng.uniform(0.3, 2.0, (3, ncols)) * rng.choice([-1, 1], (3, ncols))
+        r = rng.normal(size=(3, ncols)) + 1j * rng.normal(size=(3, ncols))
+        gws.append(sum(r[p][None, :] / (iw[:, None] - E[p][None, :]) for p in range(3)))
+    gws = np.stack(gws)
+    refs, tails = [], []
+    for b in range(2):
+        rt, info = O.fourier_iw_to_tau(gws[b], beta, stat, n_tau, return_info=True)
+        refs.append(rt)
+        tails.append(info["tail"])
+    gt = ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=np.stack(tails))
+    for b in range(2):
+        assert rel(gt[b], refs[b]) < TOL
+    gw2 = ctx.fourier_tau_to_iw(np.stack(refs), beta, stat, n_iw)
+    for b in range(2):
+        assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
+
+
 def test_tau_to_iw_known_moments_and_noise_warning(ctx):
     import triqs_b200
     beta, n_tau, n_iw = 10.0, 1201, 200

@@ -35,6 +35,19 @@ def test_tile_fft_engine(lib, N):
                     assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 5e-15
 
 
+@pytest.mark.parametrize("N,RA", [(250, 10), (400, 20), (256, 16), (100, 10), (500, 20), (625, 25), (128, 8)])
+def test_two_pass_tile_fft(lib, N, RA):
+    """tq_fft2.cuh: compile-time (RA x RB) passes incl. the radix-20 prime-factor and radix-25 butterflies."""
+    rng = np.random.default_rng(N + RA)
+    for tcw in (1, 5, 13):
+        for sign in (1, -1):
+            x = rng.normal(size=(N, tcw)) + 1j * rng.normal(size=(N, tcw))
+            y = x.copy()
+            assert lib.hostsim_fft2(N, RA, tcw, sign, y.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+            ref = np.fft.ifft(x, axis=0) * N if sign > 0 else np.fft.fft(x, axis=0)
+            assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 5e-15
+
+
 def test_radix_choice(lib):
     rad = (ctypes.c_int * 16)()
     n = lib.hostsim_radices(10000, rad)

@@ -672,12 +672,21 @@ template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, co
   return launch_tile_impl<IN, OUT, SGN, false>(ctx, A, n_items, batch);
 }
 
+// fourier_pipe.cu: TMA double-buffered specialisation for long meshes (runs instead of the generic kernels when it applies)
+tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in,
+                            cd *d_out, const cd *d_mom, int mom_rows, bool *handled);
+
 // runs the transform for gfs [0, batch) whose device arrays start at d_in / d_out; moments are [batch][mom_rows][n_cols]
 template <int IN_KIND /* IN_TAU: forward, IN_FREQ: inverse */>
 static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long batch, const cd *d_in, cd *d_out, const cd *d_mom, int mom_rows) {
   const MatsubaraDev &D = pl.dev;
   const long L = D.L;
   constexpr bool fwd = IN_KIND == IN_TAU;
+  {
+    bool handled = false;
+    TQ_TRY(tq_pipe_matsubara(ctx, fwd, D.beta, D.stat, L + 1, (long)D.last + 1, n_cols, batch, d_in, d_out, d_mom, mom_rows, &handled));
+    if (handled) return TQ_OK;
+  }
   constexpr int SGN = fwd ? 1 : -1;
   Tiling t;
   TQ_TRY(choose_tiling(ctx, L, n_cols, batch, &t));

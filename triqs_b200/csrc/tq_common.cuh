@@ -42,6 +42,7 @@ struct DeviceBuffer {
 struct MatsubaraPlan;  // fourier_matsubara.cu
 struct FftPlanHost;    // tq_fft_plan.cu
 struct TailFitterPlan; // tail_fit.cu
+struct PipePlanCache;  // fourier_pipe.cu
 
 struct tq_ctx {
   int device = 0;
@@ -58,6 +59,7 @@ struct tq_ctx {
   std::map<std::tuple<long, int>, std::shared_ptr<FftPlanHost>> fft_plans;                        // (N, dummy)
   std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
   std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
+  std::shared_ptr<PipePlanCache> pipe_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {

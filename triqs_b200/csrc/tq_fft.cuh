@@ -170,6 +170,61 @@ template <int SGN> struct Dft<16, SGN> {
   }
 };
 
+// 20 = 4 x 5 by the prime-factor map: n = (5 n1 + 4 n2) mod 20, k = (5 k1 + 16 k2) mod 20, no twiddles
+template <int SGN> struct Dft<20, SGN> {
+  static TQ_HD void run(cd *a) {
+    cd e[4][5];
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) {
+      cd x0 = a[(5 * n1) % 20], x1 = a[(5 * n1 + 4) % 20], x2 = a[(5 * n1 + 8) % 20], x3 = a[(5 * n1 + 12) % 20], x4 = a[(5 * n1 + 16) % 20];
+      dft5<SGN>(x0, x1, x2, x3, x4);
+      e[n1][0] = x0; e[n1][1] = x1; e[n1][2] = x2; e[n1][3] = x3; e[n1][4] = x4;
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) {
+      cd x0 = e[0][k2], x1 = e[1][k2], x2 = e[2][k2], x3 = e[3][k2];
+      dft4<SGN>(x0, x1, x2, x3);
+      a[(16 * k2) % 20] = x0; a[(5 + 16 * k2) % 20] = x1; a[(10 + 16 * k2) % 20] = x2; a[(15 + 16 * k2) % 20] = x3;
+    }
+  }
+};
+// 25 = 5 x 5: n = n1 + 5 n2, k = k2 + 5 k1;  u[n1][k2] = dft5_{n2}, times w25^{n1 k2}, then dft5_{n1}
+template <int SGN> struct Dft<25, SGN> {
+  static TQ_HD cd w25(int m) {
+    // exp(2 pi i m / 25), m = n1 * k2 in {1,2,3,4,6,8,9,12,16}
+    switch (m) {
+      case 1: return cmk(0.9685831611286311194901684, SGN * 0.2486898871648547882422837);
+      case 2: return cmk(0.8763066800438635873081159, SGN * 0.4817536741017152749871915);
+      case 3: return cmk(0.7289686274214115231467303, SGN * 0.6845471059286886737322834);
+      case 4: return cmk(0.5358267949789966182713088, SGN * 0.8443279255020150785485581);
+      case 6: return cmk(0.06279051952931337607617822, SGN * 0.9980267284282715619523368);
+      case 8: return cmk(-0.4257792915650726488625024, SGN * 0.9048270524660195277136686);
+      case 9: return cmk(-0.6374239897486897101767128, SGN * 0.7705132427757892308030096);
+      case 12: return cmk(-0.992114701314477831049793, SGN * 0.1253332335643042453731188);
+      default: return cmk(-0.6374239897486897101767128, SGN * -0.7705132427757892308030096); // 16
+    }
+  }
+  static TQ_HD void run(cd *a) {
+    cd u[5][5];
+#pragma unroll
+    for (int n1 = 0; n1 < 5; ++n1) {
+      cd x0 = a[n1], x1 = a[n1 + 5], x2 = a[n1 + 10], x3 = a[n1 + 15], x4 = a[n1 + 20];
+      dft5<SGN>(x0, x1, x2, x3, x4);
+      u[n1][0] = x0; u[n1][1] = x1; u[n1][2] = x2; u[n1][3] = x3; u[n1][4] = x4;
+    }
+#pragma unroll
+    for (int n1 = 1; n1 < 5; ++n1)
+#pragma unroll
+      for (int k2 = 1; k2 < 5; ++k2) u[n1][k2] = cmul(u[n1][k2], w25(n1 * k2));
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) {
+      cd x0 = u[0][k2], x1 = u[1][k2], x2 = u[2][k2], x3 = u[3][k2], x4 = u[4][k2];
+      dft5<SGN>(x0, x1, x2, x3, x4);
+      a[k2] = x0; a[k2 + 5] = x1; a[k2 + 10] = x2; a[k2 + 15] = x3; a[k2 + 20] = x4;
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Thread layout inside a CTA: a thread owns a fixed column lane `ct` (of `nct` column lanes) and a
 // butterfly/row lane `bt` (of `nbt`): no integer division in any inner loop, adjacent threads touch

@@ -1,0 +1,70 @@
+// Compile-time two-pass tile FFT, N = RA * RB, for the pipelined (TMA double-buffered) kernels.
+//
+// The tile s[n][c] (n in [0,N) transform axis, c in [0,tcw) columns, row pitch `pitch` >= tcw) sits in shared memory.
+//   pass A (in place): for every q in [0,RB): radix-RA butterfly over the rows q + RB r, times w_N^{SGN q s};
+//                      result s in [0,RA) goes back to row q + RB s.  The `Pre` functor produces the input
+//                      values (it reads the raw tile element and applies the fused pre-transform), so the
+//                      raw data the TMA engine dropped into the tile is touched exactly once.
+//   pass B (read only): for every s in [0,RA): radix-RB butterfly over the contiguous rows s RB + t; output
+//                      t is X[s + RA t] and is handed to the `Post` functor, which applies the fused epilogue
+//                      and stores straight to global memory (no write-back to the tile, no digit-reversal pass).
+// Both radices are template parameters: every stride is a multiple of a run-time tile width only, the
+// butterflies are fully unrolled in registers, and there is one division per work item (item -> row, column).
+// Work items are (butterfly, column) pairs with the column fastest, so a warp touches contiguous shared
+// memory (conflict free) and reads its twiddles / row factors as broadcasts.
+//
+// __host__ __device__ so tests/hostsim can run the same code on the CPU box.
+#pragma once
+#include "tq_fft.cuh"
+
+struct PreIdentity {
+  TQ_HD void begin(int) {}
+  TQ_HD cd load(int, const cd *p) const { return *p; }
+};
+
+template <int N, int RA, int RB, int SGN, class Pre>
+TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twN, int tid, int nthreads, Pre &pre) {
+  static_assert(RA * RB == N, "N = RA * RB");
+  const int nitems = RB * tcw;
+  const int stride = RB * pitch;
+  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  for (int i = tid; i < nitems; i += nthreads) {
+    const int q = fastdiv(i, magic);
+    const int c = i - q * tcw;
+    cd *p = s + q * pitch + c; // row q, column c
+    pre.begin(c);
+    cd a[RA];
+#pragma unroll
+    for (int r = 0; r < RA; ++r) a[r] = pre.load(q + RB * r, p + r * stride);
+    Dft<RA, SGN>::run(a);
+    if (q != 0) {
+#pragma unroll
+      for (int r = 1; r < RA; ++r) {
+        cd t = twN[q * r];
+        if (SGN < 0) t = cconj(t);
+        a[r] = cmul(a[r], t);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
+  }
+}
+
+template <int N, int RA, int RB, int SGN, class Post>
+TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, Post &post) {
+  static_assert(RA * RB == N, "N = RA * RB");
+  const int nitems = RA * tcw;
+  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  for (int i = tid; i < nitems; i += nthreads) {
+    const int sidx = fastdiv(i, magic);
+    const int c = i - sidx * tcw;
+    const cd *p = s + sidx * (RB * pitch) + c;
+    post.begin(c);
+    cd a[RB];
+#pragma unroll
+    for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
+    Dft<RB, SGN>::run(a);
+#pragma unroll
+    for (int t = 0; t < RB; ++t) post.store(sidx + RA * t, a[t]);
+  }
+}
