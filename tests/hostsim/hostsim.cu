@@ -37,25 +37,27 @@ extern "C" int hostsim_fft(int N, int TC, int sign, int direct_tw, int skew, dou
 }
 
 #include "../../triqs_b200/csrc/tq_fft2.cuh"
-struct PostCollect {
+template <int RA> struct PostCollect {
   cd *out;
-  int tcw, c;
-  TQ_HD void begin(int cc) { c = cc; }
-  TQ_HD void store(int k, cd v) { out[(size_t)k * tcw + c] = v; }
+  int tcw, c, sidx;
+  TQ_HD void begin(int s, int cc) { sidx = s; c = cc; }
+  template <int T> TQ_HD void store(cd v) { out[(size_t)(sidx + RA * T) * tcw + c] = v; }
 };
 template <int N, int RA, int RB> static void run_fft2(int tcw, int sign, cd *data) {
-  std::vector<cd> tw;
-  tq_fft_twiddles_host(N, tw);
+  std::vector<cd> tw1, tw((size_t)N);
+  tq_fft_twiddles_host(N, tw1);
+  for (int q = 0; q < RB; ++q)
+    for (int r = 0; r < RA; ++r) tw[(size_t)q * RA + r] = sign > 0 ? tw1[(q * r) % N] : cconj(tw1[(q * r) % N]);
   const int pitch = tcw + 2; // padded rows, like a partially filled TMA box
   std::vector<cd> s((size_t)N * pitch);
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < tcw; ++c) s[(size_t)n * pitch + c] = data[(size_t)n * tcw + c];
   const int nthreads = 37;
   PreIdentity pre;
-  PostCollect post{data, tcw, 0};
+  PostCollect<RA> post{data, tcw, 0, 0};
   for (int tid = 0; tid < nthreads; ++tid) {
-    if (sign > 0) fft2_pass_a<N, RA, RB, 1>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
-    else fft2_pass_a<N, RA, RB, -1>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
+    if (sign > 0) fft2_pass_a<N, RA, RB, 1, false>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
+    else fft2_pass_a<N, RA, RB, -1, false>(s.data(), pitch, tcw, tw.data(), tid, nthreads, pre);
   }
   for (int tid = 0; tid < nthreads; ++tid) {
     if (sign > 0) fft2_pass_b<N, RA, RB, 1>(s.data(), pitch, tcw, tid, nthreads, post);

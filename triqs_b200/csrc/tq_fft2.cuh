@@ -17,13 +17,30 @@
 #pragma once
 #include "tq_fft.cuh"
 
+
+// compile-time loops (the functors take the butterfly leg as a template argument so that per-leg constants
+// index kernel parameters with immediate offsets)
+template <int R, int I = 0, class Pre> TQ_HD void tq_unroll_load(cd *a, Pre &pre, const cd *p, int stride) {
+  if constexpr (I < R) {
+    a[I] = pre.template load<I>(p + I * stride);
+    tq_unroll_load<R, I + 1>(a, pre, p, stride);
+  }
+}
+template <int R, int I = 0, class Post> TQ_HD void tq_unroll_store(const cd *a, Post &post) {
+  if constexpr (I < R) {
+    post.template store<I>(a[I]);
+    tq_unroll_store<R, I + 1>(a, post);
+  }
+}
+
 struct PreIdentity {
-  TQ_HD void begin(int) {}
-  TQ_HD cd load(int, const cd *p) const { return *p; }
+  TQ_HD void begin(int, int) {}
+  template <int R> TQ_HD cd load(const cd *p) const { return *p; }
 };
 
-template <int N, int RA, int RB, int SGN, class Pre>
-TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twN, int tid, int nthreads, Pre &pre) {
+// twq[q * RA + s] = w_N^{SGN q s} (times whatever per-q / per-s factor the caller folded in).  TW0: entry s = 0 is not 1.
+template <int N, int RA, int RB, int SGN, bool TW0, class Pre>
+TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RB * tcw;
   const int stride = RB * pitch;
@@ -32,18 +49,14 @@ TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twN, in
     const int q = fastdiv(i, magic);
     const int c = i - q * tcw;
     cd *p = s + q * pitch + c; // row q, column c
-    pre.begin(c);
+    pre.begin(q, c);
     cd a[RA];
-#pragma unroll
-    for (int r = 0; r < RA; ++r) a[r] = pre.load(q + RB * r, p + r * stride);
+    tq_unroll_load<RA>(a, pre, p, stride);
     Dft<RA, SGN>::run(a);
-    if (q != 0) {
+    const cd *tw = twq + q * RA;
+    if (TW0 || q != 0) {
 #pragma unroll
-      for (int r = 1; r < RA; ++r) {
-        cd t = twN[q * r];
-        if (SGN < 0) t = cconj(t);
-        a[r] = cmul(a[r], t);
-      }
+      for (int r = TW0 ? 0 : 1; r < RA; ++r) a[r] = cmul(a[r], tw[r]);
     }
 #pragma unroll
     for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
@@ -59,12 +72,11 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
     const int sidx = fastdiv(i, magic);
     const int c = i - sidx * tcw;
     const cd *p = s + sidx * (RB * pitch) + c;
-    post.begin(c);
+    post.begin(sidx, c);
     cd a[RB];
 #pragma unroll
     for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
     Dft<RB, SGN>::run(a);
-#pragma unroll
-    for (int t = 0; t < RB; ++t) post.store(sidx + RA * t, a[t]);
+    tq_unroll_store<RB>(a, post);
   }
 }
