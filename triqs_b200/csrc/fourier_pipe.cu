@@ -68,7 +68,8 @@ TQ_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::
 
 // -------------------------------------------------------------------------------------------------
 enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
-constexpr int PIPE_NBUF = 3;
+constexpr int PIPE_NBUF = 3; // tile buffers
+constexpr int PIPE_NTAB = 4; // table sets (they live until the end of pass B, one stage longer than the tile)
 constexpr int PIPE_MAXR = 25; // largest radix of a pass
 
 struct PipeArgs {
@@ -77,12 +78,15 @@ struct PipeArgs {
   int tcw2;        // column tiling of pass 2 (defines the scratch layout)
   int n_items;     // Na (pass 1) or Nb (pass 2)
   int wmax;        // row pitch of the compact window-row tables (F2, I1)
+  int pitch;       // shared-memory row pitch of a pass-1 tile in columns (>= tcw; pass-2 tiles are dense)
+  int i1_rect;     // I1: the window rows are two rectangles of the [b][a] view (loaded as two tensor tiles)
+  int i1_edge;     // I1: ... and they are exactly the first and the last leg of every pass-A butterfly (pruned pass A)
   long n_tiles;    // batch * n_items * n_ct
   const cd *in;
   cd *out;
   cd *scratch;
-  const cd *moments; // [batch][mom_rows][n_cols]; rows 1..3 are used
-  long in_gf_stride, out_gf_stride, scratch_gf_stride, mom_gf_stride;
+  const cd *polew;   // [batch][n_cols][4] pole weights of this pass (k_pole_weights)
+  long in_gf_stride, out_gf_stride, scratch_gf_stride;
   int L, first, last, stat;
   double half_fact_fwd; // 0.5 beta / L
   double inv_beta;
@@ -90,10 +94,12 @@ struct PipeArgs {
   const double4 *qtab;    // F1: [RB] {E1q, E2q, E3q, -};  I2: [RA] {E1s, E2s, E3s, -}
   const double4 *itemtab; // [n_items] {C1 ea1, C2 ea2, C3 ea3, -}   (F1: item = a, I2: item = beta)
   const cd *Tfull;        // [Na][Nb] four-step twiddle x per-item phase (pass 1)
+  const int4 *wintab;     // [n_items] {r1, r2, -, -} window rows of every item (F2, I1)
   const double4 *wperm;   // [n_items][wmax] {b1 r1, w r1, b2 r2, w r2} of the window rows of every item (F2, I1)
   // per-leg constants (constant-bank operands): F1 legs r of pass A, I2 legs t of pass B
   double er[3][PIPE_MAXR];
   cd phr[PIPE_MAXR];
+  cd wedge[PIPE_MAXR]; // I1 pruned pass A: exp(-SGN 2 pi i s / RA)
   long long *dbg; // developer phase timing (TQ_PHASE_DEBUG) or nullptr
 };
 
@@ -126,15 +132,15 @@ TQ_D cd tail_iw4(cd w01, cd w23, cd a1, cd D23, cd A23) {
 // ---- functors plugged into the two-pass engine -----------------------------------------------
 struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fourier_matsubara.cpp:159-173
   const PipeArgs &A;
-  const cd *coef;
-  const double4 *qtab;
-  int TCW;
+  const cd *coef;      // [c][4] = a1, a2, a3, m1
+  const double4 *qtab; // per-q factors
+  double4 ea;          // per-item factors (C_i e_i(item))
   cd a1, a2, a3;
   TQ_D void begin(int q, int c) {
     const double4 e = qtab[q];
-    a1 = cscale(e.x, coef[c]);
-    a2 = cscale(e.y, coef[TCW + c]);
-    a3 = cscale(e.z, coef[2 * TCW + c]);
+    a1 = cscale(e.x * ea.x, coef[4 * c]);
+    a2 = cscale(e.y * ea.y, coef[4 * c + 1]);
+    a3 = cscale(e.z * ea.z, coef[4 * c + 2]);
   }
   template <int R> TQ_D cd load(const cd *p) const {
     cd v = caxpy(-A.er[0][R], a1, *p);
@@ -144,17 +150,22 @@ struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fo
   }
 };
 template <int RB> struct PreI1 { // x = (g - tail(i w)) / beta for window rows, 0 elsewhere      :254
-  const cd *wrec, *coef;
-  int TCW;
+  const cd *wrec, *coef; // coef [c][4] = a1, a2 - a3, a2 + a3, -
   Window win;
   double inv_beta;
   cd a1, D23, A23;
   int q;
   TQ_D void begin(int qq, int c) {
     q = qq;
-    a1 = coef[c];
-    D23 = coef[TCW + c];
-    A23 = coef[2 * TCW + c];
+    a1 = coef[4 * c];
+    D23 = coef[4 * c + 1];
+    A23 = coef[4 * c + 2];
+  }
+  // pruned pass A: leg 0 is window row q (compact index q), the last leg is window row RB + q
+  TQ_D cd edge(int which, const cd *p) const {
+    const int idx = which ? RB + q : q;
+    const cd t = tail_iw4(wrec[2 * idx], wrec[2 * idx + 1], a1, D23, A23);
+    return cscale(inv_beta, csub(*p, t));
   }
   template <int R> TQ_D cd load(const cd *p) const {
     const int row = q + RB * R;
@@ -187,8 +198,8 @@ template <int RA> struct PostScratch { // Y = z T[beta]  -> scratch[beta][column
   template <int TT> TQ_D void store(cd v) const { p[(long)(RA * TT) * beta_stride] = cmul(v, Ts[RA * TT]); }
 };
 template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows only      :181-183
-  const cd *wrec, *coef;
-  int TCW, n_cols, item, Nb, L, first;
+  const cd *wrec, *coef; // coef [c][4] = a1, a2 - a3, a2 + a3, trapezoid correction
+  int n_cols, item, Nb, L, first;
   Window win;
   cd *base; // out of this gf + c0
   cd a1, D23, A23, ex;
@@ -196,10 +207,10 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
   int sidx;
   TQ_D void begin(int s, int c) {
     sidx = s;
-    a1 = coef[c];
-    D23 = coef[TCW + c];
-    A23 = coef[2 * TCW + c];
-    ex = coef[3 * TCW + c];
+    a1 = coef[4 * c];
+    D23 = coef[4 * c + 1];
+    A23 = coef[4 * c + 2];
+    ex = coef[4 * c + 3];
     p = base + c;
   }
   template <int TT> TQ_D void store(cd v) const {
@@ -220,9 +231,10 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
 };
 template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i,  j = item + Nb (s + RA t)        :261-268
   const PipeArgs &A;
-  const cd *coef;
-  const double4 *qtab;
-  int TCW, n_cols, item, Nb, L;
+  const cd *coef;      // [c][4] = a1, a2, a3, m1
+  const double4 *qtab; // per-s factors
+  double4 ea;          // per-item factors
+  int n_cols, item, Nb, L;
   bool fermion;
   cd *base; // out of this gf + c0
   cd a1, a2, a3, m1;
@@ -230,10 +242,10 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
   int j0;
   TQ_D void begin(int s, int c) {
     const double4 e = qtab[s];
-    a1 = cscale(e.x, coef[c]);
-    a2 = cscale(e.y, coef[TCW + c]);
-    a3 = cscale(e.z, coef[2 * TCW + c]);
-    m1 = coef[3 * TCW + c];
+    a1 = cscale(e.x * ea.x, coef[4 * c]);
+    a2 = cscale(e.y * ea.y, coef[4 * c + 1]);
+    a3 = cscale(e.z * ea.z, coef[4 * c + 2]);
+    m1 = coef[4 * c + 3];
     j0 = item + Nb * s;
     p = base + c + (long)j0 * n_cols;
   }
@@ -250,24 +262,69 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
   }
 };
 
+// Pole weights of the 3-pole tail model per (gf, column), in the two forms the kernels use   (:151-169, :238-252)
+//   w_tau  [gf][c][4] = a1, a2, a3, m1                                   (tau side: F1 pre-transform, I2 post-transform)
+//   w_freq [gf][c][4] = a1, a2 - a3, a2 + a3, trapezoid correction        (frequency side: F2 epilogue, I1 pre-transform)
+// The trapezoid end-point correction -0.5 (beta/L) (g_0 + m1 +/- g_L) (:181) exists on the forward leg only (gt != nullptr).
+__global__ void k_pole_weights(const cd *mom, long mom_gf_stride, int n_cols, long total, int stat, const cd *gt, long gt_gf_stride, int L,
+                               double half_fact_fwd, cd *w_tau, cd *w_freq) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long gf = i / n_cols;
+  const int c = (int)(i - gf * n_cols);
+  const cd *m = mom + gf * mom_gf_stride + c;
+  const cd m1 = m[(size_t)1 * n_cols], m2 = m[(size_t)2 * n_cols], m3 = m[(size_t)3 * n_cols];
+  const bool fermion = stat == TQ_FERMION;
+  cd a1, a2, a3;
+  if (fermion) {
+    a1 = csub(m1, m3);
+    a2 = cscale(0.5, cadd(m2, m3));
+    a3 = cscale(0.5, csub(m3, m2));
+  } else {
+    a1 = cscale(4.0 / 3.0, csub(m1, m3));
+    a2 = csub(m3, cscale(0.5, cadd(m1, m2)));
+    a3 = cadd(cadd(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
+  }
+  cd ex = cmk(0.0, 0.0);
+  if (gt) {
+    const cd *g = gt + gf * gt_gf_stride + c;
+    const cd g0 = g[0], gL = g[(size_t)L * n_cols];
+    cd s = cadd(g0, m1);
+    s = fermion ? cadd(s, gL) : csub(s, gL);
+    ex = cscale(-half_fact_fwd, s);
+  }
+  w_tau[4 * i] = a1;
+  w_tau[4 * i + 1] = a2;
+  w_tau[4 * i + 2] = a3;
+  w_tau[4 * i + 3] = m1;
+  w_freq[4 * i] = a1;
+  w_freq[4 * i + 1] = csub(a2, a3);
+  w_freq[4 * i + 2] = cadd(a2, a3);
+  w_freq[4 * i + 3] = ex;
+}
+
 // shared-memory carve-up (bytes); tile buffers first, each padded to 128 B (TMA tensor destination alignment)
 template <int MODE, int N, int RA, int RB> struct PipeSmem {
   static constexpr bool PASS1 = (MODE == M_F1 || MODE == M_I1);
   static constexpr bool QTAB = (MODE == M_F1 || MODE == M_I2);
   static constexpr bool WREC = (MODE == M_F2 || MODE == M_I1);
   static constexpr int NQ = (MODE == M_F1) ? RB : RA;
-  size_t buf_stride, tw, qtab, tab0, tab_stride, coef_off, t_off, wrec_off, mbar, total;
-  __host__ __device__ PipeSmem(int tcw, int wmax) {
-    buf_stride = (sizeof(cd) * (size_t)N * tcw + 127) & ~size_t(127);
+  size_t buf_stride, stage_off, tw, qtab, tab0, tab_stride, coef_off, item_off, t_off, win_off, wrec_off, mbar, total;
+  __host__ __device__ PipeSmem(int tcw, int pitch, int wmax) {
+    stage_off = (sizeof(cd) * (size_t)N * (PASS1 ? pitch : tcw) + 127) & ~size_t(127);
+    // I1: staging rows for the last butterfly leg (pruned pass A), 128-byte aligned like the tile itself
+    buf_stride = stage_off + (MODE == M_I1 ? ((sizeof(cd) * (size_t)RB * pitch + 127) & ~size_t(127)) : 0);
     tw = PIPE_NBUF * buf_stride;
     qtab = tw + sizeof(cd) * N;
     tab0 = qtab + (QTAB ? sizeof(double4) * NQ : 0);
     coef_off = 0;
-    t_off = coef_off + sizeof(cd) * 4 * (size_t)tcw;
-    wrec_off = t_off + (PASS1 ? sizeof(cd) * N : 0);
+    item_off = coef_off + sizeof(cd) * 4 * (size_t)tcw;
+    t_off = item_off + (QTAB ? sizeof(double4) : 0);
+    win_off = t_off + (PASS1 ? sizeof(cd) * N : 0);
+    wrec_off = win_off + (WREC ? sizeof(int4) : 0);
     tab_stride = wrec_off + (WREC ? sizeof(cd) * 2 * (size_t)wmax : 0);
-    mbar = tab0 + PIPE_NBUF * tab_stride;
-    total = mbar + 8 * 3 * PIPE_NBUF;
+    mbar = tab0 + PIPE_NTAB * tab_stride;
+    total = mbar + 8 * (3 * PIPE_NBUF + PIPE_NTAB) + 16;
   }
 };
 
@@ -275,218 +332,241 @@ struct TileId {
   long gf;
   int item, c0, w;
 };
-TQ_D TileId decode_tile(long t, int n_items, int n_ct, int tcw, int n_cols) {
-  TileId id;
-  const long per_gf = (long)n_items * n_ct;
-  id.gf = t / per_gf;
-  const int rem = (int)(t - id.gf * per_gf);
-  id.item = rem / n_ct;
-  id.c0 = (rem - id.item * n_ct) * tcw;
-  id.w = min(tcw, n_cols - id.c0);
-  return id;
-}
+// tile index -> (gf, item, column tile) without integer division: the divisors are fixed for a launch
+struct TileDecoder {
+  unsigned long long m_per_gf; // ceil(2^64 / (n_items n_ct)): exact quotient for t < 2^32
+  unsigned m_nct;
+  int per_gf, n_ct, tcw, n_cols;
+  TQ_D TileDecoder(int n_items, int n_ct_, int tcw_, int n_cols_) : n_ct(n_ct_), tcw(tcw_), n_cols(n_cols_) {
+    per_gf = n_items * n_ct;
+    m_per_gf = per_gf > 1 ? ~0ull / (unsigned long long)per_gf + 1ull : 0ull;
+    m_nct = fastdiv_magic((unsigned)n_ct);
+  }
+  TQ_D TileId operator()(long t) const {
+    TileId id;
+    id.gf = per_gf > 1 ? (long)__umul64hi((unsigned long long)t, m_per_gf) : t;
+    const int rem = (int)(t - id.gf * per_gf);
+    id.item = fastdiv(rem, m_nct);
+    id.c0 = (rem - id.item * n_ct) * tcw;
+    id.w = min(tcw, n_cols - id.c0);
+    return id;
+  }
+};
 
-template <int MODE, int N, int RA, int RB, int WA, int WB>
-__global__ void __maxnreg__((16384 / (((WA + WB + 1) + 3) / 4 * 32)) & ~7) matsubara_pipe_kernel(const __grid_constant__ PipeArgs A,
-                                                                                     const __grid_constant__ CUtensorMap tmap) {
+template <int MODE, int N, int RA, int RB, int NW>
+__global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_pipe_kernel(const __grid_constant__ PipeArgs A,
+                                                                                             const __grid_constant__ CUtensorMap tmap,
+                                                                                             const __grid_constant__ CUtensorMap tmap2) {
   constexpr bool PASS1 = (MODE == M_F1 || MODE == M_I1);
   constexpr bool FWD = (MODE == M_F1 || MODE == M_F2);
   constexpr int SGN = FWD ? 1 : -1;
-  constexpr int NT = (WA + WB + 1) * 32;
+  constexpr int NT = (NW + 1) * 32;
   using Smem = PipeSmem<MODE, N, RA, RB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TCW = A.tcw;
-  const Smem S(TCW, A.wmax);
+  const Smem S(TCW, A.pitch, A.wmax);
   cd *twS = reinterpret_cast<cd *>(smem_raw + S.tw);
   double4 *qtab = reinterpret_cast<double4 *>(smem_raw + S.qtab);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + S.mbar); // TMA landed + tables written   (producer -> A)
-  uint64_t *adone = full + PIPE_NBUF;                                // pass A complete               (A -> B)
-  uint64_t *freeb = adone + PIPE_NBUF;                               // pass B has consumed the tile  (B -> producer)
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + S.mbar); // TMA landed + tables written   (producer -> pass A)
+  uint64_t *adone = full + PIPE_NBUF;                                // pass A complete               (pass A -> pass B)
+  uint64_t *freeb = adone + PIPE_NBUF;                               // pass B has read the tile      (pass B -> producer)
+  uint64_t *tabfree = freeb + PIPE_NBUF;                             // pass B is done with the tables (pass B -> producer)
+  int *next_pk = reinterpret_cast<int *>(tabfree + PIPE_NTAB);       // work-packet counter of the worker warps
+  volatile int *ready_tile = next_pk + 1;                            // newest tile the producer has started (its buffer is free)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int n_cols = A.n_cols;
   const bool fermion = A.stat == TQ_FERMION;
+  // work packets = 32 butterflies (one per lane): pa packets of pass A and pb packets of pass B per tile
+  const int pa = (RB * TCW + 31) >> 5, pb = (RA * TCW + 31) >> 5;
 
   for (int i = tid; i < N; i += NT) twS[i] = A.twq[i];
   if (Smem::QTAB)
     for (int i = tid; i < Smem::NQ; i += NT) qtab[i] = A.qtab[i];
   if (tid == 0) {
     for (int b = 0; b < PIPE_NBUF; ++b) {
-      mbar_init(&full[b], 2);
-      mbar_init(&adone[b], WA);
-      mbar_init(&freeb[b], WB);
+      mbar_init(&full[b], 1);
+      mbar_init(&adone[b], pa);
+      mbar_init(&freeb[b], pb);
     }
+    for (int b = 0; b < PIPE_NTAB; ++b) mbar_init(&tabfree[b], pb);
+    *next_pk = 0;
+    *ready_tile = -1;
     fence_mbar_init();
   }
   __syncthreads();
 
-  long long t0 = clock64(), t_wait = 0, t_work = 0;
+  const int nloc = (int)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
+  const TileDecoder decode(A.n_items, A.n_ct, TCW, n_cols);
+  const unsigned m_pa = fastdiv_magic((unsigned)pa), m_pab = fastdiv_magic((unsigned)(pa + pb));
+  long long t0 = clock64(), t_wait = 0, t_work = 0, t_sched = 0, t_ready = 0;
 #define TQ_LAP(acc)                                                                                                              \
   if (A.dbg && lane == 0) {                                                                                                      \
     const long long now = clock64();                                                                                             \
     acc += now - t0;                                                                                                             \
     t0 = now;                                                                                                                    \
   }
-  // timeline of CTA 0 (first warp of each role, first 16 tiles): trace[role][tile][0 = got the buffer, 1 = handed it on]
-  long long *trace = (A.dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == WA || warp == WA + WB)) ? A.dbg + (size_t)gridDim.x * 64 : nullptr;
-  const int trole = warp == 0 ? 0 : (warp == WA ? 1 : 2);
-#define TQ_TRACE(i, ev)                                                                                                          \
-  if (trace && (i) < 16) trace[(trole * 16 + (i)) * 2 + (ev)] = clock64();
 
-  if (warp == WA + WB) {
+  if (warp == NW) {
     // ===================== producer warp: TMA + per-tile pole weights =====================
-    int i = 0;
-    for (long t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++i) {
-      const int b = i % PIPE_NBUF, u = i / PIPE_NBUF;
-      if (u > 0) mbar_wait(&freeb[b], (uint32_t)((u - 1) & 1));
+    for (int i = 0; i < nloc; ++i) {
+      const long t = blockIdx.x + (long)i * gridDim.x;
+      const int b = i % PIPE_NBUF, u = i / PIPE_NBUF, ts = i % PIPE_NTAB, ut = i / PIPE_NTAB;
+      if (ut > 0) mbar_wait(&tabfree[ts], (uint32_t)((ut - 1) & 1)); // tile i - NTAB is completely done
+      if (u > 0) mbar_wait(&freeb[b], (uint32_t)((u - 1) & 1));       // pass B of tile i - NBUF has read its inputs
+      if (lane == 0) *ready_tile = i; // every barrier of buffer b is now in the phase of tile i
       TQ_LAP(t_wait)
-      TQ_TRACE(i, 0)
-      const TileId id = decode_tile(t, A.n_items, A.n_ct, TCW, n_cols);
+      const TileId id = decode(t);
       cd *dst = reinterpret_cast<cd *>(smem_raw + b * S.buf_stride);
-      unsigned char *tab = smem_raw + S.tab0 + b * S.tab_stride;
-      cd *coef = reinterpret_cast<cd *>(tab + S.coef_off);
+      unsigned char *tab = smem_raw + S.tab0 + ts * S.tab_stride;
       Window win{0, 0};
       int cnt = 0;
       if (Smem::WREC) {
-        win = tile_window(id.item, MODE == M_F2 ? A.Nb : A.Na, N, A.L, A.first, A.last);
+        const int4 wv = A.wintab[id.item];
+        win.r1 = wv.x;
+        win.r2 = wv.y;
         cnt = win.r1 + (N - win.r2);
       }
+      const bool i1_boxes = MODE == M_I1 && A.i1_rect; // window rows form two rectangles of the [b][a] view: two tensor tiles
       if (lane == 0) {
         uint32_t bytes = 0;
         if (MODE == M_F1)
-          bytes = (uint32_t)(sizeof(cd) * N * TCW); // the whole box, zero-filled past n_cols
+          bytes = (uint32_t)(sizeof(cd) * N * A.pitch); // the whole box, zero-filled past n_cols
         else if (MODE == M_I1)
-          bytes = (uint32_t)(sizeof(cd) * cnt * id.w);
+          bytes = i1_boxes ? (uint32_t)(sizeof(cd) * cnt * A.pitch) : (uint32_t)(sizeof(cd) * cnt * id.w);
         else
           bytes = (uint32_t)(sizeof(cd) * N * id.w);
         if (PASS1) bytes += (uint32_t)(sizeof(cd) * N);
-        if (Smem::WREC) bytes += (uint32_t)(sizeof(double4) * cnt);
+        if (Smem::WREC) bytes += (uint32_t)(sizeof(double4) * cnt + sizeof(int4));
+        bytes += (uint32_t)(sizeof(cd) * 4 * id.w);
+        if (Smem::QTAB) bytes += (uint32_t)sizeof(double4);
         mbar_arrive_expect_tx(&full[b], bytes);
-        if (MODE == M_F1)
+        // the tile's table set: pole weights of its columns (:151-169, :238-252), per-item factors, four-step twiddles, window rows
+        bulk_g2s(tab + S.coef_off, A.polew + ((size_t)id.gf * n_cols + id.c0) * 4, (uint32_t)(sizeof(cd) * 4 * id.w), &full[b]);
+        if (Smem::QTAB) bulk_g2s(tab + S.item_off, A.itemtab + id.item, (uint32_t)sizeof(double4), &full[b]);
+        if (MODE == M_F1) {
           tma_load_4d(dst, &tmap, 2 * id.c0, id.item, 0, (int)id.gf, &full[b]); // [gf][b = 0..Nb)[a = item][columns]
-        else if (MODE != M_I1)
+        } else if (MODE == M_I1) {
+          if (i1_boxes) {
+            tma_load_4d(dst, &tmap, 2 * id.c0, id.item, 0, (int)id.gf, &full[b]);                                  // rows [0, r1): n >= 0
+            cd *dst2 = A.i1_edge ? reinterpret_cast<cd *>(smem_raw + b * S.buf_stride + S.stage_off) : dst + (size_t)win.r2 * A.pitch;
+            tma_load_4d(dst2, &tmap2, 2 * id.c0, id.item, 0, (int)id.gf, &full[b]); // rows [r2, N): n < 0
+          }
+        } else {
           bulk_g2s(dst, A.scratch + id.gf * A.scratch_gf_stride + (long)id.item * A.Na * n_cols + (long)id.c0 * A.Na,
                    (uint32_t)(sizeof(cd) * N * id.w), &full[b]);
+        }
         if (PASS1) bulk_g2s(tab + S.t_off, A.Tfull + (size_t)id.item * N, (uint32_t)(sizeof(cd) * N), &full[b]);
+        if (Smem::WREC) bulk_g2s(tab + S.win_off, A.wintab + id.item, (uint32_t)sizeof(int4), &full[b]);
         if (Smem::WREC && cnt > 0)
           bulk_g2s(tab + S.wrec_off, A.wperm + (size_t)id.item * A.wmax, (uint32_t)(sizeof(double4) * cnt), &full[b]);
       }
-      if (MODE == M_I1) {
-        // window rows only (the rest of the frequency axis is zero, :254): one bulk row copy each, tile pitch = w
+      if (MODE == M_I1 && !i1_boxes) {
+        // window rows only (the rest of the frequency axis is zero, :254): one bulk row copy each
         for (int r0 = lane; r0 < cnt; r0 += 32) {
           const int r = r0 < win.r1 ? r0 : win.r2 + (r0 - win.r1);
           const int k = id.item + A.Na * r;
           const long di = (k <= A.last ? k : k - A.L) - A.first;
-          bulk_g2s(dst + (size_t)r * id.w, A.in + id.gf * A.in_gf_stride + di * n_cols + id.c0, (uint32_t)(sizeof(cd) * id.w), &full[b]);
+          bulk_g2s(dst + (size_t)r * A.pitch, A.in + id.gf * A.in_gf_stride + di * n_cols + id.c0, (uint32_t)(sizeof(cd) * id.w), &full[b]);
         }
       }
-      // pole weights of the tile's columns  (:151-169, :238-252)
-      for (int c = lane; c < id.w; c += 32) {
-        const cd *mom = A.moments + id.gf * A.mom_gf_stride + id.c0 + c;
-        const cd m1 = mom[(size_t)1 * n_cols], m2 = mom[(size_t)2 * n_cols], m3 = mom[(size_t)3 * n_cols];
-        cd a1, a2, a3;
-        if (fermion) {
-          a1 = csub(m1, m3);
-          a2 = cscale(0.5, cadd(m2, m3));
-          a3 = cscale(0.5, csub(m3, m2));
-        } else {
-          a1 = cscale(4.0 / 3.0, csub(m1, m3));
-          a2 = csub(m3, cscale(0.5, cadd(m1, m2)));
-          a3 = cadd(cadd(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
-        }
-        if (MODE == M_F1 || MODE == M_I2) {
-          const double4 ea = A.itemtab[id.item];
-          coef[c] = cscale(ea.x, a1);
-          coef[TCW + c] = cscale(ea.y, a2);
-          coef[2 * TCW + c] = cscale(ea.z, a3);
-          coef[3 * TCW + c] = m1;
-        } else {
-          coef[c] = a1;
-          coef[TCW + c] = csub(a2, a3);
-          coef[2 * TCW + c] = cadd(a2, a3);
-          if (MODE == M_F2) {
-            // trapezoid end-point correction  -0.5 (beta/L) (g_0 + m1 +/- g_L)   (:181); A.in is G(tau) here
-            const cd *g = A.in + id.gf * A.in_gf_stride + id.c0 + c;
-            const cd g0 = g[0], gL = g[(size_t)A.L * n_cols];
-            cd s = cadd(g0, m1);
-            s = fermion ? cadd(s, gL) : csub(s, gL);
-            coef[3 * TCW + c] = cscale(-A.half_fact_fwd, s);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[b]); // second arrival (release): the table set is visible to whoever sees the phase flip
       TQ_LAP(t_work)
-      TQ_TRACE(i, 1)
-    }
-  } else if (warp < WA) {
-    // ===================== A group: pass A in place =====================
-    int i = 0;
-    for (long t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++i) {
-      const int b = i % PIPE_NBUF, u = i / PIPE_NBUF;
-      const TileId id = decode_tile(t, A.n_items, A.n_ct, TCW, n_cols);
-      cd *tile = reinterpret_cast<cd *>(smem_raw + b * S.buf_stride);
-      unsigned char *tab = smem_raw + S.tab0 + b * S.tab_stride;
-      const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
-      const int pitch = (MODE == M_F1) ? TCW : id.w;
-      mbar_wait(&full[b], (uint32_t)(u & 1));
-      TQ_LAP(t_wait)
-      TQ_TRACE(i, 0)
-      if (MODE == M_F1) {
-        PreF1 pre{A, coef, qtab, TCW};
-        fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, tid, WA * 32, pre);
-      } else if (MODE == M_I1) {
-        PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, tile_window(id.item, A.Na, N, A.L, A.first, A.last),
-                      A.inv_beta};
-        fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, tid, WA * 32, pre);
-      } else {
-        PreIdentity pre;
-        fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, tid, WA * 32, pre);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&adone[b]);
-      TQ_LAP(t_work)
-      TQ_TRACE(i, 1)
     }
   } else {
-    // ===================== B group: pass B + epilogue -> global =====================
-    const int tb = tid - WA * 32;
-    int i = 0;
-    for (long t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++i) {
-      const int b = i % PIPE_NBUF, u = i / PIPE_NBUF;
-      const TileId id = decode_tile(t, A.n_items, A.n_ct, TCW, n_cols);
-      const cd *tile = reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride);
-      unsigned char *tab = smem_raw + S.tab0 + b * S.tab_stride;
-      const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
-      const int pitch = (MODE == M_F1) ? TCW : id.w;
-      mbar_wait(&adone[b], (uint32_t)(u & 1));
-      TQ_LAP(t_wait)
-      TQ_TRACE(i, 0)
-      if (PASS1) {
-        PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
-                             A.Na, A.tcw2, id.item, id.c0};
-        fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, tb, WB * 32, post);
-      } else if (MODE == M_F2) {
-        PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first,
-                        tile_window(id.item, A.Nb, N, A.L, A.first, A.last), A.out + id.gf * A.out_gf_stride + id.c0};
-        fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, tb, WB * 32, post);
+    // ===================== worker warps: pull packets  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  =====================
+    // (pass B of tile k is queued after pass A of tile k+1, so whoever takes it rarely waits; a packet only ever waits
+    //  for packets that were handed out before it, hence no deadlock)
+    for (;;) {
+      int pk = 0;
+      if (lane == 0) pk = atomicAdd(next_pk, 1);
+      pk = __shfl_sync(0xffffffffu, pk, 0);
+      int blk, r;
+      bool is_b = false;
+      if (pk < 2 * pa) {
+        blk = fastdiv(pk, m_pa);
+        r = pk - blk * pa;
       } else {
-        PostI2<RA> post{A, coef, qtab, TCW, n_cols, id.item, A.Nb, A.L, fermion, A.out + id.gf * A.out_gf_stride + id.c0};
-        fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, tb, WB * 32, post);
+        const int q = pk - 2 * pa;
+        blk = fastdiv(q, m_pab);
+        r = q - blk * (pa + pb);
+        blk += 2;
+        is_b = r < pb;
+        if (!is_b) r -= pb;
       }
-      fence_proxy_async(); // our generic-proxy reads of the tile are ordered before the TMA engine's next write to it
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&freeb[b]);
-      TQ_LAP(t_work)
-      TQ_TRACE(i, 1)
+      if (blk >= nloc + 2) break;
+      const int k = is_b ? blk - 2 : blk; // tile of this CTA
+      if (k >= nloc) continue;
+      const long t = blockIdx.x + (long)k * gridDim.x;
+      const int b = k % PIPE_NBUF, u = k / PIPE_NBUF;
+      const TileId id = decode(t);
+      cd *tile = reinterpret_cast<cd *>(smem_raw + b * S.buf_stride);
+      const int ts = k % PIPE_NTAB;
+      unsigned char *tab = smem_raw + S.tab0 + ts * S.tab_stride;
+      const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
+      const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
+      const int it = r * 32 + lane; // butterfly of this lane (the engine skips it when past the end)
+      TQ_LAP(t_sched)
+      // an mbarrier parity wait is only meaningful for the current or the previous phase: do not look at the barriers of
+      // buffer b before the producer has recycled it for tile k (matters when a tile has fewer packets than there are workers)
+      while (*ready_tile < k) __nanosleep(32);
+      TQ_LAP(t_ready)
+      if (!is_b) {
+        mbar_wait(&full[b], (uint32_t)(u & 1));
+        TQ_LAP(t_wait)
+        if (MODE == M_F1) {
+          PreF1 pre{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off)};
+          fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+        } else if (MODE == M_I1) {
+          const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
+          PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, Window{wv.x, wv.y}, A.inv_beta};
+          if (A.i1_edge) {
+            auto wedge = [&](int rr) { return A.wedge[rr]; };
+            fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS, it,
+                                               1 << 30, pre, wedge);
+          } else {
+            fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+          }
+        } else {
+          PreIdentity pre;
+          fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&adone[b]);
+        TQ_LAP(t_work)
+      } else {
+        mbar_wait(&adone[b], (uint32_t)(u & 1));
+        TQ_LAP(t_wait)
+        if (PASS1) {
+          PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
+                               A.Na, A.tcw2, id.item, id.c0};
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+        } else if (MODE == M_F2) {
+          const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
+          PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
+                          A.out + id.gf * A.out_gf_stride + id.c0};
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+        } else {
+          PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
+                          A.out + id.gf * A.out_gf_stride + id.c0};
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+        }
+        fence_proxy_async(); // our generic-proxy reads of the tile are ordered before the TMA engine's next write to it
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&freeb[b]);
+          mbar_arrive(&tabfree[ts]);
+        }
+        TQ_LAP(t_work)
+      }
     }
   }
   if (A.dbg && lane == 0) {
-    A.dbg[(size_t)blockIdx.x * 64 + 2 * warp] = t_wait;
-    A.dbg[(size_t)blockIdx.x * 64 + 2 * warp + 1] = t_work;
+    A.dbg[(size_t)blockIdx.x * 64 + 4 * warp] = t_wait;
+    A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 1] = t_work;
+    A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 2] = t_sched;
+    A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 3] = t_ready;
   }
 #undef TQ_LAP
-#undef TQ_TRACE
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -495,6 +575,7 @@ __global__ void __maxnreg__((16384 / (((WA + WB + 1) + 3) / 4 * 32)) & ~7) matsu
 struct ModeTables {
   const cd *twq = nullptr;
   const double4 *qtab = nullptr, *itemtab = nullptr, *wperm = nullptr;
+  const int4 *wintab = nullptr;
   const cd *Tfull = nullptr;
   double er[3][PIPE_MAXR];
   cd phr[PIPE_MAXR];
@@ -671,10 +752,12 @@ static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, l
       double r1 = 1.0 / (b[0] * b[0] + w * w), r2 = 1.0 / (b[1] * b[1] + w * w);
       return make_double4(b[0] * r1, w * r1, b[1] * r2, w * r2);
     };
-    auto perm = [&](int n_items, int S, int N, int wmax, std::vector<double4> &out) -> bool {
+    auto perm = [&](int n_items, int S, int N, int wmax, std::vector<double4> &out, std::vector<int4> &wins) -> bool {
       out.assign((size_t)n_items * wmax, make_double4(0, 0, 0, 0));
+      wins.assign(n_items, make_int4(0, 0, 0, 0));
       for (int item = 0; item < n_items; ++item) {
         Window win = tile_window(item, S, N, (int)L, pl->first, pl->last);
+        wins[item] = make_int4(win.r1, win.r2, 0, 0);
         int cnt = win.r1 + (N - win.r2);
         if (cnt > wmax) return false;
         for (int i = 0; i < cnt; ++i) {
@@ -687,10 +770,13 @@ static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, l
       return true;
     };
     std::vector<double4> w1, w2;
-    if (!perm(Na, Na, Nb, pl->wmax1, w1) || !perm(Nb, Nb, Na, pl->wmax2, w2))
+    std::vector<int4> i1, i2;
+    if (!perm(Na, Na, Nb, pl->wmax1, w1, i1) || !perm(Nb, Nb, Na, pl->wmax2, w2, i2))
       return tq_fail(ctx, TQ_ERR_INVALID, "internal: window-row table capacity");
     TQ_TRY(pp_upload(ctx, *pl, w1, &pl->m[M_I1].wperm));
     TQ_TRY(pp_upload(ctx, *pl, w2, &pl->m[M_F2].wperm));
+    TQ_TRY(pp_upload(ctx, *pl, i1, &pl->m[M_I1].wintab));
+    TQ_TRY(pp_upload(ctx, *pl, i2, &pl->m[M_F2].wintab));
   }
   plans[key] = pl;
   *out = pl;
@@ -724,67 +810,72 @@ static tq_status make_f1_tensor_map(tq_ctx *ctx, const cd *in, long nb, int Na, 
   return TQ_OK;
 }
 
-template <int MODE, int N, int RA, int RB, int WA, int WB>
-static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &tmap, const char *tag) {
-  constexpr int NT = (WA + WB + 1) * 32;
-  const size_t smem = PipeSmem<MODE, N, RA, RB>(A.tcw, A.wmax).total;
-  auto k = matsubara_pipe_kernel<MODE, N, RA, RB, WA, WB>;
+// G(i w) of `nb` gfs, one half of the window, as the 4-D tensor [gf][b'][a][2 n_cols doubles]: row = row0 + a + Na b'.
+// Valid only when the half is a whole number of Na-row groups (n_rows % Na == 0), so that the box never leaves the window.
+static tq_status make_i1_tensor_map(tq_ctx *ctx, const cd *in, long row0, long n_rows, long nb, int Na, long n_cols, long n_w, int pitch,
+                                    CUtensorMap *out) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const long nbp = n_rows / Na;
+  cuuint64_t dims[4] = {(cuuint64_t)(2 * n_cols), (cuuint64_t)Na, (cuuint64_t)nbp, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)(n_cols * sizeof(cd)), (cuuint64_t)((long)Na * n_cols * sizeof(cd)), (cuuint64_t)(n_w * n_cols * sizeof(cd))};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * pitch), 1u, (cuuint32_t)nbp, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)(in + row0 * n_cols), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled (I1) failed with CUresult " + std::to_string((int)r));
+  return TQ_OK;
+}
+
+template <int MODE, int N, int RA, int RB, int NW>
+static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &tmap, const CUtensorMap &tmap2, const char *tag) {
+  constexpr int NT = (NW + 1) * 32;
+  const size_t smem = PipeSmem<MODE, N, RA, RB>(A.tcw, A.pitch, A.wmax).total;
+  auto k = matsubara_pipe_kernel<MODE, N, RA, RB, NW>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
   static const bool phase_debug = getenv("TQ_PHASE_DEBUG") != nullptr;
   PipeArgs Ad = A;
   if (phase_debug) {
-    TQ_CUDA(ctx, cudaMallocManaged(&Ad.dbg, sizeof(long long) * (64 * grid + 128)));
-    TQ_CUDA(ctx, cudaMemset(Ad.dbg, 0, sizeof(long long) * (64 * grid + 128)));
+    TQ_CUDA(ctx, cudaMallocManaged(&Ad.dbg, sizeof(long long) * 64 * grid));
+    TQ_CUDA(ctx, cudaMemset(Ad.dbg, 0, sizeof(long long) * 64 * grid));
   }
   {
     KernelScope ks(ctx, tag);
-    k<<<grid, NT, smem, ctx->stream>>>(Ad, tmap);
+    k<<<grid, NT, smem, ctx->stream>>>(Ad, tmap, tmap2);
   }
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
   if (phase_debug) {
     TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // per role: average over CTAs and warps of (cycles waiting, cycles working) per tile
-    double w[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    double w[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     for (int i = 0; i < grid; ++i)
-      for (int wp = 0; wp < WA + WB + 1; ++wp) {
-        const int role = wp < WA ? 0 : (wp < WA + WB ? 1 : 2);
-        const int nw = role == 0 ? WA : (role == 1 ? WB : 1);
-        w[role][0] += (double)Ad.dbg[(size_t)i * 64 + 2 * wp] / nw;
-        w[role][1] += (double)Ad.dbg[(size_t)i * 64 + 2 * wp + 1] / nw;
+      for (int wp = 0; wp < NW + 1; ++wp) {
+        const int role = wp < NW ? 0 : 1;
+        const int nw = role == 0 ? NW : 1;
+        for (int j = 0; j < 4; ++j) w[role][j] += (double)Ad.dbg[(size_t)i * 64 + 4 * wp + j] / nw;
       }
     const double per = (double)A.n_tiles;
     fprintf(stderr,
-            "[pipe] %-13s N=%d tcw=%d tiles=%ld grid=%d smem=%zu thr=%d  cycles/tile  A: wait %.0f work %.0f | B: wait %.0f work %.0f | P: wait %.0f work "
-            "%.0f\n",
-            tag, N, A.tcw, A.n_tiles, grid, smem, NT, w[0][0] / per, w[0][1] / per, w[1][0] / per, w[1][1] / per, w[2][0] / per, w[2][1] / per);
-    if (getenv("TQ_PHASE_TRACE")) {
-      const long long *tr = Ad.dbg + (size_t)grid * 64;
-      const long long t00 = tr[(2 * 16 + 0) * 2 + 0];
-      fprintf(stderr, "   tile:   P got-slot  P issued |  A got-data  A done |  B got-A  B done     (cycles since the producer's first stamp, CTA 0)\n");
-      for (int i = 0; i < 16; ++i)
-        fprintf(stderr, "   %4d: %10lld %10lld | %10lld %8lld | %8lld %8lld\n", i, tr[(2 * 16 + i) * 2] - t00, tr[(2 * 16 + i) * 2 + 1] - t00,
-                tr[(0 * 16 + i) * 2] - t00, tr[(0 * 16 + i) * 2 + 1] - t00, tr[(1 * 16 + i) * 2] - t00, tr[(1 * 16 + i) * 2 + 1] - t00);
-    }
+            "[pipe] %-13s N=%d tcw=%d tiles=%ld grid=%d smem=%zu thr=%d  cycles/tile  workers: sched %.0f ready-spin %.0f mbar-wait %.0f work %.0f | "
+            "producer: wait %.0f work %.0f\n",
+            tag, N, A.tcw, A.n_tiles, grid, smem, NT, w[0][2] / per, w[0][3] / per, w[0][0] / per, w[0][1] / per, w[1][0] / per, w[1][1] / per);
     cudaFree(Ad.dbg);
   }
   return TQ_OK;
 }
 
 // widest balanced column tile for a tile length N: n_ct tiles of width ceil(n_cols / n_ct)
-template <int MODE, int N, int RA, int RB> static int pipe_pick_tcw(tq_ctx *ctx, long n_cols, int wmax, int cap) {
+template <int MODE, int N, int RA, int RB> static int pipe_pick_tcw(tq_ctx *ctx, long n_cols, int wmax, int cap, bool pad_pitch = false) {
   int fit = 0;
   for (int tc = 1; tc <= n_cols && tc <= cap; ++tc)
-    if (PipeSmem<MODE, N, RA, RB>(tc, wmax).total <= (size_t)ctx->max_smem_optin) fit = tc;
+    if (PipeSmem<MODE, N, RA, RB>(tc, pad_pitch ? ((tc + 7) & ~7) : tc, wmax).total <= (size_t)ctx->max_smem_optin) fit = tc;
   if (fit < 1) return 0;
   long n_ct = (n_cols + fit - 1) / fit;
   return (int)((n_cols + n_ct - 1) / n_ct);
 }
 
-// warps of the A / B groups (+ 1 producer warp).  The register file is 16K registers per SM sub-partition, so 12 warps
-// (3 per sub-partition) can have 168 registers each, 16 warps only 128.
-constexpr int P1_WA = 6, P1_WB = 5;
 static int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -802,8 +893,15 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   std::shared_ptr<PipePlan> pl;
   TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
   const int wmax1 = pl->wmax1, wmax2 = pl->wmax2;
-  static const int p2_variant = env_int("TQ_PIPE_P2", 0), cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64);
-  const int tcw1 = fwd ? pipe_pick_tcw<M_F1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1) : pipe_pick_tcw<M_I1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1);
+  // worker warps per CTA (+ 1 producer warp): the register file is 16K registers per SM sub-partition, so 12 warps get
+  // 168 registers per thread and 16 warps 128
+  static const int nw_variant = env_int("TQ_PIPE_NW", 11), cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64);
+  // I1: window rows with n >= 0 / n < 0; when both are whole groups of Na rows they are two rectangles of the [b][a] view
+  const long n_pos = (long)pl->last + 1, n_neg = -(long)pl->first;
+  const bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && !getenv("TQ_PIPE_NO_I1_BOXES");
+  const bool i1_edge = i1_rect && n_pos == (long)Na * P1_RB && n_neg == (long)Na * P1_RB && !getenv("TQ_PIPE_NO_I1_EDGE");
+  const int tcw1 = fwd ? pipe_pick_tcw<M_F1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1)
+                       : pipe_pick_tcw<M_I1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1, !i1_edge);
   const int tcw2 = fwd ? pipe_pick_tcw<M_F2, P2_N, P2_RA, P2_RB>(ctx, n_cols, wmax2, cap2) : pipe_pick_tcw<M_I2, P2_N, P2_RA, P2_RB>(ctx, n_cols, wmax2, cap2);
   if (tcw1 < 1 || tcw2 < 1) return TQ_OK;
   PipeArgs A{};
@@ -811,8 +909,18 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   A.Nb = Nb;
   A.n_cols = (int)n_cols;
   A.tcw2 = tcw2;
-  A.moments = d_mom;
-  A.mom_gf_stride = (long)mom_rows * n_cols;
+  // pole weights of all gfs (tiny): [2][batch][n_cols][4]
+  const size_t pw_elems = (size_t)batch * n_cols * 4;
+  TQ_TRY(tq_reserve(ctx, ctx->pipe_w, sizeof(cd) * 2 * pw_elems));
+  cd *w_tau = (cd *)ctx->pipe_w.p, *w_freq = w_tau + pw_elems;
+  {
+    const long total = batch * n_cols;
+    KernelScope ks(ctx, "pole_weights");
+    k_pole_weights<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_mom, (long)mom_rows * n_cols, (int)n_cols, total, stat, fwd ? d_in : nullptr,
+                                                                            (L + 1) * n_cols, (int)L, 0.5 * (beta / (double)L), w_tau, w_freq);
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+  }
   A.L = (int)L;
   A.first = pl->first;
   A.last = pl->last;
@@ -825,10 +933,10 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   A.scratch_gf_stride = L * n_cols;
   // chunk the batch so that the scratch of one chunk stays L2 resident between the two kernels
   const size_t per_gf = (size_t)L * n_cols * sizeof(cd);
-  size_t l2_budget = 96ull << 20;
+  size_t l2_budget = 128ull << 20;
   if (const char *e = getenv("TQ_TWOPASS_CHUNK_MB")) l2_budget = (size_t)atol(e) << 20;
   long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
-  chunk = std::min<long>(chunk, batch);
+  chunk = std::min<long>(std::min<long>(chunk, batch), 1L << 18); // (keeps the tile count of a launch below 2^31)
   TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));
   A.scratch = (cd *)ctx->scratch.p;
   auto set_mode = [&](PipeArgs &P, int mode) {
@@ -838,6 +946,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     P.itemtab = m.itemtab;
     P.Tfull = m.Tfull;
     P.wperm = m.wperm;
+    P.wintab = m.wintab;
     memcpy(P.er, m.er, sizeof(P.er));
     memcpy(P.phr, m.phr, sizeof(P.phr));
   };
@@ -848,7 +957,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     PipeArgs P1 = A;
     P1.in = d_in + b0 * A.in_gf_stride;
     P1.out = d_out + b0 * A.out_gf_stride;
-    P1.moments = d_mom + b0 * A.mom_gf_stride;
+    P1.polew = (fwd ? w_tau : w_freq) + (size_t)b0 * n_cols * 4;
     P1.tcw = tcw1;
     P1.n_ct = (int)((n_cols + tcw1 - 1) / tcw1);
     P1.n_items = Na;
@@ -860,27 +969,42 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     P2.n_items = Nb;
     P2.n_tiles = nb * Nb * P2.n_ct;
     P2.wmax = wmax2;
+    P2.polew = (fwd ? w_freq : w_tau) + (size_t)b0 * n_cols * 4;
+    CUtensorMap tmap2;
+    memset(&tmap2, 0, sizeof(tmap2));
+    P1.pitch = tcw1;
+    P2.pitch = tcw2;
     if (fwd) {
       set_mode(P1, M_F1);
       set_mode(P2, M_F2);
       TQ_TRY(make_f1_tensor_map(ctx, P1.in, nb, Na, Nb, n_cols, L, tcw1, &tmap));
-      TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, P1_WA, P1_WB>(ctx, P1, tmap, "tau2iw_pass1")));
-      if (p2_variant == 0)
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 6, 5>(ctx, P2, tmap, "tau2iw_pass2")));
-      else if (p2_variant == 1)
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 5, 5>(ctx, P2, tmap, "tau2iw_pass2")));
-      else
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 8, 7>(ctx, P2, tmap, "tau2iw_pass2")));
+      if (nw_variant == 15) {
+        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 15>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
+        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 15>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
+      } else {
+        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 11>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
+        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 11>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
+      }
     } else {
       set_mode(P1, M_I1);
       set_mode(P2, M_I2);
-      TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, P1_WA, P1_WB>(ctx, P1, tmap, "iw2tau_pass1")));
-      if (p2_variant == 0)
-        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 6, 5>(ctx, P2, tmap, "iw2tau_pass2")));
-      else if (p2_variant == 1)
-        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 5, 5>(ctx, P2, tmap, "iw2tau_pass2")));
-      else
-        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 8, 7>(ctx, P2, tmap, "iw2tau_pass2")));
+      P1.i1_rect = i1_rect;
+      P1.i1_edge = i1_edge;
+      // tile rows land at a pitch rounded up to 8 columns (128 B) so that the second tensor tile (rows r2..) is 128-byte
+      // aligned; the pruned path stages that tile separately and keeps the conflict-free dense pitch
+      P1.pitch = P1.i1_edge ? tcw1 : ((tcw1 + 7) & ~7);
+      for (int r = 0; r < PIPE_MAXR; ++r) P1.wedge[r] = expi(2 * PI_L * (long double)r / (long double)P1_RA); // SGN = -1: exp(+2 pi i r / RA)
+      if (P1.i1_rect) {
+        TQ_TRY(make_i1_tensor_map(ctx, P1.in, n_neg, n_pos, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap));  // k in [0, last]: data rows n - first
+        TQ_TRY(make_i1_tensor_map(ctx, P1.in, 0, n_neg, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap2));     // k in [L + first, L): data rows 0..
+      }
+      if (nw_variant == 15) {
+        TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, 15>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
+        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 15>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
+      } else {
+        TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, 11>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
+        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 11>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
+      }
     }
   }
   *handled = true;

@@ -52,7 +52,7 @@ struct tq_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   // grow-only scratch / staging
-  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small;
+  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w;
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   // caches (mesh-only data, like the reference's tail_fitter::_lss and FFTW plans)

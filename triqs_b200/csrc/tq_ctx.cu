@@ -54,6 +54,7 @@ extern "C" void tq_destroy(tq_ctx *ctx) {
   free_buf(ctx->stage_out);
   free_buf(ctx->scratch);
   free_buf(ctx->small);
+  free_buf(ctx->pipe_w);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

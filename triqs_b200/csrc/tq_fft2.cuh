@@ -80,3 +80,50 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
     tq_unroll_store<RB>(a, post);
   }
 }
+
+// Pass A when only the first and the last leg of every butterfly are non-zero (inverse Matsubara transform: the frequency
+// window occupies rows [0, RB) and [N - RB, N) of the tile, everything between is zero-fill):
+//   y_s = x_0 + x_{RA-1} w_RA^{SGN (RA-1) s} = x_0 + x_{RA-1} wedge[s],   wedge[s] = exp(-SGN 2 pi i s / RA)
+// The last-leg rows come from a separate staging area `hi` (same pitch), so the in-place write of all RA legs is hazard free.
+template <int N, int RA, int RB, bool TW0, class Pre, class Wedge>
+TQ_HD void fft2_pass_a_edge(cd *s, const cd *hi, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, const Wedge &wedge) {
+  static_assert(RA * RB == N, "N = RA * RB");
+  const int nitems = RB * tcw;
+  const int stride = RB * pitch;
+  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  for (int i = tid; i < nitems; i += nthreads) {
+    const int q = fastdiv(i, magic);
+    const int c = i - q * tcw;
+    cd *p = s + q * pitch + c;
+    pre.begin(q, c);
+    const cd x0 = pre.edge(0, p), x1 = pre.edge(1, hi + q * pitch + c);
+    const cd *tw = twq + q * RA;
+    cd a[RA];
+    a[0] = cadd(x0, x1);
+    if (TW0) a[0] = cmul(a[0], tw[0]);
+#pragma unroll
+    for (int r = 1; r < RA; ++r) {
+      a[r] = cfma(x1, wedge(r), x0);
+      if (TW0 || q != 0) a[r] = cmul(a[r], tw[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
+  }
+}
+
+// Pass B of ONE butterfly, split at the point where the tile has been read into registers (the pipelined kernels release
+// the tile buffer there, one stage before the epilogue is done).
+template <int N, int RA, int RB> TQ_HD bool fft2_b_load(const cd *s, int pitch, int tcw, int item, cd *a, int *sidx, int *c) {
+  if (item >= RA * tcw) return false;
+  *sidx = fastdiv(item, fastdiv_magic((unsigned)tcw));
+  *c = item - *sidx * tcw;
+  const cd *p = s + *sidx * (RB * pitch) + *c;
+#pragma unroll
+  for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
+  return true;
+}
+template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(cd *a, int sidx, int c, Post &post) {
+  post.begin(sidx, c);
+  Dft<RB, SGN>::run(a);
+  tq_unroll_store<RB>(a, post);
+}
