@@ -311,7 +311,7 @@ def test_g_r_k_exact(ctx):
 
 
 @pytest.mark.parametrize("dims,n_others", [((64, 64, 1), 36), ((4, 3, 5), 7), ((16, 16, 16), 9), ((2, 2, 1), 1), ((7, 1, 11), 3),
-                                           ((256, 256, 1), 18)])
+                                           ((256, 256, 1), 18), ((128, 64, 1), 5), ((64, 64, 64), 3), ((256, 1, 128), 130)])
 def test_lattice_vs_oracle(ctx, dims, n_others):
     """configs[2] shape family: data = complex normal * exp(-|r|_inf / 8), seed 3001."""
     rng = np.random.default_rng(3001)

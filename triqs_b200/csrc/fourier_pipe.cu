@@ -22,49 +22,11 @@
 //   kernel F2: scratch (fixed beta)  -> FFT_Na over a -> + trapezoid correction + tail model   -> G(i w_n), window rows only
 //   kernel I1: G(i w) rows a + Na b (window rows only, others are zero) - tail, / beta -> FFT_Nb -> x w_L^{-a beta} e^{-i pi beta/L} -> scratch
 //   kernel I2: scratch -> FFT_Na -> x e^{-i pi Nb alpha/L} + tail model in tau -> G(tau)
-#include "tq_fft2.cuh"
-
-#include <cuda.h>
+#include "tq_pipe.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-
-// -------------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier + bulk async copies (TMA engine; SASS: UBLKCP / UTMALDG) + proxy fence
-// -------------------------------------------------------------------------------------------------
-TQ_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-TQ_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
-TQ_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-TQ_D void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-TQ_D void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-TQ_D void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-     "{\n"
-     ".reg .pred P1;\n"
-     "LAB_WAIT:\n"
-     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-     "@P1 bra DONE;\n"
-     "bra LAB_WAIT;\n"
-     "DONE:\n"
-     "}\n" ::"r"(smem_u32(bar)),
-     "r"(parity)
-     : "memory");
-}
-TQ_D void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-TQ_D void tma_load_4d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-                  smem_u32(dst_smem)),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-               : "memory");
-}
-TQ_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // -------------------------------------------------------------------------------------------------
 enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
@@ -781,19 +743,6 @@ static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, l
   plans[key] = pl;
   *out = pl;
   return TQ_OK;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
 }
 
 // G(tau) of `nb` gfs as the 4-D tensor [gf][b][a][2 n_cols doubles] (row j = a + Na b); box = one F1 tile [Nb][1][2 tcw]

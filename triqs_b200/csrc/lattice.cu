@@ -72,7 +72,15 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
   }
 }
 
+// lattice_pipe.cu: TMA-pipelined fast path for axis lengths with a compile-time two-pass plan
+tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled);
+
 static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale) {
+  {
+    bool handled = false;
+    TQ_TRY(tq_lattice_pipe_axis(ctx, outer, N, inner, in, out, sign, scale, &handled));
+    if (handled) return TQ_OK;
+  }
   std::shared_ptr<FftPlanHost> fp;
   TQ_TRY(tq_get_fft_plan(ctx, N, &fp));
   const size_t budget = (size_t)ctx->max_smem_optin;

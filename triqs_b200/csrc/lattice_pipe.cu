@@ -1,0 +1,226 @@
+// TMA-pipelined batched DFT along one mesh axis (cyclat <-> brzone, the _fourier_base seam): the fast path of lattice.cu
+// for axis lengths with a compile-time two-pass plan (256 = 16 x 16, 128 = 8 x 16, 64 = 8 x 8).
+//
+// Restates c++/triqs/gfs/transform/fourier_common.cpp:25-45 / fourier_lattice.cpp:30-59 exactly like lattice.cu; only the
+// machine mapping differs.  The array is [outer][N][inner] (inner contiguous).  A tile is [N][TC] adjacent inner columns:
+//   producer warp : ONE 3-D tensor-map TMA load per tile into a ring of three shared-memory buffers (mbarrier complete_tx);
+//   worker warps  : pull 32-butterfly packets (pass A in place, then pass B whose outputs go straight to global memory,
+//                   scaled on the way when this is the last axis of a k -> r transform), same scheduler as fourier_pipe.cu.
+// No thread ever waits on a global load, the FFT of a tile overlaps the loads of the next two, and every global access is a
+// TC*16-byte run.  Bound: HBM (read + write 16 B per element per axis; ~25 FP64 instructions per element).
+#include "tq_pipe.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+constexpr int LP_NBUF = 3;
+
+struct LatPipeArgs {
+  cd *out;
+  const cd *twq; // [RB][RA] pass-A twiddle rows
+  long inner;    // contiguous elements per (outer, n)
+  long n_tiles;  // outer * tiles
+  int tiles;     // column tiles per outer index
+  int TC;
+  double scale;
+};
+
+template <int N, int RA> struct PostLattice {
+  cd *base; // out + o*N*inner + c0
+  long inner;
+  double scale;
+  bool scaled;
+  cd *p;
+  TQ_D void begin(int sidx, int c) { p = base + (long)sidx * inner + c; }
+  template <int TT> TQ_D void store(cd v) const {
+    if (scaled) v = cscale(scale, v);
+    p[(long)(RA * TT) * inner] = v;
+  }
+};
+
+template <int N, int RA, int RB, int SGN, int NW>
+__global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pipe_kernel(const __grid_constant__ LatPipeArgs A,
+                                                                                           const __grid_constant__ CUtensorMap tmap) {
+  constexpr int NT = (NW + 1) * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int TC = A.TC;
+  const size_t buf_stride = (sizeof(cd) * (size_t)N * TC + 127) & ~size_t(127);
+  cd *twS = reinterpret_cast<cd *>(smem_raw + LP_NBUF * buf_stride);
+  uint64_t *full = reinterpret_cast<uint64_t *>(twS + N);
+  uint64_t *adone = full + LP_NBUF;
+  uint64_t *freeb = adone + LP_NBUF;
+  int *next_pk = reinterpret_cast<int *>(freeb + LP_NBUF);
+  volatile int *ready_tile = next_pk + 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pa = (RB * TC + 31) >> 5, pb = (RA * TC + 31) >> 5;
+  for (int i = tid; i < N; i += NT) twS[i] = A.twq[i];
+  if (tid == 0) {
+    for (int b = 0; b < LP_NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      mbar_init(&adone[b], pa);
+      mbar_init(&freeb[b], pb);
+    }
+    *next_pk = 0;
+    *ready_tile = -1;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nloc = (int)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned long long m_tiles = A.tiles > 1 ? ~0ull / (unsigned long long)A.tiles + 1ull : 0ull;
+  auto tile_of = [&](long t, long *o, int *c0) {
+    *o = A.tiles > 1 ? (long)__umul64hi((unsigned long long)t, m_tiles) : t;
+    *c0 = (int)(t - *o * A.tiles) * TC;
+  };
+
+  if (warp == NW) {
+    for (int i = 0; i < nloc; ++i) {
+      const long t = blockIdx.x + (long)i * gridDim.x;
+      const int b = i % LP_NBUF, u = i / LP_NBUF;
+      if (u > 0) mbar_wait(&freeb[b], (uint32_t)((u - 1) & 1));
+      if (lane == 0) {
+        *ready_tile = i;
+        long o;
+        int c0;
+        tile_of(t, &o, &c0);
+        mbar_arrive_expect_tx(&full[b], (uint32_t)(sizeof(cd) * N * TC)); // the whole box; columns past `inner` are zero-filled
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                        smem_u32(smem_raw + b * buf_stride)),
+                     "l"(&tmap), "r"(2 * c0), "r"(0), "r"((int)o), "r"(smem_u32(&full[b]))
+                     : "memory");
+      }
+    }
+  } else {
+    const unsigned m_pa = fastdiv_magic((unsigned)pa), m_pab = fastdiv_magic((unsigned)(pa + pb));
+    const bool scaled = A.scale != 1.0;
+    for (;;) {
+      int pk = 0;
+      if (lane == 0) pk = atomicAdd(next_pk, 1);
+      pk = __shfl_sync(0xffffffffu, pk, 0);
+      int blk, r;
+      bool is_b = false;
+      if (pk < 2 * pa) {
+        blk = fastdiv(pk, m_pa);
+        r = pk - blk * pa;
+      } else {
+        const int q = pk - 2 * pa;
+        blk = fastdiv(q, m_pab);
+        r = q - blk * (pa + pb);
+        blk += 2;
+        is_b = r < pb;
+        if (!is_b) r -= pb;
+      }
+      if (blk >= nloc + 2) break;
+      const int k = is_b ? blk - 2 : blk;
+      if (k >= nloc) continue;
+      const long t = blockIdx.x + (long)k * gridDim.x;
+      const int b = k % LP_NBUF, u = k / LP_NBUF;
+      long o;
+      int c0;
+      tile_of(t, &o, &c0);
+      const int w = (int)min((long)TC, A.inner - c0);
+      cd *tile = reinterpret_cast<cd *>(smem_raw + b * buf_stride);
+      const int it = r * 32 + lane;
+      while (*ready_tile < k) __nanosleep(32); // (see fourier_pipe.cu: never look at a barrier more than one phase ahead)
+      if (!is_b) {
+        mbar_wait(&full[b], (uint32_t)(u & 1));
+        PreIdentity pre;
+        fft2_pass_a<N, RA, RB, SGN, false>(tile, TC, w, twS, it, 1 << 30, pre);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&adone[b]);
+      } else {
+        mbar_wait(&adone[b], (uint32_t)(u & 1));
+        PostLattice<N, RA> post{A.out + (o * N) * A.inner + c0, A.inner, A.scale, scaled, nullptr};
+        fft2_pass_b<N, RA, RB, SGN>(tile, TC, w, it, 1 << 30, post);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&freeb[b]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+struct LatTwiddles {
+  std::map<std::tuple<int, int>, cd *> tw; // (N, sign) -> device [RB][RA]
+  ~LatTwiddles() {
+    for (auto &kv : tw) cudaFree(kv.second);
+  }
+};
+
+template <int N, int RA, int RB, int SGN> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
+  constexpr int NW = 11;
+  const size_t buf_stride = (sizeof(cd) * (size_t)N * A.TC + 127) & ~size_t(127);
+  const size_t smem = LP_NBUF * buf_stride + sizeof(cd) * N + 8 * 3 * LP_NBUF + 16;
+  auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW>;
+  TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
+  {
+    KernelScope ks(ctx, "fft_axis_pipe");
+    k<<<grid, (NW + 1) * 32, smem, ctx->stream>>>(A, tmap);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  return TQ_OK;
+}
+
+template <int N, int RA, int RB>
+static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
+  const size_t budget = (size_t)ctx->max_smem_optin - sizeof(cd) * N - 256;
+  long tc = (long)(budget / LP_NBUF / (sizeof(cd) * N));
+  tc = std::min<long>(std::min<long>(tc, 128), inner);
+  if (tc >= 8) tc &= ~7L; // 128-byte runs
+  if (tc < 1) return TQ_OK;
+  // pointers: TMA needs 16-byte alignment (always true for complex<double> arrays from cudaMalloc / numpy)
+  if (((uintptr_t)in | (uintptr_t)out) & 15) return TQ_OK;
+  if (2 * inner >= (1L << 32) || outer >= (1L << 31)) return TQ_OK;
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return TQ_OK;
+  if (!ctx->lat_tw) ctx->lat_tw = std::make_shared<LatTwiddles>();
+  cd *&twd = ctx->lat_tw->tw[std::make_tuple(N, sign)];
+  if (!twd) {
+    std::vector<cd> w, rows((size_t)N);
+    tq_fft_twiddles_host(N, w);
+    for (int q = 0; q < RB; ++q)
+      for (int s = 0; s < RA; ++s) rows[(size_t)q * RA + s] = sign > 0 ? w[(q * s) % N] : cconj(w[(q * s) % N]);
+    TQ_CUDA(ctx, cudaMalloc(&twd, sizeof(cd) * N));
+    TQ_CUDA(ctx, cudaMemcpyAsync(twd, rows.data(), sizeof(cd) * N, cudaMemcpyHostToDevice, ctx->stream));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  CUtensorMap tmap;
+  cuuint64_t dims[3] = {(cuuint64_t)(2 * inner), (cuuint64_t)N, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)(inner * sizeof(cd)), (cuuint64_t)((long)N * inner * sizeof(cd))};
+  cuuint32_t box[3] = {(cuuint32_t)(2 * tc), (cuuint32_t)N, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled (lattice) failed with CUresult " + std::to_string((int)r));
+  LatPipeArgs A{};
+  A.out = out;
+  A.twq = twd;
+  A.inner = inner;
+  A.TC = (int)tc;
+  A.tiles = (int)((inner + tc - 1) / tc);
+  A.n_tiles = outer * A.tiles;
+  A.scale = scale;
+  if (A.n_tiles >= (1L << 31)) return TQ_OK;
+  if (sign > 0)
+    TQ_TRY((launch_lat<N, RA, RB, 1>(ctx, A, tmap)));
+  else
+    TQ_TRY((launch_lat<N, RA, RB, -1>(ctx, A, tmap)));
+  *handled = true;
+  return TQ_OK;
+}
+
+// DFT along the middle axis of [outer][N][inner]; *handled = false when there is no specialisation for N (caller falls back)
+tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
+  *handled = false;
+  if (getenv("TQ_NO_PIPE")) return TQ_OK;
+  switch (N) {
+    case 256: return run_lat<256, 16, 16>(ctx, outer, inner, in, out, sign, scale, handled);
+    case 128: return run_lat<128, 8, 16>(ctx, outer, inner, in, out, sign, scale, handled);
+    case 64: return run_lat<64, 8, 8>(ctx, outer, inner, in, out, sign, scale, handled);
+    default: return TQ_OK;
+  }
+}

@@ -43,6 +43,7 @@ struct MatsubaraPlan;  // fourier_matsubara.cu
 struct FftPlanHost;    // tq_fft_plan.cu
 struct TailFitterPlan; // tail_fit.cu
 struct PipePlanCache;  // fourier_pipe.cu
+struct LatTwiddles;    // lattice_pipe.cu
 
 struct tq_ctx {
   int device = 0;
@@ -60,6 +61,7 @@ struct tq_ctx {
   std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
   std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
   std::shared_ptr<PipePlanCache> pipe_cache;
+  std::shared_ptr<LatTwiddles> lat_tw;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {

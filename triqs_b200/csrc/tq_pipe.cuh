@@ -1,0 +1,60 @@
+// Shared plumbing of the TMA-pipelined kernels (fourier_pipe.cu, lattice_pipe.cu): PTX wrappers for mbarriers and bulk
+// asynchronous copies, and the driver entry point that encodes tensor maps.
+#pragma once
+#include "tq_fft2.cuh"
+
+#include <cuda.h>
+
+// -------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + bulk async copies (TMA engine; SASS: UBLKCP / UTMALDG) + proxy fence
+// -------------------------------------------------------------------------------------------------
+TQ_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TQ_D void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+TQ_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+TQ_D void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+TQ_D void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+TQ_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+     "{\n"
+     ".reg .pred P1;\n"
+     "LAB_WAIT:\n"
+     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+     "@P1 bra DONE;\n"
+     "bra LAB_WAIT;\n"
+     "DONE:\n"
+     "}\n" ::"r"(smem_u32(bar)),
+     "r"(parity)
+     : "memory");
+}
+TQ_D void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+TQ_D void tma_load_4d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                  smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+               : "memory");
+}
+TQ_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
+// -------------------------------------------------------------------------------------------------
+// host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
