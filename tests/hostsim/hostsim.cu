@@ -96,6 +96,29 @@ template <int N> static void inv_all(long n_pts, cd *a) {
       for (int j = 0; j < N; ++j) a[(size_t)p * N * N + i * N + j] = M[i][j];
   }
 }
+// guarded no-interchange variant: ok[p] tells whether the natural pivots were accepted; rejected matrices are left to the caller
+template <int N> static void inv_all_nopivot(long n_pts, cd *a, int *ok) {
+  for (long p = 0; p < n_pts; ++p) {
+    cd M[N][N];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) M[i][j] = a[(size_t)p * N * N + i * N + j];
+    ok[p] = tq_invert_inplace_nopivot<N>(M) ? 1 : 0;
+    if (ok[p])
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) a[(size_t)p * N * N + i * N + j] = M[i][j];
+  }
+}
+extern "C" int hostsim_invert_nopivot(int n, long n_pts, double *data, int *ok) {
+  cd *a = (cd *)data;
+  switch (n) {
+    case 2: inv_all_nopivot<2>(n_pts, a, ok); break;
+    case 3: inv_all_nopivot<3>(n_pts, a, ok); break;
+    case 5: inv_all_nopivot<5>(n_pts, a, ok); break;
+    case 8: inv_all_nopivot<8>(n_pts, a, ok); break;
+    default: return -1;
+  }
+  return 0;
+}
 extern "C" int hostsim_invert(int n, long n_pts, double *data) {
   cd *a = (cd *)data;
   switch (n) {

@@ -71,3 +71,25 @@ def test_register_inverse(lib, n):
     ref = np.linalg.inv(a)
     err = np.max(np.abs(b - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
     assert np.all(err < 1e-15 * 100 * np.linalg.cond(a))
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8])
+def test_register_inverse_threshold_no_interchange(lib, n):
+    """tq_invert_inplace_nopivot: accepted matrices are inverted to LAPACK accuracy, matrices whose natural pivot is too
+    small are rejected (the kernels then fall back to the partially pivoted routine)."""
+    rng = np.random.default_rng(100 + n)
+    # Dyson-like matrices: (i w + mu) - H - Sigma with a definite anti-Hermitian part
+    h = rng.normal(size=(400, n, n)) + 1j * rng.normal(size=(400, n, n))
+    h = h + h.conj().transpose(0, 2, 1)
+    w = rng.uniform(0.05, 30.0, 400)
+    a = (1j * w + 0.1)[:, None, None] * np.eye(n)[None] - h
+    a[::4, 0, 0] = 0.0       # natural first pivot unusable -> must be rejected
+    b = a.copy()
+    ok = np.zeros(400, dtype=np.int32)
+    assert lib.hostsim_invert_nopivot(n, 400, b.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
+    assert not ok[::4].any()
+    acc = ok.astype(bool)
+    assert acc.sum() > 200
+    ref = np.linalg.inv(a[acc])
+    err = np.max(np.abs(b[acc] - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
+    assert np.all(err < 1e-15 * 200 * np.linalg.cond(a[acc]))

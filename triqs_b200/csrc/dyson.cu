@@ -33,7 +33,13 @@ template <int N> __global__ void __launch_bounds__(128) k_invert_batched(cd *a, 
     for (int i = 0; i < N; ++i)
 #pragma unroll
       for (int j = 0; j < N; ++j) M[i][j] = sm[threadIdx.x * STR + i * N + j];
-    tq_invert_inplace<N>(M);
+    if (!tq_invert_inplace_nopivot<N>(M)) { // natural pivots rejected: redo with partial pivoting
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) M[i][j] = sm[threadIdx.x * STR + i * N + j];
+      tq_invert_inplace<N>(M);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -140,7 +146,16 @@ template <int N> __global__ void __launch_bounds__(128) k_dyson_partial(const cd
         cd ev = __ldg(&e[i * N + j]);
         M[i][j] = cmk(As[2 * (i * N + j)][threadIdx.x] - ev.x, As[2 * (i * N + j) + 1][threadIdx.x] - ev.y);
       }
-    tq_invert_inplace<N>(M);
+    if (!tq_invert_inplace_nopivot<N>(M)) { // natural pivots rejected (rare): redo this matrix with partial pivoting
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          cd ev = __ldg(&e[i * N + j]);
+          M[i][j] = cmk(As[2 * (i * N + j)][threadIdx.x] - ev.x, As[2 * (i * N + j) + 1][threadIdx.x] - ev.y);
+        }
+      tq_invert_inplace<N>(M);
+    }
     const double wk = weights ? __ldg(&weights[k]) : uniform_weight;
 #pragma unroll
     for (int i = 0; i < N; ++i)

@@ -880,9 +880,11 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   A.in_gf_stride = in_rows * n_cols;
   A.out_gf_stride = out_rows * n_cols;
   A.scratch_gf_stride = L * n_cols;
-  // chunk the batch so that the scratch of one chunk stays L2 resident between the two kernels
+  // Chunk the batch by scratch size.  Measured on B200 (tools/gpu_probe.py c2): keeping the scratch L2 resident (chunks of
+  // <= 3 blocks = 120 MB) costs more in per-launch prologue / pipeline fill and drain than it saves in HBM traffic while the
+  // kernels are FP64-bound, so the default is one launch pair per 1.5 GB of scratch.
   const size_t per_gf = (size_t)L * n_cols * sizeof(cd);
-  size_t l2_budget = 128ull << 20;
+  size_t l2_budget = 1536ull << 20;
   if (const char *e = getenv("TQ_TWOPASS_CHUNK_MB")) l2_budget = (size_t)atol(e) << 20;
   long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
   chunk = std::min<long>(std::min<long>(chunk, batch), 1L << 18); // (keeps the tile count of a launch below 2^31)

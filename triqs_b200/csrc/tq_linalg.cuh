@@ -61,3 +61,37 @@ template <int N> TQ_HD void tq_invert_inplace(cd (&M)[N][N]) {
     }
   }
 }
+
+// Gauss-Jordan WITHOUT row interchanges, guarded by threshold pivoting: step p keeps the natural pivot only if
+// |a_pp|^2 >= TQ_PIVOT_TAU max_i |a_ip|^2 (element growth <= 1/sqrt(TAU) per step, like partial pivoting with a relaxed
+// choice).  Returns false -- with M destroyed -- as soon as a pivot fails the test (or is 0 / NaN); the caller then redoes
+// the matrix with tq_invert_inplace.  For the Dyson matrices (i w + mu) - eps_k - Sigma(i w) the anti-Hermitian part is
+// definite, the natural pivots are essentially always accepted, and the ~800 predicated register moves of the pivoted
+// version (more instructions than its floating-point work) disappear from the hot loop.
+#define TQ_PIVOT_TAU 0.015625
+template <int N> TQ_HD bool tq_invert_inplace_nopivot(cd (&M)[N][N]) {
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < N; ++p) {
+    const cd d = M[p][p];
+    const double d2 = cabs2(d);
+    double mx = 0.0;
+#pragma unroll
+    for (int i = p + 1; i < N; ++i) mx = fmax(mx, cabs2(M[i][p]));
+    ok = ok && (d2 >= TQ_PIVOT_TAU * mx) && (d2 > 0.0);
+    const double inv = 1.0 / d2;
+    const cd ip = cmk(d.x * inv, -d.y * inv);
+    M[p][p] = cmk(1.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) M[p][j] = cmul(M[p][j], ip);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i == p) continue;
+      const cd f = M[i][p];
+      M[i][p] = cmk(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) M[i][j] = cfma(cneg(f), M[p][j], M[i][j]);
+    }
+  }
+  return ok;
+}
