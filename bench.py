@@ -327,6 +327,12 @@ def run_extras(ctx, stream, dev, world, rank, timed_fn):
     out = {}
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
+    timed_raw = timed_fn
+
+    def timed_fn(fn, steps):  # noqa: F811  (one untimed call first: plan creation, table uploads, attribute calls)
+        fn()
+        return timed_raw(fn, steps)
+
     def guard(name, fn):
         try:
             fn()
