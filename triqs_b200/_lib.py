@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_long, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtqgpu.so")
+LIB_PATH = os.environ.get("TQ_LIB_PATH", os.path.join(_HERE, "libtqgpu.so"))  # (override: A/B builds of the kernels)
 
 TQ_OK = 0
 TQ_ERR_CUDA, TQ_ERR_INVALID, TQ_ERR_RUNTIME, TQ_ERR_UNSUPPORTED, TQ_ERR_NO_DEVICE, TQ_ERR_COMM = -1, -2, -3, -4, -5, -6
