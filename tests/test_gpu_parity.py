@@ -183,6 +183,32 @@ def test_long_mesh_pipelined_variants(ctx, stat, ncols, n_iw):
         assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
 
 
+def test_long_mesh_chunked_launches_and_wide_targets(ctx, monkeypatch):
+    """Pipelined path with the batch split over several launch pairs (scratch budget below one batch) and with more
+    target columns than one column tile holds (70 columns -> 5 ragged tiles in pass 1, more in pass 2)."""
+    monkeypatch.setenv("TQ_TWOPASS_CHUNK_MB", "120")  # 70 columns x 1e5 x 16 B = 112 MB per gf -> one gf per launch pair
+    beta, n_tau, n_iw, ncols, stat = 25.0, 100001, 10000, 70, F
+    rng = np.random.default_rng(77)
+    iw = O.imfreq_values(beta, stat, n_iw)
+    gws = []
+    for b in range(3):
+        E = rng.uniform(0.3, 2.0, (2, ncols)) * rng.choice([-1, 1], (2, ncols))
+        r = rng.normal(size=(2, ncols)) + 1j * rng.normal(size=(2, ncols))
+        gws.append(sum(r[p][None, :] / (iw[:, None] - E[p][None, :]) for p in range(2)))
+    gws = np.stack(gws)
+    refs, tails = [], []
+    for b in range(3):
+        rt, info = O.fourier_iw_to_tau(gws[b], beta, stat, n_tau, return_info=True)
+        refs.append(rt)
+        tails.append(info["tail"])
+    gt = ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=np.stack(tails))
+    for b in range(3):
+        assert rel(gt[b], refs[b]) < TOL
+    gw2 = ctx.fourier_tau_to_iw(np.stack(refs), beta, stat, n_iw)
+    for b in range(3):
+        assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
+
+
 def test_tau_to_iw_known_moments_and_noise_warning(ctx):
     import triqs_b200
     beta, n_tau, n_iw = 10.0, 1201, 200
