@@ -388,7 +388,17 @@ def run_extras(ctx, stream, dev, world, rank, timed_fn):
         ms = timed_fn(lambda: ctx.interp_tau(table, 10.0, taus, out=o), 3) / 3
         out["c5_interp_2.5e7pts_5x5_block"] = {"ms": ms, "points_per_s": world * npts / (ms * 1e-3), "GBps_per_gpu": npts * 408.0 / (ms * 1e-3) / 1e9}
 
-    for name, fn in (("c1", c1), ("c3", c3), ("c4", c4), ("c5", c5)):
+    def dens():
+        # density of 32 blocks of G(i w) [20000][5][5] with known moments (HBM-bound streaming reduction)
+        nb, nw, n = 32, 20000, 5
+        gw = torch.randn(nb, nw, n, n, dtype=torch.complex128, device=dev, generator=g) * 1e-3
+        mom = torch.zeros(nb, 4, n, n, dtype=torch.complex128, device=dev)
+        mom[:, 1] = torch.eye(n, dtype=torch.complex128, device=dev)
+        o = torch.empty(nb, n, n, dtype=torch.complex128, device=dev)
+        ms = timed_fn(lambda: ctx.density(gw, 100.0, F, moments=mom, out=o), 5) / 5
+        out["density_32blocks_20000iw_5x5"] = {"ms": ms, "points_per_s": world * nb * nw / (ms * 1e-3), "GBps_per_gpu": nb * nw * n * n * 16.0 / (ms * 1e-3) / 1e9}
+
+    for name, fn in (("c1", c1), ("c3", c3), ("c4", c4), ("c5", c5), ("density", dens)):
         guard(name, fn)
         torch.cuda.empty_cache()
     return out

@@ -100,6 +100,15 @@ tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_i
                                const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
                                double *tail_err);
 
+/* density(G(i w)) of matrix-valued gfs on the full Matsubara mesh -- replaces
+ *   nda::matrix<dcomplex> density(gf_const_view<imfreq> g, array_const_view<dcomplex, 3> known_moments)
+ *     c++/triqs/gfs/functions/density.cpp:32-120   (scalar overload :123-128)
+ * gw [batch][n_w][n][n]; moments [batch][n_moments][n][n] or NULL (then / with fewer than 4 rows the tail is fitted like
+ * fit_tail, :40,:47); out [batch][n][n] (upper triangle summed, lower = conjugate, :115).  tail_err[batch] / warn[batch] may
+ * be NULL.  Errors as the reference throws them: non-vanishing 0th moment, tail error > 1e-2, fewer than 3 fitted moments. */
+tq_status tq_density(tq_ctx *ctx, double beta, int statistic, long n_iw, int n, long batch, const tq_complex *gw,
+                     const tq_complex *moments, int n_moments, tq_complex *out, int *warn, double *tail_err);
+
 /* ---- least-squares tail fit ------------------------------------------------------------------ */
 
 /* Replaces  tail_fitter::fit<0, hermitian>(mesh, g_data, normalize=true, known_moments, inner_matrix_dim)

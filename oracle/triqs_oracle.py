@@ -453,6 +453,57 @@ def tail_eval(moments: np.ndarray, om: complex) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# density  (the immediate consumer of G_loc in a DMFT loop)
+# ----------------------------------------------------------------------------------------------
+
+
+def density(gw: np.ndarray, beta: float, stat: int, known_moments: np.ndarray | None = None, return_info: bool = False):
+    """n = -xi [ (1/beta) sum_n (G(i w_n) - tail model) + m1 + sum_i F(a_i, b_i) ] for a matrix-valued gf on the FULL
+    Matsubara mesh.  gw [n_w, n, n]; known_moments [n_mom, n, n] or None.  c++/triqs/gfs/functions/density.cpp:32-120:
+    only the upper triangle is summed, the lower one is its conjugate (:115); moments are fitted with fit_tail when
+    fewer than four are known (:47-58)."""
+    gw = np.asarray(gw, dtype=np.complex128)
+    n_w, n1, n2 = gw.shape
+    info = {"tail_err": 0.0, "warn": 0}
+    if known_moments is None or np.size(known_moments) == 0:
+        known_moments = np.zeros((1, n1, n2), dtype=np.complex128)  # make_zero_tail(g, 1)   :40
+    km = np.asarray(known_moments, dtype=np.complex128)
+    a0 = float(np.max(np.abs(km[0])))
+    if not a0 < 1e-8:
+        raise TriqsRuntimeError("ERROR: Density implementation requires vanishing 0th moment\n  error is :%f\n" % a0)  # :42-44
+    if km.shape[0] < 4:
+        tail, err = fit_tail(gw.reshape(n_w, n1 * n2), beta, stat, km.reshape(km.shape[0], n1 * n2))  # :47
+        info["tail_err"] = err
+        if not err < 1e-2:
+            raise TriqsRuntimeError("ERROR: High frequency moments have an error greater than 1e-2.\n  Error = %f\n" % err)
+        if err > 1e-4:
+            info["warn"] |= WARN_TAIL_ERR
+        if not tail.shape[0] > 3:
+            raise TriqsRuntimeError("ERROR: Density implementation requires at least a proper 3rd high-frequency moment\n")
+        km = tail.reshape(tail.shape[0], n1, n2)
+    m1, m2, m3 = km[1], km[2], km[3]
+    if stat == FERMION:  # :70-79
+        xi, b = -1.0, (0.0, 1.0, -1.0)
+        a = (m1 - m3, (m2 + m3) / 2, (m3 - m2) / 2)  # :98-101
+    else:
+        xi, b = 1.0, (-1.0, 1.0, 0.5)
+        a = (m1 / 6.0 - m2 / 2.0 + m3 / 3.0, -m1 / 2.0 + m2 / 2.0 + m3, 4.0 * m1 / 3.0 - 4.0 * m3 / 3.0)  # :102-105
+    n_iw = n_w // 2 if stat == FERMION else (n_w + 1) // 2
+    iw = imfreq_values(beta, stat, n_iw)
+    res = np.zeros((n1, n2), dtype=np.complex128)
+    F = lambda amp, bb: xi * amp / (-xi + math.exp(-beta * bb))  # :84
+    model = sum(a[i][None, :, :] / (iw[:, None, None] - b[i]) for i in range(3))
+    r = np.sum(gw - model, axis=0)  # :110
+    full = (r / beta + m1 + F(a[0], b[0]) + F(a[1], b[1]) + F(a[2], b[2])) * (-xi)  # :111-112
+    for i in range(n1):
+        for j in range(i, n2):
+            res[i, j] = full[i, j]
+            if j > i:
+                res[j, i] = np.conj(full[i, j])  # :115
+    return (res, info) if return_info else res
+
+
+# ----------------------------------------------------------------------------------------------
 # lattice transforms
 # ----------------------------------------------------------------------------------------------
 

@@ -153,7 +153,24 @@ void test_eval_and_inverse() { // meshes/eval.cpp:62-89, gf_inverse.cpp
   for (long i = 0; i < m.mesh().size(); ++i) EXPECT(std::abs(mi[i][0] - 1.0 / (m.mesh()[i] - 0.3)) < 1e-14);
 }
 
+void test_density() { // gf_density.cpp:22-55, gf_base.cpp:69
+  gf<mesh::imfreq, scalar_valued> g{{1.0, Fermion, 400}};
+  for (long i = 0; i < g.mesh().size(); ++i) g[i][0] = 1.0 / (g.mesh()[i] + 2.3);
+  EXPECT(std::abs(density(g) - 1.0 / (1.0 + std::exp(-2.3))) < 1e-9);
+  gf<mesh::imfreq, scalar_valued> gb{{1.0, Boson, 400}};
+  for (long i = 0; i < gb.mesh().size(); ++i) gb[i][0] = 1.0 / (gb.mesh()[i] - 2.3);
+  EXPECT(std::abs(density(gb) - 1.0 / (-1.0 + std::exp(2.3))) < 1e-9);
+  gf<mesh::imfreq, matrix_valued> g3{{1.0, Fermion, 100}, {2, 2}};
+  for (long i = 0; i < g3.mesh().size(); ++i) {
+    g3[i][0] = g3[i][3] = 2.0 / (g3.mesh()[i] + 2.3);
+    g3[i][1] = g3[i][2] = 0.0;
+  }
+  auto n = density(g3);
+  EXPECT(std::abs(n[0] - 1.8177540779781256) < 1e-7 && std::abs(n[3] - 1.8177540779781256) < 1e-7 && std::abs(n[1]) < 1e-12);
+}
+
 int main() {
+  test_density();
   test_fourier<scalar_valued>(Fermion, {});
   test_fourier<matrix_valued>(Fermion, {2, 2});
   test_fourier<tensor_valued<3>>(Fermion, {2, 2, 2});

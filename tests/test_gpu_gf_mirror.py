@@ -81,3 +81,23 @@ def test_dyson_k_sum_sharded_on_one_gpu():
         parts.append(G.dyson_k_sum(ctx, eps, sigma, 0.2, rank=r, n_ranks=4, reduce_fn=lambda p: p).data)
     assert np.max(np.abs(sum(parts) - ref)) / np.max(np.abs(ref)) < 1e-12
     ctx.close()
+
+
+def test_density_of_local_gf():
+    """density(G_loc) after a Dyson k-sum, the DMFT-loop use of the two together (lattice_utils.py:155-166 pattern)."""
+    import triqs_b200
+    from triqs_b200 import gf as G
+    ctx = triqs_b200.Context(0, print_warnings=False)
+    rng = np.random.default_rng(8)
+    n, beta, n_iw = 3, 10.0, 300
+    eps = rng.normal(size=(64, n, n)) + 1j * rng.normal(size=(64, n, n))
+    eps = 0.3 * (eps + eps.conj().transpose(0, 2, 1))
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    sig = np.stack([0.1 * np.eye(n) / (w - 0.4) for w in iw])
+    sigma = G.Gf(G.MeshImFreq(beta, O.FERMION, n_iw), (n, n), sig, ctx=ctx)
+    gloc = G.dyson_k_sum(ctx, eps, sigma, 0.1, weights=np.full(64, 1 / 64), reduce_fn=lambda p: p)
+    dens = G.density(gloc)
+    ref = O.density(O.dyson_ksum(eps, sig, beta, O.FERMION, 0.1, weights=np.full(64, 1 / 64)), beta, O.FERMION)
+    assert np.max(np.abs(dens - ref)) < 1e-9
+    assert 0.0 < dens.trace().real < n
+    ctx.close()

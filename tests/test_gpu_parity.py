@@ -463,3 +463,52 @@ def test_device_pointers_same_result(ctx):
     dev = ctx.fourier_tau_to_iw(torch.from_numpy(gts).cuda(), 10.0, F, 1025)
     assert dev.is_cuda
     assert np.array_equal(dev.cpu().numpy(), host)
+
+
+# ---------------------------------------------------------------------------------------------
+# density
+# ---------------------------------------------------------------------------------------------
+def test_density_reference_known_answers(ctx):
+    """test/c++/gfs/gf_density.cpp:22-72 and gf_base.cpp:69 through the C ABI."""
+    beta, n_iw = 1.0, 400
+    iw = O.imfreq_values(beta, F, n_iw)
+    g = (1 / (iw + 2.3)).reshape(1, -1, 1, 1)
+    assert abs(ctx.density(g, beta, F)[0, 0, 0] - 1 / (1 + math.exp(-beta * 2.3))) < 1e-9
+    iwb = O.imfreq_values(beta, B, n_iw)
+    gb = (1 / (iwb - 2.3)).reshape(1, -1, 1, 1)
+    assert abs(ctx.density(gb, beta, B)[0, 0, 0] - 1 / (-1 + math.exp(beta * 2.3))) < 1e-9
+    iw3 = O.imfreq_values(1.0, F, 100)
+    g3 = np.zeros((1, 200, 2, 2), complex)
+    g3[0, :, 0, 0] = g3[0, :, 1, 1] = 2 / (iw3 + 2.3)
+    assert np.max(np.abs(ctx.density(g3, 1.0, F)[0] - np.diag([1.8177540779781256] * 2))) < 1e-7
+    import triqs_b200
+    with pytest.raises(triqs_b200.TriqsRuntimeError):  # gf_density.cpp:66-72
+        ctx.density(np.ones((1, 800, 1, 1), complex), beta, F)
+    with pytest.raises(triqs_b200.TriqsRuntimeError):
+        ctx.density(iw.reshape(1, -1, 1, 1).copy(), beta, F)
+
+
+@pytest.mark.parametrize("stat,n,n_iw", [(F, 5, 1025), (B, 3, 700), (F, 1, 10000), (F, 8, 300)])
+def test_density_vs_oracle(ctx, stat, n, n_iw):
+    """Batch of matrix-valued gfs (not Hermitian on purpose: only the upper triangle may be used), fitted and known tails."""
+    rng = np.random.default_rng(100 * n + stat)
+    beta = 12.0
+    iw = O.imfreq_values(beta, stat, n_iw)
+    gs, kms = [], []
+    for b in range(3):
+        E = rng.uniform(0.4, 2.0, (2, n, n)) * rng.choice([-1, 1], (2, n, n)) if stat == F else rng.uniform(0.4, 2.0, (2, n, n))
+        r = rng.normal(size=(2, n, n)) + 1j * rng.normal(size=(2, n, n))
+        gs.append(sum(r[p][None] / (iw[:, None, None] - E[p][None]) for p in range(2)))
+        kms.append(np.stack([np.zeros((n, n)), r.sum(0), (r * E).sum(0), (r * E * E).sum(0)]))
+    gs, kms = np.stack(gs), np.stack(kms)
+    out = ctx.density(gs, beta, stat)
+    out_km = ctx.density(gs, beta, stat, moments=kms)
+    out_k2 = ctx.density(gs, beta, stat, moments=kms[:, :2])
+    for b in range(3):
+        ref_km = O.density(gs[b], beta, stat, kms[b])
+        assert rel(out_km[b], ref_km) < TOL
+        # fitted tails: the transform is pinned to 1e-12 above, the LSQ moments to cond * eps (see DESIGN.md section 4)
+        assert rel(out[b], O.density(gs[b], beta, stat)) < 1e-9
+        assert rel(out_k2[b], O.density(gs[b], beta, stat, kms[b][:2])) < 1e-9
+        iu = np.triu_indices(n, 1)
+        assert np.array_equal(out_km[b].T[iu], out_km[b][iu].conj())  # lower triangle = conjugate of the upper one (:115)

@@ -218,3 +218,45 @@ def test_slice_bounds_matches_mpi_rule():
     n, size = 11, 4
     pieces = [O.slice_bounds(n, size, r) for r in range(size)]
     assert pieces == [(0, 3), (3, 6), (6, 9), (9, 11)]
+
+
+# ---------------------------------------------------------------------------------------------
+# density  (test/c++/gfs/gf_density.cpp:22-72, gf_base.cpp:55-69)
+# ---------------------------------------------------------------------------------------------
+def test_density_reference_known_answers():
+    beta, n_iw = 1.0, 400
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    g = (1 / (iw + 2.3)).reshape(-1, 1, 1)
+    assert abs(O.density(g, beta, O.FERMION)[0, 0] - 1 / (1 + math.exp(-beta * 2.3))) < 1e-9  # gf_density.cpp:35
+    iwb = O.imfreq_values(beta, O.BOSON, n_iw)
+    gb = (1 / (iwb - 2.3)).reshape(-1, 1, 1)
+    assert abs(O.density(gb, beta, O.BOSON)[0, 0] - 1 / (-1 + math.exp(beta * 2.3))) < 1e-9  # gf_density.cpp:53
+    # gf_base.cpp:40-69: G3 = 2 / (iw + 2.3) on a 2x2 diagonal target, beta = 1, 100 frequencies
+    iw3 = O.imfreq_values(1.0, O.FERMION, 100)
+    g3 = np.zeros((200, 2, 2), complex)
+    g3[:, 0, 0] = g3[:, 1, 1] = 2 / (iw3 + 2.3)
+    n = O.density(g3, 1.0, O.FERMION)
+    assert np.max(np.abs(n - np.diag([1.8177540779781256] * 2))) < 1e-7
+    # gf_density.cpp:66-72: a constant / a linear function have no usable tail -> runtime_error
+    with pytest.raises(O.TriqsRuntimeError):
+        O.density(np.ones((800, 1, 1), complex), beta, O.FERMION)
+    with pytest.raises(O.TriqsRuntimeError):
+        O.density(iw.reshape(-1, 1, 1).copy(), beta, O.FERMION)
+
+
+def test_density_matrix_hermitian_and_known_moments():
+    """(iw - H)^-1 with Hermitian H: n = f(H) (Fermi function of the matrix); supplying exact moments changes nothing."""
+    rng = np.random.default_rng(5)
+    beta, n_iw, n = 8.0, 600, 3
+    a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    H = (a + a.conj().T) / 2
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(n) - H)
+    w, v = np.linalg.eigh(H)
+    exact = (v * (1 / (1 + np.exp(beta * w)))) @ v.conj().T
+    d = O.density(g, beta, O.FERMION)
+    # the reference returns G(tau = 0^-) = <c^dag_j c_i>, the transpose of f(H)_ij ... for Hermitian H: conj
+    assert np.max(np.abs(d - exact)) < 2e-6 or np.max(np.abs(d - exact.conj())) < 2e-6
+    km = np.stack([np.zeros((n, n)), np.eye(n), H, H @ H]).astype(complex)
+    d2 = O.density(g, beta, O.FERMION, km)
+    assert np.max(np.abs(d2 - d)) < 2e-6

@@ -181,6 +181,29 @@ class Context:
             return gt, np.frombuffer(err, dtype=np.float64).copy()
         return gt
 
+    # -- density ---------------------------------------------------------------------------------
+    def density(self, gw, beta, statistic, moments=None, out=None, return_err=False):
+        """gw [batch, n_w, n, n] (full mesh) -> n [batch, n, n]  (tq_density; density.cpp:32-120)."""
+        gw = _as_c128(gw)
+        batch, n_w, n, n2 = gw.shape
+        if n != n2:
+            raise TriqsRuntimeError("density: the target must be square")
+        if (statistic == FERMION) == bool(n_w % 2):
+            raise TriqsRuntimeError("density is only implemented for g(i omega_n) with full mesh (positive and negative frequencies)")
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        n_mom = 0
+        if moments is not None:
+            moments = _as_c128(moments)
+            n_mom = moments.shape[1]
+        res = out if out is not None else _empty_like_kind(gw, (batch, n, n))
+        warn = (ctypes.c_int * batch)()
+        err = (ctypes.c_double * batch)()
+        self._check(self._lib.tq_density(self._h, beta, statistic, n_iw, n, batch, _ptr(gw), _ptr(moments), n_mom, _ptr(res), warn, err))
+        self._emit(np.frombuffer(warn, dtype=np.int32))
+        if return_err:
+            return res, np.frombuffer(err, dtype=np.float64).copy()
+        return res
+
     # -- tail fit ----------------------------------------------------------------------------
     def fit_tail(self, g, beta, statistic, known_moments=None, hermitian=False, inner_dim=1, tail_fraction=0.2, n_tail_max=30,
                  expansion_order=None):

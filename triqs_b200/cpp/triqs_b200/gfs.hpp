@@ -390,6 +390,26 @@ namespace triqs_b200 {
   }
 
   // ------------------------------------------------------------------------------------------------
+  // density  (c++/triqs/gfs/functions/density.cpp:32-128): n x n matrix of a matrix-valued gf, the scalar for a scalar-valued one
+  // ------------------------------------------------------------------------------------------------
+  inline std::vector<dcomplex> density(gf<mesh::imfreq, matrix_valued> const &g, moment_array const &known_moments = {}) {
+    auto const &ts = g.target_shape();
+    if (ts[0] != ts[1]) throw runtime_error("density: target is not square");
+    std::vector<dcomplex> res(size_t(ts[0] * ts[1]));
+    check(tq_density(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), (int)ts[0], 1, detail::cptr(g.data()),
+                     known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v), (int)known_moments.n_rows, detail::ptr(res), nullptr,
+                     nullptr));
+    return res;
+  }
+  inline dcomplex density(gf<mesh::imfreq, scalar_valued> const &g, moment_array const &known_moments = {}) {
+    std::vector<dcomplex> res(1);
+    check(tq_density(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), 1, 1, detail::cptr(g.data()),
+                     known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v), (int)known_moments.n_rows, detail::ptr(res), nullptr,
+                     nullptr));
+    return res[0];
+  }
+
+  // ------------------------------------------------------------------------------------------------
   // inverse  (functions2.hpp:197-209)
   // ------------------------------------------------------------------------------------------------
   template <typename M> void invert_in_place(gf<M, matrix_valued> &g) {

@@ -949,3 +949,201 @@ extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statisti
   TQ_TRY(tq_stage_out_finish(ctx, gt, out_bytes, d_out, out_host));
   return TQ_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// density(G(i w))   c++/triqs/gfs/functions/density.cpp:32-120        (the consumer of G_loc in a DMFT loop)
+//   n = -xi [ (1/beta) sum_n (G(i w_n) - sum_i a_i / (i w_n - b_i)) + m1 + sum_i F(a_i, b_i) ],  F = xi a / (-xi + e^{-beta b})
+// One streaming pass over G(i w): k_density_partial sums row chunks (the per-row factors 1/(i w - b_i) are computed once per
+// row into shared memory and shared by all columns), k_density_final adds the chunks in fixed order (deterministic),
+// applies the closed-form tail terms and mirrors the upper triangle (:115).  Bound: HBM read, 16 B per element.
+// -------------------------------------------------------------------------------------------------
+struct DensityPoles {
+  double b[3], xi;
+};
+TQ_HD void density_amplitudes(int stat, cd m1, cd m2, cd m3, cd a[3]) {
+  if (stat == TQ_FERMION) { // :98-101
+    a[0] = csub(m1, m3);
+    a[1] = cscale(0.5, cadd(m2, m3));
+    a[2] = cscale(0.5, csub(m3, m2));
+  } else { // :102-105
+    a[0] = cadd(csub(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
+    a[1] = cadd(cadd(cscale(-0.5, m1), cscale(0.5, m2)), m3);
+    a[2] = csub(cscale(4.0 / 3.0, m1), cscale(4.0 / 3.0, m3));
+  }
+}
+constexpr int DENS_ROWS = 256; // rows per chunk = threads per CTA
+
+__global__ void __launch_bounds__(DENS_ROWS) k_density_partial(const cd *__restrict__ g, long g_gf_stride, int n_w, int n_cols,
+                                                               const cd *__restrict__ mom, long mom_gf_stride, double beta, int stat, int first,
+                                                               DensityPoles P, cd *__restrict__ partial /* [batch][chunks][n_cols] */) {
+  __shared__ cd kap[DENS_ROWS][3];
+  extern __shared__ double2 red[]; // [row lanes][n_cols]
+  const int gf = blockIdx.y, chunk = blockIdx.x;
+  const int r0 = chunk * DENS_ROWS;
+  const int nr = min(DENS_ROWS, n_w - r0);
+  {
+    const int r = threadIdx.x;
+    if (r < nr) {
+      const double w = M_PI * (double)(2 * (long)(first + r0 + r) + stat) / beta; // matsubara.hpp:55
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { // 1 / (i w - b) = (-b - i w) / (b^2 + w^2)
+        const double inv = 1.0 / (P.b[i] * P.b[i] + w * w);
+        kap[r][i] = cmk(-P.b[i] * inv, -w * inv);
+      }
+    }
+  }
+  __syncthreads();
+  const int cl = min(n_cols, DENS_ROWS);        // column lanes
+  const int rl = DENS_ROWS / cl;                // row lanes
+  const int c_lane = threadIdx.x % cl, r_lane = threadIdx.x / cl;
+  const cd *gg = g + (size_t)gf * g_gf_stride + (size_t)r0 * n_cols;
+  const cd *mm = mom + (size_t)gf * mom_gf_stride;
+  for (int c = c_lane; c < n_cols; c += cl) {
+    cd acc = cmk(0.0, 0.0);
+    if (r_lane < rl) {
+      cd a[3];
+      density_amplitudes(stat, mm[(size_t)1 * n_cols + c], mm[(size_t)2 * n_cols + c], mm[(size_t)3 * n_cols + c], a);
+      for (int r = r_lane; r < nr; r += rl) {
+        cd v = gg[(size_t)r * n_cols + c];
+        v = csub(v, cmul(a[0], kap[r][0]));
+        v = csub(v, cmul(a[1], kap[r][1]));
+        v = csub(v, cmul(a[2], kap[r][2]));
+        acc = cadd(acc, v);
+      }
+      red[r_lane * n_cols + c] = acc;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_cols; c += DENS_ROWS) {
+    cd s = cmk(0.0, 0.0);
+    for (int l = 0; l < rl; ++l) s = cadd(s, red[l * n_cols + c]);
+    partial[((size_t)gf * gridDim.x + chunk) * n_cols + c] = s;
+  }
+}
+
+__global__ void k_density_final(const cd *__restrict__ partial, int n_chunks, int n, const cd *__restrict__ mom, long mom_gf_stride, double beta,
+                                int stat, DensityPoles P, long total /* batch * n * n */, cd *__restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int nn = n * n;
+  const long gf = i / nn;
+  const int c = (int)(i - gf * nn);
+  const int n1 = c / n, n2 = c - n1 * n;
+  if (n2 < n1) return; // :89 only the upper triangle is summed
+  cd r = cmk(0.0, 0.0);
+  for (int k = 0; k < n_chunks; ++k) r = cadd(r, partial[((size_t)gf * n_chunks + k) * nn + c]);
+  const cd *mm = mom + (size_t)gf * mom_gf_stride;
+  const cd m1 = mm[(size_t)1 * nn + c];
+  cd a[3];
+  density_amplitudes(stat, m1, mm[(size_t)2 * nn + c], mm[(size_t)3 * nn + c], a);
+  cd res = cadd(cscale(1.0 / beta, r), m1);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) res = cadd(res, cscale(P.xi / (-P.xi + exp(-beta * P.b[k])), a[k])); // F(a, b)  :84
+  res = cscale(-P.xi, res); // :112
+  out[(size_t)gf * nn + n1 * n + n2] = res;
+  if (n2 > n1) out[(size_t)gf * nn + n2 * n + n1] = cconj(res); // :115
+}
+
+extern "C" tq_status tq_density(tq_ctx *ctx, double beta, int statistic, long n_iw, int n, long batch, const tq_complex *gw,
+                                const tq_complex *moments, int n_moments, tq_complex *out, int *warn, double *tail_err) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!gw || !out || n_iw < 1 || n < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_density: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long n_cols = (long)n * n;
+  const long last = n_iw - 1, first = -(last + (statistic == TQ_FERMION ? 1 : 0));
+  const long n_w = last - first + 1;
+  const size_t in_bytes = sizeof(cd) * (size_t)batch * n_w * n_cols, out_bytes = sizeof(cd) * (size_t)batch * n_cols;
+  const void *d_in = nullptr, *d_known = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, gw, in_bytes, ctx->stage_in, &d_in));
+  const bool have_moments = moments != nullptr && n_moments > 0;
+  if (have_moments) TQ_TRY(tq_stage_in(ctx, moments, sizeof(cd) * (size_t)batch * n_moments * n_cols, ctx->stage_in2, &d_known));
+  const int n_chunks = (int)((n_w + DENS_ROWS - 1) / DENS_ROWS);
+  // small buffer: moments [batch][TQ_MAX_MOMENTS][n_cols], err double[batch], status, zero known moment, partial sums
+  const size_t mom_bytes = sizeof(cd) * (size_t)batch * TQ_MAX_MOMENTS * n_cols;
+  const size_t err_off = (mom_bytes + 255) & ~size_t(255);
+  const size_t st_off = (err_off + sizeof(double) * batch + 255) & ~size_t(255);
+  const size_t zk_off = (st_off + sizeof(StatusWords) + 255) & ~size_t(255);
+  const size_t part_off = (zk_off + sizeof(cd) * (size_t)batch * n_cols + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->small, part_off + sizeof(cd) * (size_t)batch * n_chunks * n_cols));
+  cd *d_mom = (cd *)ctx->small.p;
+  double *d_err = (double *)((char *)ctx->small.p + err_off);
+  StatusWords *d_st = (StatusWords *)((char *)ctx->small.p + st_off);
+  cd *d_zero_known = (cd *)((char *)ctx->small.p + zk_off);
+  cd *d_part = (cd *)((char *)ctx->small.p + part_off);
+  TQ_CUDA(ctx, cudaMemsetAsync(d_err, 0, part_off - err_off, ctx->stream));
+  int mom_rows = 0;
+  bool fitted = false;
+  const long total = batch * n_cols;
+  if (have_moments && n_moments >= 4) {
+    k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_cols, total, d_mom,
+                                                                                        &d_st->max_m0_bits);
+    tq_count_launch(ctx);
+    mom_rows = 4;
+  } else {
+    // :40 no moments -> make_zero_tail(g, 1);  :47 fewer than 4 -> fit_tail(g, known_moments)
+    const cd *kn = have_moments ? (const cd *)d_known : d_zero_known;
+    const int nk = have_moments ? n_moments : 1;
+    if (have_moments) { // the 0th-moment assertion (:42-44) is made on the user's moments before the fit
+      TQ_TRY(tq_reserve(ctx, ctx->stage_in3, sizeof(cd) * (size_t)batch * 4 * n_cols));
+      k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)n_cols, total,
+                                                                                          (cd *)ctx->stage_in3.p, &d_st->max_m0_bits);
+      tq_count_launch(ctx);
+    }
+    tq_status st = tq_fit_tail_device(ctx, beta, statistic, n_iw, 0.2, 30, -1, 0, 1, n_cols, batch, (const cd *)d_in, kn, nk, d_mom, &mom_rows, d_err);
+    if (st != TQ_OK) return st;
+    fitted = true;
+    if (!(mom_rows > 3)) // :57
+      return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR: Density implementation requires at least a proper 3rd high-frequency moment\n");
+  }
+  TQ_TRY(tq_stage_out_begin(ctx, out, out_bytes, ctx->stage_out, &d_out, &out_host));
+  DensityPoles P;
+  if (statistic == TQ_FERMION) { // :70-74
+    P.xi = -1.0; P.b[0] = 0.0; P.b[1] = 1.0; P.b[2] = -1.0;
+  } else { // :75-79
+    P.xi = 1.0; P.b[0] = -1.0; P.b[1] = 1.0; P.b[2] = 0.5;
+  }
+  {
+    const int cl = (int)std::min<long>(n_cols, DENS_ROWS), rl = DENS_ROWS / cl;
+    const size_t smem = sizeof(cd) * (size_t)rl * n_cols;
+    if (smem > 48 * 1024) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_density: target too large");
+    if (batch > 65535) return tq_fail(ctx, TQ_ERR_INVALID, "tq_density: batch > 65535");
+    KernelScope ks(ctx, "density_partial");
+    k_density_partial<<<dim3(n_chunks, (unsigned)batch), DENS_ROWS, smem, ctx->stream>>>((const cd *)d_in, n_w * n_cols, (int)n_w, (int)n_cols, d_mom,
+                                                                                         (long)mom_rows * n_cols, beta, statistic, (int)first, P, d_part);
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+  }
+  {
+    KernelScope ks(ctx, "density_final");
+    k_density_final<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_part, n_chunks, n, d_mom, (long)mom_rows * n_cols, beta, statistic, P,
+                                                                             total, (cd *)d_out);
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+  }
+  TQ_TRY(tq_reserve_pinned(ctx, sizeof(double) * batch + sizeof(StatusWords)));
+  double *h_err = (double *)ctx->pinned;
+  StatusWords *h_st = (StatusWords *)((char *)ctx->pinned + sizeof(double) * batch);
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_st, d_st, sizeof(StatusWords), cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (have_moments) {
+    double a0;
+    memcpy(&a0, &h_st->max_m0_bits, sizeof(double));
+    if (!(a0 < 1e-8)) // :42-44
+      return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR: Density implementation requires vanishing 0th moment\n  error is :" + std::to_string(a0) + "\n");
+  }
+  for (long b = 0; b < batch; ++b) {
+    const double e = fitted ? h_err[b] : 0.0;
+    if (fitted && !(e < 1e-2)) // :48-50
+      return tq_fail(ctx, TQ_ERR_RUNTIME,
+                     "ERROR: High frequency moments have an error greater than 1e-2.\n  Error = " + std::to_string(e) +
+                        "\n Please make sure you treat the constant offset analytically!\n");
+    if (warn) warn[b] = (fitted && e > 1e-4) ? TQ_WARN_TAIL_ERR : 0; // :51-53
+    if (tail_err) tail_err[b] = e;
+  }
+  TQ_TRY(tq_stage_out_finish(ctx, out, out_bytes, d_out, out_host));
+  return TQ_OK;
+}

@@ -249,6 +249,25 @@ def fit_hermitian_tail(g, known_moments=None, **fit_params):
     return fit_tail(g, known_moments, hermitian=True, **fit_params)
 
 
+def density(g, known_moments=None):
+    """density.cpp:32-128: n[target] of an imfreq gf (matrix- or scalar-valued); for a BlockGf the list over blocks."""
+    if isinstance(g, BlockGf):
+        return [density(b, None if known_moments is None else known_moments[i]) for i, b in enumerate(g.blocks)]
+    if not isinstance(g.mesh, MeshImFreq):
+        raise TriqsRuntimeError("density needs an imfreq gf")
+    ts = g.target_shape
+    if len(ts) == 0:
+        n = 1
+    elif len(ts) == 2 and ts[0] == ts[1]:
+        n = ts[0]
+    else:
+        raise TriqsRuntimeError("density: the target must be scalar or a square matrix")
+    data = g.flat().reshape(1, -1, n, n)
+    km = None if known_moments is None else known_moments.reshape(1, known_moments.shape[0], n, n)
+    res = g.ctx.density(data, g.mesh.beta, g.mesh.statistic, moments=km)[0]
+    return res[0, 0] if len(ts) == 0 else res
+
+
 def inverse(g: Gf) -> Gf:
     """functions2.hpp:203-209"""
     return g.copy().invert()
