@@ -323,6 +323,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   constexpr bool FWD = (MODE == M_F1 || MODE == M_F2);
   constexpr int SGN = FWD ? 1 : -1;
   constexpr int NT = (NW + 1) * 32;
+  constexpr bool PK_AHEAD = false; // fetching the next packet id one packet ahead was measured slower (register pressure)
   using Smem = PipeSmem<MODE, N, RA, RB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TCW = A.tcw;
@@ -438,10 +439,12 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
     // ===================== worker warps: pull packets  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  =====================
     // (pass B of tile k is queued after pass A of tile k+1, so whoever takes it rarely waits; a packet only ever waits
     //  for packets that were handed out before it, hence no deadlock)
+    int pk_next = 0;
+    if (PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
     for (;;) {
-      int pk = 0;
-      if (lane == 0) pk = atomicAdd(next_pk, 1);
-      pk = __shfl_sync(0xffffffffu, pk, 0);
+      if (!PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
+      const int pk = __shfl_sync(0xffffffffu, pk_next, 0);
+      if (PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1); // fetched while this packet is processed (hides the atomic's latency)
       int blk, r;
       bool is_b = false;
       if (pk < 2 * pa) {
@@ -512,9 +515,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
                           A.out + id.gf * A.out_gf_stride + id.c0};
           fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
         }
-        fence_proxy_async(); // our generic-proxy reads of the tile are ordered before the TMA engine's next write to it
-        __syncwarp();
+        __syncwarp(); // every lane's reads of the tile are done ...
         if (lane == 0) {
+          fence_proxy_async(); // ... and ordered before the TMA engine's (async proxy) next write to the buffer
           mbar_arrive(&freeb[b]);
           mbar_arrive(&tabfree[ts]);
         }
