@@ -935,6 +935,9 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       if (nw_variant == 15) {
         TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 15>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
         TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 15>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
+      } else if (nw_variant == 7) {
+        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 7>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
+        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 7>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
       } else {
         TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 11>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
         TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 11>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
