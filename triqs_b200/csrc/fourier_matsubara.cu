@@ -676,6 +676,10 @@ template <int IN, int OUT, int SGN> static tq_status launch_tile(tq_ctx *ctx, co
 tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in,
                             cd *d_out, const cd *d_mom, int mom_rows, bool *handled);
 
+// fourier_col.cu: compile-time single-column kernel for scalar gfs on the 10^4 mesh (direct transform)
+tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in, cd *d_out,
+                               const cd *d_mom, int mom_rows, bool *handled);
+
 // runs the transform for gfs [0, batch) whose device arrays start at d_in / d_out; moments are [batch][mom_rows][n_cols]
 template <int IN_KIND /* IN_TAU: forward, IN_FREQ: inverse */>
 static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long batch, const cd *d_in, cd *d_out, const cd *d_mom, int mom_rows) {
@@ -686,6 +690,10 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
     bool handled = false;
     TQ_TRY(tq_pipe_matsubara(ctx, fwd, D.beta, D.stat, L + 1, (long)D.last + 1, n_cols, batch, d_in, d_out, d_mom, mom_rows, &handled));
     if (handled) return TQ_OK;
+    if (fwd) {
+      TQ_TRY(tq_col_matsubara_fwd(ctx, D.beta, D.stat, L + 1, (long)D.last + 1, n_cols, batch, d_in, d_out, d_mom, mom_rows, &handled));
+      if (handled) return TQ_OK;
+    }
   }
   constexpr int SGN = fwd ? 1 : -1;
   Tiling t;

@@ -79,18 +79,6 @@ TQ_HD Window tile_window(int item, int S, int N, int L, int first, int last) {
   return w;
 }
 
-// sum_i a_i / (i w - b_i) with b3 = -b2:   -(b1 r1) a1 - i (w r1) a1 - (b2 r2)(a2 - a3) - i (w r2)(a2 + a3)
-TQ_D cd tail_iw4(cd w01, cd w23, cd a1, cd D23, cd A23) {
-  const double p1 = w01.x, u = w01.y, p2 = w23.x, v = w23.y;
-  double re = fma(u, a1.y, -p1 * a1.x);
-  re = fma(-p2, D23.x, re);
-  re = fma(v, A23.y, re);
-  double im = fma(-u, a1.x, -p1 * a1.y);
-  im = fma(-p2, D23.y, im);
-  im = fma(-v, A23.x, im);
-  return cmk(re, im);
-}
-
 // ---- functors plugged into the two-pass engine -----------------------------------------------
 struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fourier_matsubara.cpp:159-173
   const PipeArgs &A;

@@ -44,6 +44,7 @@ struct FftPlanHost;    // tq_fft_plan.cu
 struct TailFitterPlan; // tail_fit.cu
 struct PipePlanCache;  // fourier_pipe.cu
 struct LatTwiddles;    // lattice_pipe.cu
+struct ColPlanCache;   // fourier_col.cu
 
 struct tq_ctx {
   int device = 0;
@@ -62,6 +63,7 @@ struct tq_ctx {
   std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
   std::shared_ptr<PipePlanCache> pipe_cache;
   std::shared_ptr<LatTwiddles> lat_tw;
+  std::shared_ptr<ColPlanCache> col_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {

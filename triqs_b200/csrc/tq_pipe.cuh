@@ -42,6 +42,19 @@ TQ_D void tma_load_4d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, i
 TQ_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 
+// sum_i a_i / (i w - b_i) with b3 = -b2:   -(b1 r1) a1 - i (w r1) a1 - (b2 r2)(a2 - a3) - i (w r2)(a2 + a3)
+TQ_D cd tail_iw4(cd w01, cd w23, cd a1, cd D23, cd A23) {
+  const double p1 = w01.x, u = w01.y, p2 = w23.x, v = w23.y;
+  double re = fma(u, a1.y, -p1 * a1.x);
+  re = fma(-p2, D23.x, re);
+  re = fma(v, A23.y, re);
+  double im = fma(-u, a1.x, -p1 * a1.y);
+  im = fma(-p2, D23.y, im);
+  im = fma(-v, A23.x, im);
+  return cmk(re, im);
+}
+
+
 // -------------------------------------------------------------------------------------------------
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 // -------------------------------------------------------------------------------------------------
