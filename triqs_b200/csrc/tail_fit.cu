@@ -247,7 +247,9 @@ TQ_D cd fit_rhs(const FitArgs &A, const cd *g, const cd *known, int i, int c) {
 }
 
 // one column of one gf; `rhs(i, c)` returns the fit-row value with the known moments removed
-template <class Rhs> TQ_D void fit_column(const FitArgs &A, long gf, int c, const cd *known, Rhs rhs) {
+// The fit rows are split over `NL` cooperating lanes (1 = this thread alone, 32 = its warp; partial sums are combined by
+// xor-shuffles, so every lane ends up with the same totals and lane 0 writes the results).
+template <int NL, class Rhs> TQ_D void fit_column(const FitArgs &A, long gf, int c, const cd *known, Rhs rhs, int lane = 0) {
   int cp = c; // partner column (inner adjoint), hermitian fit only
   if (A.herm) {
     int dd = A.d * A.d;
@@ -259,7 +261,7 @@ template <class Rhs> TQ_D void fit_column(const FitArgs &A, long gf, int c, cons
 #pragma unroll
   for (int v = 0; v < TQ_MAX_MOMENTS; ++v) x[v] = xp[v] = cmk(0, 0);
   const int M = A.M;
-  for (int i = 0; i < M; ++i) {
+  for (int i = lane; i < M; i += NL) {
     cd b = rhs(i, c);
     if (!A.herm) {
 #pragma unroll
@@ -277,9 +279,22 @@ template <class Rhs> TQ_D void fit_column(const FitArgs &A, long gf, int c, cons
         }
     }
   }
+  if (NL > 1) {
+#pragma unroll
+    for (int v = 0; v < TQ_MAX_MOMENTS; ++v)
+      if (v < A.n_var) {
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) {
+          x[v].x += __shfl_xor_sync(0xffffffffu, x[v].x, o);
+          x[v].y += __shfl_xor_sync(0xffffffffu, x[v].y, o);
+          xp[v].x += __shfl_xor_sync(0xffffffffu, xp[v].x, o);
+          xp[v].y += __shfl_xor_sync(0xffffffffu, xp[v].y, o);
+        }
+      }
+  }
   // residual of the (stacked) least-squares problem == || U_null^H B || of gelss_worker
   double r2 = 0.0;
-  for (int i = 0; i < M; ++i) {
+  for (int i = lane; i < M; i += NL) {
     cd b = rhs(i, c);
     cd ax = cmk(0, 0), axc = cmk(0, 0);
 #pragma unroll
@@ -294,6 +309,11 @@ template <class Rhs> TQ_D void fit_column(const FitArgs &A, long gf, int c, cons
       cd bp = rhs(i, cp);
       r2 += cabs2(csub(cconj(bp), axc));
     }
+  }
+  if (NL > 1) {
+#pragma unroll
+    for (int o = NL / 2; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    if (lane != 0) return;
   }
   double e = (A.rows_total == A.n_var) ? 0.0 : sqrt(r2) / sqrt((double)A.rows_total);
   if (e == e) {
@@ -325,7 +345,17 @@ __global__ void __launch_bounds__(128) k_fit_tail(const FitArgs A) {
   const int c = (int)(t - gf * A.n_cols);
   const cd *g = A.g + (size_t)gf * A.n_w * A.n_cols;
   const cd *known = A.known + (size_t)gf * A.n_fixed * A.n_cols;
-  fit_column(A, gf, c, known, [&](int i, int cc) { return fit_rhs(A, g, known, i, cc); });
+  fit_column<1>(A, gf, c, known, [&](int i, int cc) { return fit_rhs(A, g, known, i, cc); });
+}
+// warp version (few columns, many gfs): one warp per (gf, column), the fit rows split over its lanes
+__global__ void __launch_bounds__(128) k_fit_tail_warp(const FitArgs A) {
+  const long t = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= A.total) return; // (whole warps)
+  const long gf = t / A.n_cols;
+  const int c = (int)(t - gf * A.n_cols);
+  const cd *g = A.g + (size_t)gf * A.n_w * A.n_cols;
+  const cd *known = A.known + (size_t)gf * A.n_fixed * A.n_cols;
+  fit_column<32>(A, gf, c, known, [&](int i, int cc) { return fit_rhs(A, g, known, i, cc); }, (int)(threadIdx.x & 31));
 }
 // staged version (one CTA per gf): the M x n_cols right-hand sides are gathered into shared memory by the whole CTA first
 // (independent loads in flight instead of a chain of ~2 M dependent row reads per thread); same arithmetic, same results
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(128) k_fit_tail_staged(const FitArgs A) {
     sB[idx] = fit_rhs(A, g, known, i, c);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < A.n_cols; c += 128) fit_column(A, gf, c, known, [&](int i, int cc) { return sB[i * A.n_cols + cc]; });
+  for (int c = threadIdx.x; c < A.n_cols; c += 128) fit_column<1>(A, gf, c, known, [&](int i, int cc) { return sB[i * A.n_cols + cc]; });
 }
 
 static tq_status get_tail_plan(tq_ctx *ctx, double beta, int stat, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
@@ -404,7 +434,9 @@ tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw,
   *n_moments = S.n_var + n_known;
   KernelScope ks(ctx, "fit_tail");
   const size_t stage_bytes = sizeof(cd) * (size_t)A.M * (size_t)n_cols;
-  if (stage_bytes <= 48 * 1024 && batch <= 0x7fffffffL)
+  if (n_cols < 32 && (A.total + 3) / 4 <= 0x7fffffffL)
+    k_fit_tail_warp<<<(unsigned)((A.total + 3) / 4), 128, 0, ctx->stream>>>(A);
+  else if (stage_bytes <= 48 * 1024 && batch <= 0x7fffffffL)
     k_fit_tail_staged<<<(unsigned)batch, 128, stage_bytes, ctx->stream>>>(A);
   else
     k_fit_tail<<<(unsigned)((A.total + 127) / 128), 128, 0, ctx->stream>>>(A);
