@@ -979,7 +979,7 @@ TQ_HD void density_amplitudes(int stat, cd m1, cd m2, cd m3, cd a[3]) {
     a[2] = csub(cscale(4.0 / 3.0, m1), cscale(4.0 / 3.0, m3));
   }
 }
-constexpr int DENS_ROWS = 256; // rows per chunk = threads per CTA
+constexpr int DENS_ROWS = 512; // rows per chunk = threads per CTA
 
 __global__ void __launch_bounds__(DENS_ROWS) k_density_partial(const cd *__restrict__ g, long g_gf_stride, int n_w, int n_cols,
                                                                const cd *__restrict__ mom, long mom_gf_stride, double beta, int stat, int first,
@@ -1011,13 +1011,29 @@ __global__ void __launch_bounds__(DENS_ROWS) k_density_partial(const cd *__restr
     if (r_lane < rl) {
       cd a[3];
       density_amplitudes(stat, mm[(size_t)1 * n_cols + c], mm[(size_t)2 * n_cols + c], mm[(size_t)3 * n_cols + c], a);
-      for (int r = r_lane; r < nr; r += rl) {
-        cd v = gg[(size_t)r * n_cols + c];
-        v = csub(v, cmul(a[0], kap[r][0]));
-        v = csub(v, cmul(a[1], kap[r][1]));
-        v = csub(v, cmul(a[2], kap[r][2]));
-        acc = cadd(acc, v);
+      // four independent loads / partial sums in flight per thread (the loop is a pure stream over G(i w))
+      cd acc4[4] = {cmk(0.0, 0.0), cmk(0.0, 0.0), cmk(0.0, 0.0), cmk(0.0, 0.0)};
+      int r = r_lane;
+      for (; r + 3 * rl < nr; r += 4 * rl) {
+        cd v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = gg[(size_t)(r + u * rl) * n_cols + c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r + u * rl;
+          cd t = csub(v[u], cmul(a[0], kap[rr][0]));
+          t = csub(t, cmul(a[1], kap[rr][1]));
+          t = csub(t, cmul(a[2], kap[rr][2]));
+          acc4[u] = cadd(acc4[u], t);
+        }
       }
+      for (; r < nr; r += rl) {
+        cd t = csub(gg[(size_t)r * n_cols + c], cmul(a[0], kap[r][0]));
+        t = csub(t, cmul(a[1], kap[r][1]));
+        t = csub(t, cmul(a[2], kap[r][2]));
+        acc4[0] = cadd(acc4[0], t);
+      }
+      acc = cadd(cadd(acc4[0], acc4[1]), cadd(acc4[2], acc4[3]));
       red[r_lane * n_cols + c] = acc;
     }
   }
