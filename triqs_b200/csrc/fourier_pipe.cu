@@ -33,6 +33,10 @@ enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
 constexpr int PIPE_NBUF = 3; // tile buffers
 constexpr int PIPE_NTAB = 4; // table sets (they live until the end of pass B, one stage longer than the tile)
 constexpr int PIPE_MAXR = 25; // largest radix of a pass
+// worker warps per CTA (+ 1 producer warp).  The register file is 16 K registers per SM sub-partition: 12 warps (3 per
+// sub-partition) get 168 registers per thread, 16 warps only 128 (radix 20 / 25 then spill); measured: 7 workers reach 86 %
+// of the throughput of 11, 15 workers at 128 registers are slower.
+constexpr int PIPE_NW = 11;
 
 struct PipeArgs {
   int Na, Nb, n_cols;
@@ -833,9 +837,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   std::shared_ptr<PipePlan> pl;
   TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
   const int wmax1 = pl->wmax1, wmax2 = pl->wmax2;
-  // worker warps per CTA (+ 1 producer warp): the register file is 16K registers per SM sub-partition, so 12 warps get
-  // 168 registers per thread and 16 warps 128
-  static const int nw_variant = env_int("TQ_PIPE_NW", 11), cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64);
+  static const int cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64); // (tile-width caps: tuning experiments)
   // I1: window rows with n >= 0 / n < 0; when both are whole groups of Na rows they are two rectangles of the [b][a] view
   const long n_pos = (long)pl->last + 1, n_neg = -(long)pl->first;
   const bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && !getenv("TQ_PIPE_NO_I1_BOXES");
@@ -920,16 +922,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       set_mode(P1, M_F1);
       set_mode(P2, M_F2);
       TQ_TRY(make_f1_tensor_map(ctx, P1.in, nb, Na, Nb, n_cols, L, tcw1, &tmap));
-      if (nw_variant == 15) {
-        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 15>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 15>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
-      } else if (nw_variant == 7) {
-        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 7>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 7>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
-      } else {
-        TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, 11>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
-        TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, 11>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
-      }
+      TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, PIPE_NW>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
+      TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, PIPE_NW>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
     } else {
       set_mode(P1, M_I1);
       set_mode(P2, M_I2);
@@ -943,13 +937,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
         TQ_TRY(make_i1_tensor_map(ctx, P1.in, n_neg, n_pos, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap));  // k in [0, last]: data rows n - first
         TQ_TRY(make_i1_tensor_map(ctx, P1.in, 0, n_neg, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap2));     // k in [L + first, L): data rows 0..
       }
-      if (nw_variant == 15) {
-        TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, 15>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
-        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 15>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
-      } else {
-        TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, 11>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
-        TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, 11>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
-      }
+      TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, PIPE_NW>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
+      TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, PIPE_NW>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
     }
   }
   *handled = true;
