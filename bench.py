@@ -60,27 +60,71 @@ def block_gtau(b, n_tau=N_TAU, beta=BETA):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region.  NVML in-process (a sample every ~2 ms, the timed region is tens of
+    milliseconds); falls back to polling nvidia-smi when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.stop = index, uuid, False
+        self.sm, self.mx, self.reasons, self.n = [], [], set(), 0
         self.t = None
+        self.how = "nvidia-smi"
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for cand in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.how = "nvml"
+        while not self.stop:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for k, m in masks.items():
+                if r & m:
+                    self.reasons.add(k)
+            self.n += 1
+            time.sleep(0.002)
+
+    def _run_smi(self):
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if out and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0]))
+                    self.mx.append(float(r[1]))
+                    for i, k in enumerate(self.NAMES):
+                        if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                            self.reasons.add(k)
+                    self.n += 1
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
+        time.sleep(0.05)  # let the sampler initialise before the timed region starts
         return self
 
     def __exit__(self, *a):
@@ -88,12 +132,8 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": [k for k in self.NAMES if k in self.reasons], "samples": self.n, "source": self.how}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -209,7 +249,11 @@ def run_native(args):
     for _ in range(args.warmup):
         step()
     l0 = ctx.launch_count()
-    with ClockSampler(local) as cs:
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as cs:
         ms = timed(step, args.steps)
     launches = ctx.launch_count() - l0
     clocks = cs.summary()
