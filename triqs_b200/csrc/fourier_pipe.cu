@@ -354,6 +354,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   const int nloc = (int)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
   const TileDecoder decode(A.n_items, A.n_ct, TCW, n_cols);
   const unsigned m_pa = fastdiv_magic((unsigned)pa), m_pab = fastdiv_magic((unsigned)(pa + pb));
+  // With at least NW packets per 5 tiles no worker can be two ring cycles ahead of an unfinished packet, and the phase of
+  // buffer b can be established by waiting on its `free` barrier; tiny tiles fall back to polling the producer's counter.
+  const bool poll_ready = 5 * (pa + pb) < NW;
+  // item -> (butterfly, column) division magics of the two possible tile widths (full / last column tile)
+  const unsigned m_w_full = fastdiv_magic((unsigned)TCW), m_w_last = fastdiv_magic((unsigned)(n_cols - (A.n_ct - 1) * TCW));
   long long t0 = clock64(), t_wait = 0, t_work = 0, t_sched = 0, t_ready = 0;
 #define TQ_LAP(acc)                                                                                                              \
   if (A.dbg && lane == 0) {                                                                                                      \
@@ -462,30 +467,36 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
       const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
       const int it = r * 32 + lane; // butterfly of this lane (the engine skips it when past the end)
+      // (I2 sits at the register limit: one more live value makes it spill, so it recomputes the magic per packet)
+      const unsigned m_w = MODE == M_I2 ? ~0u : (id.w == TCW ? m_w_full : m_w_last);
       TQ_LAP(t_sched)
       // an mbarrier parity wait is only meaningful for the current or the previous phase: do not look at the barriers of
       // buffer b before the producer has recycled it for tile k (matters when a tile has fewer packets than there are workers)
-      while (*ready_tile < k) __nanosleep(32);
+      if (poll_ready) {
+        while (*ready_tile < k) __nanosleep(32);
+      } else if (u > 0) {
+        mbar_wait(&freeb[b], (uint32_t)((u - 1) & 1)); // pass B of tile k - NBUF is complete: buffer b is in (or entering) its phase u
+      }
       TQ_LAP(t_ready)
       if (!is_b) {
         mbar_wait(&full[b], (uint32_t)(u & 1));
         TQ_LAP(t_wait)
         if (MODE == M_F1) {
           PreF1 pre{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off)};
-          fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+          fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
         } else if (MODE == M_I1) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
           PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, Window{wv.x, wv.y}, A.inv_beta};
           if (A.i1_edge) {
             auto wedge = [&](int rr) { return A.wedge[rr]; };
             fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS, it,
-                                               1 << 30, pre, wedge);
+                                               1 << 30, pre, wedge, m_w);
           } else {
-            fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+            fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
           }
         } else {
           PreIdentity pre;
-          fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, it, 1 << 30, pre);
+          fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&adone[b]);
@@ -496,16 +507,16 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         if (PASS1) {
           PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
                                A.Na, A.tcw2, id.item, id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
         } else if (MODE == M_F2) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
           PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
                           A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
         } else {
           PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
                           A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
         }
         __syncwarp(); // every lane's reads of the tile are done ...
         if (lane == 0) {
@@ -834,6 +845,12 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   if (!pipe_supported_length(L, &Na, &Nb)) return TQ_OK;
   if (getenv("TQ_NO_PIPE")) return TQ_OK;
   if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return TQ_OK; // bulk copies need 16-byte aligned rows
+#ifdef TQ_KNOCKOUT
+  {
+    const int kv = env_int("TQ_KNOCK", 0);
+    cudaMemcpyToSymbol(g_tq_knock, &kv, sizeof(int));
+  }
+#endif
   std::shared_ptr<PipePlan> pl;
   TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
   const int wmax1 = pl->wmax1, wmax2 = pl->wmax2;

@@ -33,6 +33,17 @@ template <int R, int I = 0, class Post> TQ_HD void tq_unroll_store(const cd *a, 
   }
 }
 
+// Developer knock-out switches (compiled in only with -DTQ_KNOCKOUT, never in the product): remove one ingredient of the
+// packet loops at a time to see what the tile period is made of.  Results are wrong by construction.
+#ifdef TQ_KNOCKOUT
+__device__ int g_tq_knock = 0;
+#endif
+#if defined(TQ_KNOCKOUT) && defined(__CUDA_ARCH__)
+#define TQ_KNOCK(bit) (g_tq_knock & (bit))
+#else
+#define TQ_KNOCK(bit) 0
+#endif
+
 struct PreIdentity {
   TQ_HD void begin(int, int) {}
   template <int R> TQ_HD cd load(const cd *p) const { return *p; }
@@ -40,11 +51,11 @@ struct PreIdentity {
 
 // twq[q * RA + s] = w_N^{SGN q s} (times whatever per-q / per-s factor the caller folded in).  TW0: entry s = 0 is not 1.
 template <int N, int RA, int RB, int SGN, bool TW0, class Pre>
-TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre) {
+TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, unsigned magic = ~0u) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RB * tcw;
   const int stride = RB * pitch;
-  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw); // (a 64-bit division: hot callers pass the precomputed value)
   for (int i = tid; i < nitems; i += nthreads) {
     const int q = fastdiv(i, magic);
     const int c = i - q * tcw;
@@ -52,22 +63,26 @@ TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, in
     pre.begin(q, c);
     cd a[RA];
     tq_unroll_load<RA>(a, pre, p, stride);
-    Dft<RA, SGN>::run(a);
+    if (!TQ_KNOCK(1)) Dft<RA, SGN>::run(a);
     const cd *tw = twq + q * RA;
-    if (TW0 || q != 0) {
+    if ((TW0 || q != 0) && !TQ_KNOCK(16)) {
 #pragma unroll
       for (int r = TW0 ? 0 : 1; r < RA; ++r) a[r] = cmul(a[r], tw[r]);
     }
+    if (!TQ_KNOCK(2)) {
 #pragma unroll
-    for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
+      for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
+    } else if (a[0].x == 1.2345e300) {
+      p[0] = a[1];
+    }
   }
 }
 
 template <int N, int RA, int RB, int SGN, class Post>
-TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, Post &post) {
+TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, Post &post, unsigned magic = ~0u) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RA * tcw;
-  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw);
   for (int i = tid; i < nitems; i += nthreads) {
     const int sidx = fastdiv(i, magic);
     const int c = i - sidx * tcw;
@@ -76,8 +91,15 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
     cd a[RB];
 #pragma unroll
     for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
-    Dft<RB, SGN>::run(a);
-    tq_unroll_store<RB>(a, post);
+    if (!TQ_KNOCK(1)) Dft<RB, SGN>::run(a);
+    if (!TQ_KNOCK(4)) {
+      tq_unroll_store<RB>(a, post);
+    } else {
+      cd acc = a[0];
+#pragma unroll
+      for (int t = 1; t < RB; ++t) acc = cadd(acc, a[t]);
+      if (acc.x == 1.2345e300) post.template store<0>(acc);
+    }
   }
 }
 
@@ -86,11 +108,12 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
 //   y_s = x_0 + x_{RA-1} w_RA^{SGN (RA-1) s} = x_0 + x_{RA-1} wedge[s],   wedge[s] = exp(-SGN 2 pi i s / RA)
 // The last-leg rows come from a separate staging area `hi` (same pitch), so the in-place write of all RA legs is hazard free.
 template <int N, int RA, int RB, bool TW0, class Pre, class Wedge>
-TQ_HD void fft2_pass_a_edge(cd *s, const cd *hi, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, const Wedge &wedge) {
+TQ_HD void fft2_pass_a_edge(cd *s, const cd *hi, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, const Wedge &wedge,
+                            unsigned magic = ~0u) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RB * tcw;
   const int stride = RB * pitch;
-  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw);
   for (int i = tid; i < nitems; i += nthreads) {
     const int q = fastdiv(i, magic);
     const int c = i - q * tcw;
