@@ -109,6 +109,17 @@ tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_i
 tq_status tq_density(tq_ctx *ctx, double beta, int statistic, long n_iw, int n, long batch, const tq_complex *gw,
                      const tq_complex *moments, int n_moments, tq_complex *out, int *warn, double *tail_err);
 
+/* Elementwise companions on the same data; data [batch][n_pts][d][d], d = 1 for scalar targets, d = n1*n2 for a
+ * rank-4 target viewed as an (ij),(kl) matrix.  mesh_kind: 0 = full imfreq mesh (-i w_n is the mirrored point), 1 = imtime.
+ *   make_hermitian     c++/triqs/gfs/functions/imfreq.hpp:175-215   out = 0.5 (g[w] + dagger(g[-w]))     (out != g)
+ *   is_gf_hermitian    imfreq.hpp:81-124                            *result = 1 iff max |dagger(g[-w]) - g[w]| <= tolerance
+ *   replace_by_tail    imfreq.hpp:258-261 (+ tail_eval, mesh/tail_fitter.hpp:49-64): g[iw] = sum_n tail[n] / (iw)^n for
+ *                      iw.n >= n_min or iw.n < -n_min, in place; g [batch][n_w][n_cols], tail [batch][n_moments][n_cols] */
+tq_status tq_make_hermitian(tq_ctx *ctx, int mesh_kind, long n_pts, int d, long batch, const tq_complex *g, tq_complex *out);
+tq_status tq_is_gf_hermitian(tq_ctx *ctx, int mesh_kind, long n_pts, int d, long batch, const tq_complex *g, double tolerance, int *result);
+tq_status tq_replace_by_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_cols, long batch, tq_complex *g,
+                             const tq_complex *tail, int n_moments, int n_min);
+
 /* ---- least-squares tail fit ------------------------------------------------------------------ */
 
 /* Replaces  tail_fitter::fit<0, hermitian>(mesh, g_data, normalize=true, known_moments, inner_matrix_dim)

@@ -453,6 +453,40 @@ def tail_eval(moments: np.ndarray, om: complex) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# hermiticity helpers and replace_by_tail  
+# ----------------------------------------------------------------------------------------------
+
+
+def make_hermitian(g: np.ndarray, imtime: bool = False) -> np.ndarray:
+    """0.5 (g[w] + dagger(g[-w])) on a full imfreq mesh (-w is the mirrored data index), 0.5 (g[t] + dagger(g[t])) on imtime.
+    g [n_pts, d, d].  c++/triqs/gfs/functions/imfreq.hpp:175-215."""
+    g = np.asarray(g, dtype=np.complex128)
+    other = g if imtime else g[::-1]
+    return 0.5 * (g + other.conj().transpose(0, 2, 1))
+
+
+def is_gf_hermitian(g: np.ndarray, imtime: bool = False, tolerance: float = 1e-12) -> bool:
+    """imfreq.hpp:81-124."""
+    g = np.asarray(g, dtype=np.complex128)
+    other = g if imtime else g[::-1]
+    return bool(np.max(np.abs(other.conj().transpose(0, 2, 1) - g)) <= tolerance)
+
+
+def replace_by_tail(gw: np.ndarray, beta: float, stat: int, tail: np.ndarray, n_min: int) -> np.ndarray:
+    """g[iw] = tail_eval(tail, iw) for iw.n >= n_min or iw.n < -n_min.  gw [n_w, ncols], tail [n_mom, ncols].  imfreq.hpp:258-261."""
+    gw = np.array(gw, dtype=np.complex128)
+    n_w = gw.shape[0]
+    n_iw = n_w // 2 if stat == FERMION else (n_w + 1) // 2
+    first, _ = imfreq_first_last(stat, n_iw)
+    iw = imfreq_values(beta, stat, n_iw)
+    for i in range(n_w):
+        n = first + i
+        if n >= n_min or n < -n_min:
+            gw[i] = tail_eval(tail, iw[i])
+    return gw
+
+
+# ----------------------------------------------------------------------------------------------
 # density  (SURVEY 8(f).1: the immediate consumer of G_loc in a DMFT loop)
 # ----------------------------------------------------------------------------------------------
 

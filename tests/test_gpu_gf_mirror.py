@@ -101,3 +101,35 @@ def test_density_of_local_gf():
     assert np.max(np.abs(dens - ref)) < 1e-9
     assert 0.0 < dens.trace().real < n
     ctx.close()
+
+
+def test_hermiticity_and_replace_by_tail_mirror():
+    """hermiticity.cpp:25-80 and fit_and_replace.cpp:42-72 with the Gf mirror (fit on the full mesh instead of a window)."""
+    import triqs_b200
+    from triqs_b200 import gf as G
+    ctx = triqs_b200.Context(0, print_warnings=False)
+    beta = 1.0
+    mesh = G.MeshImFreq(beta, O.FERMION, 1025)
+    iw = O.imfreq_values(beta, O.FERMION, 1025)
+    h = np.array([[1, 1j], [-1j, 2]], complex)
+    g = G.Gf(mesh, (2, 2), np.linalg.inv(iw[:, None, None] * np.eye(2) - h), ctx)
+    assert G.is_gf_hermitian(g)
+    assert np.max(np.abs(G.make_hermitian(g).data - g.data)) < 1e-15
+    gt = G.make_gf_from_fourier(g)
+    assert G.is_gf_hermitian(gt, 1e-10)
+    hb = np.array([[1, 1j], [1j, 2]], complex)
+    gb = G.Gf(mesh, (2, 2), np.linalg.inv(iw[:, None, None] * np.eye(2) - hb), ctx)
+    assert not G.is_gf_hermitian(gb)
+    assert G.is_gf_hermitian(G.make_hermitian(gb))
+    # replace the outer part of a gf by its fitted tail: close to the exact function
+    beta2, n_iw = 10.0, 400
+    mesh2 = G.MeshImFreq(beta2, O.FERMION, n_iw)
+    iw2 = O.imfreq_values(beta2, O.FERMION, n_iw)
+    exact = (1 / (iw2 - 1.0 - (1 / (iw2 - 2) + 3 / (iw2 + 3)))).reshape(-1, 1, 1)
+    g2 = G.Gf(mesh2, (1, 1), exact.copy(), ctx)
+    tail, err = G.fit_tail(g2)
+    n = -n_iw + np.arange(2 * n_iw)
+    g2.data[np.abs(n + 0.5) > 330] = 123.0  # garbage in the outer part
+    G.replace_by_tail(g2, tail, 330)
+    assert np.max(np.abs(g2.data - exact)) < 1e-8
+    ctx.close()

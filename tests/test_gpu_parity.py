@@ -512,3 +512,44 @@ def test_density_vs_oracle(ctx, stat, n, n_iw):
         assert rel(out_k2[b], O.density(gs[b], beta, stat, kms[b][:2])) < 1e-9
         iu = np.triu_indices(n, 1)
         assert np.array_equal(out_km[b].T[iu], out_km[b][iu].conj())  # lower triangle = conjugate of the upper one (:115)
+
+
+# ---------------------------------------------------------------------------------------------
+# hermiticity helpers, replace_by_tail
+# ---------------------------------------------------------------------------------------------
+def test_hermiticity_helpers(ctx):
+    """hermiticity.cpp:25-80 through the C ABI + parity with the oracle on non-symmetric data."""
+    beta, n_iw = 1.0, 1025
+    iw = O.imfreq_values(beta, F, n_iw)
+    h = np.array([[1, 1j], [-1j, 2]], complex)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(2) - h)[None]
+    assert ctx.is_gf_hermitian(g)
+    assert np.max(np.abs(ctx.make_hermitian(g) - g)) < 1e-15
+    hb = np.array([[1, 1j], [1j, 2]], complex)
+    gb = np.linalg.inv(iw[:, None, None] * np.eye(2) - hb)[None]
+    assert not ctx.is_gf_hermitian(gb)
+    assert ctx.is_gf_hermitian(ctx.make_hermitian(gb))
+    rng = np.random.default_rng(3)
+    for npts, d, imtime in [(2050, 3, False), (1999, 4, False), (1001, 2, True), (64, 1, False)]:
+        x = rng.normal(size=(3, npts, d, d)) + 1j * rng.normal(size=(3, npts, d, d))
+        out = ctx.make_hermitian(x, imtime=imtime)
+        for b in range(3):
+            assert np.array_equal(out[b], O.make_hermitian(x[b], imtime=imtime))  # one add and one multiply by 0.5: bit exact
+        assert ctx.is_gf_hermitian(out, imtime=imtime, tolerance=1e-15)
+        assert not ctx.is_gf_hermitian(x, imtime=imtime)
+
+
+@pytest.mark.parametrize("stat", [F, B])
+def test_replace_by_tail(ctx, stat):
+    beta, n_iw, ncols = 10.0, 300, 4
+    rng = np.random.default_rng(12 + stat)
+    n_w = 2 * n_iw - (0 if stat == F else 1)
+    g = rng.normal(size=(2, n_w, ncols)) + 1j * rng.normal(size=(2, n_w, ncols))
+    tail = rng.normal(size=(2, 6, ncols)) + 1j * rng.normal(size=(2, 6, ncols))
+    ref = np.stack([O.replace_by_tail(g[b], beta, stat, tail[b], 120) for b in range(2)])
+    out = ctx.replace_by_tail(g.copy(), beta, stat, tail, 120)
+    assert rel(out, ref) < TOL
+    first, _ = O.imfreq_first_last(stat, n_iw)
+    n = first + np.arange(n_w)
+    inside = (n < 120) & (n >= -120)
+    assert np.array_equal(out[:, inside], g[:, inside])

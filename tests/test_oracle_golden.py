@@ -260,3 +260,47 @@ def test_density_matrix_hermitian_and_known_moments():
     km = np.stack([np.zeros((n, n)), np.eye(n), H, H @ H]).astype(complex)
     d2 = O.density(g, beta, O.FERMION, km)
     assert np.max(np.abs(d2 - d)) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# hermiticity helpers, replace_by_tail  (test/c++/gfs/functions/hermiticity.cpp:25-80, fit_and_replace.cpp:30-72)
+# ---------------------------------------------------------------------------------------------
+def test_hermiticity_reference_known_answers():
+    beta, n_iw = 1.0, 1025  # gf<imfreq>{{beta, Fermion}, {2, 2}}: default n_iw
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    h = np.array([[1, 1j], [-1j, 2]], complex)
+    g = np.linalg.inv(iw[:, None, None] * np.eye(2) - h)
+    assert O.is_gf_hermitian(g)                                            # hermiticity.cpp:38
+    assert np.max(np.abs(O.make_hermitian(g) - g)) < 1e-15                 # :41
+    hb = np.array([[1, 1j], [1j, 2]], complex)                             # :49 broken hermiticity
+    gb = np.linalg.inv(iw[:, None, None] * np.eye(2) - hb)
+    assert not O.is_gf_hermitian(gb)                                       # :52
+    assert O.is_gf_hermitian(O.make_hermitian(gb))                         # :55
+    # tensor_valued<4> case (:63-69) viewed as a 4 x 4 (ij),(kl) matrix
+    idx = np.arange(2)
+    i, j, k, l = np.meshgrid(idx, idx, idx, idx, indexing="ij")
+    chi = 1.0 / (iw[:, None, None, None, None] - (1 + 1j) * (i * j)[None] - (1 - 1j) * (k * l)[None])
+    chi4 = chi.reshape(-1, 4, 4)
+    assert O.is_gf_hermitian(chi4)
+    assert np.max(np.abs(O.make_hermitian(chi4) - chi4)) < 1e-15
+    # imtime: G(tau) of the hermitian h is hermitian point by point
+    w, v = np.linalg.eigh(h)
+    tau = O.tau_values(beta, 201)
+    f = -np.exp(-w[None, :] * tau[:, None]) / (1 + np.exp(-beta * w[None, :]))
+    gt = np.einsum("ik,tk,jk->tij", v, f, v.conj())
+    assert O.is_gf_hermitian(gt, imtime=True)
+    assert np.max(np.abs(O.make_hermitian(gt, imtime=True) - gt)) < 1e-12
+
+
+def test_replace_by_tail_reference_behaviour():
+    """fit_and_replace.cpp:42-72 pattern: outside +-n_min the gf is replaced by its tail expansion; inside it is untouched."""
+    beta, n_iw = 10.0, 100
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    g = (1 / (iw - 1.0) + 1 / (iw + 2.0)).reshape(-1, 1)
+    tail = np.array([[0.0], [2.0], [-1.0], [5.0], [-7.0], [17.0]], complex)  # moments of the two poles: sum E^(n-1)
+    out = O.replace_by_tail(g, beta, O.FERMION, tail, 50)
+    first, _ = O.imfreq_first_last(O.FERMION, n_iw)
+    n = first + np.arange(2 * n_iw)
+    inside = (n < 50) & (n >= -50)
+    assert np.array_equal(out[inside], g[inside])
+    assert np.max(np.abs(out[~inside] - g[~inside])) < 1e-6 and np.max(np.abs(out[~inside] - g[~inside])) > 0

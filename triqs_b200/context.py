@@ -204,6 +204,30 @@ class Context:
             return res, np.frombuffer(err, dtype=np.float64).copy()
         return res
 
+    # -- hermiticity helpers, replace_by_tail (imfreq.hpp:81-215, 258-261) ----------------------
+    def make_hermitian(self, g, imtime=False, out=None):
+        """g [batch, n_pts, d, d] -> 0.5 (g[w] + dagger(g[-w]))  (full imfreq mesh, or imtime: the point itself)."""
+        g = _as_c128(g)
+        batch, n_pts, d, d2 = g.shape
+        res = out if out is not None else _empty_like_kind(g, g.shape)
+        self._check(self._lib.tq_make_hermitian(self._h, 1 if imtime else 0, n_pts, d, batch, _ptr(g), _ptr(res)))
+        return res
+
+    def is_gf_hermitian(self, g, imtime=False, tolerance=1e-12):
+        g = _as_c128(g)
+        batch, n_pts, d, d2 = g.shape
+        r = ctypes.c_int(0)
+        self._check(self._lib.tq_is_gf_hermitian(self._h, 1 if imtime else 0, n_pts, d, batch, _ptr(g), float(tolerance), ctypes.byref(r)))
+        return bool(r.value)
+
+    def replace_by_tail(self, g, beta, statistic, tail, n_min):
+        """in place: g [batch, n_w, n_cols], tail [batch, n_moments, n_cols]."""
+        batch, n_w, n_cols = g.shape
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        tail = _as_c128(tail)
+        self._check(self._lib.tq_replace_by_tail(self._h, beta, statistic, n_iw, n_cols, batch, _ptr(g), _ptr(tail), tail.shape[1], int(n_min)))
+        return g
+
     # -- tail fit ----------------------------------------------------------------------------
     def fit_tail(self, g, beta, statistic, known_moments=None, hermitian=False, inner_dim=1, tail_fraction=0.2, n_tail_max=30,
                  expansion_order=None):

@@ -249,6 +249,49 @@ def fit_hermitian_tail(g, known_moments=None, **fit_params):
     return fit_tail(g, known_moments, hermitian=True, **fit_params)
 
 
+def _herm_view(g):
+    """(data [1, n_pts, d, d], imtime?) of an imfreq / imtime gf with target rank 0, 2 or 4 (imfreq.hpp:81-215)."""
+    if not isinstance(g.mesh, (MeshImFreq, MeshImTime)):
+        raise TriqsRuntimeError("requires an imfreq or imtime Green function")
+    ts = g.target_shape
+    if len(ts) == 0:
+        d = 1
+    elif len(ts) == 2 and ts[0] == ts[1]:
+        d = ts[0]
+    elif len(ts) == 4 and ts[0] == ts[2] and ts[1] == ts[3]:
+        d = ts[0] * ts[1]
+    else:
+        raise TriqsRuntimeError("requires a Green function with a (square) target of rank 0, 2 or 4")
+    return g.flat().reshape(1, -1, d, d), isinstance(g.mesh, MeshImTime)
+
+
+def make_hermitian(g):
+    """imfreq.hpp:175-215 (block overload: map over blocks)."""
+    if isinstance(g, BlockGf):
+        return BlockGf(g.names, [make_hermitian(b) for b in g.blocks])
+    data, imtime = _herm_view(g)
+    out = g.ctx.make_hermitian(data, imtime=imtime)
+    return Gf(g.mesh, g.target_shape, out.reshape((len(g.mesh),) + tuple(g.target_shape)), g.ctx)
+
+
+def is_gf_hermitian(g, tolerance: float = 1e-12) -> bool:
+    """imfreq.hpp:81-124."""
+    if isinstance(g, BlockGf):
+        return all(is_gf_hermitian(b, tolerance) for b in g.blocks)
+    data, imtime = _herm_view(g)
+    return g.ctx.is_gf_hermitian(data, imtime=imtime, tolerance=tolerance)
+
+
+def replace_by_tail(g: Gf, tail, n_min: int) -> None:
+    """imfreq.hpp:258-261: in place."""
+    if not isinstance(g.mesh, MeshImFreq):
+        raise TriqsRuntimeError("replace_by_tail needs an imfreq gf")
+    data = g.flat()[None]
+    res = g.ctx.replace_by_tail(data.copy() if not data.flags.writeable else data, g.mesh.beta, g.mesh.statistic,
+                                np.asarray(tail).reshape(1, np.shape(tail)[0], g.n_others), n_min)
+    g.data[...] = np.asarray(res)[0].reshape(g.data.shape)
+
+
 def density(g, known_moments=None):
     """density.cpp:32-128: n[target] of an imfreq gf (matrix- or scalar-valued); for a BlockGf the list over blocks."""
     if isinstance(g, BlockGf):
