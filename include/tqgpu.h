@@ -120,6 +120,13 @@ tq_status tq_is_gf_hermitian(tq_ctx *ctx, int mesh_kind, long n_pts, int d, long
 tq_status tq_replace_by_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_cols, long batch, tq_complex *g,
                              const tq_complex *tail, int n_moments, int n_min);
 
+/* eps_k = sum_j hop[j] exp(2 pi i k . displ[j]) on the brzone mesh dims[3] -- replaces
+ *   tight_binding::fourier(mesh::brzone const &)   c++/triqs/lattice/tight_binding.hpp:88-123
+ * displ [n_r][3] integer lattice displacements, hop [n_r][n_orb][n_orb], out [d0 d1 d2][n_orb][n_orb] (the eps_k argument of
+ * tq_dyson_ksum). */
+tq_status tq_tight_binding_fourier(tq_ctx *ctx, int n_orb, int n_r, const int *displ, const tq_complex *hop, const long dims[3],
+                                   tq_complex *out);
+
 /* ---- least-squares tail fit ------------------------------------------------------------------ */
 
 /* Replaces  tail_fitter::fit<0, hermitian>(mesh, g_data, normalize=true, known_moments, inner_matrix_dim)

@@ -453,6 +453,23 @@ def tail_eval(moments: np.ndarray, om: complex) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# tight-binding dispersion on a brzone mesh  
+# ----------------------------------------------------------------------------------------------
+
+
+def tight_binding_fourier(displ, hop: np.ndarray, dims) -> np.ndarray:
+    """h_k = sum_j hop[j] exp(2 pi i k . displ[j]) with k = (i0/d0, i1/d1, i2/d2), C-order k index.
+    c++/triqs/lattice/tight_binding.hpp:88-123; mesh/brzone.hpp:187-190,285-288."""
+    displ = np.asarray(displ, dtype=np.int64).reshape(-1, 3)
+    hop = np.asarray(hop, dtype=np.complex128)
+    d = np.asarray(dims, dtype=np.int64)
+    idx = np.stack(np.unravel_index(np.arange(int(np.prod(d))), tuple(d)), axis=1)  # [nk, 3]
+    kfrac = idx / d[None, :]
+    phase = np.exp(2j * np.pi * (kfrac @ displ.T))  # [nk, n_r]
+    return np.einsum("kj,jab->kab", phase, hop)
+
+
+# ----------------------------------------------------------------------------------------------
 # hermiticity helpers and replace_by_tail  (SURVEY 8(f).2)
 # ----------------------------------------------------------------------------------------------
 

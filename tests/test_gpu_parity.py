@@ -553,3 +553,17 @@ def test_replace_by_tail(ctx, stat):
     n = first + np.arange(n_w)
     inside = (n < 120) & (n >= -120)
     assert np.array_equal(out[:, inside], g[:, inside])
+
+
+def test_tight_binding_fourier(ctx):
+    """tight_binding::fourier(k_mesh): known square-lattice dispersion and a random 3-D multi-orbital model vs the oracle."""
+    displ = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)]
+    e = ctx.tight_binding_fourier(displ, -np.ones((4, 1, 1), complex), (10, 10, 1)).reshape(10, 10)
+    k = 2 * np.pi * np.arange(10) / 10
+    assert np.max(np.abs(e - (-2 * (np.cos(k)[:, None] + np.cos(k)[None, :])))) < 1e-14
+    rng = np.random.default_rng(4001)
+    R = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1), (0, 0, 0), (2, -1, 3), (-2, 1, -3)]
+    t = rng.normal(size=(9, 5, 5)) + 1j * rng.normal(size=(9, 5, 5))
+    for dims in [(16, 12, 10), (64, 64, 1), (7, 1, 5)]:
+        out = ctx.tight_binding_fourier(R, t, dims)
+        assert rel(out, O.tight_binding_fourier(R, t, dims)) < TOL

@@ -304,3 +304,17 @@ def test_replace_by_tail_reference_behaviour():
     inside = (n < 50) & (n >= -50)
     assert np.array_equal(out[inside], g[inside])
     assert np.max(np.abs(out[~inside] - g[~inside])) < 1e-6 and np.max(np.abs(out[~inside] - g[~inside])) > 0
+
+
+def test_tight_binding_fourier_square_lattice():
+    """Nearest-neighbour hopping t = -1 on the square lattice: eps_k = -2 (cos kx + cos ky)  (the dispersion of g_r_k.cpp:40-58)."""
+    displ = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)]
+    hop = -np.ones((4, 1, 1), complex)
+    N = 10
+    e = O.tight_binding_fourier(displ, hop, (N, N, 1)).reshape(N, N)
+    k = 2 * np.pi * np.arange(N) / N
+    assert np.max(np.abs(e - (-2 * (np.cos(k)[:, None] + np.cos(k)[None, :])))) < 1e-14
+    # and it is the lattice Fourier transform (cyclat -> brzone) of the hopping placed on the real-space mesh
+    gr = np.zeros((N, N), complex)
+    gr[1, 0] = gr[N - 1, 0] = gr[0, 1] = gr[0, N - 1] = -1
+    assert np.max(np.abs(O.fourier_lattice_r_to_k(gr.reshape(-1, 1), (N, N, 1)).reshape(N, N) - e)) < 1e-13

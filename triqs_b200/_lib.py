@@ -37,6 +37,7 @@ SIGNATURES = {
                                      POINTER(c_int), POINTER(c_double)]),
     "tq_density": (c_int, [c_void_p, c_double, c_int, c_long, c_int, c_long, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int),
                            POINTER(c_double)]),
+    "tq_tight_binding_fourier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_long), c_void_p]),
     "tq_make_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tq_is_gf_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_double, POINTER(c_int)]),
     "tq_replace_by_tail": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_int]),

@@ -204,6 +204,18 @@ class Context:
             return res, np.frombuffer(err, dtype=np.float64).copy()
         return res
 
+    # -- tight-binding dispersion (lattice/tight_binding.hpp:88-123) ------------------------------
+    def tight_binding_fourier(self, displ, hop, dims, out=None):
+        """eps_k [d0*d1*d2, n, n] = sum_j hop[j] exp(2 pi i k.displ[j]);  displ [n_r, 3] ints (host), hop [n_r, n, n]."""
+        displ = np.ascontiguousarray(np.asarray(displ, dtype=np.int32).reshape(-1, 3))
+        hop = _as_c128(hop)
+        n_r, n, _ = hop.shape
+        d = (ctypes.c_long * 3)(*[int(x) for x in dims])
+        nk = int(dims[0]) * int(dims[1]) * int(dims[2])
+        res = out if out is not None else _empty_like_kind(hop, (nk, n, n))
+        self._check(self._lib.tq_tight_binding_fourier(self._h, n, n_r, displ.ctypes.data_as(ctypes.c_void_p), _ptr(hop), d, _ptr(res)))
+        return res
+
     # -- hermiticity helpers, replace_by_tail (imfreq.hpp:81-215, 258-261) ----------------------
     def make_hermitian(self, g, imtime=False, out=None):
         """g [batch, n_pts, d, d] -> 0.5 (g[w] + dagger(g[-w]))  (full imfreq mesh, or imtime: the point itself)."""
