@@ -309,9 +309,12 @@ def run_native(args):
 
     def e2e_part(i):
         torch.cuda.set_device(local)
-        lo, hi = bounds[i], bounds[i + 1]
-        e2e_ctxs[i].fourier_tau_to_iw(h_gt[lo:hi], BETA, F, N_IW, out=h_gw[lo:hi])
-        e2e_ctxs[i].fourier_iw_to_tau(h_gw[lo:hi], BETA, F, N_TAU, out=h_gt2[lo:hi])
+        # one BlockGf (or --e2e-group blocks) per call, forward then back: the threads drift apart, so the H2D-heavy forward
+        # calls of some overlap the D2H-heavy inverse calls of others and both directions of the link stay busy
+        for lo in range(bounds[i], bounds[i + 1], args.e2e_group):
+            hi = min(lo + args.e2e_group, bounds[i + 1])
+            e2e_ctxs[i].fourier_tau_to_iw(h_gt[lo:hi], BETA, F, N_IW, out=h_gw[lo:hi])
+            e2e_ctxs[i].fourier_iw_to_tau(h_gw[lo:hi], BETA, F, N_TAU, out=h_gt2[lo:hi])
 
     def e2e_step():
         ths = [threading.Thread(target=e2e_part, args=(i,)) for i in range(1, n_thr)]
@@ -335,7 +338,7 @@ def run_native(args):
     e2e_err = float(np.max(np.abs(h_gt2[:NBLOCK] - h_gt[:NBLOCK])))
     e2e = {"value": e2e_val, "unit": "Gf points/s", "h2d_bytes_per_step": int(h_gt.nbytes + h_gw.nbytes),
            "d2h_bytes_per_step": int(h_gw.nbytes + h_gt2.nbytes), "steps": e2e_steps, "round_trip_max_abs_err": e2e_err,
-           "host_threads": n_thr}
+           "host_threads": n_thr, "blocks_per_call": args.e2e_group}
     for c in e2e_ctxs[1:]:
         c.close()
 
@@ -457,6 +460,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=16, help="BlockGfs per GPU per step")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the end-to-end leg")
+    ap.add_argument("--e2e-group", type=int, default=NBLOCK, help="blocks per C-ABI call of the end-to-end leg (default: one BlockGf)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

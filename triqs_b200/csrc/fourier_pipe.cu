@@ -889,7 +889,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   const long in_rows = fwd ? L + 1 : pl->n_w, out_rows = fwd ? pl->n_w : L + 1;
   A.in_gf_stride = in_rows * n_cols;
   A.out_gf_stride = out_rows * n_cols;
-  A.scratch_gf_stride = L * n_cols;
+  A.scratch_gf_stride = env_int("TQ_SCRATCH_ALIAS", 0) ? 0 : L * n_cols; // (developer timing experiment: every gf through the same L2-resident scratch)
   // Chunk the batch by scratch size.  Measured on B200 (tools/gpu_probe.py c2): keeping the scratch L2 resident (chunks of
   // <= 3 blocks = 120 MB) costs more in per-launch prologue / pipeline fill and drain than it saves in HBM traffic while the
   // kernels are FP64-bound, so the default is one launch pair per 1.5 GB of scratch.
