@@ -157,6 +157,19 @@ tq_status tq_tail_fitter_setup_host(double beta, int statistic, long n_iw, doubl
                                     int expansion_order, int n_fixed, int hermitian, int *n_idx_out, long *idx_out,
                                     int *n_var_out, tq_complex *pinv_out, double *sv_out, char *errbuf, size_t errbuf_len);
 
+/* ---- retime <-> refreq ----------------------------------------------------------------------------- */
+
+/* Replace  _fourier_impl(refreq const&, gf_vec_cvt<retime>, moments)   c++/triqs/gfs/transform/fourier_real.cpp:35-78
+ *     and  _fourier_impl(retime const&, gf_vec_cvt<refreq>, moments)   c++/triqs/gfs/transform/fourier_real.cpp:82-131.
+ *   meshes    retime{t_min, t_max, n_pts}, refreq{w_min, w_max, n_pts} (mesh/retime.hpp:39, refreq.hpp:38); they must be
+ *             adjoint (delta_t delta_w n_pts = 2 pi within 1e-10, else TQ_ERR_RUNTIME "Meshes are not compatible")
+ *   gt, gw    [batch][n_pts][n_others]
+ *   moments   [batch][n_moments][n_others] known moments (n_moments >= 3, the 0th must vanish) or NULL: zero tail. */
+tq_status tq_fourier_t_to_w(tq_ctx *ctx, double t_min, double t_max, double w_min, double w_max, long n_pts, long n_others, long batch,
+                            const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw);
+tq_status tq_fourier_w_to_t(tq_ctx *ctx, double t_min, double t_max, double w_min, double w_max, long n_pts, long n_others, long batch,
+                            const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt);
+
 /* ---- plain batched DFT and lattice transforms --------------------------------------------------- */
 
 /* Replaces  _fourier_base(in, out, rank, dims, howmany, sign)   c++/triqs/gfs/transform/fourier_common.cpp:25-45

@@ -453,6 +453,80 @@ def tail_eval(moments: np.ndarray, om: complex) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# retime <-> refreq transforms     c++/triqs/gfs/transform/fourier_real.cpp:35-131
+# ----------------------------------------------------------------------------------------------
+
+
+def linear_values(xmin: float, xmax: float, n: int) -> np.ndarray:
+    """mesh/bases/linear.hpp:154-160:  x_i = xmin (1 - i/(n-1)) + xmax i/(n-1)."""
+    if n == 1:
+        return np.array([xmin])
+    wr = np.arange(n, dtype=np.float64) / (n - 1)
+    return xmin * (1 - wr) + xmax * wr
+
+
+def adjoint_real_mesh(xmin: float, xmax: float, n: int, shift_half_bin: bool = False):
+    """mesh/adjoint.hpp:43-54 (the same formula in both directions)."""
+    delta = (xmax - xmin) / (n - 1)
+    m = math.pi * (n - 1) / (n * delta)
+    if shift_half_bin:
+        return -m + math.pi / n / delta, m + math.pi / n / delta, n
+    return -m, m, n
+
+
+def _real_meshes(t_min, t_max, w_min, w_max, L):
+    t, w = linear_values(t_min, t_max, L), linear_values(w_min, w_max, L)
+    dt, dw = (t_max - t_min) / (L - 1), (w_max - w_min) / (L - 1)
+    if abs(dt * dw * L / (2 * math.pi) - 1) > 1e-10:  # fourier_real.cpp:50-51, :100-101
+        raise RuntimeError("Meshes are not compatible")
+    return t, w, dt, dw
+
+
+def _real_tail(known_moments, n_cols, dw, L):
+    if known_moments is None or np.size(known_moments) == 0:
+        known_moments = np.zeros((3, n_cols), complex)  # :41-43 make_zero_tail(g, 3)
+    known_moments = np.asarray(known_moments, dtype=np.complex128)
+    if known_moments.shape[0] < 3:
+        raise RuntimeError("Direct RealTime Fourier transform requires known moments up to order 2.")
+    if np.max(np.abs(known_moments[0])) >= 1e-8:
+        raise RuntimeError("Fourier implementation requires vanishing 0th moment")
+    a = dw * math.sqrt(float(L))  # :60
+    m1, m2 = known_moments[1], known_moments[2]
+    return a, (m1 + 1j * m2 / a) / 2.0, (m1 - 1j * m2 / a) / 2.0  # :66
+
+
+def _th_expo(t, a):  # :27
+    return np.where(t > 0, -1j * np.exp(-a * t), np.where(t < 0, 0.0, -0.5j * np.exp(-a * t)))
+
+
+def _th_expo_neg(t, a):  # :28
+    return np.where(t < 0, 1j * np.exp(a * t), np.where(t > 0, 0.0, 0.5j * np.exp(a * t)))
+
+
+def fourier_t_to_w(gt: np.ndarray, t_min: float, t_max: float, w_min: float, w_max: float, known_moments=None) -> np.ndarray:
+    """fourier_real.cpp:35-78.  gt [L, n_cols] -> gw [L, n_cols]."""
+    gt = np.asarray(gt, dtype=np.complex128)
+    L, C = gt.shape
+    t, w, dt, dw = _real_meshes(t_min, t_max, w_min, w_max, L)
+    a, a1, a2 = _real_tail(known_moments, C, dw, L)
+    gin = (gt - (a1[None] * _th_expo(t, a)[:, None] + a2[None] * _th_expo_neg(t, a)[:, None])) * np.exp(1j * t * w_min)[:, None]
+    gout = np.fft.ifft(gin, axis=0) * L  # FFTW_BACKWARD, unnormalised
+    return dt * np.exp(1j * (w - w_min) * t_min)[:, None] * gout + a1[None] / (w + 1j * a)[:, None] + a2[None] / (w - 1j * a)[:, None]
+
+
+def fourier_w_to_t(gw: np.ndarray, t_min: float, t_max: float, w_min: float, w_max: float, known_moments=None) -> np.ndarray:
+    """fourier_real.cpp:82-131.  gw [L, n_cols] -> gt [L, n_cols]."""
+    gw = np.asarray(gw, dtype=np.complex128)
+    L, C = gw.shape
+    t, w, dt, dw = _real_meshes(t_min, t_max, w_min, w_max, L)
+    a, a1, a2 = _real_tail(known_moments, C, dw, L)
+    gin = (gw - a1[None] / (w + 1j * a)[:, None] - a2[None] / (w - 1j * a)[:, None]) * np.exp(-1j * w * t_min)[:, None]
+    gout = np.fft.fft(gin, axis=0)  # FFTW_FORWARD
+    corr = 1.0 / (dt * L)
+    return corr * np.exp(1j * w_min * (t_min - t))[:, None] * gout + a1[None] * _th_expo(t, a)[:, None] + a2[None] * _th_expo_neg(t, a)[:, None]
+
+
+# ----------------------------------------------------------------------------------------------
 # tight-binding dispersion on a brzone mesh  (SURVEY 8(f).4)
 # ----------------------------------------------------------------------------------------------
 

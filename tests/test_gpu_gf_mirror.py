@@ -133,3 +133,28 @@ def test_hermiticity_and_replace_by_tail_mirror():
     G.replace_by_tail(g2, tail, 330)
     assert np.max(np.abs(g2.data - exact)) < 1e-8
     ctx.close()
+
+
+def test_real_time_transform_reads_like_the_reference_test():
+    """fourier_real.cpp:27-87 through the mirror: Gt = make_gf_from_fourier(Gw, t_mesh, tail), matrix-valued target."""
+    from triqs_b200 import gf as G
+    w_mesh = G.MeshReFreq(-40.0, 40.0, 1001)
+    t_mesh = G.make_adjoint_mesh(w_mesh)
+    E = 1.0
+    w, t = w_mesh.values(), t_mesh.values()
+    Gw1 = G.Gf(w_mesh, (2, 2), np.repeat((2 * E / (w * w + E * E)).astype(complex)[:, None], 4, axis=1).reshape(-1, 2, 2))
+    tail = np.zeros((3, 2, 2), complex)
+    tail[2] = 2 * E
+    Gt1 = G.make_gf_from_fourier(Gw1, t_mesh, tail)
+    assert isinstance(Gt1.mesh, G.MeshReTime) and Gt1.mesh == t_mesh
+    assert np.max(np.abs(Gt1.data - np.exp(-E * np.abs(t))[:, None, None])) < 1e-4
+    Gw1b = G.make_gf_from_fourier(Gt1, w_mesh, tail)
+    assert np.max(np.abs(Gw1b.data - Gw1.data)) < 1e-4
+    theta = np.where(t > 0, 1.0, np.where(t < 0, 0.0, 0.5))
+    Gt2 = G.Gf(t_mesh, (2, 2))
+    Gt2.data[:] = (0.5j * (np.exp(-E * np.abs(t)) * (1 - theta) - np.exp(-E * np.abs(t)) * theta))[:, None, None]
+    km = np.zeros((3, 2, 2), complex)
+    km[1] = 1.0
+    Gw2 = G.make_gf_from_fourier(Gt2, w_mesh, km)
+    assert np.max(np.abs(Gw2.data - (0.5 / (w + 1j * E) + 0.5 / (w - 1j * E))[:, None, None])) < 1e-4
+    assert np.max(np.abs(G.make_gf_from_fourier(Gw2, t_mesh, km).data - Gt2.data)) < 1e-4

@@ -567,3 +567,47 @@ def test_tight_binding_fourier(ctx):
     for dims in [(16, 12, 10), (64, 64, 1), (7, 1, 5)]:
         out = ctx.tight_binding_fourier(R, t, dims)
         assert rel(out, O.tight_binding_fourier(R, t, dims)) < TOL
+
+
+def test_fourier_real_time_frequency(ctx):
+    """retime <-> refreq (fourier_real.cpp): the reference test's meshes and known answers (fourier_real.cpp:27-87), random data
+    and moments against the oracle, both directions, batch > 1, lengths with large prime factors."""
+    w_max, L, E = 40.0, 1001, 1.0
+    t_lo, t_hi, _ = O.adjoint_real_mesh(-w_max, w_max, L)
+    w, t = O.linear_values(-w_max, w_max, L), O.linear_values(t_lo, t_hi, L)
+    gw = np.repeat((2 * E / (w * w + E * E)).astype(complex)[:, None], 4, axis=1)[None]
+    tail = np.zeros((1, 3, 4), complex)
+    tail[0, 2] = 2 * E
+    gt = ctx.fourier_w_to_t(gw, (t_lo, t_hi), (-w_max, w_max), moments=tail)
+    assert np.max(np.abs(gt[0] - np.exp(-E * np.abs(t))[:, None])) < 1e-4
+    assert rel(gt[0], O.fourier_w_to_t(gw[0], t_lo, t_hi, -w_max, w_max, tail[0])) < TOL
+    back = ctx.fourier_t_to_w(gt, (t_lo, t_hi), (-w_max, w_max), moments=tail)
+    assert np.max(np.abs(back - gw)) < 1e-4
+    assert rel(back[0], O.fourier_t_to_w(gt[0], t_lo, t_hi, -w_max, w_max, tail[0])) < TOL
+    rng = np.random.default_rng(77)
+    for (L, C, B, half) in [(1001, 8, 3, False), (600, 1, 2, True), (2048, 25, 1, False), (97, 5, 2, False)]:
+        w_lo, w_hi = -12.5, 12.5
+        if half:
+            t_lo, t_hi, _ = O.adjoint_real_mesh(w_lo, w_hi, L, shift_half_bin=True)
+        else:
+            t_lo, t_hi, _ = O.adjoint_real_mesh(w_lo, w_hi, L)
+        g = rng.normal(size=(B, L, C)) + 1j * rng.normal(size=(B, L, C))
+        mom = rng.normal(size=(B, 3, C)) + 1j * rng.normal(size=(B, 3, C))
+        mom[:, 0] = 0
+        for m in (mom, None):
+            f = ctx.fourier_t_to_w(g, (t_lo, t_hi), (w_lo, w_hi), moments=m)
+            i = ctx.fourier_w_to_t(g, (t_lo, t_hi), (w_lo, w_hi), moments=m)
+            for b in range(B):
+                mb = None if m is None else m[b]
+                assert rel(f[b], O.fourier_t_to_w(g[b], t_lo, t_hi, w_lo, w_hi, mb)) < TOL
+                assert rel(i[b], O.fourier_w_to_t(g[b], t_lo, t_hi, w_lo, w_hi, mb)) < TOL
+    # error behaviour of the reference: incompatible meshes, too few moments, non-vanishing 0th moment
+    import triqs_b200
+    g = np.zeros((1, 64, 2), complex)
+    t_lo, t_hi, _ = O.adjoint_real_mesh(-5.0, 5.0, 64)
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="not compatible"):
+        ctx.fourier_t_to_w(g, (t_lo, 1.01 * t_hi), (-5.0, 5.0))
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="order 2"):
+        ctx.fourier_t_to_w(g, (t_lo, t_hi), (-5.0, 5.0), moments=np.zeros((1, 2, 2), complex))
+    with pytest.raises(triqs_b200.TriqsRuntimeError, match="vanishing 0th moment"):
+        ctx.fourier_w_to_t(g, (t_lo, t_hi), (-5.0, 5.0), moments=np.ones((1, 3, 2), complex))

@@ -318,3 +318,33 @@ def test_tight_binding_fourier_square_lattice():
     gr = np.zeros((N, N), complex)
     gr[1, 0] = gr[N - 1, 0] = gr[0, 1] = gr[0, N - 1] = -1
     assert np.max(np.abs(O.fourier_lattice_r_to_k(gr.reshape(-1, 1), (N, N, 1)).reshape(N, N) - e)) < 1e-13
+
+
+def _real_test_meshes():
+    w_max, Nw = 40.0, 1001  # fourier_real.cpp:29-31
+    t_lo, t_hi, _ = O.adjoint_real_mesh(-w_max, w_max, Nw)
+    return -w_max, w_max, t_lo, t_hi, Nw
+
+
+def test_fourier_real_lorentzian_known_answers():
+    """fourier_real.cpp:49-62 (Lorentzian <-> exp(-E|t|)) and :66-87 (theta x exponential <-> two poles), precision 1e-4."""
+    w_lo, w_hi, t_lo, t_hi, L = _real_test_meshes()
+    E = 1.0
+    w, t = O.linear_values(w_lo, w_hi, L), O.linear_values(t_lo, t_hi, L)
+    gw = np.repeat((2 * E / (w * w + E * E)).astype(complex)[:, None], 4, axis=1)
+    tail = np.zeros((3, 4), complex)
+    tail[2] = 2 * E  # the exact high-frequency expansion 2E / w^2 (the reference fits it, :52)
+    gt = O.fourier_w_to_t(gw, t_lo, t_hi, w_lo, w_hi, tail)
+    assert np.max(np.abs(gt - np.exp(-E * np.abs(t))[:, None])) < 1e-4
+    assert np.max(np.abs(O.fourier_t_to_w(gt, t_lo, t_hi, w_lo, w_hi, tail) - gw)) < 1e-4
+    theta = lambda x: np.where(x > 0, 1.0, np.where(x < 0, 0.0, 0.5))
+    gt2 = np.repeat((0.5j * (np.exp(-E * np.abs(t)) * theta(-t) - np.exp(-E * np.abs(t)) * theta(t)))[:, None], 4, axis=1)
+    km = np.zeros((3, 4), complex)
+    km[1] = 1.0
+    gw2 = O.fourier_t_to_w(gt2, t_lo, t_hi, w_lo, w_hi, km)
+    assert np.max(np.abs(gw2 - (0.5 / (w + 1j * E) + 0.5 / (w - 1j * E))[:, None])) < 1e-4
+    assert np.max(np.abs(O.fourier_w_to_t(gw2, t_lo, t_hi, w_lo, w_hi, km) - gt2)) < 1e-4
+    # without moments the raw data is transformed (:41-43); incompatible meshes throw (:50-51)
+    assert np.max(np.abs(O.fourier_w_to_t(O.fourier_t_to_w(gt2, t_lo, t_hi, w_lo, w_hi), t_lo, t_hi, w_lo, w_hi) - gt2)) < 1e-12
+    with pytest.raises(RuntimeError):
+        O.fourier_t_to_w(gt2, t_lo, 1.01 * t_hi, w_lo, w_hi)

@@ -37,6 +37,8 @@ SIGNATURES = {
                                      POINTER(c_int), POINTER(c_double)]),
     "tq_density": (c_int, [c_void_p, c_double, c_int, c_long, c_int, c_long, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int),
                            POINTER(c_double)]),
+    "tq_fourier_t_to_w": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p]),
+    "tq_fourier_w_to_t": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p]),
     "tq_tight_binding_fourier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_long), c_void_p]),
     "tq_make_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tq_is_gf_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_double, POINTER(c_int)]),

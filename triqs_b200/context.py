@@ -181,6 +181,27 @@ class Context:
             return gt, np.frombuffer(err, dtype=np.float64).copy()
         return gt
 
+    # -- retime <-> refreq (fourier_real.cpp:35-131) ---------------------------------------------
+    def _fourier_real(self, fn, g, t_mesh, w_mesh, moments, out):
+        g = _as_c128(g)
+        batch, n_pts, n_others = g.shape
+        n_mom = 0
+        if moments is not None:
+            moments = _as_c128(moments)
+            n_mom = moments.shape[1]
+        res = out if out is not None else _empty_like_kind(g, (batch, n_pts, n_others))
+        self._check(fn(self._h, float(t_mesh[0]), float(t_mesh[1]), float(w_mesh[0]), float(w_mesh[1]), n_pts, n_others, batch, _ptr(g),
+                       _ptr(moments), n_mom, _ptr(res)))
+        return res
+
+    def fourier_t_to_w(self, gt, t_mesh, w_mesh, moments=None, out=None):
+        """gt [batch, n, n_others] on retime(t_min, t_max, n) -> gw on refreq(w_min, w_max, n)  (tq_fourier_t_to_w)."""
+        return self._fourier_real(self._lib.tq_fourier_t_to_w, gt, t_mesh, w_mesh, moments, out)
+
+    def fourier_w_to_t(self, gw, t_mesh, w_mesh, moments=None, out=None):
+        """gw [batch, n, n_others] on refreq(w_min, w_max, n) -> gt on retime(t_min, t_max, n)  (tq_fourier_w_to_t)."""
+        return self._fourier_real(self._lib.tq_fourier_w_to_t, gw, t_mesh, w_mesh, moments, out)
+
     # -- density ---------------------------------------------------------------------------------
     def density(self, gw, beta, statistic, moments=None, out=None, return_err=False):
         """gw [batch, n_w, n, n] (full mesh) -> n [batch, n, n]  (tq_density; density.cpp:32-120)."""

@@ -17,9 +17,13 @@ struct PlainArgs {
   int TC, tiles;  // tiles = ceil(inner / TC)
   int direct_tw, smem_tw;
   double scale;   // applied on store (1 = none)
+  // WRAP: x_r = (in_r - a1 h1_r - a2 h2_r) pin_r  ->  DFT  ->  out_k = pout_k X_k + a1 g1_k + a2 g2_k   (fourier_real.cu)
+  const cd *rin;  // [N][3] = h1, h2, pin
+  const cd *rout; // [N][3] = g1, g2, pout
+  const cd *coef; // [outer][inner][2] = a1, a2
 };
 
-template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) plain_tile_kernel(const PlainArgs A) {
+template <int SGN, int NT, int MINB, bool WRAP = false> __global__ void __launch_bounds__(NT, MINB) plain_tile_kernel(const PlainArgs A) {
   extern __shared__ double2 smem[];
   const long o = blockIdx.x / A.tiles;
   const int tile_id = blockIdx.x - (int)(o * A.tiles);
@@ -42,12 +46,23 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
     for (int c = T.ct; c < tc; c += T.nct) {
       const cd *gp = src + c;
       cd *tp = tile + c;
+      cd a1 = cmk(0.0, 0.0), a2 = a1;
+      if (WRAP) {
+        a1 = __ldg(&A.coef[2 * ((size_t)o * A.inner + c0 + c)]);
+        a2 = __ldg(&A.coef[2 * ((size_t)o * A.inner + c0 + c) + 1]);
+      }
       for (int r0 = T.bt; r0 < N; r0 += T.nbt * LU) {
         cd g[LU];
 #pragma unroll
         for (int u = 0; u < LU; ++u) {
           const int r = r0 + u * T.nbt;
-          if (r < N) g[u] = gp[(size_t)r * A.inner];
+          if (r < N) {
+            g[u] = gp[(size_t)r * A.inner];
+            if (WRAP) {
+              const cd *e = A.rin + 3 * (size_t)r;
+              g[u] = cmul(csub(csub(g[u], cmul(a1, __ldg(e))), cmul(a2, __ldg(e + 1))), __ldg(e + 2));
+            }
+          }
         }
 #pragma unroll
         for (int u = 0; u < LU; ++u) {
@@ -62,10 +77,19 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
   const bool scaled = A.scale != 1.0;
   if (T.nbt > 0) {
     for (int c = T.ct; c < tc; c += T.nct) {
+      cd a1 = cmk(0.0, 0.0), a2 = a1;
+      if (WRAP) {
+        a1 = __ldg(&A.coef[2 * ((size_t)o * A.inner + c0 + c)]);
+        a2 = __ldg(&A.coef[2 * ((size_t)o * A.inner + c0 + c) + 1]);
+      }
       for (int k = T.bt; k < N; k += T.nbt) {
         const int pos = A.smem_tw ? posS[k] : __ldg(&A.P.pos[k]);
         cd v = tile[pos * tc + c];
         if (scaled) v = cscale(A.scale, v);
+        if (WRAP) {
+          const cd *e = A.rout + 3 * (size_t)k;
+          v = cadd(cadd(cmul(__ldg(e + 2), v), cmul(a1, __ldg(e))), cmul(a2, __ldg(e + 1)));
+        }
         dst[(size_t)k * A.inner + c] = v;
       }
     }
@@ -75,8 +99,10 @@ template <int SGN, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB)
 // lattice_pipe.cu: TMA-pipelined fast path for axis lengths with a compile-time two-pass plan
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled);
 
-static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale) {
-  {
+static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, const cd *rin = nullptr,
+                              const cd *rout = nullptr, const cd *coef = nullptr) {
+  const bool wrap = rin != nullptr;
+  if (!wrap) {
     bool handled = false;
     TQ_TRY(tq_lattice_pipe_axis(ctx, outer, N, inner, in, out, sign, scale, &handled));
     if (handled) return TQ_OK;
@@ -108,17 +134,20 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   A.tiles = (int)((inner + tc - 1) / tc);
   A.direct_tw = A.smem_tw = tc >= 4;
   A.scale = scale;
+  A.rin = rin;
+  A.rout = rout;
+  A.coef = coef;
   const size_t smem = sizeof(cd) * (size_t)N * tc + (A.smem_tw ? (sizeof(cd) + sizeof(int)) * (size_t)N : 0);
   const long nblocks = outer * A.tiles;
   if (nblocks > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fft_many: too many tiles");
   const bool big = smem > budget / 2 - 1024;
 #define TQ_LAUNCH_PLAIN(SGN, NT, MINB)                                                                                           \
   do {                                                                                                                           \
-    auto k = plain_tile_kernel<SGN, NT, MINB>;                                                                                   \
+    auto k = wrap ? plain_tile_kernel<SGN, NT, MINB, true> : plain_tile_kernel<SGN, NT, MINB, false>;                            \
     TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                               \
     k<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(A);                                                                          \
   } while (0)
-  KernelScope ks(ctx, "fft_axis");
+  KernelScope ks(ctx, wrap ? "fft_axis_wrapped" : "fft_axis");
   if (sign > 0) {
     if (big) TQ_LAUNCH_PLAIN(1, 512, 1); else TQ_LAUNCH_PLAIN(1, 256, 2);
   } else {
@@ -128,6 +157,12 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
   return TQ_OK;
+}
+
+// fourier_real.cu: one axis transform with the affine pre/post wrap fused into the load and the store of the tile
+tq_status tq_wrapped_fft_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *rin, const cd *rout,
+                              const cd *coef) {
+  return launch_plain(ctx, outer, N, inner, in, out, sign, 1.0, rin, rout, coef);
 }
 
 static tq_status fft_many_device(tq_ctx *ctx, int rank, const long *dims, long howmany, const cd *d_in, cd *d_out, int sign, double scale) {

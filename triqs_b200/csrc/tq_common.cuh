@@ -45,6 +45,7 @@ struct TailFitterPlan; // tail_fit.cu
 struct PipePlanCache;  // fourier_pipe.cu
 struct LatTwiddles;    // lattice_pipe.cu
 struct ColPlanCache;   // fourier_col.cu
+struct RealPlanCache;  // fourier_real.cu
 
 struct tq_ctx {
   int device = 0;
@@ -64,6 +65,7 @@ struct tq_ctx {
   std::shared_ptr<PipePlanCache> pipe_cache;
   std::shared_ptr<LatTwiddles> lat_tw;
   std::shared_ptr<ColPlanCache> col_cache;
+  std::shared_ptr<RealPlanCache> real_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {

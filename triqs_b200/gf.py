@@ -74,6 +74,33 @@ class MeshImFreq:
 
 
 @dataclass(frozen=True)
+class _MeshLinear:
+    """c++/triqs/mesh/bases/linear.hpp: n points on [xmin, xmax], both ends included."""
+    xmin: float
+    xmax: float
+    n: int
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def delta(self):
+        return (self.xmax - self.xmin) / (self.n - 1)
+
+    def values(self):
+        wr = np.arange(self.n, dtype=np.float64) / (self.n - 1)
+        return self.xmin * (1 - wr) + self.xmax * wr
+
+
+class MeshReTime(_MeshLinear):
+    """c++/triqs/mesh/retime.hpp:39"""
+
+
+class MeshReFreq(_MeshLinear):
+    """c++/triqs/mesh/refreq.hpp:38"""
+
+
+@dataclass(frozen=True)
 class MeshCycLat:
     dims: tuple
 
@@ -99,6 +126,10 @@ def make_adjoint_mesh(m, n=-1):
         return MeshBrZone(m.dims)
     if isinstance(m, MeshBrZone):
         return MeshCycLat(m.dims)
+    if isinstance(m, (MeshReTime, MeshReFreq)):  # adjoint.hpp:43-54; `n` plays the role of shift_half_bin (True / False)
+        xm = math.pi * (m.n - 1) / (m.n * m.delta)
+        sh = math.pi / m.n / m.delta if n is True else 0.0
+        return (MeshReFreq if isinstance(m, MeshReTime) else MeshReTime)(-xm + sh, xm + sh, m.n)
     raise TypeError(m)
 
 
@@ -198,23 +229,35 @@ def make_gf_from_fourier(g, n=-1, known_moments=None):
             return BlockGf(g.names, [make_gf_from_fourier(b, n, km) for b, km in zip(g.blocks, kms)])
         b0 = g.blocks[0]
         out = _transform(b0.ctx, b0.mesh, _stack(g.blocks), n, None)
-        mo = make_adjoint_mesh(b0.mesh, n)
+        mo = _out_mesh(b0.mesh, n)
         return BlockGf(g.names, [Gf(mo, b0.target_shape, out[i].reshape((len(mo),) + b0.target_shape), b0._ctx) for i in range(len(g))])
     km = None
     if known_moments is not None:
         km = known_moments.reshape(1, known_moments.shape[0], g.n_others)
     out = _transform(g.ctx, g.mesh, g.flat()[None], n, km)
-    mo = make_adjoint_mesh(g.mesh, n)
+    mo = _out_mesh(g.mesh, n)
     return Gf(mo, g.target_shape, out[0].reshape((len(mo),) + g.target_shape), g._ctx)
+
+
+def _out_mesh(mesh, n):
+    """the target mesh: given explicitly (make_gf_from_fourier(g, mesh, ...), fourier.hpp:93-114) or the adjoint one"""
+    if hasattr(n, "__len__") and not isinstance(n, (int, bool)):
+        return n
+    return make_adjoint_mesh(mesh, n)
 
 
 def _transform(ctx, mesh, data3, n, km):
     if isinstance(mesh, MeshImTime):
-        mo = make_adjoint_mesh(mesh, n)
+        mo = _out_mesh(mesh, n)
         return ctx.fourier_tau_to_iw(data3, mesh.beta, mesh.statistic, mo.n_iw, moments=km)
     if isinstance(mesh, MeshImFreq):
-        mo = make_adjoint_mesh(mesh, n)
+        mo = _out_mesh(mesh, n)
         return ctx.fourier_iw_to_tau(data3, mesh.beta, mesh.statistic, mo.n_tau, moments=km)
+    if isinstance(mesh, (MeshReTime, MeshReFreq)):  # fourier_real.cpp:35-131
+        mo = n if isinstance(n, (MeshReTime, MeshReFreq)) else make_adjoint_mesh(mesh, n)
+        if isinstance(mesh, MeshReTime):
+            return ctx.fourier_t_to_w(data3, (mesh.xmin, mesh.xmax), (mo.xmin, mo.xmax), moments=km)
+        return ctx.fourier_w_to_t(data3, (mo.xmin, mo.xmax), (mesh.xmin, mesh.xmax), moments=km)
     if isinstance(mesh, (MeshCycLat, MeshBrZone)):
         outs = [ctx.fourier_lattice(d, tuple(mesh.dims), to_k=isinstance(mesh, MeshCycLat)) for d in data3]
         if _is_torch(outs[0]):
