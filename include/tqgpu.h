@@ -170,6 +170,18 @@ tq_status tq_fourier_t_to_w(tq_ctx *ctx, double t_min, double t_max, double w_mi
 tq_status tq_fourier_w_to_t(tq_ctx *ctx, double t_min, double t_max, double w_min, double w_max, long n_pts, long n_others, long batch,
                             const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt);
 
+/* ---- Legendre <-> Matsubara ------------------------------------------------------------------------ */
+
+/* Replace  legendre_matsubara_direct(gw | gt, gl)  and  legendre_matsubara_inverse(gl, gw | gt)
+ *          c++/triqs/gfs/transform/legendre_matsubara.hpp:37-50, :56-70, :76-93, :97-118   (T_{nl}: utility/legendre.cpp:24-42)
+ *   gl [batch][n_l][n_others] (n_l <= 128),  gw [batch][n_w][n_others] on the full imfreq mesh,  gt [batch][n_tau][n_others].
+ * tq_imfreq_to_legendre goes through G(tau) on 50000 points like the reference (:85), the tail is fitted by that transform. */
+tq_status tq_legendre_to_imfreq(tq_ctx *ctx, int statistic, long n_l, long n_iw, long n_others, long batch, const tq_complex *gl, tq_complex *gw);
+tq_status tq_legendre_to_imtime(tq_ctx *ctx, double beta, long n_l, long n_tau, long n_others, long batch, const tq_complex *gl, tq_complex *gt);
+tq_status tq_imtime_to_legendre(tq_ctx *ctx, double beta, long n_tau, long n_l, long n_others, long batch, const tq_complex *gt, tq_complex *gl);
+tq_status tq_imfreq_to_legendre(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_l, long n_others, long batch, const tq_complex *gw,
+                                tq_complex *gl);
+
 /* ---- plain batched DFT and lattice transforms --------------------------------------------------- */
 
 /* Replaces  _fourier_base(in, out, rank, dims, howmany, sign)   c++/triqs/gfs/transform/fourier_common.cpp:25-45

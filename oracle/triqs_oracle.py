@@ -527,6 +527,68 @@ def fourier_w_to_t(gw: np.ndarray, t_min: float, t_max: float, w_min: float, w_m
 
 
 # ----------------------------------------------------------------------------------------------
+# Legendre <-> Matsubara     c++/triqs/gfs/transform/legendre_matsubara.hpp:37-129, utility/legendre.{hpp,cpp}
+# ----------------------------------------------------------------------------------------------
+
+
+def legendre_T(n: int, l: int) -> complex:
+    """legendre.cpp:24-42:  sqrt(2l+1)/sqrt(2n+1) e^{i(n+1/2)pi} i^l J_{l+1/2}((n+1/2)pi), T_{-n-1,l} = conj(T_{n,l}).
+    J_{l+1/2}(x) = sqrt(2x/pi) j_l(x) and sqrt(2x/pi) = sqrt(2n+1) at x = (n+1/2)pi."""
+    from scipy.special import spherical_jn
+    neg = n < 0
+    if neg:
+        n = abs(n + 1)
+    x = (n + 0.5) * math.pi
+    res = math.sqrt(2 * l + 1) * np.exp(1j * x) * (1j ** l) * spherical_jn(l, x)
+    return np.conj(res) if neg else res
+
+
+def legendre_polynomials(x: np.ndarray, n_l: int) -> np.ndarray:
+    """legendre_generator (legendre.hpp:39-58): P_0 = 1, P_1 = x, n P_n = (2n-1) x P_{n-1} - (n-1) P_{n-2}.  Returns [n_l, len(x)]."""
+    x = np.asarray(x, dtype=np.float64)
+    P = np.empty((n_l, x.size))
+    P[0] = 1.0
+    if n_l > 1:
+        P[1] = x
+    for n in range(2, n_l):
+        P[n] = ((2 * n - 1) * x * P[n - 1] - (n - 1) * P[n - 2]) / n
+    return P
+
+
+def legendre_to_imfreq(gl: np.ndarray, stat: int, n_iw: int) -> np.ndarray:
+    """legendre_matsubara.hpp:37-50.  gl [n_l, n_cols] -> gw [n_w, n_cols] (the Matsubara *index* enters T whatever the statistic)."""
+    gl = np.asarray(gl, dtype=np.complex128)
+    first, last = imfreq_first_last(stat, n_iw)
+    T = np.array([[legendre_T(n, l) for l in range(gl.shape[0])] for n in range(first, last + 1)])
+    return T @ gl
+
+
+def legendre_to_imtime(gl: np.ndarray, beta: float, n_tau: int) -> np.ndarray:
+    """legendre_matsubara.hpp:56-70."""
+    gl = np.asarray(gl, dtype=np.complex128)
+    n_l = gl.shape[0]
+    P = legendre_polynomials(2 * tau_values(beta, n_tau) / beta - 1, n_l)
+    f = np.sqrt(2 * np.arange(n_l) + 1.0) / beta
+    return (P * f[:, None]).T @ gl
+
+
+def imtime_to_legendre(gt: np.ndarray, beta: float, n_l: int) -> np.ndarray:
+    """legendre_matsubara.hpp:97-118: trapezoid rule over tau."""
+    gt = np.asarray(gt, dtype=np.complex128)
+    n_tau = gt.shape[0]
+    P = legendre_polynomials(2 * tau_values(beta, n_tau) / beta - 1, n_l)
+    coef = np.ones(n_tau)
+    coef[0] = coef[-1] = 0.5
+    f = np.sqrt(2 * np.arange(n_l) + 1.0)
+    return ((P * f[:, None]) * coef[None, :]) @ gt * tau_delta(beta, n_tau)
+
+
+def imfreq_to_legendre(gw: np.ndarray, beta: float, stat: int, n_l: int) -> np.ndarray:
+    """legendre_matsubara.hpp:76-93: through G(tau) on 50000 points, tail fitted by the transform."""
+    return imtime_to_legendre(fourier_iw_to_tau(gw, beta, stat, 50000), beta, n_l)
+
+
+# ----------------------------------------------------------------------------------------------
 # tight-binding dispersion on a brzone mesh  (SURVEY 8(f).4)
 # ----------------------------------------------------------------------------------------------
 

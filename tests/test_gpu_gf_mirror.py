@@ -158,3 +158,18 @@ def test_real_time_transform_reads_like_the_reference_test():
     Gw2 = G.make_gf_from_fourier(Gt2, w_mesh, km)
     assert np.max(np.abs(Gw2.data - (0.5 / (w + 1j * E) + 0.5 / (w - 1j * E))[:, None, None])) < 1e-4
     assert np.max(np.abs(G.make_gf_from_fourier(Gw2, t_mesh, km).data - Gt2.data)) < 1e-4
+
+
+def test_legendre_descriptors():
+    """issue459.py / tail_issues.py:176-183: gl << MatsubaraToLegendre(gw); gw << LegendreToMatsubara(gl)."""
+    from triqs_b200 import gf as G
+    beta, n_iw = 10.0, 300
+    d, H = _gw(beta, n_iw, 2, 3)
+    gw = G.Gf(G.MeshImFreq(beta, O.FERMION, n_iw), (2, 2), d)
+    gl = G.matsubara_to_legendre(gw, 40)
+    assert isinstance(gl.mesh, G.MeshLegendre) and gl.data.shape == (40, 2, 2)
+    gw2 = G.legendre_to_matsubara(gl, gw.mesh)
+    assert np.max(np.abs(gw2.data - gw.data)) < 1e-4     # 40 coefficients resolve this G to ~1e-5
+    gt = G.legendre_to_matsubara(gl, G.MeshImTime(beta, O.FERMION, 1001))
+    ref = O.fourier_iw_to_tau(gw.flat(), beta, O.FERMION, 1001).reshape(1001, 2, 2)
+    assert np.max(np.abs(gt.data - ref)) < 1e-4

@@ -611,3 +611,58 @@ def test_fourier_real_time_frequency(ctx):
         ctx.fourier_t_to_w(g, (t_lo, t_hi), (-5.0, 5.0), moments=np.zeros((1, 2, 2), complex))
     with pytest.raises(triqs_b200.TriqsRuntimeError, match="vanishing 0th moment"):
         ctx.fourier_w_to_t(g, (t_lo, t_hi), (-5.0, 5.0), moments=np.ones((1, 3, 2), complex))
+
+
+def test_legendre_matsubara(ctx):
+    """Legendre <-> Matsubara (legendre_matsubara.hpp): known answers of gf_legendre.cpp:22-72 and parity with the oracle for
+    all four transforms; imfreq -> legendre goes through the prime-length (L = 49999) direct transform."""
+    beta, n_l, n_tau = 2.0, 10, 5
+    g = np.zeros((1, n_l, 1), complex)
+    g[0, 0] = 1
+    assert np.max(np.abs(ctx.legendre_to_imtime(g, beta, n_tau) - 1 / beta)) < 1e-16
+    g[:] = 0
+    g[0, 2] = 1
+    x = 2 * O.tau_values(beta, n_tau) / beta - 1
+    assert np.max(np.abs(ctx.legendre_to_imtime(g, beta, n_tau)[0, :, 0] - math.sqrt(5) / beta * (3 * x * x - 1) / 2)) < 1e-15
+    rng = np.random.default_rng(31)
+    B, C, n_l = 2, 6, 40
+    gl = (rng.normal(size=(B, n_l, C)) + 1j * rng.normal(size=(B, n_l, C))) / (1 + np.arange(n_l))[None, :, None] ** 2
+    for stat, n_iw in ((O.FERMION, 300), (O.BOSON, 129)):
+        gw = ctx.legendre_to_imfreq(gl, stat, n_iw)
+        for b in range(B):
+            assert rel(gw[b], O.legendre_to_imfreq(gl[b], stat, n_iw)) < TOL
+    for n_tau in (1001, 4097, 64):
+        gt = ctx.legendre_to_imtime(gl, 7.0, n_tau)
+        back = ctx.imtime_to_legendre(gt, 7.0, n_l)
+        for b in range(B):
+            ref = O.legendre_to_imtime(gl[b], 7.0, n_tau)
+            assert rel(gt[b], ref) < TOL
+            assert rel(back[b], O.imtime_to_legendre(ref, 7.0, n_l)) < TOL
+    # imfreq -> legendre of a physical G (tail fitted inside, 50000 tau points)
+    beta, n_iw = 10.0, 400
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    H = np.array([[0.7, 0.2], [0.2, -0.4]])
+    gw = np.linalg.inv(iw[:, None, None] * np.eye(2)[None] - H[None]).reshape(1, -1, 4)
+    got = ctx.imfreq_to_legendre(gw, beta, O.FERMION, 30)
+    ref = O.imfreq_to_legendre(gw[0], beta, O.FERMION, 30)
+    assert rel(got[0], ref) < 1e-10  # the LSQ tail fit inside is conditioning-limited (DESIGN.md section 4)
+    with pytest.raises(Exception, match="128 Legendre"):
+        ctx.legendre_to_imtime(np.zeros((1, 200, 1), complex), 1.0, 10)
+
+
+def test_matsubara_meshes_with_large_prime_factors(ctx):
+    """time meshes whose length the tile FFT cannot factor (FFTW takes any length, fourier_common.cpp:30): direct window DFT"""
+    rng = np.random.default_rng(12)
+    for (L, n_iw, stat, C, B) in [(6 * 1031, 1031, O.FERMION, 4, 2), (4999, 500, O.BOSON, 3, 1), (49999, 64, O.FERMION, 9, 1)]:
+        beta = 5.0
+        iw = O.imfreq_values(beta, stat, n_iw)
+        e = rng.uniform(0.3, 2.0, size=(B, C))
+        gw = 1 / (iw[None, :, None] - e[:, None, :])
+        mom = np.zeros((B, 4, C), complex)
+        mom[:, 1], mom[:, 2], mom[:, 3] = 1, e, e ** 2
+        gt = ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+        back = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=mom)
+        for b in range(B):
+            rt = O.fourier_iw_to_tau(gw[b], beta, stat, L + 1, mom[b])
+            assert rel(gt[b], rt) < TOL
+            assert rel(back[b], O.fourier_tau_to_iw(rt, beta, stat, n_iw, mom[b])) < TOL

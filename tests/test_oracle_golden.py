@@ -348,3 +348,35 @@ def test_fourier_real_lorentzian_known_answers():
     assert np.max(np.abs(O.fourier_w_to_t(O.fourier_t_to_w(gt2, t_lo, t_hi, w_lo, w_hi), t_lo, t_hi, w_lo, w_hi) - gt2)) < 1e-12
     with pytest.raises(RuntimeError):
         O.fourier_t_to_w(gt2, t_lo, 1.01 * t_hi, w_lo, w_hi)
+
+
+def test_legendre_known_answers():
+    """gf_legendre.cpp:22-72: g_l = delta_{l0} -> g(tau) = 1/beta;  g_l = delta_{l2} -> sqrt(5)/beta (3x^2-1)/2; and the
+    properties of T_{nl} (legendre.cpp:24-42): T_{-n-1,l} = conj T_{nl}, unitarity of the l <-> tau pair."""
+    beta, n_l, n_tau = 2.0, 10, 5
+    g = np.zeros((n_l, 1), complex)
+    g[0] = 1
+    assert np.array_equal(O.legendre_to_imtime(g, beta, n_tau)[:, 0], np.full(n_tau, 1 / beta, complex))
+    g[:] = 0
+    g[2] = 1
+    x = 2 * O.tau_values(beta, n_tau) / beta - 1
+    assert np.max(np.abs(O.legendre_to_imtime(g, beta, n_tau)[:, 0] - math.sqrt(5) / beta * (3 * x * x - 1) / 2)) < 1e-15
+    for n in range(0, 5):
+        for l in range(0, 6):
+            assert O.legendre_T(-n - 1, l) == np.conj(O.legendre_T(n, l))
+    # T_{n0} = i (-1)^n j_0((n+1/2) pi) = i / ((n+1/2) pi):  G(iw) of g_l = delta_{l0} is 1/(i w_n) x (-2/beta)... check the value itself
+    assert abs(O.legendre_T(3, 0) - 1j * (-1) ** 3 * math.sin(3.5 * math.pi) / (3.5 * math.pi)) < 1e-15
+    # tau -> l -> tau is the identity on the span of the first n_l polynomials (up to the trapezoid error)
+    rng = np.random.default_rng(5)
+    gl = rng.normal(size=(8, 3)) + 1j * rng.normal(size=(8, 3))
+    back = O.imtime_to_legendre(O.legendre_to_imtime(gl, 3.0, 20001), 3.0, 8)
+    assert np.max(np.abs(back - gl)) < 1e-5
+    # l -> iw -> l (through 50000 tau points, legendre_matsubara.hpp:85) for a smooth physical G
+    beta = 10.0
+    tau = O.tau_values(beta, 40001)
+    gtau = (-np.exp(-0.7 * tau) / (1 + np.exp(-beta * 0.7)))[:, None]
+    gl = O.imtime_to_legendre(gtau, beta, 30)
+    gw = O.legendre_to_imfreq(gl, O.FERMION, 200)
+    iw = O.imfreq_values(beta, O.FERMION, 200)
+    assert np.max(np.abs(gw[:, 0] - 1 / (iw - 0.7))) < 2e-6
+    assert np.max(np.abs(O.imfreq_to_legendre(gw, beta, O.FERMION, 30) - gl)) < 1e-5

@@ -39,6 +39,10 @@ SIGNATURES = {
                            POINTER(c_double)]),
     "tq_fourier_t_to_w": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p]),
     "tq_fourier_w_to_t": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p]),
+    "tq_legendre_to_imfreq": (c_int, [c_void_p, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p]),
+    "tq_legendre_to_imtime": (c_int, [c_void_p, c_double, c_long, c_long, c_long, c_long, c_void_p, c_void_p]),
+    "tq_imtime_to_legendre": (c_int, [c_void_p, c_double, c_long, c_long, c_long, c_long, c_void_p, c_void_p]),
+    "tq_imfreq_to_legendre": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p]),
     "tq_tight_binding_fourier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_long), c_void_p]),
     "tq_make_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tq_is_gf_hermitian": (c_int, [c_void_p, c_int, c_long, c_int, c_long, c_void_p, c_double, POINTER(c_int)]),

@@ -202,6 +202,38 @@ class Context:
         """gw [batch, n, n_others] on refreq(w_min, w_max, n) -> gt on retime(t_min, t_max, n)  (tq_fourier_w_to_t)."""
         return self._fourier_real(self._lib.tq_fourier_w_to_t, gw, t_mesh, w_mesh, moments, out)
 
+    # -- Legendre <-> Matsubara (legendre_matsubara.hpp:37-129) ------------------------------------
+    def legendre_to_imfreq(self, gl, statistic, n_iw, out=None):
+        """gl [batch, n_l, n_others] -> gw [batch, n_w, n_others] on the full imfreq mesh."""
+        gl = _as_c128(gl)
+        batch, n_l, n_others = gl.shape
+        n_w = 2 * n_iw if statistic == FERMION else 2 * n_iw - 1
+        res = out if out is not None else _empty_like_kind(gl, (batch, n_w, n_others))
+        self._check(self._lib.tq_legendre_to_imfreq(self._h, statistic, n_l, n_iw, n_others, batch, _ptr(gl), _ptr(res)))
+        return res
+
+    def legendre_to_imtime(self, gl, beta, n_tau, out=None):
+        gl = _as_c128(gl)
+        batch, n_l, n_others = gl.shape
+        res = out if out is not None else _empty_like_kind(gl, (batch, n_tau, n_others))
+        self._check(self._lib.tq_legendre_to_imtime(self._h, beta, n_l, n_tau, n_others, batch, _ptr(gl), _ptr(res)))
+        return res
+
+    def imtime_to_legendre(self, gt, beta, n_l, out=None):
+        gt = _as_c128(gt)
+        batch, n_tau, n_others = gt.shape
+        res = out if out is not None else _empty_like_kind(gt, (batch, n_l, n_others))
+        self._check(self._lib.tq_imtime_to_legendre(self._h, beta, n_tau, n_l, n_others, batch, _ptr(gt), _ptr(res)))
+        return res
+
+    def imfreq_to_legendre(self, gw, beta, statistic, n_l, out=None):
+        gw = _as_c128(gw)
+        batch, n_w, n_others = gw.shape
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        res = out if out is not None else _empty_like_kind(gw, (batch, n_l, n_others))
+        self._check(self._lib.tq_imfreq_to_legendre(self._h, beta, statistic, n_iw, n_l, n_others, batch, _ptr(gw), _ptr(res)))
+        return res
+
     # -- density ---------------------------------------------------------------------------------
     def density(self, gw, beta, statistic, moments=None, out=None, return_err=False):
         """gw [batch, n_w, n, n] (full mesh) -> n [batch, n, n]  (tq_density; density.cpp:32-120)."""

@@ -321,6 +321,176 @@ __global__ void __launch_bounds__(NT, MINB) matsubara_tile_kernel(const TileArgs
 }
 
 // -------------------------------------------------------------------------------------------------
+// Direct evaluation for mesh lengths the tile FFT cannot factor (a prime factor > 128, e.g. L = 49999 of the 50000-point
+// mesh legendre_matsubara.hpp:85 goes through).  Only n_w of the L frequencies are non-zero / wanted (:182, :254), so the
+// window DFT is a skinny matrix product with n_w L n_cols terms, the matrix e^{+-2 pi i jk/L} generated from the two-level
+// twiddle table.  Same pre / post arithmetic as the tile kernel.  The long sum is split into chunks whose partial sums
+// are added in fixed order (deterministic).
+// -------------------------------------------------------------------------------------------------
+TQ_D void pole_weights(bool fermion, cd m1, cd m2, cd m3, cd &a1, cd &a2, cd &a3) { // :151-169, :238-252
+  if (fermion) {
+    a1 = csub(m1, m3);
+    a2 = cscale(0.5, cadd(m2, m3));
+    a3 = cscale(0.5, csub(m3, m2));
+  } else {
+    a1 = cscale(4.0 / 3.0, csub(m1, m3));
+    a2 = csub(m3, cscale(0.5, cadd(m1, m2)));
+    a3 = cadd(cadd(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
+  }
+}
+
+struct DirectArgs {
+  MatsubaraDev D;
+  BigTw btw;
+  int n_cols, n_in, n_out, chunk, n_chunks; // rows summed over / produced; inner chunking
+  const cd *in;
+  cd *out;
+  cd *x;       // [gf][n_in][n_cols] pre-transformed input
+  cd *partial; // [gf][n_chunks][n_out][n_cols]
+  const cd *moments;
+  long in_gf_stride, out_gf_stride, mom_gf_stride;
+};
+
+// x_j = phase_j (g_j - sum_i a_i h_i(tau_j))  (FWD, :159-173)   or   y_di = (g_di - tail(i w)) / beta  (:254)
+template <bool FWD> __global__ void k_direct_pre(const DirectArgs A) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long per_gf = (long)A.n_in * A.n_cols;
+  if (i >= per_gf) return;
+  const int gf = blockIdx.y, r = (int)(i / A.n_cols), c = (int)(i - (long)r * A.n_cols);
+  const MatsubaraDev &D = A.D;
+  const bool fermion = D.stat == TQ_FERMION;
+  const cd *mom = A.moments + (size_t)gf * A.mom_gf_stride;
+  cd a1, a2, a3;
+  pole_weights(fermion, mom[(size_t)1 * A.n_cols + c], mom[(size_t)2 * A.n_cols + c], mom[(size_t)3 * A.n_cols + c], a1, a2, a3);
+  cd x = A.in[(size_t)gf * A.in_gf_stride + i];
+  if (FWD) {
+    double h[3];
+    row_model(D, r, h);
+    x = caxpy(-h[2], a3, caxpy(-h[1], a2, caxpy(-h[0], a1, x)));
+    x = fermion ? cmul(phase_fwd(D, r), x) : cscale(D.fact_fwd, x);
+  } else {
+    x = cscale(D.inv_beta, csub(x, tail_iw(D, load_w(D, r), a1, a2, a3)));
+  }
+  A.x[(size_t)gf * per_gf + i] = x;
+}
+
+// partial[chunk][o][c] = sum_{i in chunk} x[i][c] w^{+-(k j)},  FWD: o = frequency data index, i = j;  inverse: o = j, i = data index
+constexpr int DIRECT_CW = 8;
+template <bool FWD> __global__ void __launch_bounds__(128) k_direct_dft(const DirectArgs A) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int gf = blockIdx.z / ((A.n_cols + DIRECT_CW - 1) / DIRECT_CW), ct = blockIdx.z - gf * ((A.n_cols + DIRECT_CW - 1) / DIRECT_CW);
+  const int c0 = ct * DIRECT_CW, w = min(DIRECT_CW, A.n_cols - c0);
+  const MatsubaraDev &D = A.D;
+  const long L = D.L;
+  const bool active = o < A.n_out;
+  const int oo = active ? o : 0;
+  // multiplier of the running index and the first product (mod L)
+  long s, first_i;
+  if (FWD) {
+    const long n = (long)D.first + oo;
+    s = ((n % L) + L) % L;
+    first_i = 0;
+  } else {
+    s = oo;
+    first_i = (((long)D.first % L) + L) % L;
+  }
+  const int i0 = chunk * A.chunk, i1 = min(i0 + A.chunk, A.n_in);
+  long m = (long)(((unsigned long long)((first_i + i0) % L) * (unsigned long long)s) % (unsigned long long)L);
+  cd acc[DIRECT_CW];
+#pragma unroll
+  for (int c = 0; c < DIRECT_CW; ++c) acc[c] = cmk(0.0, 0.0);
+  const cd *x = A.x + ((size_t)gf * A.n_in + i0) * A.n_cols + c0;
+  for (int i = i0; i < i1; ++i) {
+    cd tw = bigtw(A.btw, (int)m);
+    if (!FWD) tw = cconj(tw);
+    m += s;
+    if (m >= L) m -= L;
+#pragma unroll
+    for (int c = 0; c < DIRECT_CW; ++c)
+      if (c < w) acc[c] = cfma(tw, __ldg(x + c), acc[c]);
+    x += A.n_cols;
+  }
+  if (!active) return;
+  cd *p = A.partial + (((size_t)gf * A.n_chunks + chunk) * A.n_out + o) * A.n_cols + c0;
+  for (int c = 0; c < w; ++c) p[c] = acc[c];
+}
+
+// G(i w_n) = X + corr + tail (:181-183)   or   G(tau_j) = Y e^{-i pi j/L} + sum_i a_i h_i  and  G(tau_L) = -/+ (G(0) + m1)  (:261-268)
+template <bool FWD> __global__ void k_direct_post(const DirectArgs A) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long per_gf = (long)A.n_out * A.n_cols;
+  if (i >= per_gf) return;
+  const int gf = blockIdx.y, r = (int)(i / A.n_cols), c = (int)(i - (long)r * A.n_cols);
+  const MatsubaraDev &D = A.D;
+  const bool fermion = D.stat == TQ_FERMION;
+  const cd *mom = A.moments + (size_t)gf * A.mom_gf_stride;
+  const cd m1 = mom[(size_t)1 * A.n_cols + c];
+  cd a1, a2, a3;
+  pole_weights(fermion, m1, mom[(size_t)2 * A.n_cols + c], mom[(size_t)3 * A.n_cols + c], a1, a2, a3);
+  cd v = cmk(0.0, 0.0);
+  for (int k = 0; k < A.n_chunks; ++k) v = cadd(v, A.partial[((size_t)gf * A.n_chunks + k) * per_gf + i]);
+  cd *out = A.out + (size_t)gf * A.out_gf_stride;
+  if (FWD) {
+    const cd *g = A.in + (size_t)gf * A.in_gf_stride;
+    cd t = cadd(g[c], m1);
+    const cd gL = g[(size_t)D.L * A.n_cols + c];
+    t = fermion ? cadd(t, gL) : csub(t, gL);
+    out[i] = cadd(cadd(v, cscale(-0.5 * D.fact_fwd, t)), tail_iw(D, load_w(D, r), a1, a2, a3));
+  } else {
+    if (fermion) v = cmul(v, phase_inv(D, r));
+    double h[3];
+    row_model(D, r, h);
+    v = caxpy(h[2], a3, caxpy(h[1], a2, caxpy(h[0], a1, v)));
+    out[i] = v;
+    if (r == 0) {
+      const cd t = cadd(v, m1);
+      out[(size_t)D.L * A.n_cols + c] = fermion ? cneg(t) : t;
+    }
+  }
+}
+
+template <bool FWD>
+static tq_status run_direct(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw, long n_cols, long batch, const cd *d_in, cd *d_out, const cd *d_mom,
+                            int mom_rows) {
+  DirectArgs A{};
+  A.D = D;
+  A.btw = btw;
+  A.n_cols = (int)n_cols;
+  A.n_in = FWD ? D.L : D.n_w;
+  A.n_out = FWD ? D.n_w : D.L;
+  A.chunk = 2048;
+  A.n_chunks = (A.n_in + A.chunk - 1) / A.chunk;
+  A.in_gf_stride = (long)(FWD ? D.L + 1 : D.n_w) * n_cols;
+  A.out_gf_stride = (long)(FWD ? D.n_w : D.L + 1) * n_cols;
+  A.mom_gf_stride = (long)mom_rows * n_cols;
+  const size_t x_gf = sizeof(cd) * (size_t)A.n_in * n_cols, p_gf = sizeof(cd) * (size_t)A.n_chunks * A.n_out * n_cols;
+  const int n_ct = (int)((n_cols + DIRECT_CW - 1) / DIRECT_CW);
+  // gfs per pass: bounded scratch (256 MB) and grid.z
+  long per = std::max<long>(1, std::min<long>((long)((256ull << 20) / (x_gf + p_gf)), 65535 / n_ct));
+  per = std::min(per, batch);
+  const size_t x_off = (p_gf * per + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, x_off + x_gf * per));
+  A.partial = (cd *)ctx->scratch.p;
+  A.x = (cd *)((char *)ctx->scratch.p + x_off);
+  for (long b0 = 0; b0 < batch; b0 += per) {
+    const long nb = std::min(per, batch - b0);
+    A.in = d_in + b0 * A.in_gf_stride;
+    A.out = d_out + b0 * A.out_gf_stride;
+    A.moments = d_mom + b0 * A.mom_gf_stride;
+    {
+      KernelScope ks(ctx, FWD ? "tau2iw_direct" : "iw2tau_direct");
+      k_direct_pre<FWD><<<dim3((unsigned)(((long)A.n_in * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
+      k_direct_dft<FWD><<<dim3((unsigned)((A.n_out + 127) / 128), (unsigned)A.n_chunks, (unsigned)(nb * n_ct)), 128, 0, ctx->stream>>>(A);
+      k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
+    }
+    tq_count_launch(ctx, 3);
+    TQ_CUDA(ctx, cudaGetLastError());
+  }
+  return TQ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // moments of G(tau) from one-sided finite differences  (fourier_matsubara.cpp:39-92, noise check :100-114)
 // -------------------------------------------------------------------------------------------------
 __constant__ double c_vinv[2][8] = {
@@ -697,7 +867,10 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   }
   constexpr int SGN = fwd ? 1 : -1;
   Tiling t;
-  TQ_TRY(choose_tiling(ctx, L, n_cols, batch, &t));
+  if (choose_tiling(ctx, L, n_cols, batch, &t) != TQ_OK) { // no factorisation the tile FFT supports: direct window DFT
+    ctx->err.clear();
+    return run_direct<fwd>(ctx, D, pl.btw, n_cols, batch, d_in, d_out, d_mom, mom_rows);
+  }
   TileArgs A{};
   A.n_cols = (int)n_cols;
   A.D = D;

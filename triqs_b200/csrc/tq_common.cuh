@@ -46,6 +46,7 @@ struct PipePlanCache;  // fourier_pipe.cu
 struct LatTwiddles;    // lattice_pipe.cu
 struct ColPlanCache;   // fourier_col.cu
 struct RealPlanCache;  // fourier_real.cu
+struct LegendrePlanCache; // legendre.cu
 
 struct tq_ctx {
   int device = 0;
@@ -55,7 +56,7 @@ struct tq_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   // grow-only scratch / staging
-  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w;
+  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w, leg_tmp;
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   // caches (mesh-only data, like the reference's tail_fitter::_lss and FFTW plans)
@@ -66,6 +67,7 @@ struct tq_ctx {
   std::shared_ptr<LatTwiddles> lat_tw;
   std::shared_ptr<ColPlanCache> col_cache;
   std::shared_ptr<RealPlanCache> real_cache;
+  std::shared_ptr<LegendrePlanCache> leg_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {

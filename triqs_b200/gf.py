@@ -101,6 +101,17 @@ class MeshReFreq(_MeshLinear):
 
 
 @dataclass(frozen=True)
+class MeshLegendre:
+    """c++/triqs/mesh/legendre.hpp: n_l Legendre coefficients of a gf on [0, beta]"""
+    beta: float
+    statistic: int
+    n_l: int
+
+    def __len__(self):
+        return self.n_l
+
+
+@dataclass(frozen=True)
 class MeshCycLat:
     dims: tuple
 
@@ -237,6 +248,33 @@ def make_gf_from_fourier(g, n=-1, known_moments=None):
     out = _transform(g.ctx, g.mesh, g.flat()[None], n, km)
     mo = _out_mesh(g.mesh, n)
     return Gf(mo, g.target_shape, out[0].reshape((len(mo),) + g.target_shape), g._ctx)
+
+
+def legendre_to_matsubara(gl: "Gf", mesh) -> "Gf":
+    """`g << LegendreToMatsubara(gl)` (python/triqs/gf/descriptors.py:170-182; legendre_matsubara.hpp:37-70): onto an imfreq
+    or an imtime mesh."""
+    if not isinstance(gl.mesh, MeshLegendre):
+        raise TriqsRuntimeError("LegendreToMatsubara needs a Legendre gf")
+    if isinstance(mesh, MeshImFreq):
+        out = gl.ctx.legendre_to_imfreq(gl.flat()[None], mesh.statistic, mesh.n_iw)
+    elif isinstance(mesh, MeshImTime):
+        out = gl.ctx.legendre_to_imtime(gl.flat()[None], mesh.beta, mesh.n_tau)
+    else:
+        raise TypeError(mesh)
+    return Gf(mesh, gl.target_shape, out[0].reshape((len(mesh),) + gl.target_shape), gl._ctx)
+
+
+def matsubara_to_legendre(g: "Gf", n_l: int) -> "Gf":
+    """`gl << MatsubaraToLegendre(g)` (descriptors.py:184-196; legendre_matsubara.hpp:76-118) from an imfreq or an imtime gf."""
+    m = g.mesh
+    if isinstance(m, MeshImFreq):
+        out = g.ctx.imfreq_to_legendre(g.flat()[None], m.beta, m.statistic, n_l)
+    elif isinstance(m, MeshImTime):
+        out = g.ctx.imtime_to_legendre(g.flat()[None], m.beta, n_l)
+    else:
+        raise TypeError(m)
+    ml = MeshLegendre(m.beta, m.statistic, n_l)
+    return Gf(ml, g.target_shape, out[0].reshape((n_l,) + g.target_shape), g._ctx)
 
 
 def _out_mesh(mesh, n):
