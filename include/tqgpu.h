@@ -88,6 +88,13 @@ tq_status tq_profile_report(tq_ctx *ctx, char *buf, size_t len);
 tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
                                const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn);
 
+/* The same transform along mesh N > 0 of a product mesh, i.e. what  _fourier<N>  does after flatten_2d
+ * (c++/triqs/gfs/transform/fourier.hpp:78-84, gfs/gf/flatten.hpp:33-47), without the two copies: gt is [outer][n_tau][inner],
+ * gw [outer][n_w][inner], and the outer x inner columns form ONE gf -- the noise check of fourier_matsubara.cpp:100-114 is a
+ * maximum over all of them and *warn is a single word.  moments: [outer][n_moments][inner] or NULL. */
+tq_status tq_fourier_tau_to_iw_axis(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long outer, long inner,
+                                    const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn);
+
 /* Replaces  gf_vec_t<imtime> _fourier_impl(imtime const&, gf_vec_cvt<imfreq>, array_const_view<dcomplex,2>)
  *           c++/triqs/gfs/transform/fourier.hpp:47-48, fourier_matsubara.cpp:190-271.
  *   gw       [batch][n_w][n_others] on the FULL mesh (a positive-only mesh throws, :192)

@@ -173,3 +173,40 @@ def test_legendre_descriptors():
     gt = G.legendre_to_matsubara(gl, G.MeshImTime(beta, O.FERMION, 1001))
     ref = O.fourier_iw_to_tau(gw.flat(), beta, O.FERMION, 1001).reshape(1001, 2, 2)
     assert np.max(np.abs(gt.data - ref)) < 1e-4
+
+
+def test_multivar_fourier_reads_like_the_reference_test():
+    """test/c++/gfs/multivar/fourier.cpp:24-93: g(k, iW, iw) = 1 / (iw + iW - cos kx cos ky) on brzone x imfreq(Boson) x imfreq;
+    transform mesh 0, mesh 2, and both, and come back (precision 1e-4); each leg also against the oracle."""
+    from triqs_b200 import gf as G
+    beta, N_iw, N_iW, N_k = 1.0, 100, 4, 4
+    k_mesh, r_mesh = G.MeshBrZone((N_k, N_k, 1)), G.MeshCycLat((N_k, N_k, 1))
+    iw_mesh, iW_mesh = G.MeshImFreq(beta, O.FERMION, N_iw), G.MeshImFreq(beta, O.BOSON, N_iW)
+    kk = 2 * np.pi * np.arange(N_k) / N_k
+    eps = (np.cos(kk)[:, None] * np.cos(kk)[None, :]).reshape(-1)
+    val = 1 / (iw_mesh.values()[None, None, :] + iW_mesh.values()[None, :, None] - eps[:, None, None])
+    for target in ((), (2, 2)):
+        data = val.reshape(val.shape + (1,) * len(target)) * np.ones(target)
+        g = G.Gf(G.MeshProduct((k_mesh, iW_mesh, iw_mesh)), target, np.ascontiguousarray(data))
+        # mesh 0 and back
+        g_r = G.make_gf_from_fourier_axes(g, (0,), (r_mesh,))
+        assert g_r.mesh[0] == r_mesh
+        ref = O.fourier_lattice_k_to_r(g.data.reshape(N_k * N_k, -1), (N_k, N_k, 1)).reshape(g.data.shape)
+        assert np.max(np.abs(g_r.data - ref)) < 1e-13
+        assert np.max(np.abs(G.make_gf_from_fourier_axes(g_r, (0,), (k_mesh,)).data - g.data)) < 1e-12
+        # mesh 2 and back
+        tau_mesh = G.MeshImTime(beta, O.FERMION, 2 * N_iw + 1)
+        g_tau = G.make_gf_from_fourier_axes(g, (2,), (tau_mesh,))
+        assert g_tau.data.shape[:3] == (N_k * N_k, 2 * N_iW - 1, 2 * N_iw + 1)
+        d3 = g.data.reshape(N_k * N_k * (2 * N_iW - 1), 2 * N_iw, -1)
+        for b in (0, 17, d3.shape[0] - 1):
+            ref = O.fourier_iw_to_tau(d3[b], beta, O.FERMION, 2 * N_iw + 1)
+            got = g_tau.data.reshape(d3.shape[0], 2 * N_iw + 1, -1)[b]
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-10
+        gb = G.make_gf_from_fourier_axes(g_tau, (2,), (iw_mesh,))
+        assert np.max(np.abs(gb.data - g.data)) < 1e-4
+        # meshes 0 and 2 together, default adjoint meshes, and back with the meshes given
+        g_r_tau = G.make_gf_from_fourier_axes(g, (0, 2))
+        assert isinstance(g_r_tau.mesh[0], G.MeshCycLat) and isinstance(g_r_tau.mesh[2], G.MeshImTime)
+        gb1 = G.make_gf_from_fourier_axes(g_r_tau, (0, 2), (k_mesh, iw_mesh))
+        assert np.max(np.abs(gb1.data - g.data)) < 1e-4

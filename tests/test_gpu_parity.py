@@ -666,3 +666,23 @@ def test_matsubara_meshes_with_large_prime_factors(ctx):
             rt = O.fourier_iw_to_tau(gw[b], beta, stat, L + 1, mom[b])
             assert rel(gt[b], rt) < TOL
             assert rel(back[b], O.fourier_tau_to_iw(rt, beta, stat, n_iw, mom[b])) < TOL
+
+
+def test_tau_to_iw_along_inner_mesh_is_one_gf(ctx):
+    """tq_fourier_tau_to_iw_axis = _fourier<N>, N > 0 (fourier.hpp:78-84): [outer][n_tau][inner] is ONE gf with outer*inner
+    columns; the noise check (fourier_matsubara.cpp:100-114) is joint.  Column (0, 0) is G = 1/(i w) whose G(tau) = -1/2 is
+    flat: on its own its differences are pure round-off and the per-gf heuristic would drop the tail."""
+    beta, n_iw, n_tau, outer, inner = 1.0, 100, 201, 5, 3
+    iw = O.imfreq_values(beta, O.FERMION, n_iw)
+    e = np.linspace(0.0, 2.0, outer * inner).reshape(outer, inner)
+    gw = 1 / (iw[None, :, None] - e[:, None, :])
+    gt = np.stack([O.fourier_iw_to_tau(gw[o], beta, O.FERMION, n_tau) for o in range(outer)])
+    flat = np.ascontiguousarray(gt.transpose(1, 0, 2).reshape(n_tau, outer * inner))   # flatten_2d<N>
+    ref = O.fourier_tau_to_iw(flat, beta, O.FERMION, n_iw).reshape(2 * n_iw, outer, inner).transpose(1, 0, 2)
+    got = ctx.fourier_tau_to_iw(gt, beta, O.FERMION, n_iw, one_gf=True)
+    assert rel(got, ref) < TOL
+    assert np.max(np.abs(got - gw)) < 1e-4
+    assert not (ctx.last_warn[0] & 1)
+    # per-gf semantics (independent gfs): the flat one is declared noisy, like the reference called on that gf alone
+    sep = ctx.fourier_tau_to_iw(gt, beta, O.FERMION, n_iw)
+    assert rel(sep[0], O.fourier_tau_to_iw(gt[0], beta, O.FERMION, n_iw)) < TOL

@@ -33,6 +33,8 @@ SIGNATURES = {
     "tq_profile_report": (c_int, [c_void_p, ctypes.c_char_p, c_size_t]),
     "tq_fourier_tau_to_iw": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
                                      POINTER(c_int)]),
+    "tq_fourier_tau_to_iw_axis": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
+                                          POINTER(c_int)]),
     "tq_fourier_iw_to_tau": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
                                      POINTER(c_int), POINTER(c_double)]),
     "tq_density": (c_int, [c_void_p, c_double, c_int, c_long, c_int, c_long, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int),

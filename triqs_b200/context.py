@@ -139,8 +139,9 @@ class Context:
         return json.loads(buf.value.decode())
 
     # -- Matsubara transforms -------------------------------------------------------------------
-    def fourier_tau_to_iw(self, gt, beta, statistic, n_iw, moments=None, out=None):
-        """gt [batch, n_tau, n_others] -> gw [batch, n_w, n_others]  (tq_fourier_tau_to_iw)."""
+    def fourier_tau_to_iw(self, gt, beta, statistic, n_iw, moments=None, out=None, one_gf=False):
+        """gt [batch, n_tau, n_others] -> gw [batch, n_w, n_others]  (tq_fourier_tau_to_iw).
+        one_gf: the leading index is an outer mesh of ONE gf (tq_fourier_tau_to_iw_axis): joint noise check, one warning."""
         gt = _as_c128(gt)
         batch, n_tau, n_others = gt.shape
         n_w = 2 * n_iw if statistic == FERMION else 2 * n_iw - 1
@@ -149,9 +150,13 @@ class Context:
             moments = _as_c128(moments)
             n_mom = moments.shape[1]
         gw = out if out is not None else _empty_like_kind(gt, (batch, n_w, n_others))
-        warn = (ctypes.c_int * batch)()
-        self._check(self._lib.tq_fourier_tau_to_iw(self._h, beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments), n_mom,
-                                                   _ptr(gw), warn))
+        warn = (ctypes.c_int * (1 if one_gf else batch))()
+        if one_gf:
+            self._check(self._lib.tq_fourier_tau_to_iw_axis(self._h, beta, statistic, n_tau, n_iw, batch, n_others, _ptr(gt), _ptr(moments),
+                                                            n_mom, _ptr(gw), warn))
+        else:
+            self._check(self._lib.tq_fourier_tau_to_iw(self._h, beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments),
+                                                       n_mom, _ptr(gw), warn))
         self._emit(np.frombuffer(warn, dtype=np.int32))
         return gw
 

@@ -516,8 +516,11 @@ __device__ double block_max(double v, double *sh) {
   return r;
 }
 
+// `joint` (or nullptr): the batch is ONE gf whose columns are spread over [outer][.][inner] (a transform along mesh N > 0 of a
+// product mesh, fourier.hpp:78-84): the reference's noise check is then a maximum over all of them.  First pass
+// (joint_pass == 1) accumulates the two maxima, second pass (joint_pass == 2) decides with them.
 __global__ void __launch_bounds__(256) k_moments_from_tau(const cd *gt, long gf_stride, int n_tau, int n_cols, double beta, int stat, cd *mom4,
-                                                          int *warn) {
+                                                          int *warn, unsigned long long *joint = nullptr, int joint_pass = 0) {
   __shared__ double sh[32];
   const int gf = blockIdx.x;
   const cd *g = gt + (size_t)gf * gf_stride;
@@ -539,8 +542,21 @@ __global__ void __launch_bounds__(256) k_moments_from_tau(const cd *gt, long gf_
     m1 = fmax(m1, a);
     m2 = fmax(m2, b);
   }
-  double der_1 = block_max(m1, sh) / delta;
-  double der_2 = 0.5 * block_max(m2, sh) / delta;
+  m1 = block_max(m1, sh);
+  m2 = block_max(m2, sh);
+  if (joint_pass == 1) { // non-negative doubles order like their bit patterns
+    if (threadIdx.x == 0) {
+      atomicMax(&joint[0], (unsigned long long)__double_as_longlong(m1));
+      atomicMax(&joint[1], (unsigned long long)__double_as_longlong(m2));
+    }
+    return;
+  }
+  if (joint_pass == 2) {
+    m1 = __longlong_as_double((long long)joint[0]);
+    m2 = __longlong_as_double((long long)joint[1]);
+  }
+  double der_1 = m1 / delta;
+  double der_2 = 0.5 * m2 / delta;
   const bool noisy = (der_1 < 0.95 * der_2) || (der_1 > 1.05 * der_2);
   if (threadIdx.x == 0 && warn) warn[gf] = noisy ? TQ_WARN_NOISY_TAU : 0;
   cd *mo = mom4 + (size_t)gf * 4 * n_cols;
@@ -963,10 +979,11 @@ tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw,
 
 struct StatusWords {
   unsigned long long max_m0_bits;
+  unsigned long long joint_der[2];
 };
 
-extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
-                                          const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                                        const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn, bool joint) {
   if (!ctx) return TQ_ERR_INVALID;
   if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_tau_to_iw: invalid argument");
@@ -1007,8 +1024,13 @@ extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statisti
   } else {
     if (batch > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "batch too large");
     KernelScope ks(ctx, "moments_from_tau");
+    if (joint) {
+      k_moments_from_tau<<<(unsigned)batch, 256, 0, ctx->stream>>>((const cd *)d_in, n_tau * n_others, (int)n_tau, (int)n_others, beta,
+                                                                    statistic, d_mom, d_warn, d_st->joint_der, 1);
+      tq_count_launch(ctx);
+    }
     k_moments_from_tau<<<(unsigned)batch, 256, 0, ctx->stream>>>((const cd *)d_in, n_tau * n_others, (int)n_tau, (int)n_others, beta, statistic,
-                                                                  d_mom, d_warn);
+                                                                  d_mom, d_warn, joint ? d_st->joint_der : nullptr, joint ? 2 : 0);
   }
   tq_count_launch(ctx);
   TQ_CUDA(ctx, cudaGetLastError());
@@ -1027,10 +1049,24 @@ extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statisti
       return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR: Direct Fourier implementation requires vanishing 0th moment\n  error is :" + std::to_string(a0));
   }
   const int mesh_warn = (L < 6 * (last + 1)) ? TQ_WARN_SHORT_TAU_MESH : 0; // :131-133
-  if (warn)
-    for (long b = 0; b < batch; ++b) warn[b] = h_warn[b] | mesh_warn;
+  if (warn) {
+    if (joint)
+      warn[0] = h_warn[0] | mesh_warn; // one gf: one decision
+    else
+      for (long b = 0; b < batch; ++b) warn[b] = h_warn[b] | mesh_warn;
+  }
   TQ_TRY(tq_stage_out_finish(ctx, gw, out_bytes, d_out, out_host));
   return TQ_OK;
+}
+
+extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                                          const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+  return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, n_others, batch, gt, moments, n_moments, gw, warn, false);
+}
+
+extern "C" tq_status tq_fourier_tau_to_iw_axis(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long outer, long inner,
+                                               const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+  return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, inner, outer, gt, moments, n_moments, gw, warn, true);
 }
 
 extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,

@@ -127,6 +127,22 @@ class MeshBrZone:
         return int(np.prod(self.dims))
 
 
+@dataclass(frozen=True)
+class MeshProduct:
+    """c++/triqs/mesh/prod.hpp:72-208: a tuple of meshes; the data rank grows by one per mesh (C order)."""
+    meshes: tuple
+
+    def __len__(self):
+        return int(np.prod([len(m) for m in self.meshes]))
+
+    @property
+    def shape(self):
+        return tuple(len(m) for m in self.meshes)
+
+    def __getitem__(self, i):
+        return self.meshes[i]
+
+
 def make_adjoint_mesh(m, n=-1):
     """c++/triqs/mesh/adjoint.hpp:31-57"""
     if isinstance(m, MeshImTime):
@@ -153,7 +169,7 @@ class Gf:
     def __init__(self, mesh, target_shape=(), data=None, ctx: Context | None = None):
         self.mesh = mesh
         self.target_shape = tuple(target_shape)
-        shape = (len(mesh),) + self.target_shape
+        shape = (mesh.shape if isinstance(mesh, MeshProduct) else (len(mesh),)) + self.target_shape
         if data is None:
             data = np.zeros(shape, dtype=np.complex128)
         elif tuple(data.shape) != shape:
@@ -231,6 +247,28 @@ def _stack(blocks):
     return np.stack([b.flat() for b in blocks])
 
 
+def make_gf_from_fourier_axes(g: Gf, axes, meshes=None) -> Gf:
+    """make_gf_from_fourier<N1, N2, ...>(g[, m1, m2, ...]) on a product mesh (fourier.hpp:60-85, :159-181;
+    test/c++/gfs/multivar/fourier.cpp).  The reference copies the data twice per transformed mesh (flatten_2d / unflatten_2d,
+    flatten.hpp:33-47); here mesh N of [n_0 .. n_N .. n_k, target] is simply the middle index of [outer][n_N][inner]."""
+    if not isinstance(g.mesh, MeshProduct):
+        raise TriqsRuntimeError("make_gf_from_fourier<N...>: a product mesh is required")
+    axes = tuple(axes)
+    meshes = tuple(meshes) if meshes is not None else (None,) * len(axes)
+    cur_meshes, data = list(g.mesh.meshes), g.data
+    for N, mo in zip(axes, meshes):
+        mi = cur_meshes[N]
+        mo = mo if mo is not None else make_adjoint_mesh(mi)
+        shp = tuple(len(m) for m in cur_meshes)
+        outer = int(np.prod(shp[:N])) if N else 1
+        inner = int(np.prod(shp[N + 1:])) * g.n_others
+        d3 = data.reshape(outer, shp[N], inner)
+        out = _transform(g.ctx, mi, d3, mo, None, one_gf=True)
+        cur_meshes[N] = mo
+        data = out.reshape(tuple(len(m) for m in cur_meshes) + g.target_shape)
+    return Gf(MeshProduct(tuple(cur_meshes)), g.target_shape, data, g._ctx)
+
+
 def make_gf_from_fourier(g, n=-1, known_moments=None):
     """fourier.hpp:93-245: imtime <-> imfreq and cyclat <-> brzone; a BlockGf of equally shaped blocks is ONE batched launch."""
     if isinstance(g, BlockGf):
@@ -284,10 +322,10 @@ def _out_mesh(mesh, n):
     return make_adjoint_mesh(mesh, n)
 
 
-def _transform(ctx, mesh, data3, n, km):
+def _transform(ctx, mesh, data3, n, km, one_gf=False):
     if isinstance(mesh, MeshImTime):
         mo = _out_mesh(mesh, n)
-        return ctx.fourier_tau_to_iw(data3, mesh.beta, mesh.statistic, mo.n_iw, moments=km)
+        return ctx.fourier_tau_to_iw(data3, mesh.beta, mesh.statistic, mo.n_iw, moments=km, one_gf=one_gf)
     if isinstance(mesh, MeshImFreq):
         mo = _out_mesh(mesh, n)
         return ctx.fourier_iw_to_tau(data3, mesh.beta, mesh.statistic, mo.n_tau, moments=km)
