@@ -169,7 +169,99 @@ void test_density() { // gf_density.cpp:22-55, gf_base.cpp:69
   EXPECT(std::abs(n[0] - 1.8177540779781256) < 1e-7 && std::abs(n[3] - 1.8177540779781256) < 1e-7 && std::abs(n[1]) < 1e-12);
 }
 
+template <typename T> void test_fourier_real(std::vector<long> shape) { // fourier_real.cpp:27-87
+  double precision = 1e-4, w_max = 40, E = 1;
+  long Nw = 1001;
+  auto w_mesh = mesh::refreq{-w_max, w_max, Nw};
+  auto t_mesh = mesh::make_adjoint_mesh(w_mesh);
+  auto Gw1 = gf<mesh::refreq, T>{w_mesh, shape};
+  long no = Gw1.n_others();
+  for (long i = 0; i < Nw; ++i)
+    for (long c = 0; c < no; ++c) Gw1[i][c] = 2 * E / (w_mesh[i] * w_mesh[i] + E * E);
+  auto tail = make_zero_tail(Gw1, 3);
+  for (long c = 0; c < no; ++c) tail(2, c) = 2 * E; // exact expansion of the Lorentzian (the reference fits it)
+  auto Gt1 = make_gf_from_fourier(Gw1, t_mesh, tail);
+  auto Gw1b = make_gf_from_fourier(Gt1, w_mesh, tail);
+  EXPECT(max_diff(Gw1, Gw1b) < precision);
+  auto Gt1_exact = Gt1;
+  for (long i = 0; i < Nw; ++i)
+    for (long c = 0; c < no; ++c) Gt1_exact[i][c] = std::exp(-E * std::abs(t_mesh[i]));
+  EXPECT(max_diff(Gt1, Gt1_exact) < precision);
+  auto theta = [](double x) { return x > 0 ? 1.0 : (x < 0 ? 0.0 : 0.5); };
+  for (long i = 0; i < Nw; ++i) {
+    double t = t_mesh[i];
+    for (long c = 0; c < no; ++c) Gt1[i][c] = dcomplex(0, 0.5) * (std::exp(-E * std::abs(t)) * theta(-t) - std::exp(-E * std::abs(t)) * theta(t));
+  }
+  auto known_moments = make_zero_tail(Gt1, 3);
+  for (long c = 0; c < no; ++c) known_moments(1, c) = 1.;
+  set_from_fourier(Gw1, Gt1, known_moments);
+  auto Gt1b = make_gf_from_fourier(Gw1, t_mesh, known_moments);
+  EXPECT(max_diff(Gt1, Gt1b) < precision);
+  auto Gw1_exact = Gw1;
+  for (long i = 0; i < Nw; ++i)
+    for (long c = 0; c < no; ++c) Gw1_exact[i][c] = 0.5 / (w_mesh[i] + dcomplex(0, E)) + 0.5 / (w_mesh[i] - dcomplex(0, E));
+  EXPECT(max_diff(Gw1, Gw1_exact) < precision);
+  // incompatible meshes throw like the reference (fourier_real.cpp:50-51)
+  bool thrown = false;
+  try {
+    make_gf_from_fourier(Gw1, mesh::retime{t_mesh.t_min(), 1.01 * t_mesh.t_max(), Nw});
+  } catch (runtime_error const &) { thrown = true; }
+  EXPECT(thrown);
+}
+
+void test_hermiticity() { // functions/hermiticity.cpp:25-80
+  double beta = 1;
+  gf<mesh::imfreq, matrix_valued> G{{beta, Fermion, 100}, {2, 2}};
+  double H[2][2] = {{1, 0.2}, {0.2, -0.5}};
+  for (long i = 0; i < G.mesh().size(); ++i) { // (iw - H)^-1 by hand
+    dcomplex a = G.mesh()[i] - H[0][0], b = -H[0][1], c = -H[1][0], d = G.mesh()[i] - H[1][1], det = a * d - b * c;
+    G[i][0] = d / det, G[i][1] = -b / det, G[i][2] = -c / det, G[i][3] = a / det;
+  }
+  EXPECT(is_gf_hermitian(G));
+  G[0][1] += dcomplex(0, 1e-3);
+  EXPECT(!is_gf_hermitian(G));
+  auto Gh = make_hermitian(G);
+  EXPECT(is_gf_hermitian(Gh));
+  // replace_by_tail: beyond n_min the data becomes the tail expansion
+  moment_array tail(4, 4);
+  tail(1, 0) = tail(1, 3) = 1.0;
+  replace_by_tail(Gh, tail, 50);
+  dcomplex iw = Gh.mesh()[Gh.mesh().to_data_index(70)];
+  EXPECT(std::abs(Gh[Gh.mesh().to_data_index(70)][0] - 1.0 / iw) < 1e-14);
+  EXPECT(std::abs(Gh[Gh.mesh().to_data_index(70)][1]) < 1e-14);
+}
+
+void test_legendre_and_tight_binding() { // gf_legendre.cpp:22-72;  g_r_k.cpp:40-58 dispersion
+  double beta = 2.0;
+  gf<mesh::legendre, scalar_valued> gl{{beta, Fermion, 10}};
+  gl[2][0] = 1;
+  gf<mesh::imtime, scalar_valued> gt{{beta, Fermion, 5}};
+  legendre_matsubara_direct(gt, gl);
+  for (long i = 0; i < 5; ++i) {
+    double x = 2 * gt.mesh()[i] / beta - 1;
+    EXPECT(std::abs(gt[i][0] - std::sqrt(5.0) / beta * (3 * x * x - 1) / 2) < 1e-15);
+  }
+  gf<mesh::imtime, scalar_valued> gt2{{beta, Fermion, 20001}};
+  legendre_matsubara_direct(gt2, gl);
+  gf<mesh::legendre, scalar_valued> gl2{{beta, Fermion, 10}};
+  legendre_matsubara_inverse(gl2, gt2);
+  EXPECT(max_diff(gl, gl2) < 1e-6);
+  tight_binding tb;
+  tb.n_orb = 1;
+  tb.displ_vec = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}};
+  tb.overlap_mat_vec = {{-1.0}, {-1.0}, {-1.0}, {-1.0}};
+  long N = 10;
+  auto ek = tb.fourier(mesh::brzone{N, N, 1});
+  for (long i = 0; i < N; ++i)
+    for (long j = 0; j < N; ++j) EXPECT(std::abs(ek[i * N + j][0] + 2 * (std::cos(2 * M_PI * i / N) + std::cos(2 * M_PI * j / N))) < 1e-14);
+}
+
 int main() {
+  test_fourier_real<scalar_valued>({});
+  test_fourier_real<matrix_valued>({2, 2});
+  test_fourier_real<tensor_valued<3>>({2, 2, 2});
+  test_hermiticity();
+  test_legendre_and_tight_binding();
   test_density();
   test_fourier<scalar_valued>(Fermion, {});
   test_fourier<matrix_valued>(Fermion, {2, 2});

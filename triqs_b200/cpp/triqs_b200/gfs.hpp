@@ -128,7 +128,60 @@ namespace triqs_b200 {
       bool operator==(brzone const &m) const { return _dims == m._dims; }
     };
 
+    // n points on [xmin, xmax], both ends included (bases/linear.hpp:47-55, :154-160)
+    struct linear_mesh_base {
+      double _xmin = 0, _xmax = 0;
+      long _n = 0;
+      long size() const { return _n; }
+      double delta() const { return _n == 1 ? 0. : (_xmax - _xmin) / (_n - 1); }
+      double to_value(long i) const {
+        if (_n == 1) return _xmin;
+        double wr = double(i) / (_n - 1);
+        return _xmin * (1 - wr) + _xmax * wr;
+      }
+      double operator[](long i) const { return to_value(i); }
+    };
+    struct retime : linear_mesh_base { // retime.hpp:39
+      retime() = default;
+      retime(double t_min, double t_max, long n_t) { _xmin = t_min, _xmax = t_max, _n = n_t; }
+      double t_min() const { return _xmin; }
+      double t_max() const { return _xmax; }
+      bool operator==(retime const &m) const { return _xmin == m._xmin && _xmax == m._xmax && _n == m._n; }
+    };
+    struct refreq : linear_mesh_base { // refreq.hpp:38
+      refreq() = default;
+      refreq(double w_min, double w_max, long n_w) { _xmin = w_min, _xmax = w_max, _n = n_w; }
+      double w_min() const { return _xmin; }
+      double w_max() const { return _xmax; }
+      bool operator==(refreq const &m) const { return _xmin == m._xmin && _xmax == m._xmax && _n == m._n; }
+    };
+    class legendre { // legendre.hpp: n_l coefficients of a gf on [0, beta]
+      double _beta = 1;
+      statistic_enum _stat = Fermion;
+      long _n = 0;
+
+      public:
+      legendre() = default;
+      legendre(double beta, statistic_enum s, long n_l) : _beta(beta), _stat(s), _n(n_l) {}
+      double beta() const { return _beta; }
+      statistic_enum statistic() const { return _stat; }
+      long size() const { return _n; }
+      bool operator==(legendre const &m) const { return _beta == m._beta && _stat == m._stat && _n == m._n; }
+    };
+
     // c++/triqs/mesh/adjoint.hpp:31-57
+    inline refreq make_adjoint_mesh(retime const &m, bool shift_half_bin = false) {
+      long L = m.size();
+      double wmax = M_PI * (L - 1) / (L * m.delta());
+      if (shift_half_bin) return {-wmax + M_PI / L / m.delta(), wmax + M_PI / L / m.delta(), L};
+      return {-wmax, wmax, L};
+    }
+    inline retime make_adjoint_mesh(refreq const &m, bool shift_half_bin = false) {
+      long L = m.size();
+      double tmax = M_PI * (L - 1) / (L * m.delta());
+      if (shift_half_bin) return {-tmax + M_PI / L / m.delta(), tmax + M_PI / L / m.delta(), L};
+      return {-tmax, tmax, L};
+    }
     inline imfreq make_adjoint_mesh(imtime const &m, long n_iw = -1) {
       if (n_iw == -1) n_iw = (m.size() - 1) / 6;
       return {m.beta(), m.statistic(), n_iw};
@@ -262,6 +315,60 @@ namespace triqs_b200 {
     auto d = gk.mesh().dims();
     long dims[3] = {d[0], d[1], d[2]};
     check(tq_fourier_lattice(context(), dims, 0, gk.n_others(), detail::cptr(gk.data()), detail::ptr(gr.data())));
+  }
+
+  // retime <-> refreq  (fourier_real.cpp:35-131)
+  template <typename T>
+  void set_from_fourier(gf<mesh::refreq, T> &gw, gf<mesh::retime, T> const &gt, moment_array const &known_moments = {}) {
+    if (gw.target_shape() != gt.target_shape()) throw runtime_error("fourier: target shapes differ");
+    if (gw.mesh().size() != gt.mesh().size()) throw runtime_error("Meshes are different");
+    check(tq_fourier_t_to_w(context(), gt.mesh().t_min(), gt.mesh().t_max(), gw.mesh().w_min(), gw.mesh().w_max(), gt.mesh().size(), gt.n_others(),
+                            1, detail::cptr(gt.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                            (int)known_moments.n_rows, detail::ptr(gw.data())));
+  }
+  template <typename T>
+  void set_from_fourier(gf<mesh::retime, T> &gt, gf<mesh::refreq, T> const &gw, moment_array const &known_moments = {}) {
+    if (gw.target_shape() != gt.target_shape()) throw runtime_error("fourier: target shapes differ");
+    if (gw.mesh().size() != gt.mesh().size()) throw runtime_error("Meshes are of different size");
+    check(tq_fourier_w_to_t(context(), gt.mesh().t_min(), gt.mesh().t_max(), gw.mesh().w_min(), gw.mesh().w_max(), gw.mesh().size(), gw.n_others(),
+                            1, detail::cptr(gw.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                            (int)known_moments.n_rows, detail::ptr(gt.data())));
+  }
+  template <typename T>
+  gf<mesh::retime, T> make_gf_from_fourier(gf<mesh::refreq, T> const &gw, mesh::retime const &m, moment_array const &known_moments = {}) {
+    gf<mesh::retime, T> gt{m, gw.target_shape()};
+    set_from_fourier(gt, gw, known_moments);
+    return gt;
+  }
+  template <typename T>
+  gf<mesh::refreq, T> make_gf_from_fourier(gf<mesh::retime, T> const &gt, mesh::refreq const &m, moment_array const &known_moments = {}) {
+    gf<mesh::refreq, T> gw{m, gt.target_shape()};
+    set_from_fourier(gw, gt, known_moments);
+    return gw;
+  }
+  template <typename T> gf<mesh::retime, T> make_gf_from_fourier(gf<mesh::refreq, T> const &gw, bool shift_half_bin = false) {
+    return make_gf_from_fourier(gw, mesh::make_adjoint_mesh(gw.mesh(), shift_half_bin));
+  }
+  template <typename T> gf<mesh::refreq, T> make_gf_from_fourier(gf<mesh::retime, T> const &gt, bool shift_half_bin = false) {
+    return make_gf_from_fourier(gt, mesh::make_adjoint_mesh(gt.mesh(), shift_half_bin));
+  }
+
+  // Legendre <-> Matsubara  (legendre_matsubara.hpp:37-118)
+  template <typename T> void legendre_matsubara_direct(gf<mesh::imfreq, T> &gw, gf<mesh::legendre, T> const &gl) {
+    check(tq_legendre_to_imfreq(context(), gw.mesh().statistic(), gl.mesh().size(), gw.mesh().n_iw(), gl.n_others(), 1, detail::cptr(gl.data()),
+                                detail::ptr(gw.data())));
+  }
+  template <typename T> void legendre_matsubara_direct(gf<mesh::imtime, T> &gt, gf<mesh::legendre, T> const &gl) {
+    check(tq_legendre_to_imtime(context(), gt.mesh().beta(), gl.mesh().size(), gt.mesh().size(), gl.n_others(), 1, detail::cptr(gl.data()),
+                                detail::ptr(gt.data())));
+  }
+  template <typename T> void legendre_matsubara_inverse(gf<mesh::legendre, T> &gl, gf<mesh::imfreq, T> const &gw) {
+    check(tq_imfreq_to_legendre(context(), gw.mesh().beta(), gw.mesh().statistic(), gw.mesh().n_iw(), gl.mesh().size(), gw.n_others(), 1,
+                                detail::cptr(gw.data()), detail::ptr(gl.data())));
+  }
+  template <typename T> void legendre_matsubara_inverse(gf<mesh::legendre, T> &gl, gf<mesh::imtime, T> const &gt) {
+    check(tq_imtime_to_legendre(context(), gt.mesh().beta(), gt.mesh().size(), gl.mesh().size(), gt.n_others(), 1, detail::cptr(gt.data()),
+                                detail::ptr(gl.data())));
   }
 
   // factories  (fourier.hpp:122-144, 238-245)
@@ -408,6 +515,54 @@ namespace triqs_b200 {
                      nullptr));
     return res[0];
   }
+
+  // ------------------------------------------------------------------------------------------------
+  // hermiticity helpers, replace_by_tail  (gfs/functions/imfreq.hpp:81-124, :175-215, :258-267)
+  // ------------------------------------------------------------------------------------------------
+  namespace detail {
+    template <typename M> constexpr int mesh_kind() { return std::is_same<M, mesh::imtime>::value ? 1 : 0; }
+    template <typename G> long herm_dim(G const &g) { // matrix: n;  rank-4 tensor [a,b,c,d]: the (ab),(cd) matrix
+      auto const &ts = g.target_shape();
+      if (ts.empty()) return 1;
+      if (ts.size() == 2 && ts[0] == ts[1]) return ts[0];
+      if (ts.size() == 4 && ts[0] * ts[1] == ts[2] * ts[3]) return ts[0] * ts[1];
+      throw runtime_error("hermiticity: incompatible target shape");
+    }
+  } // namespace detail
+  template <typename M, typename T> bool is_gf_hermitian(gf<M, T> const &g, double tolerance = 1.e-12) {
+    int res = 0;
+    check(tq_is_gf_hermitian(context(), detail::mesh_kind<M>(), g.mesh().size(), (int)detail::herm_dim(g), 1, detail::cptr(g.data()), tolerance,
+                             &res));
+    return res != 0;
+  }
+  template <typename M, typename T> gf<M, T> make_hermitian(gf<M, T> const &g) {
+    gf<M, T> out{g.mesh(), g.target_shape()};
+    check(tq_make_hermitian(context(), detail::mesh_kind<M>(), g.mesh().size(), (int)detail::herm_dim(g), 1, detail::cptr(g.data()),
+                            detail::ptr(out.data())));
+    return out;
+  }
+  template <typename T> void replace_by_tail(gf<mesh::imfreq, T> &g, moment_array const &tail, int n_min) {
+    check(tq_replace_by_tail(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), g.n_others(), 1, detail::ptr(g.data()),
+                             detail::cptr(tail.v), (int)tail.n_rows, n_min));
+  }
+
+  // eps_k on a brzone mesh from hoppings  (lattice/tight_binding.hpp:88-123)
+  struct tight_binding {
+    std::vector<std::array<int, 3>> displ_vec;
+    std::vector<std::vector<dcomplex>> overlap_mat_vec; // each [n_orb * n_orb]
+    int n_orb = 1;
+    gf<mesh::brzone, matrix_valued> fourier(mesh::brzone const &k_mesh) const {
+      gf<mesh::brzone, matrix_valued> out{k_mesh, {n_orb, n_orb}};
+      std::vector<int> d;
+      std::vector<dcomplex> h;
+      for (auto const &r : displ_vec) d.insert(d.end(), r.begin(), r.end());
+      for (auto const &m : overlap_mat_vec) h.insert(h.end(), m.begin(), m.end());
+      auto dm = k_mesh.dims();
+      long dims[3] = {dm[0], dm[1], dm[2]};
+      check(tq_tight_binding_fourier(context(), n_orb, (int)displ_vec.size(), d.data(), detail::cptr(h), dims, detail::ptr(out.data())));
+      return out;
+    }
+  };
 
   // ------------------------------------------------------------------------------------------------
   // inverse  (functions2.hpp:197-209)

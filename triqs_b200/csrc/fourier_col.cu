@@ -36,6 +36,7 @@ struct ColArgs {
   double C[3];           // one{Fermion,Boson} prefactors
   double er[3][10];      // per-leg exponentials
   cd phr[10];            // per-leg twist e^{i pi r / 10} (Fermion) or 1
+  int skip;              // developer timing experiment (TQ_COL_SKIP): 1 passes 1-3, 2 pass 0, 4 epilogue, 8 load
 };
 
 TQ_D double4 ldg4(const double4 *p) {
@@ -54,8 +55,14 @@ template <int MSUB, int COL_NT> TQ_D void col_pass(cd *tile, const cd *__restric
     for (int r = 0; r < 10; ++r) a[r] = p[r * MSUB];
     Dft<10, 1>::run(a);
     if (MSUB > 1 && q != 0) {
+      // w_M^{q r} by a product chain from the one (coalesced) entry w_M^q: a gather of tw[q r] costs r x 4 wavefronts per warp
+      const cd w = __ldg(&tw[q]);
+      cd pw[10];
+      pw[1] = w;
 #pragma unroll
-      for (int r = 1; r < 10; ++r) a[r] = cmul(a[r], __ldg(&tw[q * r]));
+      for (int r = 2; r < 10; ++r) pw[r] = (r & 1) ? cmul(pw[r - 1], w) : cmul(pw[r >> 1], pw[r >> 1]);
+#pragma unroll
+      for (int r = 1; r < 10; ++r) a[r] = cmul(a[r], pw[r]);
     }
 #pragma unroll
     for (int r = 0; r < 10; ++r) p[r * MSUB] = a[r];
@@ -76,7 +83,7 @@ template <int COL_NT> __global__ void __launch_bounds__(COL_NT, 1) matsubara_col
   __syncthreads();
   int it = 0;
   for (long gf = blockIdx.x; gf < A.batch; gf += gridDim.x, ++it) {
-    if (tid == 0) {
+    if (tid == 0 && !(A.skip & 8 && it > 0)) {
       mbar_arrive_expect_tx(mbar, (uint32_t)(sizeof(cd) * (COL_L + 1)));
       bulk_g2s(tile, A.in + gf * (COL_L + 1), (uint32_t)(sizeof(cd) * (COL_L + 1)), mbar);
     }
@@ -96,7 +103,7 @@ template <int COL_NT> __global__ void __launch_bounds__(COL_NT, 1) matsubara_col
         a3 = cadd(cadd(cscale(1.0 / 6.0, m1), cscale(0.5, m2)), cscale(1.0 / 3.0, m3));
       }
     }
-    mbar_wait(mbar, (uint32_t)(it & 1));
+    if (!(A.skip & 8 && it > 0)) mbar_wait(mbar, (uint32_t)(it & 1));
     // trapezoid end-point correction -0.5 (beta/L) (g_0 + m1 +/- g_L)   (:181) -- read before pass 0 overwrites row 0
     cd ex;
     {
@@ -107,7 +114,7 @@ template <int COL_NT> __global__ void __launch_bounds__(COL_NT, 1) matsubara_col
     }
     __syncthreads();
     // ---- pass 0 (stride 1000) with the fused pre-transform:  x_j = phase_j (g_j - sum_i a_i h_i(tau_j)),  j = q + 1000 r
-    {
+    if (!(A.skip & 2)) {
       const cd c1 = cscale(A.C[0], a1), c2 = cscale(A.C[1], a2), c3 = cscale(A.C[2], a3);
       for (int q = tid; q < 1000; q += COL_NT) {
         cd *p = tile + q;
@@ -136,14 +143,16 @@ template <int COL_NT> __global__ void __launch_bounds__(COL_NT, 1) matsubara_col
       }
     }
     __syncthreads();
-    col_pass<100, COL_NT>(tile, A.tw1, tid);
-    __syncthreads();
-    col_pass<10, COL_NT>(tile, A.tw2, tid);
-    __syncthreads();
-    col_pass<1, COL_NT>(tile, nullptr, tid);
-    __syncthreads();
+    if (!(A.skip & 1)) {
+      col_pass<100, COL_NT>(tile, A.tw1, tid);
+      __syncthreads();
+      col_pass<10, COL_NT>(tile, A.tw2, tid);
+      __syncthreads();
+      col_pass<1, COL_NT>(tile, nullptr, tid);
+      __syncthreads();
+    }
     // ---- epilogue: gw[n] = X[(n + L) % L] + corr + sum_i a_i / (i w_n - b_i)    (:181-183)
-    {
+    if (!(A.skip & 4)) {
       const cd D23 = csub(a2, a3), A23 = cadd(a2, a3);
       cd *o = A.out + gf * A.n_w;
       for (int di = tid; di < A.n_w; di += COL_NT) {
@@ -273,6 +282,7 @@ tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, l
   A.mom = d_mom;
   A.mom_gf_stride = mom_rows;
   A.batch = batch;
+  A.skip = getenv("TQ_COL_SKIP") ? atoi(getenv("TQ_COL_SKIP")) : 0;
   const size_t smem = ((sizeof(cd) * (COL_L + 1) + 127) & ~size_t(127)) + 16 * sizeof(cd);
   const int grid = (int)std::min<long>(batch, ctx->sm_count);
   static const int nt = getenv("TQ_COL_NT") ? atoi(getenv("TQ_COL_NT")) : 1024;
