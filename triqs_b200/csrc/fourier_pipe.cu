@@ -316,6 +316,16 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   constexpr int SGN = FWD ? 1 : -1;
   constexpr int NT = (NW + 1) * 32;
   constexpr bool PK_AHEAD = false; // fetching the next packet id one packet ahead was measured slower (register pressure)
+  // measured (32 blocks): a static round robin over the warps (TQ_PK_STATIC) 0.57 -> 0.77 ms and fetching 2-3 packets per
+  // atomic (TQ_PK_CHUNK) 0.57 -> 0.69-0.75 ms for F1 -- a stalled warp then holds back packets others could have taken
+#ifndef TQ_PK_STATIC
+#define TQ_PK_STATIC 0
+#endif
+  constexpr bool PK_STATIC = TQ_PK_STATIC != 0;
+#ifndef TQ_PK_CHUNK
+#define TQ_PK_CHUNK 1
+#endif
+  constexpr int PK_CHUNK = TQ_PK_CHUNK;
   using Smem = PipeSmem<MODE, N, RA, RB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TCW = A.tcw;
@@ -436,12 +446,26 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
     // ===================== worker warps: pull packets  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  =====================
     // (pass B of tile k is queued after pass A of tile k+1, so whoever takes it rarely waits; a packet only ever waits
     //  for packets that were handed out before it, hence no deadlock)
-    int pk_next = 0;
-    if (PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
-    for (;;) {
-      if (!PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
-      const int pk = __shfl_sync(0xffffffffu, pk_next, 0);
-      if (PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1); // fetched while this packet is processed (hides the atomic's latency)
+    int pk_next = 0, pk_left = 0;
+    if (!PK_STATIC && PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
+    for (int pk_static = warp;; pk_static += NW) {
+      int pk;
+      if (PK_STATIC) {
+        pk = pk_static; // packets cost the same: round robin over the worker warps balances as well as a shared counter
+      } else if (PK_CHUNK > 1) {
+        // one shared-memory atomic per PK_CHUNK packets (its latency behind the data traffic in the LSU queue is paid per fetch)
+        if (pk_left == 0) {
+          if (lane == 0) pk_next = atomicAdd(next_pk, PK_CHUNK);
+          pk_next = __shfl_sync(0xffffffffu, pk_next, 0);
+          pk_left = PK_CHUNK;
+        }
+        pk = pk_next++;
+        --pk_left;
+      } else {
+        if (!PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
+        pk = __shfl_sync(0xffffffffu, pk_next, 0);
+        if (PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1); // fetched while this packet is processed (hides the atomic's latency)
+      }
       int blk, r;
       bool is_b = false;
       if (pk < 2 * pa) {
