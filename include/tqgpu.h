@@ -153,6 +153,13 @@ tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, double
                       int expansion_order, int hermitian, int inner_dim, long n_cols, long batch, const tq_complex *g,
                       const tq_complex *known, int n_known, tq_complex *out_moments, int *out_n_moments, double *out_err);
 
+/* fit_tail of a real-frequency gf: the same fitter on mesh::refreq{w_min, w_max, n_w} (tail_fitter.hpp:105-181 is generic in the
+ * mesh: first_index 0, w_max() = xmax, real mesh values; known answers test/c++/gfs/fit_tail_real.cpp:24-91).
+ *   g [batch][n_w][n_cols], known [batch][n_known][n_cols] or NULL; outputs as tq_fit_tail. */
+tq_status tq_fit_tail_refreq(tq_ctx *ctx, double w_min, double w_max, long n_w, double tail_fraction, int n_tail_max, int expansion_order,
+                             long n_cols, long batch, const tq_complex *g, const tq_complex *known, int n_known, tq_complex *out_moments,
+                             int *out_n_moments, double *out_err);
+
 /* The mesh-only part of the fit (fit indices, Vandermonde, SVD pseudo-inverse, chosen order), i.e. what the
  * reference caches in tail_fitter::_lss (tail_fitter.hpp:140-181).  Pure host code (plan creation, no GPU
  * needed, no ctx): exposed so that tests can compare it with LAPACK.

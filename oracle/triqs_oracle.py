@@ -27,6 +27,7 @@ import numpy as np
 
 FERMION = 1  # c++/triqs/mesh/domains/matsubara.hpp: statistic_enum {Boson = 0, Fermion = 1}
 BOSON = 0
+REFREQ = 2  # (oracle-internal tag: the tail fitter on a real-frequency mesh)
 
 # ----------------------------------------------------------------------------------------------
 # meshes
@@ -305,11 +306,22 @@ class TailFitter:
         self.tail_fraction, self.n_tail_max = tail_fraction, n_tail_max
         self.adjust_order = expansion_order is None
         self.expansion_order = self.max_order if expansion_order is None else expansion_order
-        self.first, self.last = imfreq_first_last(stat, n_iw)
-        self.size = self.last - self.first + 1
-        self.w_max = math.pi * (2 * self.last + stat) / beta  # |imfreq::w_max()|, imfreq.hpp:128
-        self.fit_idx = self.get_tail_fit_indices()
-        iw = 1j * (math.pi * (2 * np.asarray(self.fit_idx, dtype=np.int64) + stat).astype(np.float64) / beta)
+        if stat == REFREQ:
+            # the fitter is generic in the mesh (tail_fitter.hpp:105-181): refreq(w_min, w_max, n_w) is passed as
+            # (beta = (w_min, w_max), stat = REFREQ, n_iw = n_w); first_index 0, w_max() = xmax (refreq.hpp:52)
+            w_lo, w_hi = beta
+            self.first, self.last = 0, n_iw - 1
+            self.size = n_iw
+            self.w_max = abs(w_hi)
+            self.fit_idx = self.get_tail_fit_indices()
+            wr = np.asarray(self.fit_idx, dtype=np.float64) / (n_iw - 1)
+            iw = (w_lo * (1 - wr) + w_hi * wr).astype(np.complex128)
+        else:
+            self.first, self.last = imfreq_first_last(stat, n_iw)
+            self.size = self.last - self.first + 1
+            self.w_max = math.pi * (2 * self.last + stat) / beta  # |imfreq::w_max()|, imfreq.hpp:128
+            self.fit_idx = self.get_tail_fit_indices()
+            iw = 1j * (math.pi * (2 * np.asarray(self.fit_idx, dtype=np.int64) + stat).astype(np.float64) / beta)
         # vander, tail_fitter.hpp:34-44 (z *= p accumulation), :149-155 (C = om_max / iw)
         C = self.w_max / iw
         V = np.empty((len(self.fit_idx), self.expansion_order + 1), dtype=np.complex128)
@@ -433,6 +445,11 @@ def fit_tail(gw, beta, stat, known_moments=None, **fitter_kw):
     n_w = gw.shape[0]
     n_iw = n_w // 2 if stat == FERMION else (n_w + 1) // 2
     return TailFitter(beta, stat, n_iw, **fitter_kw).fit(gw, known_moments)
+
+
+def fit_tail_refreq(gw, w_min: float, w_max: float, known_moments=None, **fitter_kw):
+    """fit_tail of a real-frequency gf (functions2.hpp:50-56 on a refreq mesh; test/c++/gfs/fit_tail_real.cpp).  gw [n_w, ncols]."""
+    return TailFitter((w_min, w_max), REFREQ, gw.shape[0], **fitter_kw).fit(gw, known_moments)
 
 
 def fit_hermitian_tail(gw, beta, stat, known_moments=None, inner_dim: int = 1, **fitter_kw):

@@ -19,7 +19,7 @@ def test_header_declares_expected_entry_points():
     names = _declared()
     for must in ["tq_fourier_tau_to_iw", "tq_fourier_iw_to_tau", "tq_fit_tail", "tq_fft_many", "tq_fourier_lattice", "tq_invert_batched",
                  "tq_dyson_ksum", "tq_interp_tau", "tq_comm_init", "tq_all_reduce_sum", "tq_density", "tq_make_hermitian",
-                 "tq_is_gf_hermitian", "tq_replace_by_tail", "tq_tight_binding_fourier", "tq_fourier_t_to_w", "tq_fourier_w_to_t", "tq_legendre_to_imfreq", "tq_legendre_to_imtime", "tq_fourier_tau_to_iw_axis",
+                 "tq_is_gf_hermitian", "tq_replace_by_tail", "tq_tight_binding_fourier", "tq_fourier_t_to_w", "tq_fourier_w_to_t", "tq_legendre_to_imfreq", "tq_legendre_to_imtime", "tq_fourier_tau_to_iw_axis", "tq_fit_tail_refreq",
             "tq_imtime_to_legendre", "tq_imfreq_to_legendre"]:
         assert must in names
 

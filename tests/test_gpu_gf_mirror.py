@@ -150,6 +150,12 @@ def test_real_time_transform_reads_like_the_reference_test():
     assert np.max(np.abs(Gt1.data - np.exp(-E * np.abs(t))[:, None, None])) < 1e-4
     Gw1b = G.make_gf_from_fourier(Gt1, w_mesh, tail)
     assert np.max(np.abs(Gw1b.data - Gw1.data)) < 1e-4
+    # exactly as the reference test: the tail comes from fit_tail(Gw1) on the refreq mesh (fourier_real.cpp:52-53)
+    ftail, err = G.fit_tail(Gw1)
+    assert ftail.shape[1:] == (2, 2) and abs(ftail[2, 0, 0] - 2 * E) < 1e-3
+    Gt1f = G.make_gf_from_fourier(Gw1, t_mesh, ftail)
+    assert np.max(np.abs(Gt1f.data - np.exp(-E * np.abs(t))[:, None, None])) < 1e-4
+    assert np.max(np.abs(G.make_gf_from_fourier(Gt1f, w_mesh, ftail).data - Gw1.data)) < 1e-4
     theta = np.where(t > 0, 1.0, np.where(t < 0, 0.0, 0.5))
     Gt2 = G.Gf(t_mesh, (2, 2))
     Gt2.data[:] = (0.5j * (np.exp(-E * np.abs(t)) * (1 - theta) - np.exp(-E * np.abs(t)) * theta))[:, None, None]

@@ -686,3 +686,35 @@ def test_tau_to_iw_along_inner_mesh_is_one_gf(ctx):
     # per-gf semantics (independent gfs): the flat one is declared noisy, like the reference called on that gf alone
     sep = ctx.fourier_tau_to_iw(gt, beta, O.FERMION, n_iw)
     assert rel(sep[0], O.fourier_tau_to_iw(gt[0], beta, O.FERMION, n_iw)) < TOL
+
+
+def test_fit_tail_real_frequency(ctx):
+    """fit_tail on a refreq mesh: test/c++/gfs/fit_tail_real.cpp:24-91 (Basic, Complex, the k x w multivar case as a batch)
+    and parity with the oracle's fitter."""
+    L, om = 201, 10.0
+    w = O.linear_values(-om, om, L)
+    c = np.array([0, 1, 3, 5], complex)
+    g = (c[0] + c[1] / (w + 1e-14) + c[2] / (w * w + 1e-14) + c[3] / (w * w * w + 1e-14)).astype(complex)[None, :, None]
+    for known in (np.zeros((1, 1, 1), complex), np.array([[[0.0], [1.0]]], complex)):
+        tail, err = ctx.fit_tail_refreq(g, (-om, om), known_moments=known, tail_fraction=0.3)
+        assert np.max(np.abs(tail[0, :4, 0] - c)) < 1e-9
+    om = 100.0
+    w = O.linear_values(-om, om, L)
+    a = 1.0 + 0.4j
+    known = np.array([[[0.0], [1.0]]], complex)
+    tail, err = ctx.fit_tail_refreq((1 / (w - a))[None, :, None], (-om, om), known_moments=known)
+    assert np.max(np.abs(tail[0, :5, 0] - np.array([0, 1, a, a ** 2, a ** 3]))) < 1e-7
+    # Multivar (:95-130): g(k, w) = 1 / (w - cos kx cos ky - i eta), one fit per k-point = batch
+    kk = 2 * np.pi * np.arange(4) / 4
+    eps = (np.cos(kk)[:, None] * np.cos(kk)[None, :]).reshape(-1)
+    gk = 1 / (w[None, :, None] - eps[:, None, None] - 0.001j)
+    known = np.zeros((16, 2, 1), complex)
+    known[:, 1] = 1.0
+    tail, err = ctx.fit_tail_refreq(gk, (-om, om), known_moments=known)
+    for k in range(16):
+        ex = np.array([0, 1, eps[k] + 0.001j, (eps[k] + 0.001j) ** 2])
+        assert np.max(np.abs(tail[k, :4, 0] - ex)) < 1e-6
+        rt, re = O.fit_tail_refreq(gk[k], -om, om, known[k])
+        assert tail.shape[1] == rt.shape[0]
+        assert np.max(np.abs(tail[k, :4] - rt[:4])) < 1e-9
+        assert abs(err[k] - re) < 1e-9 + 1e-6 * re

@@ -380,3 +380,20 @@ def test_legendre_known_answers():
     iw = O.imfreq_values(beta, O.FERMION, 200)
     assert np.max(np.abs(gw[:, 0] - 1 / (iw - 0.7))) < 2e-6
     assert np.max(np.abs(O.imfreq_to_legendre(gw, beta, O.FERMION, 30) - gl)) < 1e-5
+
+
+def test_fit_tail_real_known_answers():
+    """test/c++/gfs/fit_tail_real.cpp:24-91 (Basic, Complex)."""
+    L, om = 201, 10.0
+    w = O.linear_values(-om, om, L)
+    c = np.array([0, 1, 3, 5], complex)
+    g = (c[0] + c[1] / (w + 1e-14) + c[2] / (w * w + 1e-14) + c[3] / (w * w * w + 1e-14)).astype(complex)[:, None]
+    for known in (np.zeros((1, 1), complex), np.array([[0.0], [1.0]], complex)):
+        tail, err = O.fit_tail_refreq(g, -om, om, known, tail_fraction=0.3)
+        assert np.max(np.abs(tail[:4, 0] - c)) < 1e-9
+    om = 100.0
+    w = O.linear_values(-om, om, L)
+    a = 1.0 + 0.4j
+    g = (1 / (w - a))[:, None]
+    tail, err = O.fit_tail_refreq(g, -om, om, np.array([[0.0], [1.0]], complex))
+    assert np.max(np.abs(tail[:5, 0] - np.array([0, 1, a, a ** 2, a ** 3]))) < 1e-7

@@ -51,6 +51,8 @@ SIGNATURES = {
     "tq_replace_by_tail": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_int]),
     "tq_fit_tail": (c_int, [c_void_p, c_double, c_int, c_long, c_double, c_int, c_int, c_int, c_int, c_long, c_long, c_void_p, c_void_p,
                             c_int, c_void_p, POINTER(c_int), POINTER(c_double)]),
+    "tq_fit_tail_refreq": (c_int, [c_void_p, c_double, c_double, c_long, c_double, c_int, c_int, c_long, c_long, c_void_p, c_void_p, c_int,
+                                   c_void_p, POINTER(c_int), POINTER(c_double)]),
     "tq_tail_fitter_setup_host": (c_int, [c_double, c_int, c_long, c_double, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_long),
                                           POINTER(c_int), c_void_p, POINTER(c_double), ctypes.c_char_p, c_size_t]),
     "tq_fft_many": (c_int, [c_void_p, c_int, POINTER(c_int), c_long, c_void_p, c_void_p, c_int]),

@@ -321,6 +321,26 @@ class Context:
         flat = out.reshape(-1)[: batch * n_moments * n_cols].reshape(batch, n_moments, n_cols)
         return flat, np.frombuffer(err, dtype=np.float64).copy()
 
+    def fit_tail_refreq(self, g, w_mesh, known_moments=None, tail_fraction=0.2, n_tail_max=30, expansion_order=None):
+        """fit_tail of real-frequency gfs g [batch, n_w, n_cols] on refreq(w_min, w_max, n_w)  (tq_fit_tail_refreq)."""
+        g = _as_c128(g)
+        batch, n_w, n_cols = g.shape
+        n_known = 0
+        if known_moments is not None:
+            known_moments = _as_c128(known_moments)
+            n_known = known_moments.shape[1]
+            if known_moments.shape[2] != n_cols:
+                raise TriqsRuntimeError("known_moments shape incompatible with shape of data")
+        out = _empty_like_kind(g, (batch, max(L.TQ_MAX_MOMENTS, n_known), n_cols))
+        nm = ctypes.c_int(0)
+        err = (ctypes.c_double * batch)()
+        self._check(self._lib.tq_fit_tail_refreq(self._h, float(w_mesh[0]), float(w_mesh[1]), n_w, tail_fraction, n_tail_max,
+                                                 -1 if expansion_order is None else int(expansion_order), n_cols, batch, _ptr(g),
+                                                 _ptr(known_moments), n_known, _ptr(out), ctypes.byref(nm), err))
+        n_moments = nm.value
+        flat = out.reshape(-1)[: batch * n_moments * n_cols].reshape(batch, n_moments, n_cols)
+        return flat, np.frombuffer(err, dtype=np.float64).copy()
+
     def tail_fitter_setup(self, beta, statistic, n_iw, n_fixed=0, hermitian=False, tail_fraction=0.2, n_tail_max=30, expansion_order=None):
         return tail_fitter_setup(beta, statistic, n_iw, n_fixed, hermitian, tail_fraction, n_tail_max, expansion_order)
 

@@ -93,14 +93,25 @@ static void pinv_from_svd(int M, int N, const std::vector<zc> &Uw, const std::ve
     }
 }
 
+// The fitter is generic in the mesh (tail_fitter.hpp:105-181 only uses size / first_index / last_index / w_max / to_value):
+//   imfreq (stat = TQ_FERMION / TQ_BOSON):  beta, n_iw                                   values i w_n
+//   refreq (stat = TAIL_MESH_REFREQ):       `beta` carries w_max, `w_min` the lower end, n_iw = number of points;  values w_i (real)
+constexpr int TAIL_MESH_REFREQ = 2;
 static std::string tail_setup_host(double beta, int stat, long n_iw, double tail_fraction, int n_tail_max, int expansion_order, int n_fixed,
-                                   int hermitian, TailSetup &S) {
+                                   int hermitian, TailSetup &S, double w_min = 0.0) {
+  const bool refreq = stat == TAIL_MESH_REFREQ;
+  auto mesh_value = [&](long n) -> zc { // mesh.to_value(n)
+    if (!refreq) return zc(0.0, M_PI * (double)(2 * n + stat) / beta);
+    if (n_iw == 1) return zc(w_min, 0.0);
+    const double wr = double(n) / (n_iw - 1); // linear.hpp:154-160
+    return zc(w_min * (1 - wr) + beta * wr, 0.0);
+  };
   const int max_order = 9;      // tail_fitter.hpp:69
   const double rcond = 1e-8;    // :74
   const bool adjust = expansion_order < 0;
   S.order = adjust ? max_order : expansion_order;
   const long last = n_iw - 1;
-  const long first = -(last + (stat == TQ_FERMION ? 1 : 0));
+  const long first = refreq ? 0 : -(last + (stat == TQ_FERMION ? 1 : 0));
   S.first = first;
   const long size = last - first + 1;
   // get_tail_fit_indices, :105-128
@@ -119,12 +130,11 @@ static std::string tail_setup_host(double beta, int stat, long n_iw, double tail
     }
   }
   const int M = (int)S.idx.size();
-  S.w_max = std::abs(M_PI * (double)(2 * last + stat) / beta); // |w_max()|, imfreq.hpp:128
+  S.w_max = refreq ? std::abs(beta) : std::abs(M_PI * (double)(2 * last + stat) / beta); // |w_max()|, imfreq.hpp:128, refreq.hpp:52
   // vander, :34-44, :149-155
   S.vander.assign((size_t)M * (S.order + 1), zc(0, 0));
   for (int i = 0; i < M; ++i) {
-    double w = M_PI * (double)(2 * S.idx[i] + stat) / beta;
-    zc c = S.w_max / zc(0.0, w);
+    zc c = S.w_max / mesh_value(S.idx[i]);
     zc z = 1;
     for (int n = 0; n <= S.order; ++n) {
       S.vander[(size_t)i * (S.order + 1) + n] = z;
@@ -374,15 +384,15 @@ __global__ void __launch_bounds__(128) k_fit_tail_staged(const FitArgs A) {
 }
 
 static tq_status get_tail_plan(tq_ctx *ctx, double beta, int stat, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
-                               int n_fixed, int hermitian, std::shared_ptr<TailFitterPlan> *out) {
-  auto key = std::make_tuple(beta, stat, n_iw, tail_fraction, n_tail_max, expansion_order, n_fixed, hermitian);
+                               int n_fixed, int hermitian, std::shared_ptr<TailFitterPlan> *out, double w_min = 0.0) {
+  auto key = std::make_tuple(beta, stat, n_iw, tail_fraction, n_tail_max, expansion_order, n_fixed, hermitian, w_min);
   auto it = ctx->tail_plans.find(key);
   if (it != ctx->tail_plans.end()) {
     *out = it->second;
     return TQ_OK;
   }
   auto pl = std::make_shared<TailFitterPlan>();
-  std::string e = tail_setup_host(beta, stat, n_iw, tail_fraction, n_tail_max, expansion_order, n_fixed, hermitian, pl->S);
+  std::string e = tail_setup_host(beta, stat, n_iw, tail_fraction, n_tail_max, expansion_order, n_fixed, hermitian, pl->S, w_min);
   if (!e.empty()) return tq_fail(ctx, TQ_ERR_RUNTIME, e);
   TailSetup &S = pl->S;
   std::vector<int> rows(S.idx.size());
@@ -400,15 +410,24 @@ static tq_status get_tail_plan(tq_ctx *ctx, double beta, int stat, long n_iw, do
 }
 
 // device-pointer entry used by the inverse transform and by tq_fit_tail.  out is dense [batch][n_moments][n_cols].
+static tq_status fit_tail_device_mesh(tq_ctx *ctx, double beta, int statistic, long n_iw, double w_min, double tail_fraction, int n_tail_max,
+                                      int expansion_order, int hermitian, int inner_dim, long n_cols, long batch, const cd *d_g,
+                                      const cd *d_known, int n_known, cd *d_out_moments, int *n_moments, double *d_err);
 tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
                              int hermitian, int inner_dim, long n_cols, long batch, const cd *d_g, const cd *d_known, int n_known,
                              cd *d_out_moments, int *n_moments, double *d_err) {
+  return fit_tail_device_mesh(ctx, beta, statistic, n_iw, 0.0, tail_fraction, n_tail_max, expansion_order, hermitian, inner_dim, n_cols, batch, d_g,
+                              d_known, n_known, d_out_moments, n_moments, d_err);
+}
+static tq_status fit_tail_device_mesh(tq_ctx *ctx, double beta, int statistic, long n_iw, double w_min, double tail_fraction, int n_tail_max,
+                                      int expansion_order, int hermitian, int inner_dim, long n_cols, long batch, const cd *d_g,
+                                      const cd *d_known, int n_known, cd *d_out_moments, int *n_moments, double *d_err) {
   if (expansion_order > TQ_MAX_MOMENTS - 1)
     return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tail fit: expansion_order > " + std::to_string(TQ_MAX_MOMENTS - 1) + " is not supported");
   if (hermitian && (inner_dim < 1 || n_cols % ((long)inner_dim * inner_dim) != 0))
     return tq_fail(ctx, TQ_ERR_RUNTIME, "ERROR in hermitian least square fitting: Data shape incompatible with given dimension");
   std::shared_ptr<TailFitterPlan> pl;
-  TQ_TRY(get_tail_plan(ctx, beta, statistic, n_iw, tail_fraction, n_tail_max, expansion_order, n_known, hermitian, &pl));
+  TQ_TRY(get_tail_plan(ctx, beta, statistic, n_iw, tail_fraction, n_tail_max, expansion_order, n_known, hermitian, &pl, w_min));
   const TailSetup &S = pl->S;
   FitArgs A{};
   A.M = (int)S.idx.size();
@@ -420,7 +439,7 @@ tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw,
   A.d = inner_dim;
   A.n_cols = (int)n_cols;
   const long last = n_iw - 1;
-  const long first = -(last + (statistic == TQ_FERMION ? 1 : 0));
+  const long first = statistic == TAIL_MESH_REFREQ ? 0 : -(last + (statistic == TQ_FERMION ? 1 : 0));
   A.n_w = (int)(last - first + 1);
   A.w_max = S.w_max;
   A.rows = pl->d_rows;
@@ -445,19 +464,20 @@ tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw,
   return TQ_OK;
 }
 
-extern "C" tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
-                                 int hermitian, int inner_dim, long n_cols, long batch, const tq_complex *g, const tq_complex *known,
-                                 int n_known, tq_complex *out_moments, int *out_n_moments, double *out_err) {
+static tq_status fit_tail_impl(tq_ctx *ctx, double beta, int statistic, long n_iw, double w_min, double tail_fraction, int n_tail_max,
+                               int expansion_order, int hermitian, int inner_dim, long n_cols, long batch, const tq_complex *g,
+                               const tq_complex *known, int n_known, tq_complex *out_moments, int *out_n_moments, double *out_err) {
   if (!ctx) return TQ_ERR_INVALID;
-  if (!g || !out_moments || !out_n_moments || n_iw < 1 || n_cols < 1 || batch < 1 || !(beta > 0) || n_known < 0 ||
-      (statistic != TQ_FERMION && statistic != TQ_BOSON))
+  const bool refreq = statistic == TAIL_MESH_REFREQ;
+  if (!g || !out_moments || !out_n_moments || n_iw < 1 || n_cols < 1 || batch < 1 || (!refreq && !(beta > 0)) || n_known < 0 ||
+      (statistic != TQ_FERMION && statistic != TQ_BOSON && !refreq))
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_fit_tail: invalid argument");
   if (hermitian && inner_dim < 1) // tail_fitter.hpp:196-197
     return tq_fail(ctx, TQ_ERR_RUNTIME, "Enforcing the hermiticity in tail_fit requires inner matrix dimension");
   TQ_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!known) n_known = 0;
   const long last = n_iw - 1;
-  const long first = -(last + (statistic == TQ_FERMION ? 1 : 0));
+  const long first = refreq ? 0 : -(last + (statistic == TQ_FERMION ? 1 : 0));
   const long n_w = last - first + 1;
   const int order_eff = expansion_order < 0 ? 9 : expansion_order;
   const void *d_g = nullptr, *d_known = nullptr;
@@ -484,8 +504,8 @@ extern "C" tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n
   const bool out_dev = tq_is_device_ptr(out_moments);
   cd *d_out = out_dev ? (cd *)out_moments : (cd *)ctx->stage_out.p;
   int nm = 0;
-  TQ_TRY(tq_fit_tail_device(ctx, beta, statistic, n_iw, tail_fraction, n_tail_max, expansion_order, hermitian, inner_dim, n_cols, batch,
-                            (const cd *)d_g, (const cd *)d_known, n_known, d_out, &nm, d_err));
+  TQ_TRY(fit_tail_device_mesh(ctx, beta, statistic, n_iw, w_min, tail_fraction, n_tail_max, expansion_order, hermitian, inner_dim, n_cols, batch,
+                              (const cd *)d_g, (const cd *)d_known, n_known, d_out, &nm, d_err));
   *out_n_moments = nm;
   TQ_TRY(tq_reserve_pinned(ctx, sizeof(double) * batch));
   TQ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_err, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
@@ -494,4 +514,20 @@ extern "C" tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n
   TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (out_err) memcpy(out_err, ctx->pinned, sizeof(double) * batch);
   return TQ_OK;
+}
+
+extern "C" tq_status tq_fit_tail(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
+                                 int hermitian, int inner_dim, long n_cols, long batch, const tq_complex *g, const tq_complex *known,
+                                 int n_known, tq_complex *out_moments, int *out_n_moments, double *out_err) {
+  if (ctx && statistic != TQ_FERMION && statistic != TQ_BOSON) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fit_tail: invalid argument");
+  return fit_tail_impl(ctx, beta, statistic, n_iw, 0.0, tail_fraction, n_tail_max, expansion_order, hermitian, inner_dim, n_cols, batch, g, known,
+                       n_known, out_moments, out_n_moments, out_err);
+}
+
+// fit_tail of a real-frequency gf: the same fitter on a refreq mesh (tail_fitter.hpp is generic in the mesh; test/c++/gfs/fit_tail_real.cpp)
+extern "C" tq_status tq_fit_tail_refreq(tq_ctx *ctx, double w_min, double w_max, long n_w, double tail_fraction, int n_tail_max,
+                                        int expansion_order, long n_cols, long batch, const tq_complex *g, const tq_complex *known, int n_known,
+                                        tq_complex *out_moments, int *out_n_moments, double *out_err) {
+  return fit_tail_impl(ctx, w_max, TAIL_MESH_REFREQ, n_w, w_min, tail_fraction, n_tail_max, expansion_order, 0, 1, n_cols, batch, g, known, n_known,
+                       out_moments, out_n_moments, out_err);
 }

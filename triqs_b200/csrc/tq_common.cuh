@@ -62,7 +62,7 @@ struct tq_ctx {
   // caches (mesh-only data, like the reference's tail_fitter::_lss and FFTW plans)
   std::map<std::tuple<long, int>, std::shared_ptr<FftPlanHost>> fft_plans;                        // (N, dummy)
   std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
-  std::map<std::tuple<double, int, long, double, int, int, int, int>, std::shared_ptr<TailFitterPlan>> tail_plans;
+  std::map<std::tuple<double, int, long, double, int, int, int, int, double>, std::shared_ptr<TailFitterPlan>> tail_plans;
   std::shared_ptr<PipePlanCache> pipe_cache;
   std::shared_ptr<LatTwiddles> lat_tw;
   std::shared_ptr<ColPlanCache> col_cache;

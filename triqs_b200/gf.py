@@ -345,6 +345,10 @@ def _transform(ctx, mesh, data3, n, km, one_gf=False):
 
 def fit_tail(g: Gf, known_moments=None, hermitian=False, **fit_params):
     """functions2.hpp:50-56 (and :94-110 with hermitian=True): returns (tail[n_moments, target...], err)."""
+    if isinstance(g.mesh, MeshReFreq) and not hermitian:  # fit_tail_real.cpp
+        km = None if known_moments is None else np.asarray(known_moments).reshape(1, np.shape(known_moments)[0], g.n_others)
+        tail, err = g.ctx.fit_tail_refreq(g.flat()[None], (g.mesh.xmin, g.mesh.xmax), known_moments=km, **fit_params)
+        return tail[0].reshape((tail.shape[1],) + g.target_shape), float(err[0])
     if not isinstance(g.mesh, MeshImFreq):
         raise TriqsRuntimeError("fit_tail needs an imfreq gf")
     inner = 1
