@@ -216,3 +216,19 @@ def test_multivar_fourier_reads_like_the_reference_test():
         assert isinstance(g_r_tau.mesh[0], G.MeshCycLat) and isinstance(g_r_tau.mesh[2], G.MeshImTime)
         gb1 = G.make_gf_from_fourier_axes(g_r_tau, (0, 2), (k_mesh, iw_mesh))
         assert np.max(np.abs(gb1.data - g.data)) < 1e-4
+
+
+def test_imfreq_evaluator_uses_the_tail_outside_the_mesh():
+    """evaluator.hpp:50-76: g(n) = data inside the window, the fitted tail expansion outside."""
+    from triqs_b200 import gf as G
+    beta, n_iw = 10.0, 400
+    d, H = _gw(beta, n_iw, 2, 11)
+    g = G.Gf(G.MeshImFreq(beta, O.FERMION, n_iw), (2, 2), d)
+    assert np.array_equal(g(5), d[5 + n_iw])
+    for n in (n_iw + 10, -3 * n_iw, 5000):
+        iw = 1j * np.pi * (2 * n + 1) / beta
+        exact = np.linalg.inv(iw * np.eye(2) - H)
+        tail, _ = O.fit_tail(g.flat(), beta, O.FERMION)
+        ref = O.tail_eval(tail, iw).reshape(2, 2)
+        assert np.max(np.abs(g(n) - ref)) < 1e-10
+        assert np.max(np.abs(g(n) - exact)) < 1e-6

@@ -86,15 +86,15 @@ TQ_HD Window tile_window(int item, int S, int N, int L, int first, int last) {
 // ---- functors plugged into the two-pass engine -----------------------------------------------
 struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fourier_matsubara.cpp:159-173
   const PipeArgs &A;
-  const cd *coef;      // [c][4] = a1, a2, a3, m1
+  const cd *coef;      // [4][tcw] = a1, a2, a3, m1
   const double4 *qtab; // per-q factors
   double4 ea;          // per-item factors (C_i e_i(item))
   cd a1, a2, a3;
   TQ_D void begin(int q, int c) {
     const double4 e = qtab[q];
-    a1 = cscale(e.x * ea.x, coef[4 * c]);
-    a2 = cscale(e.y * ea.y, coef[4 * c + 1]);
-    a3 = cscale(e.z * ea.z, coef[4 * c + 2]);
+    a1 = cscale(e.x * ea.x, coef[c]);
+    a2 = cscale(e.y * ea.y, coef[c + A.tcw]);
+    a3 = cscale(e.z * ea.z, coef[c + 2 * A.tcw]);
   }
   template <int R> TQ_D cd load(const cd *p) const {
     cd v = caxpy(-A.er[0][R], a1, *p);
@@ -104,16 +104,17 @@ struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fo
   }
 };
 template <int RB> struct PreI1 { // x = (g - tail(i w)) / beta for window rows, 0 elsewhere      :254
-  const cd *wrec, *coef; // coef [c][4] = a1, a2 - a3, a2 + a3, -
+  const cd *wrec, *coef; // coef [4][tcw] = a1, a2 - a3, a2 + a3, -
+  int tcw;
   Window win;
   double inv_beta;
   cd a1, D23, A23;
   int q;
   TQ_D void begin(int qq, int c) {
     q = qq;
-    a1 = coef[4 * c];
-    D23 = coef[4 * c + 1];
-    A23 = coef[4 * c + 2];
+    a1 = coef[c];
+    D23 = coef[c + tcw];
+    A23 = coef[c + 2 * tcw];
   }
   // pruned pass A: leg 0 is window row q (compact index q), the last leg is window row RB + q
   TQ_D cd edge(int which, const cd *p) const {
@@ -152,7 +153,8 @@ template <int RA> struct PostScratch { // Y = z T[beta]  -> scratch[beta][column
   template <int TT> TQ_D void store(cd v) const { p[(long)(RA * TT) * beta_stride] = cmul(v, Ts[RA * TT]); }
 };
 template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows only      :181-183
-  const cd *wrec, *coef; // coef [c][4] = a1, a2 - a3, a2 + a3, trapezoid correction
+  const cd *wrec, *coef; // coef [4][tcw] = a1, a2 - a3, a2 + a3, trapezoid correction
+  int tcw;
   int n_cols, item, Nb, L, first;
   Window win;
   cd *base; // out of this gf + c0
@@ -161,10 +163,10 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
   int sidx;
   TQ_D void begin(int s, int c) {
     sidx = s;
-    a1 = coef[4 * c];
-    D23 = coef[4 * c + 1];
-    A23 = coef[4 * c + 2];
-    ex = coef[4 * c + 3];
+    a1 = coef[c];
+    D23 = coef[c + tcw];
+    A23 = coef[c + 2 * tcw];
+    ex = coef[c + 3 * tcw];
     p = base + c;
   }
   template <int TT> TQ_D void store(cd v) const {
@@ -185,7 +187,7 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
 };
 template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i,  j = item + Nb (s + RA t)        :261-268
   const PipeArgs &A;
-  const cd *coef;      // [c][4] = a1, a2, a3, m1
+  const cd *coef;      // [4][tcw] = a1, a2, a3, m1
   const double4 *qtab; // per-s factors
   double4 ea;          // per-item factors
   int n_cols, item, Nb, L;
@@ -196,10 +198,10 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
   int j0;
   TQ_D void begin(int s, int c) {
     const double4 e = qtab[s];
-    a1 = cscale(e.x * ea.x, coef[4 * c]);
-    a2 = cscale(e.y * ea.y, coef[4 * c + 1]);
-    a3 = cscale(e.z * ea.z, coef[4 * c + 2]);
-    m1 = coef[4 * c + 3];
+    a1 = cscale(e.x * ea.x, coef[c]);
+    a2 = cscale(e.y * ea.y, coef[c + A.tcw]);
+    a3 = cscale(e.z * ea.z, coef[c + 2 * A.tcw]);
+    m1 = coef[c + 3 * A.tcw];
     j0 = item + Nb * s;
     p = base + c + (long)j0 * n_cols;
   }
@@ -217,8 +219,8 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
 };
 
 // Pole weights of the 3-pole tail model per (gf, column), in the two forms the kernels use   (:151-169, :238-252)
-//   w_tau  [gf][c][4] = a1, a2, a3, m1                                   (tau side: F1 pre-transform, I2 post-transform)
-//   w_freq [gf][c][4] = a1, a2 - a3, a2 + a3, trapezoid correction        (frequency side: F2 epilogue, I1 pre-transform)
+//   w_tau  [gf][4][c] = a1, a2, a3, m1                                   (tau side: F1 pre-transform, I2 post-transform)
+//   w_freq [gf][4][c] = a1, a2 - a3, a2 + a3, trapezoid correction        (frequency side: F2 epilogue, I1 pre-transform)
 // The trapezoid end-point correction -0.5 (beta/L) (g_0 + m1 +/- g_L) (:181) exists on the forward leg only (gt != nullptr).
 __global__ void k_pole_weights(const cd *mom, long mom_gf_stride, int n_cols, long total, int stat, const cd *gt, long gt_gf_stride, int L,
                                double half_fact_fwd, cd *w_tau, cd *w_freq) {
@@ -247,14 +249,18 @@ __global__ void k_pole_weights(const cd *mom, long mom_gf_stride, int n_cols, lo
     s = fermion ? cadd(s, gL) : csub(s, gL);
     ex = cscale(-half_fact_fwd, s);
   }
-  w_tau[4 * i] = a1;
-  w_tau[4 * i + 1] = a2;
-  w_tau[4 * i + 2] = a3;
-  w_tau[4 * i + 3] = m1;
-  w_freq[4 * i] = a1;
-  w_freq[4 * i + 1] = csub(a2, a3);
-  w_freq[4 * i + 2] = cadd(a2, a3);
-  w_freq[4 * i + 3] = ex;
+  // [gf][4][n_cols]: the four weights of a tile's columns are four contiguous runs, so that lanes with consecutive columns read
+  // consecutive 16-byte words of shared memory (the [c][4] layout cost a 4-way bank conflict on every read: 10-18 % of the
+  // shared-memory wavefronts of the pipelined kernels, ncu source view)
+  cd *wt = w_tau + (size_t)gf * 4 * n_cols + c, *wf = w_freq + (size_t)gf * 4 * n_cols + c;
+  wt[0] = a1;
+  wt[(size_t)n_cols] = a2;
+  wt[(size_t)2 * n_cols] = a3;
+  wt[(size_t)3 * n_cols] = m1;
+  wf[0] = a1;
+  wf[(size_t)n_cols] = csub(a2, a3);
+  wf[(size_t)2 * n_cols] = cadd(a2, a3);
+  wf[(size_t)3 * n_cols] = ex;
 }
 
 // shared-memory carve-up (bytes); tile buffers first, each padded to 128 B (TMA tensor destination alignment)
@@ -412,7 +418,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         if (Smem::QTAB) bytes += (uint32_t)sizeof(double4);
         mbar_arrive_expect_tx(&full[b], bytes);
         // the tile's table set: pole weights of its columns (:151-169, :238-252), per-item factors, four-step twiddles, window rows
-        bulk_g2s(tab + S.coef_off, A.polew + ((size_t)id.gf * n_cols + id.c0) * 4, (uint32_t)(sizeof(cd) * 4 * id.w), &full[b]);
+        for (int k = 0; k < 4; ++k)
+          bulk_g2s(tab + S.coef_off + sizeof(cd) * (size_t)k * TCW, A.polew + ((size_t)id.gf * 4 + k) * n_cols + id.c0, (uint32_t)(sizeof(cd) * id.w),
+                   &full[b]);
         if (Smem::QTAB) bulk_g2s(tab + S.item_off, A.itemtab + id.item, (uint32_t)sizeof(double4), &full[b]);
         if (MODE == M_F1) {
           tma_load_4d(dst, &tmap, 2 * id.c0, id.item, 0, (int)id.gf, &full[b]); // [gf][b = 0..Nb)[a = item][columns]
@@ -510,7 +518,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
         } else if (MODE == M_I1) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
-          PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, Window{wv.x, wv.y}, A.inv_beta};
+          PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, Window{wv.x, wv.y}, A.inv_beta};
           if (A.i1_edge) {
             auto wedge = [&](int rr) { return A.wedge[rr]; };
             fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS, it,
@@ -534,7 +542,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
         } else if (MODE == M_F2) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
-          PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
+          PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
                           A.out + id.gf * A.out_gf_stride + id.c0};
           fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
         } else {

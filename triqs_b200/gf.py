@@ -202,7 +202,21 @@ class Gf:
         return self
 
     def __call__(self, tau):
-        """off-mesh evaluation on an imtime mesh (c++/triqs/gfs/evaluator.hpp:35-43); accepts a scalar or an array of tau."""
+        """off-mesh evaluation: linear interpolation on an imtime mesh (c++/triqs/gfs/evaluator.hpp:35-43; a scalar or an array
+        of tau), or g(n) on an imfreq mesh -- the mesh value inside the window, the fitted tail outside (evaluator.hpp:50-76)."""
+        if isinstance(self.mesh, MeshImFreq):
+            n = int(tau)
+            m = self.mesh
+            if m.first_index <= n <= m.last_index:
+                return self.data[n - m.first_index]
+            tail, _ = fit_tail(self)  # moments A_p: g = sum_p A_p / (i w)^p  (fit_tail_no_normalize with x = |w_max| / i w is the same sum)
+            iw = 1j * math.pi * (2 * n + m.statistic) / m.beta
+            z, res = 1.0 + 0j, 0
+            tail = tail.cpu().numpy() if _is_torch(tail) else tail
+            for p in range(tail.shape[0]):
+                res = res + tail[p] * z
+                z = z / iw
+            return res
         if not isinstance(self.mesh, MeshImTime):
             raise TriqsRuntimeError("Gf.__call__ is implemented for imtime meshes")
         scalar = np.isscalar(tau)
