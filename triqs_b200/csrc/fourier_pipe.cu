@@ -332,6 +332,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #define TQ_PK_CHUNK 1
 #endif
   constexpr int PK_CHUNK = TQ_PK_CHUNK;
+#ifndef TQ_PK_LATE
+#define TQ_PK_LATE 6 // F2 and I1; F1 and I2 have no register to spare (they spill 160-180 B and lose 40-70 %)
+#endif
+  constexpr bool PK_LATE = !PK_STATIC && PK_CHUNK == 1 && !PK_AHEAD && ((TQ_PK_LATE >> MODE) & 1); // bit per mode
   using Smem = PipeSmem<MODE, N, RA, RB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TCW = A.tcw;
@@ -455,10 +459,17 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
     // (pass B of tile k is queued after pass A of tile k+1, so whoever takes it rarely waits; a packet only ever waits
     //  for packets that were handed out before it, hence no deadlock)
     int pk_next = 0, pk_left = 0;
-    if (!PK_STATIC && PK_AHEAD && lane == 0) pk_next = atomicAdd(next_pk, 1);
+    if (!PK_STATIC && (PK_AHEAD || PK_LATE) && lane == 0) pk_next = atomicAdd(next_pk, 1);
+    // PK_LATE: the next packet is claimed between the arithmetic and the stores of the current one, so that the round trip of the
+    // shared-memory atomic (it queues behind the data traffic) overlaps the stores instead of sitting in front of the next packet
+    const auto fetch_next = [&]() {
+      if (PK_LATE && lane == 0) pk_next = atomicAdd(next_pk, 1);
+    };
     for (int pk_static = warp;; pk_static += NW) {
       int pk;
-      if (PK_STATIC) {
+      if (PK_LATE) {
+        pk = __shfl_sync(0xffffffffu, pk_next, 0);
+      } else if (PK_STATIC) {
         pk = pk_static; // packets cost the same: round robin over the worker warps balances as well as a shared counter
       } else if (PK_CHUNK > 1) {
         // one shared-memory atomic per PK_CHUNK packets (its latency behind the data traffic in the LSU queue is paid per fetch)
@@ -489,7 +500,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       }
       if (blk >= nloc + 2) break;
       const int k = is_b ? blk - 2 : blk; // tile of this CTA
-      if (k >= nloc) continue;
+      if (k >= nloc) {
+        fetch_next();
+        continue;
+      }
       const long t = blockIdx.x + (long)k * gridDim.x;
       const int b = k % PIPE_NBUF, u = k / PIPE_NBUF;
       const TileId id = decode(t);
@@ -499,6 +513,8 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
       const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
       const int it = r * 32 + lane; // butterfly of this lane (the engine skips it when past the end)
+      // a packet of a narrower (last) column tile can be empty for lane 0: its hook never runs, claim the next packet here
+      if (PK_LATE && r * 32 >= (is_b ? RA : RB) * id.w) fetch_next();
       // (I2 sits at the register limit: one more live value makes it spill, so it recomputes the magic per packet)
       const unsigned m_w = MODE == M_I2 ? ~0u : (id.w == TCW ? m_w_full : m_w_last);
       TQ_LAP(t_sched)
@@ -515,7 +531,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         TQ_LAP(t_wait)
         if (MODE == M_F1) {
           PreF1 pre{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off)};
-          fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
+          fft2_pass_a<N, RA, RB, SGN, true>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w, fetch_next);
         } else if (MODE == M_I1) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
           PreI1<RB> pre{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, Window{wv.x, wv.y}, A.inv_beta};
@@ -523,12 +539,13 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
             auto wedge = [&](int rr) { return A.wedge[rr]; };
             fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS, it,
                                                1 << 30, pre, wedge, m_w);
+            if (r * 32 < RB * id.w) fetch_next(); // (an empty packet has claimed its successor above)
           } else {
-            fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
+            fft2_pass_a<N, RA, RB, SGN, false>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w, fetch_next);
           }
         } else {
           PreIdentity pre;
-          fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w);
+          fft2_pass_a<N, RA, RB, SGN, MODE == M_I2>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w, fetch_next);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&adone[b]);
@@ -539,16 +556,16 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         if (PASS1) {
           PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
                                A.Na, A.tcw2, id.item, id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
         } else if (MODE == M_F2) {
           const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
           PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
                           A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
         } else {
           PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
                           A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
         }
         __syncwarp(); // every lane's reads of the tile are done ...
         if (lane == 0) {

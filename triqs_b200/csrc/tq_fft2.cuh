@@ -44,14 +44,21 @@ __device__ int g_tq_knock = 0;
 #define TQ_KNOCK(bit) 0
 #endif
 
+struct NoHook {
+  TQ_HD void operator()() const {}
+};
+
 struct PreIdentity {
   TQ_HD void begin(int, int) {}
   template <int R> TQ_HD cd load(const cd *p) const { return *p; }
 };
 
 // twq[q * RA + s] = w_N^{SGN q s} (times whatever per-q / per-s factor the caller folded in).  TW0: entry s = 0 is not 1.
-template <int N, int RA, int RB, int SGN, bool TW0, class Pre>
-TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, unsigned magic = ~0u) {
+// `before_store` runs once per butterfly between the arithmetic and the stores (the pipelined kernels fetch their next work
+// packet there, so that the fetch latency overlaps the stores).
+template <int N, int RA, int RB, int SGN, bool TW0, class Pre, class Hook = NoHook>
+TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int tid, int nthreads, Pre &pre, unsigned magic = ~0u,
+                       const Hook &before_store = Hook()) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RB * tcw;
   const int stride = RB * pitch;
@@ -69,6 +76,7 @@ TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, in
 #pragma unroll
       for (int r = TW0 ? 0 : 1; r < RA; ++r) a[r] = cmul(a[r], tw[r]);
     }
+    before_store();
     if (!TQ_KNOCK(2)) {
 #pragma unroll
       for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
@@ -78,8 +86,9 @@ TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, in
   }
 }
 
-template <int N, int RA, int RB, int SGN, class Post>
-TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, Post &post, unsigned magic = ~0u) {
+template <int N, int RA, int RB, int SGN, class Post, class Hook = NoHook>
+TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, Post &post, unsigned magic = ~0u,
+                       const Hook &before_store = Hook()) {
   static_assert(RA * RB == N, "N = RA * RB");
   const int nitems = RA * tcw;
   if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw);
@@ -92,6 +101,7 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
 #pragma unroll
     for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
     if (!TQ_KNOCK(1)) Dft<RB, SGN>::run(a);
+    before_store();
     if (!TQ_KNOCK(4)) {
       tq_unroll_store<RB>(a, post);
     } else {
