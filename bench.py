@@ -72,7 +72,8 @@ class ClockSampler:
         self.t = None
         self.how = "nvidia-smi"
 
-    def _run_nvml(self):
+    def _init_nvml(self):
+        """NVML initialisation takes tens of milliseconds: done before the sampling thread starts, not inside the timed region."""
         import pynvml as nv
         nv.nvmlInit()
         h = None
@@ -85,18 +86,26 @@ class ClockSampler:
                     h = None
         if h is None:
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self._nv, self._h = nv, h
+        self._masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                       "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # first call warms the driver path
         self.how = "nvml"
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for k, m in self._masks.items():
+            if r & m:
+                self.reasons.add(k)
+        self.n += 1
+
+    def _run_nvml(self):
         while not self.stop:
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            for k, m in masks.items():
-                if r & m:
-                    self.reasons.add(k)
-            self.n += 1
-            time.sleep(0.002)
+            self._sample_nvml()
+            time.sleep(0.001)
 
     def _run_smi(self):
         while not self.stop:
@@ -116,15 +125,24 @@ class ClockSampler:
             time.sleep(0.1)
 
     def _run(self):
-        try:
-            self._run_nvml()
-        except Exception:
-            self._run_smi()
+        if self.how == "nvml":
+            try:
+                self._run_nvml()
+                return
+            except Exception:
+                pass
+        self._run_smi()
 
     def __enter__(self):
+        try:
+            self._init_nvml()
+        except Exception:
+            self.how = "nvidia-smi"
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
-        time.sleep(0.05)  # let the sampler initialise before the timed region starts
+        time.sleep(0.02)  # the sampler is running before the timed region starts
+        self.sm.clear()   # (keep only samples taken under load)
+        self.n = 0
         return self
 
     def __exit__(self, *a):
