@@ -30,13 +30,35 @@
 
 // -------------------------------------------------------------------------------------------------
 enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
-constexpr int PIPE_NBUF = 3; // tile buffers
-constexpr int PIPE_NTAB = 4; // table sets (they live until the end of pass B, one stage longer than the tile)
+// Tile buffers of the ring.  Measured (32 blocks, one B200): the pass-1 kernels gain from a 4-deep ring of 9-column tiles
+// (F1 0.559 -> 0.530 ms, I1 0.555 -> 0.482 ms: the TMA row gather of the next-but-one tile has a full tile period more to land),
+// the pass-2 kernels lose with the narrower tiles a fourth buffer would force (F2 0.463 -> 0.486 ms, I2 0.480 -> 0.839 ms).
+#ifndef TQ_PIPE_NBUF1
+#define TQ_PIPE_NBUF1 4
+#endif
+#ifndef TQ_PIPE_NBUF2
+#define TQ_PIPE_NBUF2 3
+#endif
+__host__ __device__ constexpr int pipe_nbuf(int mode) { return (mode == 0 || mode == 2) ? TQ_PIPE_NBUF1 : TQ_PIPE_NBUF2; } // M_F1, M_I1 : M_F2, M_I2
+__host__ __device__ constexpr int pipe_ntab(int mode) { return pipe_nbuf(mode) + 1; } // table sets live until the end of pass B, one stage longer than the tile
 constexpr int PIPE_MAXR = 25; // largest radix of a pass
 // worker warps per CTA (+ 1 producer warp).  The register file is 16 K registers per SM sub-partition: 12 warps (3 per
 // sub-partition) get 168 registers per thread, 16 warps only 128 (radix 20 / 25 then spill); measured: 7 workers reach 86 %
 // of the throughput of 11, 15 workers at 128 registers are slower.
 constexpr int PIPE_NW = 11;
+// per-kernel worker counts (developer A/B switches; > 11 workers means 128 registers per thread)
+#ifndef TQ_NW_F1
+#define TQ_NW_F1 PIPE_NW
+#endif
+#ifndef TQ_NW_F2
+#define TQ_NW_F2 PIPE_NW
+#endif
+#ifndef TQ_NW_I1
+#define TQ_NW_I1 PIPE_NW
+#endif
+#ifndef TQ_NW_I2
+#define TQ_NW_I2 PIPE_NW
+#endif
 
 struct PipeArgs {
   int Na, Nb, n_cols;
@@ -274,7 +296,7 @@ template <int MODE, int N, int RA, int RB> struct PipeSmem {
     stage_off = (sizeof(cd) * (size_t)N * (PASS1 ? pitch : tcw) + 127) & ~size_t(127);
     // I1: staging rows for the last butterfly leg (pruned pass A), 128-byte aligned like the tile itself
     buf_stride = stage_off + (MODE == M_I1 ? ((sizeof(cd) * (size_t)RB * pitch + 127) & ~size_t(127)) : 0);
-    tw = PIPE_NBUF * buf_stride;
+    tw = pipe_nbuf(MODE) * buf_stride;
     qtab = tw + sizeof(cd) * N;
     tab0 = qtab + (QTAB ? sizeof(double4) * NQ : 0);
     coef_off = 0;
@@ -283,8 +305,8 @@ template <int MODE, int N, int RA, int RB> struct PipeSmem {
     win_off = t_off + (PASS1 ? sizeof(cd) * N : 0);
     wrec_off = win_off + (WREC ? sizeof(int4) : 0);
     tab_stride = wrec_off + (WREC ? sizeof(cd) * 2 * (size_t)wmax : 0);
-    mbar = tab0 + PIPE_NTAB * tab_stride;
-    total = mbar + 8 * (3 * PIPE_NBUF + PIPE_NTAB) + 16;
+    mbar = tab0 + pipe_ntab(MODE) * tab_stride;
+    total = mbar + 8 * (3 * pipe_nbuf(MODE) + pipe_ntab(MODE)) + 16;
   }
 };
 
@@ -343,10 +365,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   cd *twS = reinterpret_cast<cd *>(smem_raw + S.tw);
   double4 *qtab = reinterpret_cast<double4 *>(smem_raw + S.qtab);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + S.mbar); // TMA landed + tables written   (producer -> pass A)
-  uint64_t *adone = full + PIPE_NBUF;                                // pass A complete               (pass A -> pass B)
-  uint64_t *freeb = adone + PIPE_NBUF;                               // pass B has read the tile      (pass B -> producer)
-  uint64_t *tabfree = freeb + PIPE_NBUF;                             // pass B is done with the tables (pass B -> producer)
-  int *next_pk = reinterpret_cast<int *>(tabfree + PIPE_NTAB);       // work-packet counter of the worker warps
+  uint64_t *adone = full + pipe_nbuf(MODE);                                // pass A complete               (pass A -> pass B)
+  uint64_t *freeb = adone + pipe_nbuf(MODE);                               // pass B has read the tile      (pass B -> producer)
+  uint64_t *tabfree = freeb + pipe_nbuf(MODE);                             // pass B is done with the tables (pass B -> producer)
+  int *next_pk = reinterpret_cast<int *>(tabfree + pipe_ntab(MODE));       // work-packet counter of the worker warps
   volatile int *ready_tile = next_pk + 1;                            // newest tile the producer has started (its buffer is free)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -359,12 +381,12 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   if (Smem::QTAB)
     for (int i = tid; i < Smem::NQ; i += NT) qtab[i] = A.qtab[i];
   if (tid == 0) {
-    for (int b = 0; b < PIPE_NBUF; ++b) {
+    for (int b = 0; b < pipe_nbuf(MODE); ++b) {
       mbar_init(&full[b], 1);
       mbar_init(&adone[b], pa);
       mbar_init(&freeb[b], pb);
     }
-    for (int b = 0; b < PIPE_NTAB; ++b) mbar_init(&tabfree[b], pb);
+    for (int b = 0; b < pipe_ntab(MODE); ++b) mbar_init(&tabfree[b], pb);
     *next_pk = 0;
     *ready_tile = -1;
     fence_mbar_init();
@@ -391,7 +413,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
     // ===================== producer warp: TMA + per-tile pole weights =====================
     for (int i = 0; i < nloc; ++i) {
       const long t = blockIdx.x + (long)i * gridDim.x;
-      const int b = i % PIPE_NBUF, u = i / PIPE_NBUF, ts = i % PIPE_NTAB, ut = i / PIPE_NTAB;
+      const int b = i % pipe_nbuf(MODE), u = i / pipe_nbuf(MODE), ts = i % pipe_ntab(MODE), ut = i / pipe_ntab(MODE);
       if (ut > 0) mbar_wait(&tabfree[ts], (uint32_t)((ut - 1) & 1)); // tile i - NTAB is completely done
       if (u > 0) mbar_wait(&freeb[b], (uint32_t)((u - 1) & 1));       // pass B of tile i - NBUF has read its inputs
       if (lane == 0) *ready_tile = i; // every barrier of buffer b is now in the phase of tile i
@@ -505,10 +527,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         continue;
       }
       const long t = blockIdx.x + (long)k * gridDim.x;
-      const int b = k % PIPE_NBUF, u = k / PIPE_NBUF;
+      const int b = k % pipe_nbuf(MODE), u = k / pipe_nbuf(MODE);
       const TileId id = decode(t);
       cd *tile = reinterpret_cast<cd *>(smem_raw + b * S.buf_stride);
-      const int ts = k % PIPE_NTAB;
+      const int ts = k % pipe_ntab(MODE);
       unsigned char *tab = smem_raw + S.tab0 + ts * S.tab_stride;
       const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
       const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
@@ -988,8 +1010,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       set_mode(P1, M_F1);
       set_mode(P2, M_F2);
       TQ_TRY(make_f1_tensor_map(ctx, P1.in, nb, Na, Nb, n_cols, L, tcw1, &tmap));
-      TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, PIPE_NW>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
-      TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, PIPE_NW>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
+      TQ_TRY((launch_pipe<M_F1, P1_N, P1_RA, P1_RB, TQ_NW_F1>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
+      TQ_TRY((launch_pipe<M_F2, P2_N, P2_RA, P2_RB, TQ_NW_F2>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
     } else {
       set_mode(P1, M_I1);
       set_mode(P2, M_I2);
@@ -1003,8 +1025,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
         TQ_TRY(make_i1_tensor_map(ctx, P1.in, n_neg, n_pos, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap));  // k in [0, last]: data rows n - first
         TQ_TRY(make_i1_tensor_map(ctx, P1.in, 0, n_neg, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap2));     // k in [L + first, L): data rows 0..
       }
-      TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, PIPE_NW>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
-      TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, PIPE_NW>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
+      TQ_TRY((launch_pipe<M_I1, P1_N, P1_RA, P1_RB, TQ_NW_I1>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
+      TQ_TRY((launch_pipe<M_I2, P2_N, P2_RA, P2_RB, TQ_NW_I2>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
     }
   }
   *handled = true;
