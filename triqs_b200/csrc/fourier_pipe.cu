@@ -901,11 +901,17 @@ static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &
 }
 
 // widest balanced column tile for a tile length N: n_ct tiles of width ceil(n_cols / n_ct)
+static int env_int_early(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 template <int MODE, int N, int RA, int RB> static int pipe_pick_tcw(tq_ctx *ctx, long n_cols, int wmax, int cap, bool pad_pitch = false) {
   int fit = 0;
   for (int tc = 1; tc <= n_cols && tc <= cap; ++tc)
     if (PipeSmem<MODE, N, RA, RB>(tc, pad_pitch ? ((tc + 7) & ~7) : tc, wmax).total <= (size_t)ctx->max_smem_optin) fit = tc;
   if (fit < 1) return 0;
+  static const int unbalanced = env_int_early("TQ_PIPE_UNBALANCED", 0); // (tuning experiment: widest tiles + a narrow remainder)
+  if (unbalanced) return fit;
   long n_ct = (n_cols + fit - 1) / fit;
   return (int)((n_cols + n_ct - 1) / n_ct);
 }
