@@ -718,3 +718,34 @@ def test_fit_tail_real_frequency(ctx):
         assert tail.shape[1] == rt.shape[0]
         assert np.max(np.abs(tail[k, :4] - rt[:4])) < 1e-9
         assert abs(err[k] - re) < 1e-9 + 1e-6 * re
+
+
+def test_plain_and_lattice_lengths_the_tile_fft_cannot_factor(ctx):
+    """FFTW takes any length (fourier_common.cpp:30): axis lengths with a prime factor > 128, or longer than one SM's shared
+    memory, go through the direct evaluation -- plain DFT (both signs, in place), lattice meshes, real-time meshes."""
+    rng = np.random.default_rng(91)
+    for (dims, hm) in [((131,), 5), ((2 * 139, 3), 9), ((7, 149, 2), 4), ((20011,), 2)]:
+        n = int(np.prod(dims))
+        x = rng.normal(size=(n, hm)) + 1j * rng.normal(size=(n, hm))
+        for sign in (1, -1):
+            assert rel(ctx.fft_many(x, dims, sign), O.fft_many(x, dims, sign)) < TOL
+        y = x.copy()
+        ctx.fft_many(y, dims, 1, out=y)  # in place
+        assert rel(y, O.fft_many(x, dims, 1)) < TOL
+    dims = (131, 4, 1)
+    g = rng.normal(size=(131 * 4, 6)) + 1j * rng.normal(size=(131 * 4, 6))
+    gk = ctx.fourier_lattice(g, dims, to_k=True)
+    assert rel(gk, O.fourier_lattice_r_to_k(g, dims)) < TOL
+    assert rel(ctx.fourier_lattice(gk, dims, to_k=False), g) < TOL
+    # retime <-> refreq on a prime-length mesh
+    L, C = 1009, 3
+    w_lo, w_hi = -9.0, 9.0
+    t_lo, t_hi, _ = O.adjoint_real_mesh(w_lo, w_hi, L)
+    g = rng.normal(size=(2, L, C)) + 1j * rng.normal(size=(2, L, C))
+    mom = rng.normal(size=(2, 3, C)) + 1j * rng.normal(size=(2, 3, C))
+    mom[:, 0] = 0
+    f = ctx.fourier_t_to_w(g, (t_lo, t_hi), (w_lo, w_hi), moments=mom)
+    i = ctx.fourier_w_to_t(g, (t_lo, t_hi), (w_lo, w_hi), moments=mom)
+    for b in range(2):
+        assert rel(f[b], O.fourier_t_to_w(g[b], t_lo, t_hi, w_lo, w_hi, mom[b])) < TOL
+        assert rel(i[b], O.fourier_w_to_t(g[b], t_lo, t_hi, w_lo, w_hi, mom[b])) < TOL

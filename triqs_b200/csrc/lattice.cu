@@ -8,6 +8,9 @@
 #include "tq_fft.cuh"
 
 #include <algorithm>
+#include <map>
+#include <memory>
+#include <vector>
 
 struct PlainArgs {
   FftPlan P;
@@ -96,6 +99,104 @@ template <int SGN, int NT, int MINB, bool WRAP = false> __global__ void __launch
   }
 }
 
+// Direct O(N^2) evaluation for axis lengths the tile FFT cannot take (a prime factor > 128, or longer than one SM's shared
+// memory): FFTW accepts any length (fourier_common.cpp:30), so these must work, if slowly.  One thread per output row k and
+// DIRECT_CW columns; the input rows are warp-uniform (broadcast) loads, w^{nk} comes from the N-entry table by the running
+// index (n k) mod N.  The affine wrap of fourier_real.cu is applied on the fly.
+constexpr int DIRECT_CW = 8;
+template <bool WRAP> __global__ void __launch_bounds__(128) k_direct_axis(const cd *__restrict__ in, cd *__restrict__ out, const cd *__restrict__ w,
+                                                                         int N, long inner, int sign, double scale, const cd *__restrict__ rin,
+                                                                         const cd *__restrict__ rout, const cd *__restrict__ coef) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const long c0 = (long)blockIdx.y * DIRECT_CW;
+  const long o = blockIdx.z;
+  const int wd = (int)min((long)DIRECT_CW, inner - c0);
+  const cd *src = in + (size_t)o * N * inner + c0;
+  cd a1[DIRECT_CW], a2[DIRECT_CW], acc[DIRECT_CW];
+#pragma unroll
+  for (int c = 0; c < DIRECT_CW; ++c) {
+    acc[c] = cmk(0.0, 0.0);
+    a1[c] = a2[c] = cmk(0.0, 0.0);
+    if (WRAP && c < wd) {
+      a1[c] = __ldg(&coef[2 * ((size_t)o * inner + c0 + c)]);
+      a2[c] = __ldg(&coef[2 * ((size_t)o * inner + c0 + c) + 1]);
+    }
+  }
+  const int kk = k < N ? k : 0;
+  int m = 0;
+  for (int n = 0; n < N; ++n) {
+    cd tw = __ldg(&w[m]);
+    if (sign < 0) tw = cconj(tw);
+    m += kk;
+    if (m >= N) m -= N;
+    cd h1 = cmk(0.0, 0.0), h2 = h1, pin = cmk(1.0, 0.0);
+    if (WRAP) {
+      h1 = __ldg(&rin[3 * (size_t)n]);
+      h2 = __ldg(&rin[3 * (size_t)n + 1]);
+      pin = __ldg(&rin[3 * (size_t)n + 2]);
+    }
+#pragma unroll
+    for (int c = 0; c < DIRECT_CW; ++c)
+      if (c < wd) {
+        cd x = __ldg(src + (size_t)n * inner + c);
+        if (WRAP) x = cmul(csub(csub(x, cmul(a1[c], h1)), cmul(a2[c], h2)), pin);
+        acc[c] = cfma(tw, x, acc[c]);
+      }
+  }
+  if (k >= N) return;
+  cd *dst = out + (size_t)o * N * inner + (size_t)k * inner + c0;
+  for (int c = 0; c < wd; ++c) {
+    cd v = acc[c];
+    if (scale != 1.0) v = cscale(scale, v);
+    if (WRAP) {
+      const cd *e = rout + 3 * (size_t)k;
+      v = cadd(cadd(cmul(__ldg(e + 2), v), cmul(a1[c], __ldg(e))), cmul(a2[c], __ldg(e + 1)));
+    }
+    dst[c] = v;
+  }
+}
+
+struct DirectTwiddles {
+  std::map<long, cd *> w;
+  ~DirectTwiddles() {
+    for (auto &kv : w) cudaFree(kv.second);
+  }
+};
+
+static tq_status launch_direct(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, const cd *rin,
+                               const cd *rout, const cd *coef) {
+  if (N > 65536) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length " + std::to_string(N) + " is neither factorisable nor <= 65536");
+  if (outer > 65535) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: too many outer slices for the direct transform");
+  if (!ctx->direct_tw) ctx->direct_tw = std::make_shared<DirectTwiddles>();
+  cd *&w = ctx->direct_tw->w[N];
+  if (!w) {
+    std::vector<cd> h;
+    tq_fft_twiddles_host((int)N, h);
+    TQ_CUDA(ctx, cudaMalloc(&w, sizeof(cd) * N));
+    TQ_CUDA(ctx, cudaMemcpyAsync(w, h.data(), sizeof(cd) * N, cudaMemcpyHostToDevice, ctx->stream));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  cd *dst = out;
+  const size_t bytes = sizeof(cd) * (size_t)outer * N * inner;
+  if (in == out) { // every output needs every input: go through a temporary
+    TQ_TRY(tq_reserve(ctx, ctx->scratch, bytes));
+    dst = (cd *)ctx->scratch.p;
+  }
+  const dim3 grid((unsigned)((N + 127) / 128), (unsigned)((inner + DIRECT_CW - 1) / DIRECT_CW), (unsigned)outer);
+  if (grid.y > 65535) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: too many columns for the direct transform");
+  {
+    KernelScope ks(ctx, "fft_axis_direct");
+    if (rin)
+      k_direct_axis<true><<<grid, 128, 0, ctx->stream>>>(in, dst, w, (int)N, inner, sign, scale, rin, rout, coef);
+    else
+      k_direct_axis<false><<<grid, 128, 0, ctx->stream>>>(in, dst, w, (int)N, inner, sign, scale, nullptr, nullptr, nullptr);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  if (dst != out) TQ_CUDA(ctx, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return TQ_OK;
+}
+
 // lattice_pipe.cu: TMA-pipelined fast path for axis lengths with a compile-time two-pass plan
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled);
 
@@ -107,9 +208,13 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
     TQ_TRY(tq_lattice_pipe_axis(ctx, outer, N, inner, in, out, sign, scale, &handled));
     if (handled) return TQ_OK;
   }
+  const size_t budget = (size_t)ctx->max_smem_optin;
+  {
+    FftPlan probe;
+    if (!tq_fft_factorize((int)N, probe) || sizeof(cd) * (size_t)N > budget) return launch_direct(ctx, outer, N, inner, in, out, sign, scale, rin, rout, coef);
+  }
   std::shared_ptr<FftPlanHost> fp;
   TQ_TRY(tq_get_fft_plan(ctx, N, &fp));
-  const size_t budget = (size_t)ctx->max_smem_optin;
   size_t half = budget / 2 - 1024;
   if (const char *e = getenv("TQ_TILE_BYTES")) half = std::min<size_t>((size_t)atol(e), budget);
   if (sizeof(cd) * (size_t)N > budget)

@@ -47,6 +47,7 @@ struct LatTwiddles;    // lattice_pipe.cu
 struct ColPlanCache;   // fourier_col.cu
 struct RealPlanCache;  // fourier_real.cu
 struct LegendrePlanCache; // legendre.cu
+struct DirectTwiddles;    // lattice.cu
 
 struct tq_ctx {
   int device = 0;
@@ -68,6 +69,7 @@ struct tq_ctx {
   std::shared_ptr<ColPlanCache> col_cache;
   std::shared_ptr<RealPlanCache> real_cache;
   std::shared_ptr<LegendrePlanCache> leg_cache;
+  std::shared_ptr<DirectTwiddles> direct_tw;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {
