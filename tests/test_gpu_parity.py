@@ -749,3 +749,41 @@ def test_plain_and_lattice_lengths_the_tile_fft_cannot_factor(ctx):
     for b in range(2):
         assert rel(f[b], O.fourier_t_to_w(g[b], t_lo, t_hi, w_lo, w_hi, mom[b])) < TOL
         assert rel(i[b], O.fourier_w_to_t(g[b], t_lo, t_hi, w_lo, w_hi, mom[b])) < TOL
+
+
+def test_matsubara_transforms_randomised_shapes(ctx):
+    """Seeded sweep over mesh lengths (single pass, generic four-step, direct), statistics, column counts, batch sizes and
+    known / fitted moments: both directions against the oracle."""
+    rng = np.random.default_rng(20261019)
+    lengths = [96, 210, 1000, 1024, 1500, 3125, 4097, 6144, 12000, 14406, 30000, 2 * 3 * 5 * 7 * 11 * 13]
+    for case in range(18):
+        L = int(rng.choice(lengths))
+        stat = int(rng.integers(0, 2))
+        n_iw = int(rng.integers(3, max(4, min(L // 2, 600))))
+        C = int(rng.choice([1, 2, 3, 5, 9, 16, 25, 36]))
+        B = int(rng.choice([1, 2, 5]))
+        beta = float(rng.choice([1.0, 10.0, 50.0]))
+        iw = O.imfreq_values(beta, stat, n_iw)
+        e = rng.uniform(0.2, 2.0, size=(B, 3, C)) * rng.choice([-1.0, 1.0], size=(B, 3, C))
+        r = rng.uniform(0.2, 1.0, size=(B, 3, C))
+        gw = np.sum(r[:, None] / (iw[None, :, None, None] - e[:, None]), axis=2)
+        known = case % 2 == 0
+        mom = None
+        if known:
+            mom = np.zeros((B, 4, C), complex)
+            for p in range(1, 4):
+                mom[:, p] = np.sum(r * e ** (p - 1), axis=1)
+        try:
+            refs = [O.fourier_iw_to_tau(gw[b], beta, stat, L + 1, None if mom is None else mom[b]) for b in range(B)]
+        except Exception:  # e.g. a window too short for the tail fit: the reference throws, and so must the library
+            with pytest.raises(Exception):
+                ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+            continue
+        gt = ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+        back = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=mom)
+        for b in range(B):
+            rt = refs[b]
+            tol = TOL if known else 1e-10  # the LSQ tail fit inside is conditioning-limited (DESIGN.md section 4)
+            assert rel(gt[b], rt) < tol, (case, L, stat, n_iw, C, B, known)
+            rb = O.fourier_tau_to_iw(rt, beta, stat, n_iw, None if mom is None else mom[b])
+            assert rel(back[b], rb) < tol, (case, L, stat, n_iw, C, B, known)
