@@ -55,6 +55,7 @@ extern "C" void tq_destroy(tq_ctx *ctx) {
   free_buf(ctx->scratch);
   free_buf(ctx->small);
   free_buf(ctx->pipe_w);
+  free_buf(ctx->leg_tmp);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
