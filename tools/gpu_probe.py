@@ -73,7 +73,7 @@ if "c3" in which:
     nk, no = 65536, 9216
     x = torch.randn(nk, no, dtype=torch.float64, device="cuda", generator=g).to(torch.complex128)
     y = torch.empty_like(x)
-    timeit("c3_lattice_256x256x9216", lambda: ctx.fourier_lattice(x, (256, 256, 1), True, out=y), reps=3, warm=1, bytes_=2.0 * nk * no * 16,
+    timeit("c3_lattice_256x256x9216", lambda: ctx.fourier_lattice(x, (256, 256, 1), True, out=y), reps=10, warm=3, bytes_=2.0 * nk * no * 16,
            pts=nk * 1024)
     del x, y
 

@@ -13,7 +13,10 @@
 #include <algorithm>
 #include <cstring>
 
-constexpr int LP_NBUF = 3;
+#ifndef TQ_LP_NBUF
+#define TQ_LP_NBUF 3
+#endif
+constexpr int LP_NBUF = TQ_LP_NBUF;
 
 struct LatPipeArgs {
   cd *out;
@@ -171,6 +174,7 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
   long tc = (long)(budget / LP_NBUF / (sizeof(cd) * N));
   tc = std::min<long>(std::min<long>(tc, 128), inner);
   if (tc >= 8) tc &= ~7L; // 128-byte runs
+  if (const char *e = getenv("TQ_LP_TC")) tc = std::min<long>(tc, atol(e)); // (tuning experiments)
   if (tc < 1) return TQ_OK;
   // pointers: TMA needs 16-byte alignment (always true for complex<double> arrays from cudaMalloc / numpy)
   if (((uintptr_t)in | (uintptr_t)out) & 15) return TQ_OK;
