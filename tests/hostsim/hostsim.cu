@@ -78,6 +78,54 @@ extern "C" int hostsim_fft2(int N, int RA, int tcw, int sign, double *data /* [N
   return 0;
 }
 
+// three-pass small-radix tile FFT (tools/tq_fft3.cuh: an experiment that lost against the two-pass engine, kept with its test)
+#include "../../tools/tq_fft3.cuh"
+template <int STEP> struct PostCollect3 {
+  cd *out;
+  int tcw, c, klow;
+  TQ_HD void begin(int k, int cc) { klow = k; c = cc; }
+  template <int T> TQ_HD void store(cd v) { out[(size_t)(klow + STEP * T) * tcw + c] = v; }
+};
+template <int N, int R1, int R2, int R3> static void run_fft3(int tcw, int sign, cd *data) {
+  constexpr int M = R2 * R3;
+  std::vector<cd> wN, wM, tw1((size_t)N), tw2((size_t)M);
+  tq_fft_twiddles_host(N, wN);
+  tq_fft_twiddles_host(M, wM);
+  for (int m = 0; m < M; ++m)
+    for (int r = 0; r < R1; ++r) tw1[(size_t)m * R1 + r] = sign > 0 ? wN[(m * r) % N] : cconj(wN[(m * r) % N]);
+  for (int q = 0; q < R3; ++q)
+    for (int r = 0; r < R2; ++r) tw2[(size_t)q * R2 + r] = sign > 0 ? wM[(q * r) % M] : cconj(wM[(q * r) % M]);
+  const int pitch = tcw + 1;
+  std::vector<cd> s((size_t)N * pitch);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < tcw; ++c) s[(size_t)n * pitch + c] = data[(size_t)n * tcw + c];
+  const int nthreads = 41;
+  PreIdentity pre;
+  PostCollect3<R1 * R2> post{data, tcw, 0, 0};
+  for (int tid = 0; tid < nthreads; ++tid) {
+    if (sign > 0) fft3_pass1<N, R1, R2, R3, 1>(s.data(), pitch, tcw, tw1.data(), tid, nthreads, pre);
+    else fft3_pass1<N, R1, R2, R3, -1>(s.data(), pitch, tcw, tw1.data(), tid, nthreads, pre);
+  }
+  for (int tid = 0; tid < nthreads; ++tid) {
+    if (sign > 0) fft3_pass2<N, R1, R2, R3, 1>(s.data(), pitch, tcw, tw2.data(), tid, nthreads);
+    else fft3_pass2<N, R1, R2, R3, -1>(s.data(), pitch, tcw, tw2.data(), tid, nthreads);
+  }
+  for (int tid = 0; tid < nthreads; ++tid) {
+    if (sign > 0) fft3_pass3<N, R1, R2, R3, 1>(s.data(), pitch, tcw, tid, nthreads, post);
+    else fft3_pass3<N, R1, R2, R3, -1>(s.data(), pitch, tcw, tid, nthreads, post);
+  }
+}
+extern "C" int hostsim_fft3(int N, int R1, int R2, int tcw, int sign, double *data /* [N][tcw] complex, in place */) {
+  cd *d = (cd *)data;
+  if (N == 250 && R1 == 10 && R2 == 5) run_fft3<250, 10, 5, 5>(tcw, sign, d);
+  else if (N == 250 && R1 == 5 && R2 == 10) run_fft3<250, 5, 10, 5>(tcw, sign, d);
+  else if (N == 400 && R1 == 10 && R2 == 8) run_fft3<400, 10, 8, 5>(tcw, sign, d);
+  else if (N == 400 && R1 == 8 && R2 == 10) run_fft3<400, 8, 10, 5>(tcw, sign, d);
+  else if (N == 400 && R1 == 5 && R2 == 8) run_fft3<400, 5, 8, 10>(tcw, sign, d);
+  else return -1;
+  return 0;
+}
+
 extern "C" int hostsim_radices(int N, int *radix) {
   FftPlan P;
   if (!tq_fft_factorize(N, P)) return -1;

@@ -48,6 +48,19 @@ def test_two_pass_tile_fft(lib, N, RA):
             assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 5e-15
 
 
+def test_three_pass_small_radix_tile_fft(lib):
+    """tools/tq_fft3.cuh: N = R1 R2 R3 with radices <= 10 (an experiment: correct, but slower than the two-pass engine)."""
+    rng = np.random.default_rng(9)
+    for (N, R1, R2) in [(250, 10, 5), (250, 5, 10), (400, 10, 8), (400, 8, 10), (400, 5, 8)]:
+        for tcw in (1, 5, 13):
+            for sign in (1, -1):
+                x = rng.normal(size=(N, tcw)) + 1j * rng.normal(size=(N, tcw))
+                y = np.ascontiguousarray(x.copy())
+                assert lib.hostsim_fft3(N, R1, R2, tcw, sign, y.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+                ref = np.fft.ifft(x, axis=0) * N if sign > 0 else np.fft.fft(x, axis=0)
+                assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 5e-15
+
+
 def test_radix_choice(lib):
     rad = (ctypes.c_int * 16)()
     n = lib.hostsim_radices(10000, rad)
