@@ -358,6 +358,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #ifndef TQ_PK_LATE
 #define TQ_PK_LATE 6 // F2 and I1; F1 and I2 have no register to spare (they spill 160-180 B and lose 40-70 %)
 #endif
+#ifndef TQ_PK_LAG0
+#define TQ_PK_LAG0 15
+#endif
+  constexpr bool PK_LAG0 = ((TQ_PK_LAG0 >> MODE) & 1) != 0; // bit per mode
   constexpr bool PK_LATE = !PK_STATIC && PK_CHUNK == 1 && !PK_AHEAD && ((TQ_PK_LATE >> MODE) & 1); // bit per mode
   using Smem = PipeSmem<MODE, N, RA, RB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -483,9 +487,8 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       TQ_LAP(t_work)
     }
   } else {
-    // ===================== worker warps: pull packets  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  =====================
-    // (pass B of tile k is queued after pass A of tile k+1, so whoever takes it rarely waits; a packet only ever waits
-    //  for packets that were handed out before it, hence no deadlock)
+    // ===================== worker warps: pull packets in a fixed order (below) =====================
+    // (a packet only ever waits for packets that were handed out before it, hence no deadlock)
     int pk_next = 0, pk_left = 0;
     if (!PK_STATIC && (PK_AHEAD || PK_LATE) && lane == 0) pk_next = atomicAdd(next_pk, 1);
     // PK_LATE: the next packet is claimed between the arithmetic and the stores of the current one, so that the round trip of the
@@ -515,18 +518,33 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       }
       int blk, r;
       bool is_b = false;
-      if (pk < 2 * pa) {
-        blk = fastdiv(pk, m_pa);
-        r = pk - blk * pa;
+      if (PK_LAG0) {
+        // order A(0) B(0) | A(1) B(1) | ...: pass B right behind pass A of the same tile.  Its first packets wait for the last
+        // pass-A packets, but the tile buffer goes back to the producer one tile period earlier, and the ring -- not the
+        // arithmetic -- is what limits these kernels (buffer residency = TMA flight + pass A + pass B).  Measured, 32 blocks:
+        // F1 0.512 -> 0.478 ms, F2 0.462 -> 0.443, I1 0.466 -> 0.460, I2 0.483 -> 0.462; placing pass B a quarter or half a
+        // tile later gives the same within noise, a full tile later (the old order) is 5 % slower.
+        blk = fastdiv(pk, m_pab);
+        r = pk - blk * (pa + pb);
+        is_b = r >= pa;
+        if (is_b) r -= pa;
+        if (blk >= nloc) break;
+        blk += is_b ? 2 : 0; // (keeps the common "k = is_b ? blk - 2 : blk" below)
       } else {
-        const int q = pk - 2 * pa;
-        blk = fastdiv(q, m_pab);
-        r = q - blk * (pa + pb);
-        blk += 2;
-        is_b = r < pb;
-        if (!is_b) r -= pb;
+        // order A(0) A(1) | B(0) A(2) | B(1) A(3) | ...: pass B one tile behind pass A (nobody waits for pass-A stragglers)
+        if (pk < 2 * pa) {
+          blk = fastdiv(pk, m_pa);
+          r = pk - blk * pa;
+        } else {
+          const int q = pk - 2 * pa;
+          blk = fastdiv(q, m_pab);
+          r = q - blk * (pa + pb);
+          blk += 2;
+          is_b = r < pb;
+          if (!is_b) r -= pb;
+        }
+        if (blk >= nloc + 2) break;
       }
-      if (blk >= nloc + 2) break;
       const int k = is_b ? blk - 2 : blk; // tile of this CTA
       if (k >= nloc) {
         fetch_next();
