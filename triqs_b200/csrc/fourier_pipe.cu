@@ -358,6 +358,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #ifndef TQ_PK_LATE
 #define TQ_PK_LATE 6 // F2 and I1; F1 and I2 have no register to spare (they spill 160-180 B and lose 40-70 %)
 #endif
+#ifndef TQ_PIPE_L2PF
+#define TQ_PIPE_L2PF 10 // F2, I2 (contiguous scratch tiles): -1 %; no gain on the tensor-map gathers of F1 / I1
+#endif
+  constexpr bool L2PF = ((TQ_PIPE_L2PF >> MODE) & 1) != 0; // bit per mode
 #ifndef TQ_PK_LAG0
 #define TQ_PK_LAG0 15
 #endif
@@ -471,6 +475,18 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
                    (uint32_t)(sizeof(cd) * N * id.w), &full[b]);
         }
         if (PASS1) bulk_g2s(tab + S.t_off, A.Tfull + (size_t)id.item * N, (uint32_t)(sizeof(cd) * N), &full[b]);
+        if (L2PF && i + 1 < nloc) { // the next tile of this CTA: in L2 by the time its buffer is free
+          const TileId nx = decode(t + gridDim.x);
+          if (MODE == M_F1)
+            tma_prefetch_4d(&tmap, 2 * nx.c0, nx.item, 0, (int)nx.gf);
+          else if (MODE == M_F2 || MODE == M_I2)
+            bulk_prefetch_l2(A.scratch + nx.gf * A.scratch_gf_stride + (long)nx.item * A.Na * n_cols + (long)nx.c0 * A.Na,
+                             (uint32_t)(sizeof(cd) * N * nx.w));
+          else if (i1_boxes) {
+            tma_prefetch_4d(&tmap, 2 * nx.c0, nx.item, 0, (int)nx.gf);
+            tma_prefetch_4d(&tmap2, 2 * nx.c0, nx.item, 0, (int)nx.gf);
+          }
+        }
         if (Smem::WREC) bulk_g2s(tab + S.win_off, A.wintab + id.item, (uint32_t)sizeof(int4), &full[b]);
         if (Smem::WREC && cnt > 0)
           bulk_g2s(tab + S.wrec_off, A.wperm + (size_t)id.item * A.wmax, (uint32_t)(sizeof(double4) * cnt), &full[b]);

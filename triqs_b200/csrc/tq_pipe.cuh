@@ -39,6 +39,14 @@ TQ_D void tma_load_4d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, i
                "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of a future tile (no shared-memory destination, no barrier): shortens the flight time of the real copy
+TQ_D void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+TQ_D void tma_prefetch_4d(const CUtensorMap *tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 TQ_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 
