@@ -358,6 +358,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #ifndef TQ_PK_LATE
 #define TQ_PK_LATE 6 // F2 and I1; F1 and I2 have no register to spare (they spill 160-180 B and lose 40-70 %)
 #endif
+#ifndef TQ_EARLY_FREE
+#define TQ_EARLY_FREE 4 // bit per mode; only the pass-1 kernels (PostScratch) have the code path
+#endif
+  constexpr bool EARLY_FREE = PASS1 && ((TQ_EARLY_FREE >> MODE) & 1) != 0;
 #ifndef TQ_PIPE_L2PF
 #define TQ_PIPE_L2PF 10 // F2, I2 (contiguous scratch tiles): -1 %; no gain on the tensor-map gathers of F1 / I1
 #endif
@@ -617,25 +621,51 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       } else {
         mbar_wait(&adone[b], (uint32_t)(u & 1));
         TQ_LAP(t_wait)
-        if (PASS1) {
+        if constexpr (!EARLY_FREE) {
+          if (PASS1) {
+            PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
+                                 A.Na, A.tcw2, id.item, id.c0};
+            fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
+          } else if (MODE == M_F2) {
+            const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
+            PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
+                            A.out + id.gf * A.out_gf_stride + id.c0};
+            fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
+          } else {
+            PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
+                            A.out + id.gf * A.out_gf_stride + id.c0};
+            fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
+          }
+          __syncwarp(); // every lane's reads of the tile are done ...
+          if (lane == 0) {
+            fence_proxy_async(); // ... and ordered before the TMA engine's (async proxy) next write to the buffer
+            mbar_arrive(&freeb[b]);
+            mbar_arrive(&tabfree[ts]);
+          }
+        } else {
+          // EARLY_FREE (I1): the tile buffer goes back to the producer as soon as the packet's loads are in registers (the butterfly
+          // has consumed them when the hook runs), not after the epilogue and its scratch stores; the tables stay until the
+          // stores are done (`tabfree`).  I1: 0.454 -> 0.436 ms.  No gain on F1 / F2, and I2 has no register to spare.
+          const unsigned act = __ballot_sync(0xffffffffu, it < RA * id.w);
+          const auto release = [&]() {
+            __syncwarp(act);
+            if (lane == 0) {
+              fence_proxy_async();
+              mbar_arrive(&freeb[b]);
+            }
+            fetch_next();
+          };
           PostScratch<RA> post{reinterpret_cast<const cd *>(tab + S.t_off), A.scratch + id.gf * A.scratch_gf_stride, (long)A.Na * n_cols, n_cols,
                                A.Na, A.tcw2, id.item, id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
-        } else if (MODE == M_F2) {
-          const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
-          PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
-                          A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
-        } else {
-          PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
-                          A.out + id.gf * A.out_gf_stride + id.c0};
-          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, fetch_next);
-        }
-        __syncwarp(); // every lane's reads of the tile are done ...
-        if (lane == 0) {
-          fence_proxy_async(); // ... and ordered before the TMA engine's (async proxy) next write to the buffer
-          mbar_arrive(&freeb[b]);
-          mbar_arrive(&tabfree[ts]);
+          fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, release);
+          __syncwarp();
+          if (lane == 0) {
+            if (act == 0u) { // empty packet: nobody ran the hook
+              fence_proxy_async();
+              mbar_arrive(&freeb[b]);
+            }
+            mbar_arrive(&tabfree[ts]);
+          }
         }
         TQ_LAP(t_work)
       }
