@@ -51,3 +51,23 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.replace("the oracle", ""), f"{fn} references the oracle"
+
+
+def test_pipelined_kernels_do_not_spill():
+    """The pipelined Matsubara kernels run 12 warps per SM at the register limit: a source change or another
+    compiler can tip them into hundreds of bytes of spills, which costs 40-70 % on the headline.  Checked on the built library."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    from triqs_b200 import _lib
+    out = subprocess.run([exe, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    found = 0
+    for m in re.finditer(r"Function (\S*matsubara_pipe_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        found += 1
+        regs, stack = int(m.group(2)), int(m.group(3))
+        assert regs <= 168, (m.group(1), regs)
+        assert stack <= 32, (m.group(1), stack)
+    assert found == 4
