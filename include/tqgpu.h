@@ -62,6 +62,22 @@ const char *tq_last_error(const tq_ctx *ctx);
 void *tq_stream(tq_ctx *ctx);
 /* block until all work enqueued by this context has finished */
 tq_status tq_synchronize(tq_ctx *ctx);
+/* Stream-ordering contract.  The context's stream is created cudaStreamNonBlocking: it does NOT order against the
+ * legacy default stream or any other stream.  Calls with HOST pointers are complete when they return.  Calls with
+ * DEVICE pointers are asynchronous on the context's stream: a caller that produces inputs or consumes outputs on
+ * another stream (cudaStream_t `other`; NULL = the legacy default stream) brackets the call with
+ *   tq_stream_wait_external(ctx, other)    -- work enqueued on the context after this waits for everything
+ *                                             already enqueued on `other`
+ *   tq_stream_signal_external(ctx, other)  -- work enqueued on `other` after this waits for everything already
+ *                                             enqueued on the context
+ * (event record + cudaStreamWaitEvent, no host synchronisation), or calls tq_synchronize.  The Python binding does
+ * this automatically around every call that takes torch CUDA tensors. */
+tq_status tq_stream_wait_external(tq_ctx *ctx, void *other);
+tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
+/* Engine options that never change results (tests run the same inputs through both engines):
+ *   "no_pipe"          1: skip the TMA-pipelined / single-column specialisations, use the generic tile kernels only
+ *   "scratch_chunk_mb" > 0: four-step scratch budget per launch pair in MiB (default: 1536 pipelined, 64 generic) */
+tq_status tq_set_option(tq_ctx *ctx, const char *name, long value);
 /* number of kernel launches issued by this context since creation (bench.py reports the delta) */
 uint64_t tq_launch_count(const tq_ctx *ctx);
 /* library build id string ("tqgpu <version> sm_100a") */

@@ -71,3 +71,25 @@ def test_pipelined_kernels_do_not_spill():
         assert regs <= 168, (m.group(1), regs)
         assert stack <= 32, (m.group(1), stack)
     assert found == 4
+
+
+def test_release_library_has_no_developer_switches():
+    """Result-altering developer knobs are compiled out of the release library: the environment-variable names
+    are not even in the binary (they exist only in -DTQ_DEVELOPER builds)."""
+    from triqs_b200 import _lib
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for name in [b"TQ_SCRATCH_ALIAS", b"TQ_COL_SKIP", b"TQ_KNOCK", b"TQ_PIPE_GUARD", b"TQ_PHASE_DEBUG", b"TQ_NO_PIPE", b"TQ_TWOPASS_CHUNK_MB",
+                 b"TQ_PIPE_TCW1", b"TQ_TILE_BYTES", b"TQ_PIPE_NO_I1_EDGE", b"TQ_COL_NT", b"TQ_LP_TC"]:
+        assert name not in blob, name
+
+
+def test_missing_nccl_library_is_an_error_not_a_crash():
+    """a failing dlopen of libnccl must surface as TQ_ERR_COMM (it used to dereference a NULL dlerror())."""
+    import subprocess
+    import sys
+    code = ("import ctypes, os, sys; sys.path.insert(0, %r); from triqs_b200 import _lib; lib = _lib.load(); "
+            "buf = (ctypes.c_ubyte * 128)(); st = lib.tq_comm_unique_id(buf); print('status', st)") % ROOT
+    env = dict(os.environ, TQ_NCCL_LIB="/nonexistent/libnccl-bogus.so.2")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "status -6" in r.stdout, r.stdout

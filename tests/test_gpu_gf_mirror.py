@@ -232,3 +232,58 @@ def test_imfreq_evaluator_uses_the_tail_outside_the_mesh():
         ref = O.tail_eval(tail, iw).reshape(2, 2)
         assert np.max(np.abs(g(n) - ref)) < 1e-10
         assert np.max(np.abs(g(n) - exact)) < 1e-6
+
+
+def test_torch_producer_and_consumer_need_no_manual_sync():
+    """the context's stream is non-blocking; the binding orders it against torch's current stream on both sides
+    (tq_stream_wait_external / tq_stream_signal_external), so torch kernel -> library -> torch read chains are race free."""
+    import torch
+    import triqs_b200
+    ctx = triqs_b200.Context(0, print_warnings=False)
+    dev = torch.device("cuda", 0)
+    n, npts = 4, 200_000
+    g = torch.Generator(device=dev).manual_seed(3)
+    base = torch.randn(npts, n, n, dtype=torch.complex128, device=dev, generator=g)
+    eye = torch.eye(n, dtype=torch.complex128, device=dev)
+    for it in range(5):
+        big = torch.randn(4096, 4096, device=dev)
+        junk = big @ big                      # keeps torch's stream busy so that an unordered library call would start too early
+        a = base * (1.0 + it) + (3.0 + it) * eye * (junk[0, 0] * 0 + 1)   # produced on torch's stream, after the matmul
+        ref = torch.linalg.inv(a.clone())
+        ctx.invert_in_place(a)                # library stream
+        err = (a - ref).abs().max() / ref.abs().max()   # consumed on torch's stream
+        assert float(err) < 1e-12
+    # device outputs of a transform feed a torch op directly
+    beta, n_iw, n_tau = 10.0, 100, 601
+    iw = torch.from_numpy(O.imfreq_values(beta, O.FERMION, n_iw)).to(dev)
+    gw = (1.0 / (iw - 0.7))[None, :, None].contiguous()
+    gt = ctx.fourier_iw_to_tau(gw, beta, O.FERMION, n_tau)
+    s = gt.sum().cpu()
+    ref = O.fourier_iw_to_tau(gw[0].cpu().numpy(), beta, O.FERMION, n_tau)
+    assert abs(complex(s) - ref.sum()) < 1e-9 * abs(ref.sum())
+    ctx.close()
+
+
+def test_gf_invert_strided_view_and_device_replace_by_tail():
+    """Gf.invert on a non-contiguous view must write the result back; replace_by_tail must work on torch data."""
+    import torch
+    from triqs_b200 import gf as G
+    d, H = _gw(10.0, 40, 2, 11)
+    wide = np.zeros((80, 2, 4), complex)
+    wide[:, :, :2] = d
+    g = G.Gf(G.MeshImFreq(10.0, O.FERMION, 40), (2, 2), wide[:, :, :2])   # strided view
+    assert not g.data.flags.c_contiguous
+    g.invert()
+    iw = g.mesh.values()
+    assert np.max(np.abs(wide[:, :, :2] - (iw[:, None, None] * np.eye(2)[None] - H[None]))) < 1e-12
+    # device-resident gf
+    gd = G.Gf(G.MeshImFreq(10.0, O.FERMION, 40), (2, 2), torch.from_numpy(d.copy()).cuda())
+    tail = np.zeros((4, 2, 2), complex)
+    tail[1] = np.eye(2)
+    tail[2] = H
+    tail[3] = H @ H
+    G.replace_by_tail(gd, tail, 30)
+    ref = O.replace_by_tail(d.reshape(80, 4), 10.0, O.FERMION, tail.reshape(4, 4), 30).reshape(80, 2, 2)
+    assert np.max(np.abs(gd.data.cpu().numpy() - ref)) < 1e-14
+    gd.invert()
+    assert np.max(np.abs(gd.data.cpu().numpy() - np.linalg.inv(ref))) / np.max(np.abs(np.linalg.inv(ref))) < 1e-12

@@ -183,10 +183,10 @@ def test_long_mesh_pipelined_variants(ctx, stat, ncols, n_iw):
         assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
 
 
-def test_long_mesh_chunked_launches_and_wide_targets(ctx, monkeypatch):
+def test_long_mesh_chunked_launches_and_wide_targets(ctx):
     """Pipelined path with the batch split over several launch pairs (scratch budget below one batch) and with more
     target columns than one column tile holds (70 columns -> 5 ragged tiles in pass 1, more in pass 2)."""
-    monkeypatch.setenv("TQ_TWOPASS_CHUNK_MB", "120")  # 70 columns x 1e5 x 16 B = 112 MB per gf -> one gf per launch pair
+    ctx.set_option("scratch_chunk_mb", 120)  # 70 columns x 1e5 x 16 B = 112 MB per gf -> one gf per launch pair
     beta, n_tau, n_iw, ncols, stat = 25.0, 100001, 10000, 70, F
     rng = np.random.default_rng(77)
     iw = O.imfreq_values(beta, stat, n_iw)
@@ -205,6 +205,7 @@ def test_long_mesh_chunked_launches_and_wide_targets(ctx, monkeypatch):
     for b in range(3):
         assert rel(gt[b], refs[b]) < TOL
     gw2 = ctx.fourier_tau_to_iw(np.stack(refs), beta, stat, n_iw)
+    ctx.set_option("scratch_chunk_mb", 0)
     for b in range(3):
         assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
 

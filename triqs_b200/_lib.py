@@ -27,6 +27,9 @@ SIGNATURES = {
     "tq_last_error": (c_char_p, [c_void_p]),
     "tq_stream": (c_void_p, [c_void_p]),
     "tq_synchronize": (c_int, [c_void_p]),
+    "tq_stream_wait_external": (c_int, [c_void_p, c_void_p]),
+    "tq_stream_signal_external": (c_int, [c_void_p, c_void_p]),
+    "tq_set_option": (c_int, [c_void_p, c_char_p, c_long]),
     "tq_launch_count": (c_uint64, [c_void_p]),
     "tq_version": (c_char_p, []),
     "tq_profile_enable": (c_int, [c_void_p, c_int]),

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import sys
+import threading
 import warnings
 
 import numpy as np
@@ -57,10 +58,15 @@ def _as_f64(x):
     return np.ascontiguousarray(x, dtype=np.float64)
 
 
+_tls = threading.local()  # set by _ptr when an argument is a torch CUDA tensor; read and cleared by Context._run
+
+
 def _ptr(x):
     if x is None:
         return None
     if _is_torch(x):
+        if x.is_cuda:
+            _tls.device_args = True
         return ctypes.c_void_p(x.data_ptr())
     return ctypes.c_void_p(x.ctypes.data)
 
@@ -76,7 +82,7 @@ def _empty_like_kind(ref, shape, dtype=np.complex128):
 class Context:
     """One per process/GPU: owns the stream, the plan caches and (optionally) the NCCL communicator."""
 
-    def __init__(self, device: int = 0, print_warnings: bool = True):
+    def __init__(self, device: int = 0, print_warnings: bool = True, torch_ordering: bool = True):
         self._lib = L.load()  # raises if libtqgpu.so is missing -- no CPU fallback
         h = ctypes.c_void_p()
         st = self._lib.tq_create(device, ctypes.byref(h))
@@ -87,6 +93,7 @@ class Context:
         self._h = h
         self.device = device
         self.print_warnings = print_warnings
+        self.torch_ordering = torch_ordering  # False: the caller orders the streams itself (tq_synchronize / events)
         self.last_warn = None
 
     def close(self):
@@ -118,8 +125,29 @@ class Context:
             if bits & b:
                 sys.stderr.write(text)
 
+    def _run(self, name, *args):
+        """One library call.  When an argument is a torch CUDA tensor the call is asynchronous on the context's own
+        (non-blocking) stream: it is ordered after the work already enqueued on torch's current stream, and torch's current
+        stream is ordered after it (include/tqgpu.h "Stream-ordering contract"), so torch producers / consumers on either side
+        need no manual synchronisation."""
+        fn = getattr(self._lib, name)
+        device_args = getattr(_tls, "device_args", False)
+        _tls.device_args = False
+        if not (device_args and self.torch_ordering):
+            return fn(self._h, *args)
+        import torch
+        other = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._check(self._lib.tq_stream_wait_external(self._h, other))
+        st = fn(self._h, *args)
+        self._check(self._lib.tq_stream_signal_external(self._h, other))
+        return st
+
     def synchronize(self):
         self._check(self._lib.tq_synchronize(self._h))
+
+    def set_option(self, name: str, value: int):
+        """tq_set_option: "no_pipe" (generic engine only), "scratch_chunk_mb" -- neither changes results."""
+        self._check(self._lib.tq_set_option(self._h, name.encode(), int(value)))
 
     @property
     def stream(self):
@@ -152,10 +180,10 @@ class Context:
         gw = out if out is not None else _empty_like_kind(gt, (batch, n_w, n_others))
         warn = (ctypes.c_int * (1 if one_gf else batch))()
         if one_gf:
-            self._check(self._lib.tq_fourier_tau_to_iw_axis(self._h, beta, statistic, n_tau, n_iw, batch, n_others, _ptr(gt), _ptr(moments),
+            self._check(self._run("tq_fourier_tau_to_iw_axis", beta, statistic, n_tau, n_iw, batch, n_others, _ptr(gt), _ptr(moments),
                                                             n_mom, _ptr(gw), warn))
         else:
-            self._check(self._lib.tq_fourier_tau_to_iw(self._h, beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments),
+            self._check(self._run("tq_fourier_tau_to_iw", beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments),
                                                        n_mom, _ptr(gw), warn))
         self._emit(np.frombuffer(warn, dtype=np.int32))
         return gw
@@ -179,7 +207,7 @@ class Context:
         gt = out if out is not None else _empty_like_kind(gw, (batch, n_tau, n_others))
         warn = (ctypes.c_int * batch)()
         err = (ctypes.c_double * batch)()
-        self._check(self._lib.tq_fourier_iw_to_tau(self._h, beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
+        self._check(self._run("tq_fourier_iw_to_tau", beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
                                                    _ptr(gt), warn, err))
         self._emit(np.frombuffer(warn, dtype=np.int32))
         if return_err:
@@ -195,17 +223,17 @@ class Context:
             moments = _as_c128(moments)
             n_mom = moments.shape[1]
         res = out if out is not None else _empty_like_kind(g, (batch, n_pts, n_others))
-        self._check(fn(self._h, float(t_mesh[0]), float(t_mesh[1]), float(w_mesh[0]), float(w_mesh[1]), n_pts, n_others, batch, _ptr(g),
+        self._check(self._run(fn, float(t_mesh[0]), float(t_mesh[1]), float(w_mesh[0]), float(w_mesh[1]), n_pts, n_others, batch, _ptr(g),
                        _ptr(moments), n_mom, _ptr(res)))
         return res
 
     def fourier_t_to_w(self, gt, t_mesh, w_mesh, moments=None, out=None):
         """gt [batch, n, n_others] on retime(t_min, t_max, n) -> gw on refreq(w_min, w_max, n)  (tq_fourier_t_to_w)."""
-        return self._fourier_real(self._lib.tq_fourier_t_to_w, gt, t_mesh, w_mesh, moments, out)
+        return self._fourier_real("tq_fourier_t_to_w", gt, t_mesh, w_mesh, moments, out)
 
     def fourier_w_to_t(self, gw, t_mesh, w_mesh, moments=None, out=None):
         """gw [batch, n, n_others] on refreq(w_min, w_max, n) -> gt on retime(t_min, t_max, n)  (tq_fourier_w_to_t)."""
-        return self._fourier_real(self._lib.tq_fourier_w_to_t, gw, t_mesh, w_mesh, moments, out)
+        return self._fourier_real("tq_fourier_w_to_t", gw, t_mesh, w_mesh, moments, out)
 
     # -- Legendre <-> Matsubara (legendre_matsubara.hpp:37-129) ------------------------------------
     def legendre_to_imfreq(self, gl, statistic, n_iw, out=None):
@@ -214,21 +242,21 @@ class Context:
         batch, n_l, n_others = gl.shape
         n_w = 2 * n_iw if statistic == FERMION else 2 * n_iw - 1
         res = out if out is not None else _empty_like_kind(gl, (batch, n_w, n_others))
-        self._check(self._lib.tq_legendre_to_imfreq(self._h, statistic, n_l, n_iw, n_others, batch, _ptr(gl), _ptr(res)))
+        self._check(self._run("tq_legendre_to_imfreq", statistic, n_l, n_iw, n_others, batch, _ptr(gl), _ptr(res)))
         return res
 
     def legendre_to_imtime(self, gl, beta, n_tau, out=None):
         gl = _as_c128(gl)
         batch, n_l, n_others = gl.shape
         res = out if out is not None else _empty_like_kind(gl, (batch, n_tau, n_others))
-        self._check(self._lib.tq_legendre_to_imtime(self._h, beta, n_l, n_tau, n_others, batch, _ptr(gl), _ptr(res)))
+        self._check(self._run("tq_legendre_to_imtime", beta, n_l, n_tau, n_others, batch, _ptr(gl), _ptr(res)))
         return res
 
     def imtime_to_legendre(self, gt, beta, n_l, out=None):
         gt = _as_c128(gt)
         batch, n_tau, n_others = gt.shape
         res = out if out is not None else _empty_like_kind(gt, (batch, n_l, n_others))
-        self._check(self._lib.tq_imtime_to_legendre(self._h, beta, n_tau, n_l, n_others, batch, _ptr(gt), _ptr(res)))
+        self._check(self._run("tq_imtime_to_legendre", beta, n_tau, n_l, n_others, batch, _ptr(gt), _ptr(res)))
         return res
 
     def imfreq_to_legendre(self, gw, beta, statistic, n_l, out=None):
@@ -236,7 +264,7 @@ class Context:
         batch, n_w, n_others = gw.shape
         n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
         res = out if out is not None else _empty_like_kind(gw, (batch, n_l, n_others))
-        self._check(self._lib.tq_imfreq_to_legendre(self._h, beta, statistic, n_iw, n_l, n_others, batch, _ptr(gw), _ptr(res)))
+        self._check(self._run("tq_imfreq_to_legendre", beta, statistic, n_iw, n_l, n_others, batch, _ptr(gw), _ptr(res)))
         return res
 
     # -- density ---------------------------------------------------------------------------------
@@ -256,7 +284,7 @@ class Context:
         res = out if out is not None else _empty_like_kind(gw, (batch, n, n))
         warn = (ctypes.c_int * batch)()
         err = (ctypes.c_double * batch)()
-        self._check(self._lib.tq_density(self._h, beta, statistic, n_iw, n, batch, _ptr(gw), _ptr(moments), n_mom, _ptr(res), warn, err))
+        self._check(self._run("tq_density", beta, statistic, n_iw, n, batch, _ptr(gw), _ptr(moments), n_mom, _ptr(res), warn, err))
         self._emit(np.frombuffer(warn, dtype=np.int32))
         if return_err:
             return res, np.frombuffer(err, dtype=np.float64).copy()
@@ -271,7 +299,7 @@ class Context:
         d = (ctypes.c_long * 3)(*[int(x) for x in dims])
         nk = int(dims[0]) * int(dims[1]) * int(dims[2])
         res = out if out is not None else _empty_like_kind(hop, (nk, n, n))
-        self._check(self._lib.tq_tight_binding_fourier(self._h, n, n_r, displ.ctypes.data_as(ctypes.c_void_p), _ptr(hop), d, _ptr(res)))
+        self._check(self._run("tq_tight_binding_fourier", n, n_r, displ.ctypes.data_as(ctypes.c_void_p), _ptr(hop), d, _ptr(res)))
         return res
 
     # -- hermiticity helpers, replace_by_tail (imfreq.hpp:81-215, 258-261) ----------------------
@@ -280,14 +308,14 @@ class Context:
         g = _as_c128(g)
         batch, n_pts, d, d2 = g.shape
         res = out if out is not None else _empty_like_kind(g, g.shape)
-        self._check(self._lib.tq_make_hermitian(self._h, 1 if imtime else 0, n_pts, d, batch, _ptr(g), _ptr(res)))
+        self._check(self._run("tq_make_hermitian", 1 if imtime else 0, n_pts, d, batch, _ptr(g), _ptr(res)))
         return res
 
     def is_gf_hermitian(self, g, imtime=False, tolerance=1e-12):
         g = _as_c128(g)
         batch, n_pts, d, d2 = g.shape
         r = ctypes.c_int(0)
-        self._check(self._lib.tq_is_gf_hermitian(self._h, 1 if imtime else 0, n_pts, d, batch, _ptr(g), float(tolerance), ctypes.byref(r)))
+        self._check(self._run("tq_is_gf_hermitian", 1 if imtime else 0, n_pts, d, batch, _ptr(g), float(tolerance), ctypes.byref(r)))
         return bool(r.value)
 
     def replace_by_tail(self, g, beta, statistic, tail, n_min):
@@ -295,7 +323,7 @@ class Context:
         batch, n_w, n_cols = g.shape
         n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
         tail = _as_c128(tail)
-        self._check(self._lib.tq_replace_by_tail(self._h, beta, statistic, n_iw, n_cols, batch, _ptr(g), _ptr(tail), tail.shape[1], int(n_min)))
+        self._check(self._run("tq_replace_by_tail", beta, statistic, n_iw, n_cols, batch, _ptr(g), _ptr(tail), tail.shape[1], int(n_min)))
         return g
 
     # -- tail fit ----------------------------------------------------------------------------
@@ -314,7 +342,7 @@ class Context:
         out = _empty_like_kind(g, (batch, max(L.TQ_MAX_MOMENTS, n_known), n_cols))
         nm = ctypes.c_int(0)
         err = (ctypes.c_double * batch)()
-        self._check(self._lib.tq_fit_tail(self._h, beta, statistic, n_iw, tail_fraction, n_tail_max,
+        self._check(self._run("tq_fit_tail", beta, statistic, n_iw, tail_fraction, n_tail_max,
                                           -1 if expansion_order is None else int(expansion_order), int(bool(hermitian)), int(inner_dim), n_cols,
                                           batch, _ptr(g), _ptr(known_moments), n_known, _ptr(out), ctypes.byref(nm), err))
         n_moments = nm.value
@@ -334,7 +362,7 @@ class Context:
         out = _empty_like_kind(g, (batch, max(L.TQ_MAX_MOMENTS, n_known), n_cols))
         nm = ctypes.c_int(0)
         err = (ctypes.c_double * batch)()
-        self._check(self._lib.tq_fit_tail_refreq(self._h, float(w_mesh[0]), float(w_mesh[1]), n_w, tail_fraction, n_tail_max,
+        self._check(self._run("tq_fit_tail_refreq", float(w_mesh[0]), float(w_mesh[1]), n_w, tail_fraction, n_tail_max,
                                                  -1 if expansion_order is None else int(expansion_order), n_cols, batch, _ptr(g),
                                                  _ptr(known_moments), n_known, _ptr(out), ctypes.byref(nm), err))
         n_moments = nm.value
@@ -352,7 +380,7 @@ class Context:
         assert total == int(np.prod(dims))
         y = out if out is not None else _empty_like_kind(x, x.shape)
         d = (ctypes.c_int * len(dims))(*[int(v) for v in dims])
-        self._check(self._lib.tq_fft_many(self._h, len(dims), d, howmany, _ptr(x), _ptr(y), int(sign)))
+        self._check(self._run("tq_fft_many", len(dims), d, howmany, _ptr(x), _ptr(y), int(sign)))
         return y
 
     def fourier_lattice(self, x, dims, to_k: bool, out=None):
@@ -362,7 +390,7 @@ class Context:
         assert nk == int(np.prod(dims)) and len(dims) == 3
         y = out if out is not None else _empty_like_kind(x, x.shape)
         d = (ctypes.c_long * 3)(*[int(v) for v in dims])
-        self._check(self._lib.tq_fourier_lattice(self._h, d, int(bool(to_k)), n_others, _ptr(x), _ptr(y)))
+        self._check(self._run("tq_fourier_lattice", d, int(bool(to_k)), n_others, _ptr(x), _ptr(y)))
         return y
 
     # -- inversion / Dyson ----------------------------------------------------------------------
@@ -372,7 +400,7 @@ class Context:
             assert a.dtype == np.complex128 and a.flags.c_contiguous
         n_pts, n, n2 = a.shape
         assert n == n2
-        self._check(self._lib.tq_invert_batched(self._h, n, n_pts, _ptr(a)))
+        self._check(self._run("tq_invert_batched", n, n_pts, _ptr(a)))
         return a
 
     def dyson_ksum(self, eps_k, sigma, beta, statistic, mu, weights=None, uniform_weight=None, all_reduce=False, out=None):
@@ -387,7 +415,7 @@ class Context:
         if uniform_weight is None:
             uniform_weight = 1.0 / max(n_k, 1)
         g = out if out is not None else _empty_like_kind(sigma, sigma.shape)
-        self._check(self._lib.tq_dyson_ksum(self._h, n, n_k, n_iw, beta, statistic, mu, _ptr(eps_k), _ptr(weights), float(uniform_weight),
+        self._check(self._run("tq_dyson_ksum", n, n_k, n_iw, beta, statistic, mu, _ptr(eps_k), _ptr(weights), float(uniform_weight),
                                             _ptr(sigma), _ptr(g), int(bool(all_reduce))))
         return g
 
@@ -399,20 +427,20 @@ class Context:
         n_tau, n_elem = table.shape
         n_pts = taus.shape[0]
         y = out if out is not None else _empty_like_kind(table, (n_pts, n_elem))
-        self._check(self._lib.tq_interp_tau(self._h, beta, n_tau, n_elem, _ptr(table), n_pts, _ptr(taus), _ptr(y)))
+        self._check(self._run("tq_interp_tau", beta, n_tau, n_elem, _ptr(table), n_pts, _ptr(taus), _ptr(y)))
         return y
 
     # -- multi GPU ---------------------------------------------------------------------------------
     def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
         buf = (ctypes.c_ubyte * L.TQ_COMM_ID_BYTES).from_buffer_copy(unique_id)
-        self._check(self._lib.tq_comm_init(self._h, n_ranks, rank, buf))
+        self._check(self._run("tq_comm_init", n_ranks, rank, buf))
 
     def all_reduce_sum(self, t):
         """in-place sum over ranks of a torch CUDA tensor (float64 or complex128)."""
         import torch
         assert _is_torch(t) and t.is_cuda and t.is_contiguous()
         count = t.numel() * (2 if t.dtype == torch.complex128 else 1)
-        self._check(self._lib.tq_all_reduce_sum(self._h, ctypes.c_void_p(t.data_ptr()), count))
+        self._check(self._run("tq_all_reduce_sum", _ptr(t), count))
         return t
 
 

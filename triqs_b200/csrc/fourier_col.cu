@@ -272,7 +272,7 @@ static tq_status get_col_plan(tq_ctx *ctx, double beta, int stat, long n_iw, std
 tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in, cd *d_out,
                                const cd *d_mom, int mom_rows, bool *handled) {
   *handled = false;
-  if (n_tau - 1 != COL_L || n_cols != 1 || getenv("TQ_NO_PIPE") || getenv("TQ_NO_COL")) return TQ_OK;
+  if (n_tau - 1 != COL_L || n_cols != 1 || ctx->opt_no_pipe || TQ_DEV_ENV("TQ_NO_COL")) return TQ_OK;
   if (((uintptr_t)d_in) & 15) return TQ_OK; // bulk copies need 16-byte aligned sources (rows are 16 B, so every gf is)
   std::shared_ptr<ColPlan> pl;
   TQ_TRY(get_col_plan(ctx, beta, stat, n_iw, &pl));
@@ -282,10 +282,10 @@ tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, l
   A.mom = d_mom;
   A.mom_gf_stride = mom_rows;
   A.batch = batch;
-  A.skip = getenv("TQ_COL_SKIP") ? atoi(getenv("TQ_COL_SKIP")) : 0;
+  A.skip = TQ_DEV_ENV("TQ_COL_SKIP") ? atoi(TQ_DEV_ENV("TQ_COL_SKIP")) : 0;
   const size_t smem = ((sizeof(cd) * (COL_L + 1) + 127) & ~size_t(127)) + 16 * sizeof(cd);
   const int grid = (int)std::min<long>(batch, ctx->sm_count);
-  static const int nt = getenv("TQ_COL_NT") ? atoi(getenv("TQ_COL_NT")) : 1024;
+  static const int nt = TQ_DEV_ENV("TQ_COL_NT") ? atoi(TQ_DEV_ENV("TQ_COL_NT")) : 1024;
   {
     KernelScope ks(ctx, "tau2iw_col");
     if (nt == 512) {

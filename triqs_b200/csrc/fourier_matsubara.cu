@@ -749,7 +749,7 @@ static bool radix_ok(long N) {
 static size_t tile_target_bytes(tq_ctx *ctx) {
   static long env = -1;
   if (env < 0) {
-    const char *e = getenv("TQ_TILE_BYTES");
+    const char *e = TQ_DEV_ENV("TQ_TILE_BYTES");
     env = e ? atol(e) : 0;
   }
   return env > 0 ? std::min<size_t>((size_t)env, (size_t)ctx->max_smem_optin) : (size_t)ctx->max_smem_optin / 2 - 1024;
@@ -812,7 +812,7 @@ template <int IN, int OUT, int SGN, bool SKEW> static tq_status launch_tile_impl
   static const char *tags[3][3] = {{"tau2iw_single", "", "tau2iw_pass1"}, {"", "iw2tau_single", "iw2tau_pass1"}, {"tau2iw_pass2", "iw2tau_pass2", ""}};
   KernelScope ks(ctx, tags[IN][OUT]);
   TileArgs Ad = A;
-  static const bool phase_debug = getenv("TQ_PHASE_DEBUG") != nullptr;
+  static const bool phase_debug = TQ_DEV_ENV("TQ_PHASE_DEBUG") != nullptr;
   const size_t nblk = (size_t)n_items * tiles * batch;
   if (phase_debug) {
     TQ_CUDA(ctx, cudaMallocManaged(&Ad.dbg, sizeof(long long) * 6 * nblk));
@@ -932,7 +932,7 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   // chunk the batch so that the scratch of one chunk stays L2 resident between the two kernels
   size_t per_gf = (size_t)L * n_cols * sizeof(cd);
   size_t l2_budget = 64ull << 20;
-  if (const char *e = getenv("TQ_TWOPASS_CHUNK_MB")) l2_budget = (size_t)atol(e) << 20;
+  if (ctx->opt_scratch_chunk_mb > 0) l2_budget = (size_t)ctx->opt_scratch_chunk_mb << 20;
   long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
   chunk = std::min<long>(chunk, std::min<long>(batch, maxb));
   TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));
@@ -1015,7 +1015,7 @@ static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic,
   cd *d_mom = (cd *)ctx->small.p;
   int *d_warn = (int *)((char *)ctx->small.p + warn_off);
   StatusWords *d_st = (StatusWords *)((char *)ctx->small.p + st_off);
-  TQ_CUDA(ctx, cudaMemsetAsync(d_warn, 0, sizeof(int) * batch + 256 + sizeof(StatusWords), ctx->stream));
+  TQ_CUDA(ctx, cudaMemsetAsync(d_warn, 0, st_off - warn_off + sizeof(StatusWords), ctx->stream));
   if (have_moments) {
     long total = batch * n_others;
     KernelScope ks(ctx, "prepare_known_moments");
@@ -1193,8 +1193,9 @@ constexpr int DENS_ROWS = 512; // rows per chunk = threads per CTA
 __global__ void __launch_bounds__(DENS_ROWS) k_density_partial(const cd *__restrict__ g, long g_gf_stride, int n_w, int n_cols,
                                                                const cd *__restrict__ mom, long mom_gf_stride, double beta, int stat, int first,
                                                                DensityPoles P, cd *__restrict__ partial /* [batch][chunks][n_cols] */) {
-  __shared__ cd kap[DENS_ROWS][3];
-  extern __shared__ double2 red[]; // [row lanes][n_cols]
+  extern __shared__ double2 dens_smem[];
+  cd(*kap)[3] = reinterpret_cast<cd(*)[3]>(dens_smem); // [DENS_ROWS][3]
+  double2 *red = dens_smem + 3 * DENS_ROWS;            // [row lanes][n_cols]
   const int gf = blockIdx.y, chunk = blockIdx.x;
   const int r0 = chunk * DENS_ROWS;
   const int nr = min(DENS_ROWS, n_w - r0);
@@ -1340,8 +1341,9 @@ extern "C" tq_status tq_density(tq_ctx *ctx, double beta, int statistic, long n_
   }
   {
     const int cl = (int)std::min<long>(n_cols, DENS_ROWS), rl = DENS_ROWS / cl;
-    const size_t smem = sizeof(cd) * (size_t)rl * n_cols;
-    if (smem > 48 * 1024) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_density: target too large");
+    const size_t smem = sizeof(cd) * ((size_t)rl * n_cols + 3 * DENS_ROWS);
+    if (smem > (size_t)ctx->max_smem_optin) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_density: target too large for one SM's shared memory");
+    TQ_CUDA(ctx, cudaFuncSetAttribute(k_density_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (batch > 65535) return tq_fail(ctx, TQ_ERR_INVALID, "tq_density: batch > 65535");
     KernelScope ks(ctx, "density_partial");
     k_density_partial<<<dim3(n_chunks, (unsigned)batch), DENS_ROWS, smem, ctx->stream>>>((const cd *)d_in, n_w * n_cols, (int)n_w, (int)n_cols, d_mom,

@@ -932,7 +932,7 @@ static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &
   auto k = matsubara_pipe_kernel<MODE, N, RA, RB, NW>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
-  static const bool phase_debug = getenv("TQ_PHASE_DEBUG") != nullptr;
+  static const bool phase_debug = TQ_DEV_ENV("TQ_PHASE_DEBUG") != nullptr;
   PipeArgs Ad = A;
   if (phase_debug) {
     TQ_CUDA(ctx, cudaMallocManaged(&Ad.dbg, sizeof(long long) * 64 * grid));
@@ -966,7 +966,7 @@ static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &
 
 // widest balanced column tile for a tile length N: n_ct tiles of width ceil(n_cols / n_ct)
 static int env_int_early(const char *name, int dflt) {
-  const char *e = getenv(name);
+  const char *e = TQ_DEV_ENV_NAME(name);
   return e ? atoi(e) : dflt;
 }
 template <int MODE, int N, int RA, int RB> static int pipe_pick_tcw(tq_ctx *ctx, long n_cols, int wmax, int cap, bool pad_pitch = false) {
@@ -981,7 +981,7 @@ template <int MODE, int N, int RA, int RB> static int pipe_pick_tcw(tq_ctx *ctx,
 }
 
 static int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
+  const char *e = TQ_DEV_ENV_NAME(name);
   return e ? atoi(e) : dflt;
 }
 
@@ -992,7 +992,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   const long L = n_tau - 1;
   int Na, Nb;
   if (!pipe_supported_length(L, &Na, &Nb)) return TQ_OK;
-  if (getenv("TQ_NO_PIPE")) return TQ_OK;
+  if (ctx->opt_no_pipe) return TQ_OK;
   if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return TQ_OK; // bulk copies need 16-byte aligned rows
 #ifdef TQ_KNOCKOUT
   {
@@ -1006,8 +1006,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   static const int cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64); // (tile-width caps: tuning experiments)
   // I1: window rows with n >= 0 / n < 0; when both are whole groups of Na rows they are two rectangles of the [b][a] view
   const long n_pos = (long)pl->last + 1, n_neg = -(long)pl->first;
-  const bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && !getenv("TQ_PIPE_NO_I1_BOXES");
-  const bool i1_edge = i1_rect && n_pos == (long)Na * P1_RB && n_neg == (long)Na * P1_RB && !getenv("TQ_PIPE_NO_I1_EDGE");
+  const bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && !TQ_DEV_ENV("TQ_PIPE_NO_I1_BOXES");
+  const bool i1_edge = i1_rect && n_pos == (long)Na * P1_RB && n_neg == (long)Na * P1_RB && !TQ_DEV_ENV("TQ_PIPE_NO_I1_EDGE");
   const int tcw1 = fwd ? pipe_pick_tcw<M_F1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1)
                        : pipe_pick_tcw<M_I1, P1_N, P1_RA, P1_RB>(ctx, n_cols, wmax1, cap1, !i1_edge);
   const int tcw2 = fwd ? pipe_pick_tcw<M_F2, P2_N, P2_RA, P2_RB>(ctx, n_cols, wmax2, cap2) : pipe_pick_tcw<M_I2, P2_N, P2_RA, P2_RB>(ctx, n_cols, wmax2, cap2);
@@ -1045,7 +1045,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   // kernels are FP64-bound, so the default is one launch pair per 1.5 GB of scratch.
   const size_t per_gf = (size_t)L * n_cols * sizeof(cd);
   size_t l2_budget = 1536ull << 20;
-  if (const char *e = getenv("TQ_TWOPASS_CHUNK_MB")) l2_budget = (size_t)atol(e) << 20;
+  if (ctx->opt_scratch_chunk_mb > 0) l2_budget = (size_t)ctx->opt_scratch_chunk_mb << 20;
   long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
   chunk = std::min<long>(std::min<long>(chunk, batch), 1L << 18); // (keeps the tile count of a launch below 2^31)
   TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));

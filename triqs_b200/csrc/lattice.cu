@@ -216,7 +216,7 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   std::shared_ptr<FftPlanHost> fp;
   TQ_TRY(tq_get_fft_plan(ctx, N, &fp));
   size_t half = budget / 2 - 1024;
-  if (const char *e = getenv("TQ_TILE_BYTES")) half = std::min<size_t>((size_t)atol(e), budget);
+  if (const char *e = TQ_DEV_ENV("TQ_TILE_BYTES")) half = std::min<size_t>((size_t)atol(e), budget);
   if (sizeof(cd) * (size_t)N > budget)
     return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length " + std::to_string(N) + " does not fit one SM's shared memory");
   // per row: tc columns + (twiddle + position when tabulated in shared memory)

@@ -174,7 +174,7 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
   long tc = (long)(budget / LP_NBUF / (sizeof(cd) * N));
   tc = std::min<long>(std::min<long>(tc, 128), inner);
   if (tc >= 8) tc &= ~7L; // 128-byte runs
-  if (const char *e = getenv("TQ_LP_TC")) tc = std::min<long>(tc, atol(e)); // (tuning experiments)
+  if (const char *e = TQ_DEV_ENV("TQ_LP_TC")) tc = std::min<long>(tc, atol(e)); // (tuning experiments)
   if (tc < 1) return TQ_OK;
   // pointers: TMA needs 16-byte alignment (always true for complex<double> arrays from cudaMalloc / numpy)
   if (((uintptr_t)in | (uintptr_t)out) & 15) return TQ_OK;
@@ -220,7 +220,7 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
 // DFT along the middle axis of [outer][N][inner]; *handled = false when there is no specialisation for N (caller falls back)
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
   *handled = false;
-  if (getenv("TQ_NO_PIPE")) return TQ_OK;
+  if (ctx->opt_no_pipe) return TQ_OK;
   switch (N) {
     case 256: return run_lat<256, 16, 16>(ctx, outer, inner, in, out, sign, scale, handled);
     case 128: return run_lat<128, 8, 16>(ctx, outer, inner, in, out, sign, scale, handled);

@@ -16,6 +16,19 @@
 
 typedef double2 cd;
 
+// Developer / tuning switches (TQ_PHASE_DEBUG, TQ_PIPE_*, TQ_COL_*, TQ_SCRATCH_ALIAS, TQ_KNOCK ...: some of them change results
+// by construction) are read from the environment ONLY in -DTQ_DEVELOPER builds.  The release library never looks at them --
+// the names are not even in the binary (tests/test_cabi_symbols.py greps for them); the two switches tests and callers
+// legitimately need (engine selection, scratch chunk size) are tq_set_option() of the C ABI.
+#ifdef TQ_DEVELOPER
+#include <cstdlib>
+#define TQ_DEV_ENV(name) ::getenv(name)
+#define TQ_DEV_ENV_NAME(name) ::getenv(name)
+#else
+#define TQ_DEV_ENV(name) ((const char *)nullptr)
+#define TQ_DEV_ENV_NAME(name) ((const char *)nullptr)
+#endif
+
 TQ_HD cd cmk(double x, double y) { return make_double2(x, y); }
 TQ_HD cd cadd(cd a, cd b) { return cmk(a.x + b.x, a.y + b.y); }
 TQ_HD cd csub(cd a, cd b) { return cmk(a.x - b.x, a.y - b.y); }
@@ -52,6 +65,7 @@ struct DirectTwiddles;    // lattice.cu
 struct tq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaEvent_t order_event = nullptr; // tq_stream_wait_external / tq_stream_signal_external
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -77,6 +91,9 @@ struct tq_ctx {
     cudaEvent_t e0, e1;
   };
   std::vector<ProfRec> prof;
+  // tq_set_option
+  long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
+  long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   // NCCL
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;

@@ -57,6 +57,7 @@ extern "C" void tq_destroy(tq_ctx *ctx) {
   free_buf(ctx->pipe_w);
   free_buf(ctx->leg_tmp);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -99,10 +100,39 @@ extern "C" tq_status tq_profile_report(tq_ctx *ctx, char *buf, size_t len) {
   return TQ_OK;
 }
 
+extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
+  if (!ctx || !name) return TQ_ERR_INVALID;
+  const std::string n(name);
+  if (n == "no_pipe")
+    ctx->opt_no_pipe = value;
+  else if (n == "scratch_chunk_mb")
+    ctx->opt_scratch_chunk_mb = value;
+  else
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_set_option: unknown option '" + n + "'");
+  return TQ_OK;
+}
+
 extern "C" tq_status tq_synchronize(tq_ctx *ctx) {
   if (!ctx) return TQ_ERR_INVALID;
   TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TQ_OK;
+}
+
+// cross-stream ordering without a host synchronisation (include/tqgpu.h "Stream-ordering contract")
+static tq_status order_streams(tq_ctx *ctx, cudaStream_t first, cudaStream_t then) {
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->order_event) TQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming));
+  TQ_CUDA(ctx, cudaEventRecord(ctx->order_event, first));
+  TQ_CUDA(ctx, cudaStreamWaitEvent(then, ctx->order_event, 0));
+  return TQ_OK;
+}
+extern "C" tq_status tq_stream_wait_external(tq_ctx *ctx, void *other) {
+  if (!ctx) return TQ_ERR_INVALID;
+  return order_streams(ctx, (cudaStream_t)other, ctx->stream);
+}
+extern "C" tq_status tq_stream_signal_external(tq_ctx *ctx, void *other) {
+  if (!ctx) return TQ_ERR_INVALID;
+  return order_streams(ctx, ctx->stream, (cudaStream_t)other);
 }
 
 tq_status tq_reserve(tq_ctx *ctx, DeviceBuffer &b, size_t bytes) {
@@ -229,15 +259,19 @@ NcclApi &nccl() {
   static bool tried = false;
   if (tried) return api;
   tried = true;
-  const char *env = getenv("TQ_NCCL_LIB");
+  const char *env = ::getenv("TQ_NCCL_LIB");
   const char *cands[] = {env, "libnccl.so.2", "libnccl.so"};
+  std::string why;
   for (const char *c : cands) {
     if (!c) continue;
     api.handle = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
     if (api.handle) break;
+    const char *e = dlerror(); // (one call: dlerror() clears the message it returns)
+    why += std::string(why.empty() ? "" : "; ") + (e ? e : "?");
+    if (c == env) break; // an explicit TQ_NCCL_LIB is not silently replaced by another library
   }
   if (!api.handle) {
-    api.load_error = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+    api.load_error = "cannot dlopen libnccl.so.2: " + why;
     return api;
   }
   api.GetUniqueId = (fn_GetUniqueId)dlsym(api.handle, "ncclGetUniqueId");

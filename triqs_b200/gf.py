@@ -198,7 +198,14 @@ class Gf:
         n = self.target_shape[0]
         if len(self.target_shape) != 2 or self.target_shape[1] != n:
             raise TriqsRuntimeError("invert: matrix_valued square target required")
-        self.ctx.invert_in_place(self.data.reshape(-1, n, n))
+        d = self.data
+        contiguous = d.is_contiguous() if _is_torch(d) else d.flags.c_contiguous
+        if contiguous:
+            self.ctx.invert_in_place(d.reshape(-1, n, n))  # a view: inverted in place
+        else:  # strided view (e.g. a slice of a larger gf): reshape would copy, so invert a dense copy and write it back
+            dense = d.contiguous() if _is_torch(d) else np.ascontiguousarray(d)
+            self.ctx.invert_in_place(dense.reshape(-1, n, n))
+            self.data[...] = dense
         return self
 
     def __call__(self, tau):
@@ -423,10 +430,22 @@ def replace_by_tail(g: Gf, tail, n_min: int) -> None:
     """imfreq.hpp:258-261: in place."""
     if not isinstance(g.mesh, MeshImFreq):
         raise TriqsRuntimeError("replace_by_tail needs an imfreq gf")
-    data = g.flat()[None]
-    res = g.ctx.replace_by_tail(data.copy() if not data.flags.writeable else data, g.mesh.beta, g.mesh.statistic,
-                                np.asarray(tail).reshape(1, np.shape(tail)[0], g.n_others), n_min)
-    g.data[...] = np.asarray(res)[0].reshape(g.data.shape)
+    if _is_torch(g.data):
+        import torch
+        d = g.data
+        dense = d if d.is_contiguous() else d.contiguous()
+        t = tail if _is_torch(tail) else torch.as_tensor(np.asarray(tail), device=d.device)
+        g.ctx.replace_by_tail(dense.reshape(1, len(g.mesh), g.n_others), g.mesh.beta, g.mesh.statistic,
+                              t.reshape(1, t.shape[0], g.n_others), n_min)
+        if dense is not d:
+            d[...] = dense
+        return
+    dense = np.ascontiguousarray(g.data, dtype=np.complex128)
+    if not dense.flags.writeable or dense is not g.data:
+        dense = dense.copy()
+    g.ctx.replace_by_tail(dense.reshape(1, len(g.mesh), g.n_others), g.mesh.beta, g.mesh.statistic,
+                          np.asarray(tail).reshape(1, np.shape(tail)[0], g.n_others), n_min)
+    g.data[...] = dense
 
 
 def density(g, known_moments=None):
