@@ -788,3 +788,31 @@ def test_matsubara_transforms_randomised_shapes(ctx):
             assert rel(gt[b], rt) < tol, (case, L, stat, n_iw, C, B, known)
             rb = O.fourier_tau_to_iw(rt, beta, stat, n_iw, None if mom is None else mom[b])
             assert rel(back[b], rb) < tol, (case, L, stat, n_iw, C, B, known)
+
+
+def test_host_buffer_calls_overlap_lanes_do_not_change_a_bit(ctx):
+    """Host-pointer calls are cut into chunks over internal lanes (H2D || kernels || D2H); every gf is independent, so the
+    result must be bit-identical to the single-stream call, warnings and tail errors land in the right slots."""
+    beta, n_tau, n_iw, ncols = 10.0, 1201, 200, 3
+    rng = np.random.default_rng(9)
+    gts = []
+    for b in range(7):
+        E = rng.uniform(-2, 2, 3)
+        gts.append(np.stack([poles_gtau(beta, n_tau, E * (1 + 0.1 * c), [0.2, 0.3, 0.5])[:] for c in range(ncols)], axis=1))
+    gts = np.stack(gts)
+    gts[4] += 1e-2 * rng.normal(size=gts[4].shape)   # one noisy gf: its warning bit must stay at index 4
+    ctx.set_option("host_lanes", 1)
+    w1 = ctx.fourier_tau_to_iw(gts, beta, F, n_iw)
+    warn1 = np.array(ctx.last_warn)
+    t1, e1 = ctx.fourier_iw_to_tau(w1, beta, F, n_tau, return_err=True)
+    ctx.set_option("host_lanes", 3)
+    ctx.set_option("host_chunk_kb", 2 * n_tau * ncols * 16 // 1024 + 1)   # two gfs per chunk -> 4 chunks over 3 lanes
+    w3 = ctx.fourier_tau_to_iw(gts, beta, F, n_iw)
+    warn3 = np.array(ctx.last_warn)
+    t3, e3 = ctx.fourier_iw_to_tau(w3, beta, F, n_tau, return_err=True)
+    ctx.set_option("host_chunk_kb", 96 << 10)
+    assert np.array_equal(w1, w3) and np.array_equal(t1, t3)
+    assert np.array_equal(warn1, warn3) and warn1[4] & 1 and not warn1[0] & 1
+    assert np.array_equal(e1, e3)
+    for b in (0, 6):
+        assert rel(w3[b], O.fourier_tau_to_iw(gts[b], beta, F, n_iw)) < TOL

@@ -282,10 +282,14 @@ tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, l
   A.mom = d_mom;
   A.mom_gf_stride = mom_rows;
   A.batch = batch;
-  A.skip = TQ_DEV_ENV("TQ_COL_SKIP") ? atoi(TQ_DEV_ENV("TQ_COL_SKIP")) : 0;
+  A.skip = 0;
+  if (const char *e = TQ_DEV_ENV("TQ_COL_SKIP")) A.skip = atoi(e);
   const size_t smem = ((sizeof(cd) * (COL_L + 1) + 127) & ~size_t(127)) + 16 * sizeof(cd);
   const int grid = (int)std::min<long>(batch, ctx->sm_count);
-  static const int nt = TQ_DEV_ENV("TQ_COL_NT") ? atoi(TQ_DEV_ENV("TQ_COL_NT")) : 1024;
+  static const int nt = [] {
+    const char *e = TQ_DEV_ENV("TQ_COL_NT");
+    return e ? atoi(e) : 1024;
+  }();
   {
     KernelScope ks(ctx, "tau2iw_col");
     if (nt == 512) {

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 // -------------------------------------------------------------------------------------------------
 // device-side description of the meshes and the 3-pole tail model
@@ -1059,8 +1060,70 @@ static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic,
   return TQ_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Host-buffer calls: overlap inside the call.  The reference's call model is one host thread and one call for the whole
+// BlockGf / batch (fourier.hpp:60-85, block/map.hpp:35-40).  With HOST pointers a single stream would run H2D -> kernels ->
+// D2H strictly one after the other; instead the batch is cut into chunks that are dealt round-robin to a few internal
+// lanes (child contexts: own stream, staging buffers and plan caches, driven by short-lived host threads), so that the
+// H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap (PCIe is full duplex) -- also for
+// pageable memory, where every cudaMemcpyAsync is a staged, host-blocking copy.  Results do not depend on the chunking:
+// every gf is transformed independently.
+// -------------------------------------------------------------------------------------------------
+template <class Fn> static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, const Fn &fn /* (lane ctx, b0, nb) */) {
+  const int want = (int)std::max<long>(1, ctx->opt_host_lanes);
+  const long chunk_bytes = std::max<long>(1, ctx->opt_host_chunk_kb) << 10;
+  const long per_chunk = std::max<long>(1, chunk_bytes / (long)std::max<size_t>(bytes_per_gf, 1));
+  const long n_chunks = (batch + per_chunk - 1) / per_chunk;
+  const int lanes = (int)std::min<long>(want, n_chunks);
+  if (lanes <= 1) return fn(ctx, 0, batch);
+  while ((int)ctx->lanes.size() < lanes) {
+    tq_ctx *c = nullptr;
+    tq_status st = tq_create(ctx->device, &c);
+    if (st != TQ_OK) return tq_fail(ctx, st, "cannot create an internal lane context");
+    c->opt_host_lanes = 1;
+    ctx->lanes.push_back(c);
+  }
+  for (int l = 0; l < lanes; ++l) {
+    ctx->lanes[l]->opt_no_pipe = ctx->opt_no_pipe;
+    ctx->lanes[l]->opt_scratch_chunk_mb = ctx->opt_scratch_chunk_mb;
+    ctx->lanes[l]->profiling = false;
+  }
+  std::vector<tq_status> sts(lanes, TQ_OK);
+  std::vector<std::thread> th;
+  auto work = [&](int l) {
+    cudaSetDevice(ctx->device);
+    for (long c = l; c < n_chunks; c += lanes) {
+      const long b0 = c * per_chunk, nb = std::min(per_chunk, batch - b0);
+      tq_status st = fn(ctx->lanes[l], b0, nb);
+      if (st != TQ_OK) {
+        sts[l] = st;
+        return;
+      }
+    }
+  };
+  for (int l = 1; l < lanes; ++l) th.emplace_back(work, l);
+  work(0);
+  for (auto &t : th) t.join();
+  for (int l = 0; l < lanes; ++l) {
+    ctx->launches += ctx->lanes[l]->launches;
+    ctx->lanes[l]->launches = 0;
+  }
+  for (int l = 0; l < lanes; ++l)
+    if (sts[l] != TQ_OK) return tq_fail(ctx, sts[l], ctx->lanes[l]->err);
+  return TQ_OK;
+}
+
 extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
                                           const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+  if (ctx && gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
+      !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
+    const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
+    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, [&](tq_ctx *c, long b0, long nb) {
+      return fourier_tau_to_iw_impl(c, beta, statistic, n_tau, n_iw, n_others, nb, gt + (size_t)b0 * n_tau * n_others,
+                                    (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
+                                    gw + (size_t)b0 * n_w * n_others, warn ? warn + b0 : nullptr, false);
+    });
+  }
   return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, n_others, batch, gt, moments, n_moments, gw, warn, false);
 }
 
@@ -1069,9 +1132,9 @@ extern "C" tq_status tq_fourier_tau_to_iw_axis(tq_ctx *ctx, double beta, int sta
   return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, inner, outer, gt, moments, n_moments, gw, warn, true);
 }
 
-extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
-                                          const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
-                                          double *tail_err) {
+static tq_status fourier_iw_to_tau_impl(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                                        const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
+                                        double *tail_err) {
   if (!ctx) return TQ_ERR_INVALID;
   if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_iw_to_tau: invalid argument");
@@ -1165,6 +1228,21 @@ extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statisti
     for (long b = 0; b < batch; ++b) tail_err[b] = fitted ? h_err[b] : 0.0;
   TQ_TRY(tq_stage_out_finish(ctx, gt, out_bytes, d_out, out_host));
   return TQ_OK;
+}
+
+extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                                          const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
+                                          double *tail_err) {
+  if (ctx && gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
+      !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
+    const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
+    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, [&](tq_ctx *c, long b0, long nb) {
+      return fourier_iw_to_tau_impl(c, beta, statistic, n_iw, n_tau, n_others, nb, gw + (size_t)b0 * n_w * n_others,
+                                    (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
+                                    gt + (size_t)b0 * n_tau * n_others, warn ? warn + b0 : nullptr, tail_err ? tail_err + b0 : nullptr);
+    });
+  }
+  return fourier_iw_to_tau_impl(ctx, beta, statistic, n_iw, n_tau, n_others, batch, gw, moments, n_moments, gt, warn, tail_err);
 }
 
 // -------------------------------------------------------------------------------------------------

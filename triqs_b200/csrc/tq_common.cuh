@@ -94,6 +94,9 @@ struct tq_ctx {
   // tq_set_option
   long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
+  long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)
+  long opt_host_chunk_kb = 96L << 10; // input bytes per chunk of a host-buffer call (KiB)
+  std::vector<tq_ctx *> lanes;   // child contexts of the lanes (created on first use)
   // NCCL
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;

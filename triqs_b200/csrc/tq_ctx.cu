@@ -2,6 +2,7 @@
 #include "tq_common.cuh"
 #include "tq_fft.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
 
@@ -44,6 +45,8 @@ extern "C" void tq_destroy(tq_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (tq_ctx *c : ctx->lanes) tq_destroy(c);
+  ctx->lanes.clear();
   tq_comm_destroy_internal(ctx);
   ctx->fft_plans.clear();
   ctx->matsubara_plans.clear();
@@ -107,6 +110,10 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
     ctx->opt_no_pipe = value;
   else if (n == "scratch_chunk_mb")
     ctx->opt_scratch_chunk_mb = value;
+  else if (n == "host_chunk_kb")
+    ctx->opt_host_chunk_kb = std::max<long>(1, value);
+  else if (n == "host_lanes")
+    ctx->opt_host_lanes = std::max<long>(1, std::min<long>(value, 8));
   else
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_set_option: unknown option '" + n + "'");
   return TQ_OK;
