@@ -78,6 +78,51 @@ extern "C" int hostsim_fft2(int N, int RA, int tcw, int sign, double *data /* [N
   return 0;
 }
 
+
+// planned two-pass engine (run-time radix pair, TQ_RADIX_SWITCH; generic = direct-sum pass B)
+struct PostCollectRt {
+  cd *out;
+  int tcw, ra, c, sidx;
+  TQ_HD void begin(int s, int cc) { sidx = s; c = cc; }
+  template <int T> TQ_HD void store(cd v) { out[(size_t)(sidx + ra * T) * tcw + c] = v; }
+  TQ_HD void store_rt(int t, cd v) { out[(size_t)(sidx + ra * t) * tcw + c] = v; }
+};
+template <int SGN> static int run_fft2_rt(int RA, int RB, int generic, int tcw, cd *data) {
+  const int N = RA * RB;
+  std::vector<cd> tw1, tw((size_t)N), gtw;
+  tq_fft_twiddles_host(N, tw1);
+  tq_fft_twiddles_host(RB, gtw);
+  for (int q = 0; q < RB; ++q)
+    for (int r = 0; r < RA; ++r) tw[(size_t)q * RA + r] = SGN > 0 ? tw1[(q * r) % N] : cconj(tw1[(q * r) % N]);
+  const int pitch = tcw + 3;
+  std::vector<cd> s((size_t)N * pitch);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < tcw; ++c) s[(size_t)n * pitch + c] = data[(size_t)n * tcw + c];
+  PreIdentity pre;
+  PostCollectRt post{data, tcw, RA, 0, 0};
+  const unsigned magic = fastdiv_magic((unsigned)tcw);
+  if (!tq_radix_in_registers(RA)) return -1;
+  for (int item = 0; item < RB * tcw + 5; ++item) {
+#define CALL_A(R) fft2_item_a<R, SGN, false>(s.data(), pitch, tcw, RB, tw.data(), item, pre, magic);
+    TQ_RADIX_SWITCH(RA, CALL_A)
+#undef CALL_A
+  }
+  for (int item = 0; item < RA * tcw + 5; ++item) {
+    if (generic) {
+      fft2_item_b_generic<SGN>(s.data(), pitch, tcw, RA, RB, gtw.data(), item, post, magic);
+    } else {
+      if (!tq_radix_in_registers(RB)) return -1;
+#define CALL_B(R) fft2_item_b<R, SGN>(s.data(), pitch, tcw, RA, item, post, magic);
+      TQ_RADIX_SWITCH(RB, CALL_B)
+#undef CALL_B
+    }
+  }
+  return 0;
+}
+extern "C" int hostsim_fft2_rt(int RA, int RB, int generic, int tcw, int sign, double *data /* [RA*RB][tcw] complex, in place */) {
+  return sign > 0 ? run_fft2_rt<1>(RA, RB, generic, tcw, (cd *)data) : run_fft2_rt<-1>(RA, RB, generic, tcw, (cd *)data);
+}
+
 // three-pass small-radix tile FFT (tools/tq_fft3.cuh: an experiment that lost against the two-pass engine, kept with its test)
 #include "../../tools/tq_fft3.cuh"
 template <int STEP> struct PostCollect3 {

@@ -1,0 +1,87 @@
+"""The planned four-step engine (fourier_pipe*.cu): any mesh length L = Na * Nb whose tile lengths split into a register radix and
+a second radix (register or direct-sum), both directions, both statistics, ragged column tiles -- against the oracle at 1e-12 and
+bit-for-bit consistent with nothing else; every case is ALSO run through the generic tile kernels (tq_set_option "no_pipe") so
+that the two engines are checked against each other on identical inputs.
+
+Lengths: the default adjoint mesh L = 6 n_iw (mesh/adjoint.hpp:35-38: 6000, 6144, 6150 = 2 3 5^2 41), the reference's own test mesh
+L = 9999 = 3^2 11 101 (test/c++/gfs/fourier_matsubara.cpp:26-29), 10^4 with a matrix target, 12000, 61500, 2 10^5, powers of two."""
+import numpy as np
+import pytest
+
+from oracle import triqs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+F, B = O.FERMION, O.BOSON
+
+
+def rel(x, ref):
+    return float(np.max(np.abs(np.asarray(x) - ref)) / np.max(np.abs(ref)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import triqs_b200
+    c = triqs_b200.Context(0, print_warnings=False)
+    yield c
+    c.close()
+
+
+def pole_gw(beta, stat, n_iw, ncols, seed):
+    rng = np.random.default_rng(seed)
+    iw = O.imfreq_values(beta, stat, n_iw)
+    E = rng.uniform(0.3, 2.0, (3, ncols)) * rng.choice([-1, 1], (3, ncols))
+    r = rng.normal(size=(3, ncols)) + 1j * rng.normal(size=(3, ncols))
+    return sum(r[p][None, :] / (iw[:, None] - E[p][None, :]) for p in range(3))
+
+
+CASES = [
+    # L, n_iw, ncols, stat, batch
+    (600, 100, 5, F, 2), (1200, 200, 4, B, 1), (6000, 1000, 25, F, 2), (6144, 1024, 9, F, 1), (6150, 1025, 25, F, 2), (6150, 1025, 4, B, 1),
+    (9999, 1000, 4, F, 2), (9999, 1000, 25, B, 1), (10000, 1025, 25, F, 2), (12000, 2000, 7, F, 1), (8192, 1024, 16, F, 1),
+    (61500, 10250, 9, F, 1), (65536, 8192, 5, B, 1), (200000, 20000, 6, F, 1), (20000, 10000, 5, F, 1), (30030, 2000, 4, F, 1),
+    (100000, 3000, 9, F, 1), (50000, 25000, 3, B, 2),
+]
+
+
+@pytest.mark.parametrize("L,n_iw,ncols,stat,batch", CASES)
+def test_planned_engine_both_directions(ctx, L, n_iw, ncols, stat, batch):
+    beta, n_tau = 20.0, L + 1
+    gws = np.stack([pole_gw(beta, stat, n_iw, ncols, 1000 * L % 7919 + b) for b in range(batch)])
+    refs, tails = [], []
+    for b in range(batch):
+        r, info = O.fourier_iw_to_tau(gws[b], beta, stat, n_tau, return_info=True)
+        refs.append(r)
+        tails.append(info["tail"])
+    tails = np.stack(tails)
+    gt = ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=tails)
+    for b in range(batch):
+        assert rel(gt[b], refs[b]) < TOL
+    gt_own = ctx.fourier_iw_to_tau(gws, beta, stat, n_tau)      # the library's own least-squares tail
+    for b in range(batch):
+        assert rel(gt_own[b], refs[b]) < TOL
+    gw2 = ctx.fourier_tau_to_iw(np.stack(refs), beta, stat, n_iw)
+    for b in range(batch):
+        assert rel(gw2[b], O.fourier_tau_to_iw(refs[b], beta, stat, n_iw)) < TOL
+    # the generic engine on the same inputs
+    ctx.set_option("no_pipe", 1)
+    try:
+        gt_g = ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=tails)
+        gw_g = ctx.fourier_tau_to_iw(np.stack(refs), beta, stat, n_iw)
+    finally:
+        ctx.set_option("no_pipe", 0)
+    assert rel(gt_g, gt) < TOL and rel(gw_g, gw2) < TOL
+
+
+def test_planned_engine_launches_the_pipelined_kernels(ctx):
+    """the fast path really is the one that runs off the benchmark mesh: kernel tags of the profile report"""
+    beta, L, n_iw, ncols = 10.0, 6150, 1025, 25
+    gw = pole_gw(beta, F, n_iw, ncols, 3)[None]
+    ctx.profile_enable(True)
+    gt = ctx.fourier_iw_to_tau(gw, beta, F, L + 1)
+    ctx.fourier_tau_to_iw(gt, beta, F, n_iw)
+    rep = ctx.profile_report()
+    ctx.profile_enable(False)
+    for tag in ("iw2tau_pass1", "iw2tau_pass2", "tau2iw_pass1", "tau2iw_pass2"):
+        assert tag in rep, rep

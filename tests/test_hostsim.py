@@ -106,3 +106,22 @@ def test_register_inverse_threshold_no_interchange(lib, n):
     ref = np.linalg.inv(a[acc])
     err = np.max(np.abs(b[acc] - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
     assert np.all(err < 1e-15 * 200 * np.linalg.cond(a[acc]))
+
+
+REG_RADICES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 20, 25]
+
+
+@pytest.mark.parametrize("RA", REG_RADICES)
+def test_planned_two_pass_engine_every_radix_pair(lib, RA):
+    """tq_fft2.cuh fft2_item_a / fft2_item_b behind TQ_RADIX_SWITCH: every (RA, RB) pair of register radices, plus the direct-sum
+    pass B for radices without a register butterfly (11, 13, 41, 101: the prime factors of the reference's own meshes)."""
+    rng = np.random.default_rng(100 + RA)
+    fn = lib.hostsim_fft2_rt
+    for RB, generic in [(r, 0) for r in REG_RADICES] + [(11, 1), (13, 1), (41, 1), (101, 1), (22, 1), (8, 1), (9, 1)]:
+        N = RA * RB
+        for tcw, sign in ((1, 1), (7, -1)):
+            x = rng.normal(size=(N, tcw)) + 1j * rng.normal(size=(N, tcw))
+            y = np.ascontiguousarray(x.copy())
+            assert fn(RA, RB, generic, tcw, sign, y.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+            ref = np.fft.ifft(x, axis=0) * N if sign > 0 else np.fft.fft(x, axis=0)
+            assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 2e-14, (RA, RB, generic)

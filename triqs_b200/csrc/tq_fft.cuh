@@ -225,6 +225,104 @@ template <int SGN> struct Dft<25, SGN> {
   }
 };
 
+// ---- radices of the planned two-pass engine (tq_fft2.cuh): 1, 6, 7, 9, 12, 15 ------------------
+template <int SGN> struct Dft<1, SGN> {
+  static TQ_HD void run(cd *) {}
+};
+// 7: symmetric form  y_k, y_{7-k} = (x0 + sum_j c_{jk} t_j) +- i SGN (sum_j s_{jk} d_j),  t_j = x_j + x_{7-j},  d_j = x_j - x_{7-j}
+template <int SGN> struct Dft<7, SGN> {
+  static TQ_HD void run(cd *a) {
+    const double C1 = 0.62348980185873353053, C2 = -0.22252093395631440429, C3 = -0.90096886790241912624; // cos(2 pi j/7)
+    const double S1 = 0.78183148246802980871, S2 = 0.97492791218182360702, S3 = 0.43388373911755812048;  // sin(2 pi j/7)
+    const cd t1 = cadd(a[1], a[6]), t2 = cadd(a[2], a[5]), t3 = cadd(a[3], a[4]);
+    const cd d1 = csub(a[1], a[6]), d2 = csub(a[2], a[5]), d3 = csub(a[3], a[4]);
+    const cd x0 = a[0];
+    a[0] = cadd(cadd(x0, t1), cadd(t2, t3));
+    // k = 1: cos (C1, C2, C3), sin (S1, S2, S3);  k = 2: cos (C2, C3, C1), sin (S2, -S3, -S1);  k = 3: cos (C3, C1, C2), sin (S3, -S1, S2)
+    const cd A1 = caxpy(C3, t3, caxpy(C2, t2, caxpy(C1, t1, x0)));
+    const cd A2 = caxpy(C1, t3, caxpy(C3, t2, caxpy(C2, t1, x0)));
+    const cd A3 = caxpy(C2, t3, caxpy(C1, t2, caxpy(C3, t1, x0)));
+    const cd B1 = mul_i_sgn<SGN>(caxpy(S3, d3, caxpy(S2, d2, cscale(S1, d1))));
+    const cd B2 = mul_i_sgn<SGN>(caxpy(-S1, d3, caxpy(-S3, d2, cscale(S2, d1))));
+    const cd B3 = mul_i_sgn<SGN>(caxpy(S2, d3, caxpy(-S1, d2, cscale(S3, d1))));
+    a[1] = cadd(A1, B1); a[6] = csub(A1, B1);
+    a[2] = cadd(A2, B2); a[5] = csub(A2, B2);
+    a[3] = cadd(A3, B3); a[4] = csub(A3, B3);
+  }
+};
+// 9 = 3 x 3: n = n1 + 3 n2, k = k2 + 3 k1;  u[n1][k2] = dft3_{n2}, times w9^{n1 k2}, then dft3_{n1}
+template <int SGN> struct Dft<9, SGN> {
+  static TQ_HD void run(cd *a) {
+    const cd w1 = cmk(0.76604444311897803520, SGN * 0.64278760968653932632);  // w9^1
+    const cd w2 = cmk(0.17364817766693034885, SGN * 0.98480775301220805937);  // w9^2
+    const cd w4 = cmk(-0.93969262078590838405, SGN * 0.34202014332566873304); // w9^4
+    cd u[3][3];
+#pragma unroll
+    for (int n1 = 0; n1 < 3; ++n1) {
+      cd x0 = a[n1], x1 = a[n1 + 3], x2 = a[n1 + 6];
+      dft3<SGN>(x0, x1, x2);
+      u[n1][0] = x0; u[n1][1] = x1; u[n1][2] = x2;
+    }
+    u[1][1] = cmul(u[1][1], w1);
+    u[1][2] = cmul(u[1][2], w2);
+    u[2][1] = cmul(u[2][1], w2);
+    u[2][2] = cmul(u[2][2], w4);
+#pragma unroll
+    for (int k2 = 0; k2 < 3; ++k2) {
+      cd x0 = u[0][k2], x1 = u[1][k2], x2 = u[2][k2];
+      dft3<SGN>(x0, x1, x2);
+      a[k2] = x0; a[k2 + 3] = x1; a[k2 + 6] = x2;
+    }
+  }
+};
+// Good-Thomas prime-factor map for coprime R1, R2 (no twiddles):  n = (R2 n1 + R1 n2) mod N,  k = k1 mod R1 = k2 mod R2
+//   X[k] = sum_{n1} w_R1^{n1 k1 R2} sum_{n2} w_R2^{n2 k2 R1} x[n]:  the inner transforms see the generators w_R2^{R1}, w_R1^{R2}; to use
+//   the plain butterflies the outputs are re-labelled: inner output index j2 holds k2 = j2 R1^{-1}... done by solving k from (j1, j2)
+//   with k = (j1 R2 R2inv1 ... ) -- written out as: k = (j1 * R2 * inv(R2, R1) ... ) is avoided by the symmetric choice below:
+//   n = (R2 n1 + R1 n2) mod N  and  k = (R2 inv(R2,R1) k1 + R1 inv(R1,R2) k2) mod N   give   n k = R2 n1 k1 (R2 inv) ... = n1 k1 / R1 + n2 k2 / R2
+//   (mod 1, in units of 2 pi), i.e. plain DFT_R1 over n1 and plain DFT_R2 over n2.
+constexpr int tq_modinv(int a, int m) {
+  a %= m;
+  for (int x = 1; x < m; ++x)
+    if ((a * x) % m == 1) return x;
+  return 1;
+}
+template <int R1, int R2, int SGN> struct DftPfa {
+  static constexpr int N = R1 * R2;
+  static constexpr int E1 = R2 * tq_modinv(R2, R1); // = 1 mod R1, 0 mod R2
+  static constexpr int E2 = R1 * tq_modinv(R1, R2); // = 0 mod R1, 1 mod R2
+  static TQ_HD void run(cd *a) {
+    cd u[R2][R1];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+      cd x[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) x[n1] = a[(R2 * n1 + R1 * n2) % N];
+      Dft<R1, SGN>::run(x);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) u[n2][k1] = x[k1];
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      cd x[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) x[n2] = u[n2][k1];
+      Dft<R2, SGN>::run(x);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) a[(E1 * k1 + E2 * k2) % N] = x[k2];
+    }
+  }
+};
+template <int SGN> struct Dft<6, SGN> {
+  static TQ_HD void run(cd *a) { DftPfa<3, 2, SGN>::run(a); }
+};
+template <int SGN> struct Dft<12, SGN> {
+  static TQ_HD void run(cd *a) { DftPfa<3, 4, SGN>::run(a); }
+};
+template <int SGN> struct Dft<15, SGN> {
+  static TQ_HD void run(cd *a) { DftPfa<3, 5, SGN>::run(a); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Thread layout inside a CTA: a thread owns a fixed column lane `ct` (of `nct` column lanes) and a
 // butterfly/row lane `bt` (of `nbt`): no integer division in any inner loop, adjacent threads touch

@@ -160,3 +160,111 @@ template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(c
   Dft<RB, SGN>::run(a);
   tq_unroll_store<RB>(a, post);
 }
+
+// -------------------------------------------------------------------------------------------------
+// Planned engine: the same two passes for ANY tile length N = RA * RB.  One butterfly (`item`) per call -- the pipelined
+// kernels hand out packets of 32 butterflies, one per lane.  The radix whose butterfly is unrolled in registers is the
+// template parameter (pass A: RA, pass B: RB); the other one only enters strides and is a run-time value, so a kernel can
+// `switch` over a radix table (TQ_RADIX_SWITCH) and serve every pair without one instantiation per pair.
+// -------------------------------------------------------------------------------------------------
+// radices with a register butterfly (Dft<R, SGN>)
+#define TQ_RADIX_SWITCH(r, CALL)                                                                                                 \
+  switch (r) {                                                                                                                   \
+    case 1: CALL(1) break;                                                                                                       \
+    case 2: CALL(2) break;                                                                                                       \
+    case 3: CALL(3) break;                                                                                                       \
+    case 4: CALL(4) break;                                                                                                       \
+    case 5: CALL(5) break;                                                                                                       \
+    case 6: CALL(6) break;                                                                                                       \
+    case 7: CALL(7) break;                                                                                                       \
+    case 8: CALL(8) break;                                                                                                       \
+    case 9: CALL(9) break;                                                                                                       \
+    case 10: CALL(10) break;                                                                                                     \
+    case 12: CALL(12) break;                                                                                                     \
+    case 15: CALL(15) break;                                                                                                     \
+    case 16: CALL(16) break;                                                                                                     \
+    case 20: CALL(20) break;                                                                                                     \
+    case 25: CALL(25) break;                                                                                                     \
+    default: break;                                                                                                              \
+  }
+TQ_HD bool tq_radix_in_registers(int r) {
+  return r == 1 || r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 7 || r == 8 || r == 9 || r == 10 || r == 12 || r == 15 || r == 16 ||
+         r == 20 || r == 25;
+}
+
+template <int RA, int SGN, bool TW0, class Pre, class Hook = NoHook>
+TQ_HD void fft2_item_a(cd *s, int pitch, int tcw, int rb, const cd *__restrict__ twq, int item, Pre &pre, unsigned magic,
+                       const Hook &before_store = Hook()) {
+  if (item >= rb * tcw) return;
+  const int stride = rb * pitch;
+  const int q = fastdiv(item, magic);
+  const int c = item - q * tcw;
+  cd *p = s + q * pitch + c; // row q, column c
+  pre.begin(q, c);
+  cd a[RA];
+  tq_unroll_load<RA>(a, pre, p, stride);
+  Dft<RA, SGN>::run(a);
+  const cd *tw = twq + q * RA;
+  if (TW0 || q != 0) {
+#pragma unroll
+    for (int r = TW0 ? 0 : 1; r < RA; ++r) a[r] = cmul(a[r], tw[r]);
+  }
+  before_store();
+#pragma unroll
+  for (int r = 0; r < RA; ++r) p[r * stride] = a[r];
+}
+
+template <int RB, int SGN, class Post, class Hook = NoHook>
+TQ_HD void fft2_item_b(const cd *s, int pitch, int tcw, int ra, int item, Post &post, unsigned magic, const Hook &before_store = Hook()) {
+  if (item >= ra * tcw) return;
+  const int sidx = fastdiv(item, magic);
+  const int c = item - sidx * tcw;
+  const cd *p = s + sidx * (RB * pitch) + c;
+  post.begin(sidx, c);
+  cd a[RB];
+#pragma unroll
+  for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
+  Dft<RB, SGN>::run(a);
+  before_store();
+  tq_unroll_store<RB>(a, post);
+}
+
+// Pass B for a radix without a register butterfly (a prime 11, 13, 41, 101 ... or any rb <= TQ_MAX_GENERIC_RADIX): direct sum
+//   X_k = sum_t x_t w_rb^{SGN t k},  KO outputs at a time out of registers; x_t is read once per group, the twiddle
+//   w_rb^{(t k) mod rb} comes from the table wtab[rb] (a broadcast: the lanes of a warp differ in (butterfly, column), not in k, t).
+// The tile is read-only in pass B, so no local copy of the butterfly is needed.  4 rb / KO FP64 instructions per element.
+template <int SGN, class Post, class Hook = NoHook>
+TQ_HD void fft2_item_b_generic(const cd *s, int pitch, int tcw, int ra, int rb, const cd *__restrict__ wtab, int item, Post &post, unsigned magic,
+                               const Hook &before_store = Hook()) {
+  if (item >= ra * tcw) return;
+  constexpr int KO = 8;
+  const int sidx = fastdiv(item, magic);
+  const int c = item - sidx * tcw;
+  const cd *p = s + sidx * (rb * pitch) + c;
+  post.begin(sidx, c);
+  for (int k0 = 0; k0 < rb; k0 += KO) {
+    cd acc[KO];
+    int idx[KO];
+#pragma unroll
+    for (int u = 0; u < KO; ++u) {
+      acc[u] = cmk(0.0, 0.0);
+      idx[u] = 0;
+    }
+    for (int t = 0; t < rb; ++t) {
+      const cd x = p[t * pitch];
+#pragma unroll
+      for (int u = 0; u < KO; ++u) {
+        cd w = wtab[idx[u]];
+        if (SGN < 0) w = cconj(w);
+        acc[u] = cfma(x, w, acc[u]);
+        idx[u] += k0 + u; // (t k) mod rb, incrementally; lanes past rb (k0 + u >= rb) compute a value nobody stores
+        if (idx[u] >= rb) idx[u] -= rb;
+        if (idx[u] >= rb) idx[u] -= rb; // k0 + u < rb + KO <= 2 rb
+      }
+    }
+    if (k0 + KO >= rb) before_store(); // every read of the tile is done
+#pragma unroll
+    for (int u = 0; u < KO; ++u)
+      if (k0 + u < rb) post.store_rt(k0 + u, acc[u]);
+  }
+}
