@@ -76,6 +76,8 @@ tq_status tq_stream_wait_external(tq_ctx *ctx, void *other);
 tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
 /* Engine options that never change results (tests run the same inputs through both engines):
  *   "no_pipe"          1: skip the TMA-pipelined / single-column specialisations, use the generic tile kernels only
+ *   "force_planned"    1: the L = 10^5 mesh also runs through the planned (run-time radix) kernels instead of its compile-time
+ *                      instantiation (A/B measurements; same results)
  *   "scratch_chunk_mb" > 0: four-step scratch budget per launch pair in MiB (default: 1536 pipelined, 64 generic)
  *   "host_lanes"       1..8: internal lanes over which tq_fourier_tau_to_iw / tq_fourier_iw_to_tau cut a batch passed in HOST
  *                      buffers, so that H2D copies, kernels and D2H copies of different chunks overlap (default 3; 1 = off)

@@ -107,7 +107,7 @@ template <int SGN> static int run_fft2_rt(int RA, int RB, int generic, int tcw, 
     TQ_RADIX_SWITCH(RA, CALL_A)
 #undef CALL_A
   }
-  for (int item = 0; item < RA * tcw + 5; ++item) {
+  for (int item = 0; item < RA * tcw * (generic ? fft2_generic_groups(RB) : 1) + 5; ++item) {
     if (generic) {
       fft2_item_b_generic<SGN>(s.data(), pitch, tcw, RA, RB, gtw.data(), item, post, magic);
     } else {

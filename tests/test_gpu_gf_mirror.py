@@ -28,7 +28,7 @@ def test_gf_round_trip_blockgf_and_tail():
     bgw = G.make_gf_from_fourier(bgt, n_iw)
     for b in range(2):
         ref_t = O.fourier_iw_to_tau(blocks[b].flat(), beta, O.FERMION, 6 * n_iw + 1)
-        assert np.max(np.abs(bgt[b].flat() - ref_t)) / np.max(np.abs(ref_t)) < 1e-11
+        assert np.max(np.abs(bgt[b].flat() - ref_t)) / np.max(np.abs(ref_t)) < 1e-12
         assert np.max(np.abs(bgw[b].data - blocks[b].data)) < 1e-8
     tail, err = G.fit_hermitian_tail(blocks[0])
     assert tail.shape[1:] == (2, 2) and err < 1e-8
@@ -40,7 +40,7 @@ def test_gf_round_trip_blockgf_and_tail():
     km[1] = np.eye(2)
     gt = G.make_gf_from_fourier(blocks[0], 2001, km)
     ref = O.fourier_iw_to_tau(blocks[0].flat(), beta, O.FERMION, 2001, km.reshape(2, 4))
-    assert np.max(np.abs(gt.flat() - ref)) / np.max(np.abs(ref)) < 1e-11
+    assert np.max(np.abs(gt.flat() - ref)) / np.max(np.abs(ref)) < 1e-12
 
 
 def test_gf_call_inverse_and_lattice():

@@ -85,3 +85,23 @@ def test_planned_engine_launches_the_pipelined_kernels(ctx):
     ctx.profile_enable(False)
     for tag in ("iw2tau_pass1", "iw2tau_pass2", "tau2iw_pass1", "tau2iw_pass2"):
         assert tag in rep, rep
+
+
+@pytest.mark.parametrize("dims,n_others", [((32, 32, 32), 5), ((96, 96, 1), 9), ((512, 512, 1), 3), ((100, 100, 1), 12), ((48, 48, 48), 2), ((7, 11, 13), 6),
+                                            ((41, 1, 1), 40), ((1000, 1, 1), 9), ((1, 303, 1), 17), ((12, 1, 320), 8), ((640, 2, 1), 4)])
+def test_planned_lattice_axes(ctx, dims, n_others):
+    """cyclat <-> brzone on axis lengths outside the compile-time set {64, 128, 256}: planned pipelined kernel vs oracle and vs
+    the generic tile kernel (fourier_lattice.cpp:30-59; FFTW takes any length, fourier_common.cpp:30-44)."""
+    rng = np.random.default_rng(sum(dims) + n_others)
+    nk = int(np.prod(dims))
+    x = rng.normal(size=(nk, n_others)) + 1j * rng.normal(size=(nk, n_others))
+    yk = ctx.fourier_lattice(x, dims, True)
+    assert rel(yk, O.fourier_lattice_r_to_k(x, dims)) < TOL
+    yr = ctx.fourier_lattice(yk, dims, False)
+    assert rel(yr, x) < TOL
+    ctx.set_option("no_pipe", 1)
+    try:
+        yk_g = ctx.fourier_lattice(x, dims, True)
+    finally:
+        ctx.set_option("no_pipe", 0)
+    assert rel(yk_g, yk) < TOL

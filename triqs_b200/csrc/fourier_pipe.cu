@@ -30,13 +30,6 @@ struct ModeTables {
   double er[3][PIPE_MAXR];
   cd phr[PIPE_MAXR];
 };
-// Tile shape of one pass: length N = RA * RB; RA always has a register butterfly, RB either has one or is handled by direct
-// summation (`generic`: a prime factor 11 ... 127 of the mesh length, e.g. 41 | 6150, 101 | 9999).
-struct TileShape {
-  int N = 0, RA = 0, RB = 0;
-  bool generic = false;
-  double cost = 0; // ~ FP64 work per element relative to a register radix pass
-};
 struct PipePlan {
   int L = 0, Na = 0, Nb = 0, first = 0, last = 0, n_w = 0, stat = 0, wmax1 = 0, wmax2 = 0;
   TileShape t1, t2; // pass 1 (length Nb), pass 2 (length Na)
@@ -138,37 +131,6 @@ static std::vector<cd> twiddle_rows(int N, int RA, int RB, int sgn, const std::v
 // own test mesh L = 9999 = 3^2 11 101.  Every divisor pair is tried; a tile length is usable when it splits into a register radix
 // RA and a second radix RB that is either a register radix too or small enough for the direct-sum pass B.
 constexpr int PIPE_MAX_TILE = 640;      // longest tile (rows) the shared-memory ring is sized for
-constexpr int PIPE_MAX_GENERIC = 127;   // largest radix of the direct-sum pass B
-static const int kRegRadix[] = {25, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
-
-static bool tile_shape(int N, TileShape *out) {
-  bool found = false;
-  TileShape best;
-  for (int ra : kRegRadix) {
-    if (N % ra) continue;
-    const int rb = N / ra;
-    TileShape t;
-    t.N = N;
-    t.RA = ra;
-    t.RB = rb;
-    if (tq_radix_in_registers(rb)) {
-      t.generic = false;
-      // per-element work of a register pass grows slowly with the radix; two balanced passes beat a long and a trivial one
-      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.02 * std::abs(ra - rb);
-    } else if (rb <= PIPE_MAX_GENERIC) {
-      t.generic = true;
-      t.cost = (ra == 1 ? 0.35 : 1.0) + 0.5 + rb / 9.0; // 4 rb FP64 instructions per element against ~40 for a register pass
-    } else {
-      continue;
-    }
-    if (!found || t.cost < best.cost) {
-      best = t;
-      found = true;
-    }
-  }
-  if (found) *out = best;
-  return found;
-}
 
 static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2) {
   if (L < 64 || L > (long)PIPE_MAX_TILE * PIPE_MAX_TILE) return false;
@@ -365,10 +327,15 @@ static int env_int_early(const char *name, int dflt) {
   const char *e = TQ_DEV_ENV_NAME(name);
   return e ? atoi(e) : dflt;
 }
-template <int MODE> static int pipe_pick_tcw(tq_ctx *ctx, const TileShape &T, long n_cols, int wmax, int cap, bool pad_pitch = false) {
+// pad: 0 = dense rows, 1 = rows padded to 8 columns (128 B), 2 = padded only if `rows_per_box` rows of the tile are not a multiple of 128 B
+template <int MODE> static int pipe_pitch(int tc, int pad, int rows_per_box) {
+  if (pad == 1 || (pad == 2 && (rows_per_box * tc) % 8 != 0)) return (tc + 7) & ~7;
+  return tc;
+}
+template <int MODE> static int pipe_pick_tcw(tq_ctx *ctx, const TileShape &T, long n_cols, int wmax, int cap, int pad = 0, int rows_per_box = 0) {
   int fit = 0;
   for (int tc = 1; tc <= n_cols && tc <= cap; ++tc)
-    if (PipeSmem<MODE>(T.N, T.RA, T.RB, tc, pad_pitch ? ((tc + 7) & ~7) : tc, wmax, T.generic).total <= (size_t)ctx->max_smem_optin) fit = tc;
+    if (PipeSmem<MODE>(T.N, T.RA, T.RB, tc, pipe_pitch<MODE>(tc, pad, rows_per_box), wmax, T.generic).total <= (size_t)ctx->max_smem_optin) fit = tc;
   if (fit < 1) return 0;
   static const int unbalanced = env_int_early("TQ_PIPE_UNBALANCED", 0); // (tuning experiment: widest tiles + a narrow remainder)
   if (unbalanced) return fit;
@@ -408,19 +375,30 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
   const TileShape &T1 = pl->t1, &T2 = pl->t2;
   const int Na = pl->Na, Nb = pl->Nb;
-  const bool spec = pl->specialised;
+  const bool spec = pl->specialised && !ctx->opt_force_planned;
   const int wmax1 = pl->wmax1, wmax2 = pl->wmax2;
   static const int cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64); // (tile-width caps: tuning experiments)
   // I1: window rows with n >= 0 / n < 0; when both are whole groups of Na rows they are two rectangles of the [b][a] view
   const long n_pos = (long)pl->last + 1, n_neg = -(long)pl->first;
-  const bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && n_pos / Na <= 256 && n_neg / Na <= 256 &&
-                       !TQ_DEV_ENV("TQ_PIPE_NO_I1_BOXES");
+  bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && n_pos / Na <= 256 && n_neg / Na <= 256 &&
+                 !TQ_DEV_ENV("TQ_PIPE_NO_I1_BOXES");
   // (the pruned pass A exists in the compile-time instantiations only)
   const bool i1_edge = spec && i1_rect && n_pos == (long)Na * T1.RB && n_neg == (long)Na * T1.RB && !TQ_DEV_ENV("TQ_PIPE_NO_I1_EDGE");
   // F1 fetches its tile as tensor boxes of at most 256 rows (each box lands 128-byte aligned: rows padded to 8 columns then)
   int f1_boxes = 1;
   while (Nb % f1_boxes != 0 || Nb / f1_boxes > 256) ++f1_boxes;
-  const int tcw1 = fwd ? pipe_pick_tcw<M_F1>(ctx, T1, n_cols, wmax1, cap1, f1_boxes > 1) : pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, !i1_edge);
+  const int f1_pad = f1_boxes > 1 ? 2 : 0;
+  // I1: the two tensor tiles of the rectangle path land 128-byte aligned only with rows padded to 8 columns; when that does not fit
+  // the ring (long tiles), the row-by-row path with dense rows is used instead
+  int tcw1 = fwd ? pipe_pick_tcw<M_F1>(ctx, T1, n_cols, wmax1, cap1, f1_pad, Nb / f1_boxes)
+                 : pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, (i1_rect && !i1_edge) ? 1 : 0);
+  if (!fwd && i1_rect && !i1_edge) {
+    const int dense = pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, 0);
+    if (tcw1 < 1 || (n_cols + tcw1 - 1) / tcw1 > (n_cols + dense - 1) / std::max(dense, 1)) { // fewer column tiles without the padding
+      i1_rect = false;
+      tcw1 = dense;
+    }
+  }
   const int tcw2 = fwd ? pipe_pick_tcw<M_F2>(ctx, T2, n_cols, wmax2, cap2) : pipe_pick_tcw<M_I2>(ctx, T2, n_cols, wmax2, cap2);
   if (tcw1 < 1 || tcw2 < 1) return TQ_OK;
   PipeArgs A{};
@@ -509,7 +487,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       set_mode(P2, M_F2);
       P1.f1_boxes = f1_boxes;
       P1.f1_box_rows = Nb / f1_boxes;
-      if (f1_boxes > 1) P1.pitch = (tcw1 + 7) & ~7;
+      P1.pitch = pipe_pitch<M_F1>(tcw1, f1_pad, Nb / f1_boxes);
       TQ_TRY(make_f1_tensor_map(ctx, P1.in, nb, Na, Nb, n_cols, L, P1.pitch, P1.f1_box_rows, &tmap));
       if (spec) {
         TQ_TRY((launch_pipe<M_F1, 250, 10, 25, TQ_NW_F1>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
@@ -525,7 +503,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       P1.i1_edge = i1_edge;
       // tile rows land at a pitch rounded up to 8 columns (128 B) so that the second tensor tile (rows r2..) is 128-byte
       // aligned; the pruned path stages that tile separately and keeps the conflict-free dense pitch
-      P1.pitch = P1.i1_edge ? tcw1 : ((tcw1 + 7) & ~7);
+      P1.pitch = (P1.i1_rect && !P1.i1_edge) ? ((tcw1 + 7) & ~7) : tcw1;
       for (int r = 0; r < PIPE_MAXR; ++r) P1.wedge[r] = expi(2 * PI_L * (long double)r / (long double)T1.RA); // SGN = -1: exp(+2 pi i r / RA)
       if (P1.i1_rect) {
         TQ_TRY(make_i1_tensor_map(ctx, P1.in, n_neg, n_pos, nb, Na, n_cols, pl->n_w, P1.pitch, &tmap));  // k in [0, last]: data rows n - first

@@ -428,7 +428,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   const int n_cols = A.n_cols;
   const bool fermion = A.stat == TQ_FERMION;
   // work packets = 32 butterflies (one per lane): pa packets of pass A and pb packets of pass B per tile
-  const int pa = (RBv * TCW + 31) >> 5, pb = (RAv * TCW + 31) >> 5;
+  // (a direct-sum pass B splits every butterfly over fft2_generic_groups(RB) work items)
+  const int bgroups = rb_generic ? fft2_generic_groups(RBv) : 1;
+  const int pa = (RBv * TCW + 31) >> 5, pb = (RAv * TCW * bgroups + 31) >> 5;
   cd *gtwS = reinterpret_cast<cd *>(smem_raw + S.gtw); // generic pass B: exp(+2 pi i j / RB)
 
   for (int i = tid; i < NN; i += NT) twS[i] = A.twq[i];
@@ -459,7 +461,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   // packets of that tile (pass A waits on `full`, pass B on `adone`) block every warp that claims one, so if even the narrowest
   // column tile has at least NW non-empty packets no warp gets past them.  (Measured gain where it applies: 1 %.)
   const int w_min = n_cols - (A.n_ct - 1) * TCW;
-  const bool skip_guard = ((RBv * w_min + 31) >> 5) + ((RAv * w_min + 31) >> 5) >= NW + 2 && !A.keep_guard;
+  const bool skip_guard = ((RBv * w_min + 31) >> 5) + ((RAv * w_min * bgroups + 31) >> 5) >= NW + 2 && !A.keep_guard;
   // item -> (butterfly, column) division magics of the two possible tile widths (full / last column tile)
   const unsigned m_w_full = fastdiv_magic((unsigned)TCW), m_w_last = fastdiv_magic((unsigned)(n_cols - (A.n_ct - 1) * TCW));
   long long t0 = clock64(), t_wait = 0, t_work = 0, t_sched = 0, t_ready = 0;
@@ -628,7 +630,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
       const int it = r * 32 + lane; // butterfly of this lane (the engine skips it when past the end)
       // a packet of a narrower (last) column tile can be empty for lane 0: its hook never runs, claim the next packet here
-      if (PK_LATE && r * 32 >= (is_b ? RAv : RBv) * id.w) fetch_next();
+      if (PK_LATE && r * 32 >= (is_b ? RAv * bgroups : RBv) * id.w) fetch_next();
       // (I2 sits at the register limit: one more live value makes it spill, so it recomputes the magic per packet)
       const unsigned m_w = (MODE == M_I2 && !PLANNED) ? ~0u : (id.w == TCW ? m_w_full : m_w_last);
       TQ_LAP(t_sched)
@@ -720,7 +722,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           // EARLY_FREE (I1): the tile buffer goes back to the producer as soon as the packet's loads are in registers (the butterfly
           // has consumed them when the hook runs), not after the epilogue and its scratch stores; the tables stay until the
           // stores are done (`tabfree`).  I1: 0.454 -> 0.436 ms.  No gain on F1 / F2, and I2 has no register to spare.
-          const unsigned act = __ballot_sync(0xffffffffu, it < RAv * id.w);
+          const unsigned act = __ballot_sync(0xffffffffu, it < RAv * bgroups * id.w);
           const auto release = [&]() {
             __syncwarp(act);
             if (lane == 0) {

@@ -26,6 +26,10 @@ struct LatPipeArgs {
   int tiles;     // column tiles per outer index
   int TC;
   double scale;
+  // planned (run-time radix pair) instantiation
+  int tN, tRA, tRB, rb_generic;
+  int boxes, box_rows; // the tile is fetched as `boxes` tensor boxes of box_rows rows (a TMA box has <= 256 rows)
+  const cd *gtw;       // [tRB] exp(+2 pi i j / tRB) for the direct-sum pass B
 };
 
 template <int N, int RA> struct PostLattice {
@@ -34,10 +38,13 @@ template <int N, int RA> struct PostLattice {
   double scale;
   bool scaled;
   cd *p;
+  int ra_rt = 0; // RA == 0: run-time radix
+  TQ_D int ra() const { return RA ? RA : ra_rt; }
   TQ_D void begin(int sidx, int c) { p = base + (long)sidx * inner + c; }
-  template <int TT> TQ_D void store(cd v) const {
+  template <int TT> TQ_D void store(cd v) const { store_rt(TT, v); }
+  TQ_D void store_rt(int t, cd v) const {
     if (scaled) v = cscale(scale, v);
-    p[(long)(RA * TT) * inner] = v;
+    p[(long)(ra() * t) * inner] = v;
   }
 };
 
@@ -47,16 +54,23 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
   constexpr int NT = (NW + 1) * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TC = A.TC;
-  const size_t buf_stride = (sizeof(cd) * (size_t)N * TC + 127) & ~size_t(127);
+  constexpr bool PLANNED = (N == 0);
+  const int NN = PLANNED ? A.tN : N, RAv = PLANNED ? A.tRA : RA, RBv = PLANNED ? A.tRB : RB;
+  const bool rb_generic = PLANNED && A.rb_generic != 0;
+  const size_t buf_stride = (sizeof(cd) * (size_t)NN * TC + 127) & ~size_t(127);
   cd *twS = reinterpret_cast<cd *>(smem_raw + LP_NBUF * buf_stride);
-  uint64_t *full = reinterpret_cast<uint64_t *>(twS + N);
+  cd *gtwS = twS + NN; // [RB] (direct-sum pass B only)
+  uint64_t *full = reinterpret_cast<uint64_t *>(gtwS + (rb_generic ? RBv : 0));
   uint64_t *adone = full + LP_NBUF;
   uint64_t *freeb = adone + LP_NBUF;
   int *next_pk = reinterpret_cast<int *>(freeb + LP_NBUF);
   volatile int *ready_tile = next_pk + 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int pa = (RB * TC + 31) >> 5, pb = (RA * TC + 31) >> 5;
-  for (int i = tid; i < N; i += NT) twS[i] = A.twq[i];
+  const int bgroups = rb_generic ? fft2_generic_groups(RBv) : 1;
+  const int pa = (RBv * TC + 31) >> 5, pb = (RAv * TC * bgroups + 31) >> 5;
+  for (int i = tid; i < NN; i += NT) twS[i] = A.twq[i];
+  if (rb_generic)
+    for (int i = tid; i < RBv; i += NT) gtwS[i] = A.gtw[i];
   if (tid == 0) {
     for (int b = 0; b < LP_NBUF; ++b) {
       mbar_init(&full[b], 1);
@@ -85,11 +99,13 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
         long o;
         int c0;
         tile_of(t, &o, &c0);
-        mbar_arrive_expect_tx(&full[b], (uint32_t)(sizeof(cd) * N * TC)); // the whole box; columns past `inner` are zero-filled
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                        smem_u32(smem_raw + b * buf_stride)),
-                     "l"(&tmap), "r"(2 * c0), "r"(0), "r"((int)o), "r"(smem_u32(&full[b]))
-                     : "memory");
+        mbar_arrive_expect_tx(&full[b], (uint32_t)(sizeof(cd) * NN * TC)); // the whole box; columns past `inner` are zero-filled
+        const int nbox = PLANNED ? A.boxes : 1, brows = PLANNED ? A.box_rows : N;
+        for (int bx = 0; bx < nbox; ++bx)
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                          smem_u32(smem_raw + b * buf_stride + sizeof(cd) * (size_t)bx * brows * TC)),
+                       "l"(&tmap), "r"(2 * c0), "r"(bx * brows), "r"((int)o), "r"(smem_u32(&full[b]))
+                       : "memory");
       }
     }
   } else {
@@ -127,13 +143,31 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
       if (!is_b) {
         mbar_wait(&full[b], (uint32_t)(u & 1));
         PreIdentity pre;
-        fft2_pass_a<N, RA, RB, SGN, false>(tile, TC, w, twS, it, 1 << 30, pre);
+        if constexpr (!PLANNED) {
+          fft2_pass_a<N, RA, RB, SGN, false>(tile, TC, w, twS, it, 1 << 30, pre);
+        } else {
+          const unsigned m_w = fastdiv_magic((unsigned)w);
+#define TQ_CALL_A(R) fft2_item_a<R, SGN, false>(tile, TC, w, RBv, twS, it, pre, m_w);
+          TQ_RADIX_SWITCH(RAv, TQ_CALL_A)
+#undef TQ_CALL_A
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&adone[b]);
       } else {
         mbar_wait(&adone[b], (uint32_t)(u & 1));
-        PostLattice<N, RA> post{A.out + (o * N) * A.inner + c0, A.inner, A.scale, scaled, nullptr};
-        fft2_pass_b<N, RA, RB, SGN>(tile, TC, w, it, 1 << 30, post);
+        PostLattice<N, RA> post{A.out + (o * NN) * A.inner + c0, A.inner, A.scale, scaled, nullptr, RAv};
+        if constexpr (!PLANNED) {
+          fft2_pass_b<N, RA, RB, SGN>(tile, TC, w, it, 1 << 30, post);
+        } else {
+          const unsigned m_w = fastdiv_magic((unsigned)w);
+          if (rb_generic) {
+            fft2_item_b_generic<SGN>(tile, TC, w, RAv, RBv, gtwS, it, post, m_w);
+          } else {
+#define TQ_CALL_B(R) fft2_item_b<R, SGN>(tile, TC, w, RAv, it, post, m_w);
+            TQ_RADIX_SWITCH(RBv, TQ_CALL_B)
+#undef TQ_CALL_B
+          }
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&freeb[b]);
@@ -146,16 +180,19 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
 // host
 // ---------------------------------------------------------------------------------------------
 struct LatTwiddles {
-  std::map<std::tuple<int, int>, cd *> tw; // (N, sign) -> device [RB][RA]
+  std::map<std::tuple<int, int>, cd *> tw; // (N, sign) -> device [RB][RA]; (-RB, 0) -> exp(+2 pi i j / RB)
   ~LatTwiddles() {
     for (auto &kv : tw) cudaFree(kv.second);
   }
 };
 
+static size_t lat_smem_bytes(int N, int RB, bool generic, long tc) {
+  const size_t buf_stride = (sizeof(cd) * (size_t)N * tc + 127) & ~size_t(127);
+  return LP_NBUF * buf_stride + sizeof(cd) * (N + (generic ? RB : 0)) + 8 * 3 * LP_NBUF + 16;
+}
 template <int N, int RA, int RB, int SGN> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
   constexpr int NW = 11;
-  const size_t buf_stride = (sizeof(cd) * (size_t)N * A.TC + 127) & ~size_t(127);
-  const size_t smem = LP_NBUF * buf_stride + sizeof(cd) * N + 8 * 3 * LP_NBUF + 16;
+  const size_t smem = lat_smem_bytes(N ? N : A.tN, N ? RB : A.tRB, N ? false : A.rb_generic != 0, A.TC);
   auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
@@ -168,12 +205,17 @@ template <int N, int RA, int RB, int SGN> static tq_status launch_lat(tq_ctx *ct
   return TQ_OK;
 }
 
-template <int N, int RA, int RB>
-static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
-  const size_t budget = (size_t)ctx->max_smem_optin - sizeof(cd) * N - 256;
+// N0 / RA0 / RB0 = 0: the planned instantiation with the run-time shape T
+template <int N0, int RA0, int RB0>
+static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
+  const int N = T.N, RA = T.RA, RB = T.RB;
+  const size_t budget = (size_t)ctx->max_smem_optin - sizeof(cd) * (N + RB) - 256;
   long tc = (long)(budget / LP_NBUF / (sizeof(cd) * N));
   tc = std::min<long>(std::min<long>(tc, 128), inner);
   if (tc >= 8) tc &= ~7L; // 128-byte runs
+  int boxes = 1;
+  while (N % boxes != 0 || N / boxes > 256) ++boxes;
+  if (boxes > 1 && ((long)(N / boxes) * tc) % 8 != 0) return TQ_OK; // every box must land 128-byte aligned
   if (const char *e = TQ_DEV_ENV("TQ_LP_TC")) tc = std::min<long>(tc, atol(e)); // (tuning experiments)
   if (tc < 1) return TQ_OK;
   // pointers: TMA needs 16-byte alignment (always true for complex<double> arrays from cudaMalloc / numpy)
@@ -195,7 +237,7 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
   CUtensorMap tmap;
   cuuint64_t dims[3] = {(cuuint64_t)(2 * inner), (cuuint64_t)N, (cuuint64_t)outer};
   cuuint64_t strides[2] = {(cuuint64_t)(inner * sizeof(cd)), (cuuint64_t)((long)N * inner * sizeof(cd))};
-  cuuint32_t box[3] = {(cuuint32_t)(2 * tc), (cuuint32_t)N, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)(2 * tc), (cuuint32_t)(N / boxes), 1u};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -208,11 +250,28 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
   A.tiles = (int)((inner + tc - 1) / tc);
   A.n_tiles = outer * A.tiles;
   A.scale = scale;
+  A.tN = N;
+  A.tRA = RA;
+  A.tRB = RB;
+  A.rb_generic = T.generic ? 1 : 0;
+  A.boxes = boxes;
+  A.box_rows = N / boxes;
+  if (T.generic) {
+    cd *&g = ctx->lat_tw->tw[std::make_tuple(-RB, 0)];
+    if (!g) {
+      std::vector<cd> w;
+      tq_fft_twiddles_host(RB, w);
+      TQ_CUDA(ctx, cudaMalloc(&g, sizeof(cd) * RB));
+      TQ_CUDA(ctx, cudaMemcpyAsync(g, w.data(), sizeof(cd) * RB, cudaMemcpyHostToDevice, ctx->stream));
+      TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    A.gtw = g;
+  }
   if (A.n_tiles >= (1L << 31)) return TQ_OK;
   if (sign > 0)
-    TQ_TRY((launch_lat<N, RA, RB, 1>(ctx, A, tmap)));
+    TQ_TRY((launch_lat<N0, RA0, RB0, 1>(ctx, A, tmap)));
   else
-    TQ_TRY((launch_lat<N, RA, RB, -1>(ctx, A, tmap)));
+    TQ_TRY((launch_lat<N0, RA0, RB0, -1>(ctx, A, tmap)));
   *handled = true;
   return TQ_OK;
 }
@@ -221,10 +280,16 @@ static tq_status run_lat(tq_ctx *ctx, long outer, long inner, const cd *in, cd *
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
   *handled = false;
   if (ctx->opt_no_pipe) return TQ_OK;
+  // compile-time instantiations of the benchmark shapes (256 = 16 x 16, 128 = 8 x 16, 64 = 8 x 8) ...
   switch (N) {
-    case 256: return run_lat<256, 16, 16>(ctx, outer, inner, in, out, sign, scale, handled);
-    case 128: return run_lat<128, 8, 16>(ctx, outer, inner, in, out, sign, scale, handled);
-    case 64: return run_lat<64, 8, 8>(ctx, outer, inner, in, out, sign, scale, handled);
-    default: return TQ_OK;
+    case 256: return run_lat<256, 16, 16>(ctx, TileShape{256, 16, 16, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    case 128: return run_lat<128, 8, 16>(ctx, TileShape{128, 8, 16, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    case 64: return run_lat<64, 8, 8>(ctx, TileShape{64, 8, 8, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    default: break;
   }
+  // ... and the planned one for every other axis length that splits into a register radix and a second radix (register or direct
+  // sum): 32, 48, 96, 100, 512, 3 2^k, primes up to 127 ...   (fourier_common.cpp:30-44: FFTW takes any length)
+  TileShape T;
+  if (N < 4 || N > 1024 || !tile_shape((int)N, &T)) return TQ_OK;
+  return run_lat<0, 0, 0>(ctx, T, outer, inner, in, out, sign, scale, handled);
 }

@@ -230,41 +230,47 @@ TQ_HD void fft2_item_b(const cd *s, int pitch, int tcw, int ra, int item, Post &
 }
 
 // Pass B for a radix without a register butterfly (a prime 11, 13, 41, 101 ... or any rb <= TQ_MAX_GENERIC_RADIX): direct sum
-//   X_k = sum_t x_t w_rb^{SGN t k},  KO outputs at a time out of registers; x_t is read once per group, the twiddle
-//   w_rb^{(t k) mod rb} comes from the table wtab[rb] (a broadcast: the lanes of a warp differ in (butterfly, column), not in k, t).
-// The tile is read-only in pass B, so no local copy of the butterfly is needed.  4 rb / KO FP64 instructions per element.
+//   X_k = sum_t x_t w_rb^{SGN t k}.  One work item = (output group kg, butterfly s, column c): TQ_GENERIC_KO outputs out of registers;
+//   x_t is read once per item, the twiddle w_rb^{(t k) mod rb} comes from the table wtab[rb] (a broadcast: the lanes of a warp
+//   differ in (butterfly, column), rarely in the group).  Splitting a butterfly over ceil(rb / KO) items is what keeps the warps busy when
+//   a tile has few columns (a 101-point butterfly is 40 k FP64 instructions).  The tile is read-only in pass B, so no local
+//   copy of the butterfly is needed.  4 rb FP64 instructions per element.
+#define TQ_GENERIC_KO 8
+TQ_HD int fft2_generic_groups(int rb) { return (rb + TQ_GENERIC_KO - 1) / TQ_GENERIC_KO; }
 template <int SGN, class Post, class Hook = NoHook>
 TQ_HD void fft2_item_b_generic(const cd *s, int pitch, int tcw, int ra, int rb, const cd *__restrict__ wtab, int item, Post &post, unsigned magic,
                                const Hook &before_store = Hook()) {
-  if (item >= ra * tcw) return;
-  constexpr int KO = 8;
-  const int sidx = fastdiv(item, magic);
-  const int c = item - sidx * tcw;
+  constexpr int KO = TQ_GENERIC_KO;
+  const int per_group = ra * tcw;
+  if (item >= per_group * fft2_generic_groups(rb)) return;
+  const int kg = item / per_group; // (one division per 4 rb KO FP64 instructions)
+  const int rem = item - kg * per_group;
+  const int sidx = fastdiv(rem, magic);
+  const int c = rem - sidx * tcw;
   const cd *p = s + sidx * (rb * pitch) + c;
   post.begin(sidx, c);
-  for (int k0 = 0; k0 < rb; k0 += KO) {
-    cd acc[KO];
-    int idx[KO];
+  const int k0 = kg * KO;
+  cd acc[KO];
+  int idx[KO], step[KO];
+#pragma unroll
+  for (int u = 0; u < KO; ++u) {
+    acc[u] = cmk(0.0, 0.0);
+    idx[u] = 0;
+    step[u] = k0 + u < rb ? k0 + u : 0; // outputs past rb are computed (as X_0) and not stored
+  }
+  for (int t = 0; t < rb; ++t) {
+    const cd x = p[t * pitch];
 #pragma unroll
     for (int u = 0; u < KO; ++u) {
-      acc[u] = cmk(0.0, 0.0);
-      idx[u] = 0;
+      cd w = wtab[idx[u]];
+      if (SGN < 0) w = cconj(w);
+      acc[u] = cfma(x, w, acc[u]);
+      idx[u] += step[u]; // (t k) mod rb, incrementally
+      if (idx[u] >= rb) idx[u] -= rb;
     }
-    for (int t = 0; t < rb; ++t) {
-      const cd x = p[t * pitch];
-#pragma unroll
-      for (int u = 0; u < KO; ++u) {
-        cd w = wtab[idx[u]];
-        if (SGN < 0) w = cconj(w);
-        acc[u] = cfma(x, w, acc[u]);
-        idx[u] += k0 + u; // (t k) mod rb, incrementally; lanes past rb (k0 + u >= rb) compute a value nobody stores
-        if (idx[u] >= rb) idx[u] -= rb;
-        if (idx[u] >= rb) idx[u] -= rb; // k0 + u < rb + KO <= 2 rb
-      }
-    }
-    if (k0 + KO >= rb) before_store(); // every read of the tile is done
-#pragma unroll
-    for (int u = 0; u < KO; ++u)
-      if (k0 + u < rb) post.store_rt(k0 + u, acc[u]);
   }
+  before_store(); // every read of the tile is done
+#pragma unroll
+  for (int u = 0; u < KO; ++u)
+    if (k0 + u < rb) post.store_rt(k0 + u, acc[u]);
 }

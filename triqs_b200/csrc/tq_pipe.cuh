@@ -79,3 +79,48 @@ static inline EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// host: tile shapes of the planned two-pass engine (tq_fft2.cuh), shared by fourier_pipe.cu and lattice_pipe.cu
+// -------------------------------------------------------------------------------------------------
+#include <cmath>
+#include <cstdlib>
+// Tile shape of one pass: length N = RA * RB; RA always has a register butterfly, RB either has one or is handled by direct
+// summation (`generic`: a prime factor 11 ... 127 of the mesh length, e.g. 41 | 6150, 101 | 9999).
+struct TileShape {
+  int N = 0, RA = 0, RB = 0;
+  bool generic = false;
+  double cost = 0; // ~ FP64 work per element relative to a register radix pass
+};
+constexpr int PIPE_MAX_GENERIC = 127;   // largest radix of the direct-sum pass B
+static const int kRegRadix[] = {25, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
+
+static inline bool tile_shape(int N, TileShape *out) {
+  bool found = false;
+  TileShape best;
+  for (int ra : kRegRadix) {
+    if (N % ra) continue;
+    const int rb = N / ra;
+    TileShape t;
+    t.N = N;
+    t.RA = ra;
+    t.RB = rb;
+    if (tq_radix_in_registers(rb)) {
+      t.generic = false;
+      // per-element work of a register pass grows slowly with the radix; two balanced passes beat a long and a trivial one
+      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.02 * std::abs(ra - rb);
+    } else if (rb <= PIPE_MAX_GENERIC) {
+      t.generic = true;
+      t.cost = (ra == 1 ? 0.35 : 1.0) + 0.5 + rb / 9.0; // 4 rb FP64 instructions per element against ~40 for a register pass
+    } else {
+      continue;
+    }
+    if (!found || t.cost < best.cost) {
+      best = t;
+      found = true;
+    }
+  }
+  if (found) *out = best;
+  return found;
+}
+
