@@ -548,15 +548,21 @@ def run_extras(ctx, stream, dev, world, rank, timed_fn):
         ms_fit = timed_fn(fit, 3) / 3
         mom, _ = fit()
         gw_h, mom_h = gw[:4].cpu().numpy(), mom[:4].cpu().numpy()
-        err = 0.0
+        err, dm = 0.0, np.zeros(4)
         for b in range(4):
             ref = O.fourier_tau_to_iw(h[b], 10.0, O.FERMION, 1025)
             err = max(err, _rel(gw_h[b], ref))
             rm, _ = O.fit_hermitian_tail(ref, 10.0, O.FERMION, inner_dim=1)
-            err = max(err, _rel(mom_h[b][:4], rm[:4]))  # moments 0..3 (higher ones are conditioning limited in the reference too)
+            err = max(err, float(np.max(np.abs(mom_h[b][:2] - rm[:2]))))  # moments 0, 1 (m1 = 1 here): absolute = relative
+            dm = np.maximum(dm, np.abs(mom_h[b][:4, 0] - rm[:4, 0]))
         finish("c1_tau2iw_fit_hermitian_tail_B8192",
                {"ms": ms + ms_fit, "ms_transform": ms, "ms_fit": ms_fit, "points_per_s": world * B * 2050 / ((ms + ms_fit) * 1e-3),
-                "roofline": hbm(B * 192976.0, ms + ms_fit), "inputs": "seed 1001+b poles, b < 8192", "checked": "b = 0..3 vs oracle: G(iw) and moments 0..3"}, err)
+                "roofline": hbm(B * 192976.0, ms + ms_fit), "inputs": "seed 1001+b poles, b < 8192",
+                "checked": "b = 0..3 vs oracle: G(iw) and fitted moments 0..1 at 1e-12",
+                "moment_abs_diff_vs_oracle_m0_m3": [float(x) for x in dm],
+                "moment_note": "moments >= 2 of a least-squares tail fit are conditioning limited in the reference itself: two LAPACK drivers "
+                               "(gesvd / gesdd) of the oracle differ by 1.5e-12 (m2) and 3e-9 (m3) on the same data "
+                               "(profiles/r02_lsq_tail_error.json)"}, err)
 
     def c3():
         nk, no, ns = 65536, 9216, 64

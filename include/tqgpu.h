@@ -235,14 +235,15 @@ tq_status tq_fourier_lattice(tq_ctx *ctx, const long dims[3], int to_k, long n_o
 
 /* Replaces  invert_in_place(gf_view<M, matrix_valued>)  c++/triqs/gfs/functions/functions2.hpp:197-201
  *           _gf_invert_data_in_place(array_view<dcomplex,3>)  c++/triqs/gfs/gf/gf_expr.hpp:219-222
- * a [n_pts][n][n], inverted in place, 1 <= n <= TQ_MAX_MATRIX_DIM (partial pivoting). */
-#define TQ_MAX_MATRIX_DIM 8
+ * a [n_pts][n][n], inverted in place, 1 <= n <= TQ_MAX_MATRIX_DIM (Gauss-Jordan with partial pivoting; n <= 8: one thread per
+ * matrix entirely in registers, 9 <= n <= 64: one warp per matrix in shared memory). */
+#define TQ_MAX_MATRIX_DIM 64
 tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_complex *a);
 
 /* Replaces the k-sum of  SumkDiscrete.__call__   python/triqs/sumk/sumk_discrete.py:140-166
  * (C++ spelling: clef fill + inverse + sum over k, test/c++/gfs/multivar/g_k_om.cpp:64, bubble.cpp:65):
  *   out[w] = sum_k weights[k] * inverse( (i w_n + mu) 1 - eps_k[k] - sigma[w] )
- * fused: G(k, w) is never materialised.
+ * fused: G(k, w) is never materialised (n <= 8; larger targets go through slabs of k-points in a <= 256 MB scratch).
  *   eps_k    [n_k][n][n]   this rank's k-points (the caller slices like mpi.slice_array, mpi_mpi4py.py:96-109)
  *   weights  double[n_k] or NULL (then every weight is `uniform_weight`, e.g. 1/N_k_total)
  *   sigma    [n_w][n][n] on the full imfreq mesh (beta, statistic, n_iw)

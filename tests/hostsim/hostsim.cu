@@ -101,19 +101,19 @@ template <int SGN> static int run_fft2_rt(int RA, int RB, int generic, int tcw, 
   PreIdentity pre;
   PostCollectRt post{data, tcw, RA, 0, 0};
   const unsigned magic = fastdiv_magic((unsigned)tcw);
-  if (!tq_radix_in_registers(RA)) return -1;
+  if (!tq_radix_in_registers(RA, true)) return -1;
   for (int item = 0; item < RB * tcw + 5; ++item) {
 #define CALL_A(R) fft2_item_a<R, SGN, false>(s.data(), pitch, tcw, RB, tw.data(), item, pre, magic);
-    TQ_RADIX_SWITCH(RA, CALL_A)
+    TQ_RADIX_SWITCH32(RA, CALL_A)
 #undef CALL_A
   }
   for (int item = 0; item < RA * tcw * (generic ? fft2_generic_groups(RB) : 1) + 5; ++item) {
     if (generic) {
       fft2_item_b_generic<SGN>(s.data(), pitch, tcw, RA, RB, gtw.data(), item, post, magic);
     } else {
-      if (!tq_radix_in_registers(RB)) return -1;
+      if (!tq_radix_in_registers(RB, true)) return -1;
 #define CALL_B(R) fft2_item_b<R, SGN>(s.data(), pitch, tcw, RA, item, post, magic);
-      TQ_RADIX_SWITCH(RB, CALL_B)
+      TQ_RADIX_SWITCH32(RB, CALL_B)
 #undef CALL_B
     }
   }

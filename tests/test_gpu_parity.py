@@ -368,8 +368,9 @@ def test_fft_many_semantics(ctx):
 # ---------------------------------------------------------------------------------------------
 # inversion and the Dyson k-sum
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 8])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 8, 9, 12, 17, 32, 40, 64])
 def test_invert_batched(ctx, n):
+    """n <= 8: one thread per matrix in registers; 9..64: one warp per matrix in shared memory (nda::inverse_in_place has no limit)."""
     rng = np.random.default_rng(100 + n)
     a = rng.normal(size=(1000, n, n)) + 1j * rng.normal(size=(1000, n, n))
     ref = O.invert_batched(a)
@@ -377,7 +378,7 @@ def test_invert_batched(ctx, n):
     err = np.max(np.abs(out - ref), axis=(1, 2)) / np.max(np.abs(ref), axis=(1, 2))
     cond = np.linalg.cond(a)
     assert np.all(err < 1e-15 * cond * 50)
-    assert np.median(err) < 1e-13
+    assert np.median(err) < 1e-13 * max(1, n // 4)
 
 
 def c4_inputs(nk1, n_iw, n=5, beta=10.0):
@@ -419,7 +420,7 @@ def test_dyson_ksum_vs_oracle(ctx):
 
 
 def test_dyson_other_dims(ctx):
-    for n in (1, 2, 3):
+    for n in (1, 2, 3, 9, 14):
         eps, sig = c4_inputs(4, 16, n=n)
         assert rel(ctx.dyson_ksum(eps, sig, 10.0, F, -0.3), O.dyson_ksum(eps, sig, 10.0, F, -0.3)) < TOL
 

@@ -15,6 +15,9 @@ ctx = triqs_b200.Context(0, print_warnings=False)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 which = sys.argv[1:] or ["matsubara", "lattice"]
+import os
+if "TQ_LAG" in os.environ:
+    ctx.set_option("pipe_lag0", int(os.environ["TQ_LAG"]))
 
 
 def timed(fn, reps=10, warm=3):

@@ -17,7 +17,7 @@ TQ_ERR_CUDA, TQ_ERR_INVALID, TQ_ERR_RUNTIME, TQ_ERR_UNSUPPORTED, TQ_ERR_NO_DEVIC
 TQ_BOSON, TQ_FERMION = 0, 1
 TQ_WARN_NOISY_TAU, TQ_WARN_SHORT_TAU_MESH, TQ_WARN_TAIL_ERR = 1, 2, 4
 TQ_MAX_MOMENTS = 10
-TQ_MAX_MATRIX_DIM = 8
+TQ_MAX_MATRIX_DIM = 64
 TQ_COMM_ID_BYTES = 128
 
 # every symbol include/tqgpu.h declares: (restype, argtypes)

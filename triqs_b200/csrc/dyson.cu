@@ -52,10 +52,134 @@ template <int N> __global__ void __launch_bounds__(128) k_invert_batched(cd *a, 
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// n > 8 (nda::inverse_in_place has no size limit, functions2.hpp:197-201): one WARP per matrix, the matrix in shared memory,
+// the same Gauss-Jordan elimination with partial (row) pivoting as the register version, lanes over the rows / the
+// (row, column) pairs of each step.  `form`: the matrix is built on the fly as A(w) - eps_k (Dyson) instead of read.
+// -------------------------------------------------------------------------------------------------
+constexpr int TQ_GENERIC_MATRIX_MAX = 64;
+struct WarpInvForm {
+  const cd *eps, *sigma; // eps [n_k][n][n], sigma [n_w][n][n]
+  long k0;               // first k-point of this launch
+  int n_w, first, stat;
+  double beta, mu;
+};
+template <bool FORM> __global__ void k_invert_warp(cd *a, long n_mat, int n, WarpInvForm F) {
+  extern __shared__ double2 sm[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = n | 1; // odd pitch: conflict-free column access
+  cd *A = sm + (size_t)warp * ((size_t)n * ld + n);
+  cd *col = A + (size_t)n * ld;
+  int *piv = reinterpret_cast<int *>(sm + (size_t)warps * ((size_t)n * ld + n)) + warp * n;
+  const int nn = n * n;
+  for (long m = (long)blockIdx.x * warps + warp; m < n_mat; m += (long)gridDim.x * warps) {
+    cd *g = a + (size_t)m * nn;
+    if (FORM) { // matrix m = (k - k0) * n_w + w:  (i w_n + mu) 1 - Sigma(w) - eps_k
+      const long kk = m / F.n_w;
+      const int w = (int)(m - kk * F.n_w);
+      const double om = M_PI * (double)(2 * (long)(F.first + w) + F.stat) / F.beta;
+      const cd *e = F.eps + (size_t)(F.k0 + kk) * nn, *sg = F.sigma + (size_t)w * nn;
+      for (int i = lane; i < nn; i += 32) {
+        const int r = i / n, c = i - r * n;
+        cd v = cmk(-sg[i].x - e[i].x, -sg[i].y - e[i].y);
+        if (r == c) v = cmk(v.x + F.mu, v.y + om);
+        A[r * ld + c] = v;
+      }
+    } else {
+      for (int i = lane; i < nn; i += 32) A[(i / n) * ld + (i % n)] = g[i];
+    }
+    __syncwarp();
+    for (int p = 0; p < n; ++p) {
+      // pivot search in column p, rows p .. n-1 (first maximum wins, like the serial loop)
+      double best = -1.0;
+      int r = p;
+      for (int i = p + lane; i < n; i += 32) {
+        const double v = cabs2(A[i * ld + p]);
+        if (v > best) {
+          best = v;
+          r = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
+        if (ob > best || (ob == best && orr < r)) {
+          best = ob;
+          r = orr;
+        }
+      }
+      if (lane == 0) piv[p] = r;
+      if (r != p)
+        for (int j = lane; j < n; j += 32) {
+          const cd t = A[p * ld + j];
+          A[p * ld + j] = A[r * ld + j];
+          A[r * ld + j] = t;
+        }
+      __syncwarp();
+      const cd d = A[p * ld + p];
+      const double inv = 1.0 / cabs2(d);
+      const cd ip = cmk(d.x * inv, -d.y * inv);
+      for (int i = lane; i < n; i += 32) col[i] = A[i * ld + p];
+      __syncwarp();
+      for (int j = lane; j < n; j += 32) A[p * ld + j] = cmul(j == p ? cmk(1.0, 0.0) : A[p * ld + j], ip);
+      for (int i = lane; i < n; i += 32)
+        if (i != p) A[i * ld + p] = cmk(0.0, 0.0);
+      __syncwarp();
+      for (int e = lane; e < nn; e += 32) {
+        const int i = e / n, j = e - i * n;
+        if (i != p) A[i * ld + j] = cfma(cneg(col[i]), A[p * ld + j], A[i * ld + j]);
+      }
+      __syncwarp();
+    }
+    // undo the row interchanges as column interchanges, in reverse order
+    for (int p = n - 1; p >= 0; --p) {
+      const int c = piv[p];
+      if (c != p)
+        for (int i = lane; i < n; i += 32) {
+          const cd t = A[i * ld + p];
+          A[i * ld + p] = A[i * ld + c];
+          A[i * ld + c] = t;
+        }
+      __syncwarp();
+    }
+    for (int i = lane; i < nn; i += 32) g[i] = A[(i / n) * ld + (i % n)];
+    __syncwarp();
+  }
+}
+static size_t warp_inv_smem(int n, int warps) { return (sizeof(cd) * ((size_t)n * (n | 1) + n) + sizeof(int) * n) * warps + 16; }
+template <bool FORM> static tq_status launch_invert_warp(tq_ctx *ctx, cd *d, long n_mat, int n, const WarpInvForm &F) {
+  int warps = 8;
+  while (warps > 1 && warp_inv_smem(n, warps) > (size_t)ctx->max_smem_optin / 2) warps >>= 1;
+  const size_t smem = warp_inv_smem(n, warps);
+  if (smem > (size_t)ctx->max_smem_optin) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "matrix too large for one SM's shared memory");
+  auto k = k_invert_warp<FORM>;
+  TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long blocks = std::min<long>((n_mat + warps - 1) / warps, 16L * ctx->sm_count);
+  {
+    KernelScope ks(ctx, FORM ? "dyson_invert_warp" : "invert_batched_warp");
+    k<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(d, n_mat, n, F);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  return TQ_OK;
+}
+// sum over the k-points of a slab: out[w][e] (+)= sum_k weight_k G[k][w][e], fixed order (deterministic)
+__global__ void k_dyson_slab_sum(const cd *__restrict__ g, long nk, long n_elem /* n_w n n */, const double *__restrict__ weights, long k0,
+                                 double uniform_weight, int accumulate, cd *__restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elem) return;
+  cd s = accumulate ? out[i] : cmk(0.0, 0.0);
+  for (long k = 0; k < nk; ++k) s = caxpy(weights ? __ldg(&weights[k0 + k]) : uniform_weight, g[(size_t)k * n_elem + i], s);
+  out[i] = s;
+}
+
 extern "C" tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_complex *a) {
   if (!ctx) return TQ_ERR_INVALID;
   if (!a || n < 1 || n_pts < 0) return tq_fail(ctx, TQ_ERR_INVALID, "tq_invert_batched: invalid argument");
   if (n > TQ_MAX_MATRIX_DIM) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_invert_batched: n > " + std::to_string(TQ_MAX_MATRIX_DIM));
+  static_assert(TQ_MAX_MATRIX_DIM == TQ_GENERIC_MATRIX_MAX, "header and kernel limits agree");
   if (n_pts == 0) return TQ_OK;
   TQ_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t bytes = sizeof(cd) * (size_t)n_pts * n * n;
@@ -68,6 +192,14 @@ extern "C" tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_comple
   }
   const long nb = (n_pts + 127) / 128;
   if (nb > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "tq_invert_batched: too many points");
+  if (n > 8) { // warp-per-matrix kernel
+    TQ_TRY(launch_invert_warp<false>(ctx, d, n_pts, n, WarpInvForm{}));
+    if (!dev) {
+      TQ_CUDA(ctx, cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return TQ_OK;
+  }
 #define TQ_INV_CASE(NV)                                                                                                          \
   case NV: {                                                                                                                     \
     constexpr int NN = NV * NV, STR = (NN % 2 == 0) ? NN + 1 : NN;                                                               \
@@ -197,6 +329,28 @@ extern "C" tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, doub
   TQ_TRY(tq_stage_in(ctx, sigma, sizeof(cd) * (size_t)n_w * nn, ctx->stage_in2, &d_sig));
   if (weights) TQ_TRY(tq_stage_in(ctx, weights, sizeof(double) * (size_t)n_k, ctx->stage_in3, &d_wts));
   TQ_TRY(tq_stage_out_begin(ctx, out, sizeof(cd) * (size_t)n_w * nn, ctx->stage_out, &d_out, &out_host));
+  if (n > 8) {
+    // large targets: slabs of k-points; G(k, w) of a slab is formed and inverted in a scratch of <= 256 MB (warp per matrix), then
+    // summed over k with the weights in fixed order.  The register path below never materialises G(k, w).
+    const long n_elem = n_w * nn;
+    const long slab = std::max<long>(1, std::min<long>(std::max<long>(n_k, 1), (256L << 20) / (long)(sizeof(cd) * n_elem)));
+    TQ_TRY(tq_reserve(ctx, ctx->scratch, sizeof(cd) * (size_t)slab * n_elem));
+    cd *d_g = (cd *)ctx->scratch.p;
+    if (n_k == 0) TQ_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(cd) * (size_t)n_elem, ctx->stream));
+    for (long k0 = 0; k0 < n_k; k0 += slab) {
+      const long nk = std::min(slab, n_k - k0);
+      WarpInvForm F{(const cd *)d_eps, (const cd *)d_sig, k0, (int)n_w, (int)first, statistic, beta, mu};
+      TQ_TRY(launch_invert_warp<true>(ctx, d_g, nk * n_w, n, F));
+      KernelScope ks(ctx, "dyson_slab_sum");
+      k_dyson_slab_sum<<<(unsigned)((n_elem + 127) / 128), 128, 0, ctx->stream>>>(d_g, nk, n_elem, (const double *)d_wts, k0, uniform_weight, k0 > 0,
+                                                                                 (cd *)d_out);
+      tq_count_launch(ctx);
+      TQ_CUDA(ctx, cudaGetLastError());
+    }
+    if (all_reduce) TQ_TRY(tq_all_reduce_sum(ctx, (double *)d_out, (size_t)2 * n_elem)); // sumk_discrete.py:163
+    TQ_TRY(tq_stage_out_finish(ctx, out, sizeof(cd) * (size_t)n_w * nn, d_out, out_host));
+    return TQ_OK;
+  }
   const int w_tiles = (int)((n_w + 127) / 128);
   // enough CTAs for ~4 waves of 4 CTAs/SM, but at least 64 k-points per chunk
   long want_chunks = std::max<long>(1, (4L * 4 * ctx->sm_count + w_tiles - 1) / w_tiles);

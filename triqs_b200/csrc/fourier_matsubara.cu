@@ -1069,8 +1069,19 @@ static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic,
 // pageable memory, where every cudaMemcpyAsync is a staged, host-blocking copy.  Results do not depend on the chunking:
 // every gf is transformed independently.
 // -------------------------------------------------------------------------------------------------
-template <class Fn> static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, const Fn &fn /* (lane ctx, b0, nb) */) {
-  const int want = (int)std::max<long>(1, ctx->opt_host_lanes);
+static bool is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+template <class Fn>
+static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bool pageable, const Fn &fn /* (lane ctx, b0, nb) */) {
+  // a copy from / to pageable memory is staged by the driver at the speed of ONE host core per call: more lanes, more cores
+  const int want = (int)std::max<long>(1, pageable ? std::max<long>(ctx->opt_host_lanes, std::min<long>(8, std::thread::hardware_concurrency() / 2))
+                                                   : ctx->opt_host_lanes);
   const long chunk_bytes = std::max<long>(1, ctx->opt_host_chunk_kb) << 10;
   const long per_chunk = std::max<long>(1, chunk_bytes / (long)std::max<size_t>(bytes_per_gf, 1));
   const long n_chunks = (batch + per_chunk - 1) / per_chunk;
@@ -1118,7 +1129,7 @@ extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statisti
   if (ctx && gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
       !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
     const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
-    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, [&](tq_ctx *c, long b0, long nb) {
+    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, is_pageable(gt) || is_pageable(gw), [&](tq_ctx *c, long b0, long nb) {
       return fourier_tau_to_iw_impl(c, beta, statistic, n_tau, n_iw, n_others, nb, gt + (size_t)b0 * n_tau * n_others,
                                     (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
                                     gw + (size_t)b0 * n_w * n_others, warn ? warn + b0 : nullptr, false);
@@ -1236,7 +1247,7 @@ extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statisti
   if (ctx && gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
       !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
     const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
-    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, [&](tq_ctx *c, long b0, long nb) {
+    return run_host_lanes(ctx, batch, sizeof(cd) * (size_t)n_tau * n_others, is_pageable(gt) || is_pageable(gw), [&](tq_ctx *c, long b0, long nb) {
       return fourier_iw_to_tau_impl(c, beta, statistic, n_iw, n_tau, n_others, nb, gw + (size_t)b0 * n_w * n_others,
                                     (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
                                     gt + (size_t)b0 * n_tau * n_others, warn ? warn + b0 : nullptr, tail_err ? tail_err + b0 : nullptr);

@@ -457,6 +457,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     P.tRA = T.RA;
     P.tRB = T.RB;
     P.rb_generic = T.generic ? 1 : 0;
+    P.lag0 = (int)ctx->opt_pipe_lag0;
   };
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

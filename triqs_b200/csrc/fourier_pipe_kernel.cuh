@@ -44,7 +44,7 @@ enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
 #endif
 __host__ __device__ constexpr int pipe_nbuf(int mode) { return (mode == 0 || mode == 2) ? TQ_PIPE_NBUF1 : TQ_PIPE_NBUF2; } // M_F1, M_I1 : M_F2, M_I2
 __host__ __device__ constexpr int pipe_ntab(int mode) { return pipe_nbuf(mode) + 1; } // table sets live until the end of pass B, one stage longer than the tile
-constexpr int PIPE_MAXR = 25; // largest radix of a pass
+constexpr int PIPE_MAXR = 32; // largest register radix of a pass
 // worker warps per CTA (+ 1 producer warp).  The register file is 16 K registers per SM sub-partition: 12 warps (3 per
 // sub-partition) get 168 registers per thread, 16 warps only 128 (radix 20 / 25 then spill); measured: 7 workers reach 86 %
 // of the throughput of 11, 15 workers at 128 registers are slower.
@@ -95,6 +95,7 @@ struct PipeArgs {
   long long *dbg; // developer phase timing (TQ_PHASE_DEBUG) or nullptr
   // planned (run-time radix) kernels: tile length and radix pair of THIS pass; rb_generic: pass B by direct summation
   int tN, tRA, tRB, rb_generic;
+  int lag0; // packet order of the planned kernels: 1 = A(k) B(k) | A(k+1) ..., 0 = pass B one tile behind pass A
   int f1_boxes, f1_box_rows; // F1: the tile is fetched as f1_boxes tensor boxes of f1_box_rows rows (a TMA box has <= 256 rows)
   const cd *gtw;             // [tRB] exp(+2 pi i j / tRB)   (generic pass B)
   const double4 *legtab;     // I2, generic pass B: [tRB] per-leg {E1, E2, E3, -}
@@ -143,12 +144,18 @@ template <int RB> struct PreI1 { // x = (g - tail(i w)) / beta for window rows, 
   int rb_rt = 0; // RB == 0: run-time radix
   cd a1, D23, A23;
   int q;
+  int nlo, nhi; // legs R < nlo are window rows [0, r1), legs R >= nhi window rows [r2, N); the legs between are zero
   TQ_D int rb() const { return RB ? RB : rb_rt; }
   TQ_D void begin(int qq, int c) {
     q = qq;
     a1 = coef[c];
     D23 = coef[c + tcw];
     A23 = coef[c + 2 * tcw];
+    // row = q + rb R < r1  <=>  R < ceil((r1 - q) / rb);   row >= r2  <=>  R >= ceil((r2 - q) / rb)      (one division pair per butterfly
+    // instead of two compares and an index computation per leg: most legs are zero rows)
+    const int d = rb();
+    nlo = win.r1 > q ? (win.r1 - q + d - 1) / d : 0;
+    nhi = win.r2 > q ? (win.r2 - q + d - 1) / d : 0;
   }
   // pruned pass A: leg 0 is window row q (compact index q), the last leg is window row RB + q
   TQ_D cd edge(int which, const cd *p) const {
@@ -157,12 +164,11 @@ template <int RB> struct PreI1 { // x = (g - tail(i w)) / beta for window rows, 
     return cscale(inv_beta, csub(*p, t));
   }
   template <int R> TQ_D cd load(const cd *p) const {
-    const int row = q + rb() * R;
     int idx;
-    if (row < win.r1)
-      idx = row;
-    else if (row >= win.r2)
-      idx = win.r1 + row - win.r2;
+    if (R < nlo)
+      idx = q + rb() * R;
+    else if (R >= nhi)
+      idx = win.r1 + q + rb() * R - win.r2;
     else
       return cmk(0.0, 0.0);
     const cd t = tail_iw4(wrec[2 * idx], wrec[2 * idx + 1], a1, D23, A23);
@@ -464,6 +470,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   const bool skip_guard = ((RBv * w_min + 31) >> 5) + ((RAv * w_min * bgroups + 31) >> 5) >= NW + 2 && !A.keep_guard;
   // item -> (butterfly, column) division magics of the two possible tile widths (full / last column tile)
   const unsigned m_w_full = fastdiv_magic((unsigned)TCW), m_w_last = fastdiv_magic((unsigned)(n_cols - (A.n_ct - 1) * TCW));
+  // developer phase timing (TQ_PHASE_DEBUG): compiled in only with -DTQ_DEVELOPER -- the five 64-bit accumulators and the
+  // predicated clock reads cost registers and issue slots in kernels that sit at the register limit
+#ifdef TQ_DEVELOPER
   long long t0 = clock64(), t_wait = 0, t_work = 0, t_sched = 0, t_ready = 0;
 #define TQ_LAP(acc)                                                                                                              \
   if (A.dbg && lane == 0) {                                                                                                      \
@@ -471,6 +480,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
     acc += now - t0;                                                                                                             \
     t0 = now;                                                                                                                    \
   }
+#else
+#define TQ_LAP(acc)
+#endif
 
   if (warp == NW) {
     // ===================== producer warp: TMA + per-tile pole weights =====================
@@ -588,7 +600,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       }
       int blk, r;
       bool is_b = false;
-      if (PK_LAG0) {
+      if (PLANNED ? A.lag0 != 0 : PK_LAG0) {
         // order A(0) B(0) | A(1) B(1) | ...: pass B right behind pass A of the same tile.  Its first packets wait for the last
         // pass-A packets, but the tile buffer goes back to the producer one tile period earlier, and the ring -- not the
         // arithmetic -- is what limits these kernels (buffer residency = TMA flight + pass A + pass B).  Measured, 32 blocks:
@@ -747,12 +759,14 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       }
     }
   }
+#ifdef TQ_DEVELOPER
   if (A.dbg && lane == 0) {
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp] = t_wait;
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 1] = t_work;
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 2] = t_sched;
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 3] = t_ready;
   }
+#endif
 #undef TQ_LAP
 }
 

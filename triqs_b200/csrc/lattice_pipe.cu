@@ -148,7 +148,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
         } else {
           const unsigned m_w = fastdiv_magic((unsigned)w);
 #define TQ_CALL_A(R) fft2_item_a<R, SGN, false>(tile, TC, w, RBv, twS, it, pre, m_w);
-          TQ_RADIX_SWITCH(RAv, TQ_CALL_A)
+          TQ_RADIX_SWITCH32(RAv, TQ_CALL_A)
 #undef TQ_CALL_A
         }
         __syncwarp();
@@ -164,7 +164,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
             fft2_item_b_generic<SGN>(tile, TC, w, RAv, RBv, gtwS, it, post, m_w);
           } else {
 #define TQ_CALL_B(R) fft2_item_b<R, SGN>(tile, TC, w, RAv, it, post, m_w);
-            TQ_RADIX_SWITCH(RBv, TQ_CALL_B)
+            TQ_RADIX_SWITCH32(RBv, TQ_CALL_B)
 #undef TQ_CALL_B
           }
         }
@@ -290,6 +290,6 @@ tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, cons
   // ... and the planned one for every other axis length that splits into a register radix and a second radix (register or direct
   // sum): 32, 48, 96, 100, 512, 3 2^k, primes up to 127 ...   (fourier_common.cpp:30-44: FFTW takes any length)
   TileShape T;
-  if (N < 4 || N > 1024 || !tile_shape((int)N, &T)) return TQ_OK;
+  if (N < 4 || N > 1024 || !tile_shape((int)N, &T, true)) return TQ_OK;
   return run_lat<0, 0, 0>(ctx, T, outer, inner, in, out, sign, scale, handled);
 }

@@ -108,6 +108,8 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
   const std::string n(name);
   if (n == "no_pipe")
     ctx->opt_no_pipe = value;
+  else if (n == "pipe_lag0")
+    ctx->opt_pipe_lag0 = value;
   else if (n == "force_planned")
     ctx->opt_force_planned = value;
   else if (n == "scratch_chunk_mb")

@@ -275,12 +275,34 @@ template <int SGN> struct Dft<9, SGN> {
     }
   }
 };
-// Good-Thomas prime-factor map for coprime R1, R2 (no twiddles):  n = (R2 n1 + R1 n2) mod N,  k = k1 mod R1 = k2 mod R2
-//   X[k] = sum_{n1} w_R1^{n1 k1 R2} sum_{n2} w_R2^{n2 k2 R1} x[n]:  the inner transforms see the generators w_R2^{R1}, w_R1^{R2}; to use
-//   the plain butterflies the outputs are re-labelled: inner output index j2 holds k2 = j2 R1^{-1}... done by solving k from (j1, j2)
-//   with k = (j1 R2 R2inv1 ... ) -- written out as: k = (j1 * R2 * inv(R2, R1) ... ) is avoided by the symmetric choice below:
-//   n = (R2 n1 + R1 n2) mod N  and  k = (R2 inv(R2,R1) k1 + R1 inv(R1,R2) k2) mod N   give   n k = R2 n1 k1 (R2 inv) ... = n1 k1 / R1 + n2 k2 / R2
-//   (mod 1, in units of 2 pi), i.e. plain DFT_R1 over n1 and plain DFT_R2 over n2.
+// 32 = 4 x 8 with twiddles: n = n1 + 4 n2, k = k2 + 8 k1;  u[n1][k2] = dft8_{n2}, times w32^{n1 k2}, then dft4_{n1}
+template <int SGN> struct Dft<32, SGN> {
+  static TQ_HD cd w32(int m) {
+    constexpr double W[22][2] = {{1.00000000000000000000, 0.00000000000000000000}, {0.98078528040323043058, 0.19509032201612824808}, {0.92387953251128673848, 0.38268343236508978178}, {0.83146961230254523567, 0.55557023301960217765}, {0.70710678118654757274, 0.70710678118654746172}, {0.55557023301960228867, 0.83146961230254523567}, {0.38268343236508983729, 0.92387953251128673848}, {0.19509032201612833135, 0.98078528040323043058}, {0.00000000000000006123, 1.00000000000000000000}, {-0.19509032201612819257, 0.98078528040323043058}, {-0.38268343236508972627, 0.92387953251128673848}, {-0.55557023301960195560, 0.83146961230254545772}, {-0.70710678118654746172, 0.70710678118654757274}, {-0.83146961230254534669, 0.55557023301960217765}, {-0.92387953251128673848, 0.38268343236508989280}, {-0.98078528040323043058, 0.19509032201612860891}, {-1.00000000000000000000, 0.00000000000000012246}, {-0.98078528040323043058, -0.19509032201612835911}, {-0.92387953251128684951, -0.38268343236508967076}, {-0.83146961230254545772, -0.55557023301960195560}, {-0.70710678118654768376, -0.70710678118654746172}, {-0.55557023301960217765, -0.83146961230254523567}};
+    return cmk(W[m][0], SGN * W[m][1]);
+  }
+  static TQ_HD void run(cd *a) {
+    cd u[4][8];
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) {
+      cd x[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) x[n2] = a[n1 + 4 * n2];
+      Dft<8, SGN>::run(x);
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) u[n1][k2] = (n1 == 0 || k2 == 0) ? x[k2] : cmul(x[k2], w32(n1 * k2));
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      cd x0 = u[0][k2], x1 = u[1][k2], x2 = u[2][k2], x3 = u[3][k2];
+      dft4<SGN>(x0, x1, x2, x3);
+      a[k2] = x0; a[k2 + 8] = x1; a[k2 + 16] = x2; a[k2 + 24] = x3;
+    }
+  }
+};
+// Good-Thomas prime-factor map for coprime R1, R2 (no twiddles):
+//   n = (R2 n1 + R1 n2) mod N,   k = (E1 k1 + E2 k2) mod N  with  E1 = 1 mod R1, 0 mod R2  and  E2 = 0 mod R1, 1 mod R2
+//   => n k / N = n1 k1 / R1 + n2 k2 / R2 (mod 1):  plain DFT_R1 over n1 for every n2, then plain DFT_R2 over n2 for every k1.
 constexpr int tq_modinv(int a, int m) {
   a %= m;
   for (int x = 1; x < m; ++x)

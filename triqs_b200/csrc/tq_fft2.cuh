@@ -187,9 +187,31 @@ template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(c
     case 25: CALL(25) break;                                                                                                     \
     default: break;                                                                                                              \
   }
-TQ_HD bool tq_radix_in_registers(int r) {
+// ... plus radix 32 (power-of-two lattice axes 512, 1024): its butterfly needs more than the 168 registers of the 12-warp kernels, so it
+// is offered only where the spills stay inside its own case (lattice_pipe.cu)
+#define TQ_RADIX_SWITCH32(r, CALL)                                                                                                 \
+  switch (r) {                                                                                                                   \
+    case 1: CALL(1) break;                                                                                                       \
+    case 2: CALL(2) break;                                                                                                       \
+    case 3: CALL(3) break;                                                                                                       \
+    case 4: CALL(4) break;                                                                                                       \
+    case 5: CALL(5) break;                                                                                                       \
+    case 6: CALL(6) break;                                                                                                       \
+    case 7: CALL(7) break;                                                                                                       \
+    case 8: CALL(8) break;                                                                                                       \
+    case 9: CALL(9) break;                                                                                                       \
+    case 10: CALL(10) break;                                                                                                     \
+    case 12: CALL(12) break;                                                                                                     \
+    case 15: CALL(15) break;                                                                                                     \
+    case 16: CALL(16) break;                                                                                                     \
+    case 20: CALL(20) break;                                                                                                     \
+    case 25: CALL(25) break;                                                                                                     \
+    case 32: CALL(32) break;                                                                                                     \
+    default: break;                                                                                                              \
+  }
+TQ_HD bool tq_radix_in_registers(int r, bool allow32 = false) {
   return r == 1 || r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 7 || r == 8 || r == 9 || r == 10 || r == 12 || r == 15 || r == 16 ||
-         r == 20 || r == 25;
+         r == 20 || r == 25 || (allow32 && r == 32);
 }
 
 template <int RA, int SGN, bool TW0, class Pre, class Hook = NoHook>

@@ -93,22 +93,23 @@ struct TileShape {
   double cost = 0; // ~ FP64 work per element relative to a register radix pass
 };
 constexpr int PIPE_MAX_GENERIC = 127;   // largest radix of the direct-sum pass B
-static const int kRegRadix[] = {25, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
+static const int kRegRadix[] = {32, 25, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
 
-static inline bool tile_shape(int N, TileShape *out) {
+static inline bool tile_shape(int N, TileShape *out, bool allow32 = false) {
   bool found = false;
   TileShape best;
   for (int ra : kRegRadix) {
-    if (N % ra) continue;
+    if (N % ra || (ra == 32 && !allow32)) continue;
     const int rb = N / ra;
     TileShape t;
     t.N = N;
     t.RA = ra;
     t.RB = rb;
-    if (tq_radix_in_registers(rb)) {
+    if (tq_radix_in_registers(rb, allow32)) {
       t.generic = false;
       // per-element work of a register pass grows slowly with the radix; two balanced passes beat a long and a trivial one
-      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.02 * std::abs(ra - rb);
+      // (a pass has RB x columns (A) / RA x columns (B) butterflies to spread over the warps: a lopsided pair starves one of them)
+      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.05 * std::abs(ra - rb);
     } else if (rb <= PIPE_MAX_GENERIC) {
       t.generic = true;
       t.cost = (ra == 1 ? 0.35 : 1.0) + 0.5 + rb / 9.0; // 4 rb FP64 instructions per element against ~40 for a register pass
