@@ -261,6 +261,14 @@ tq_status tq_dyson_ksum(tq_ctx *ctx, int n, long n_k, long n_iw, double beta, in
 tq_status tq_interp_tau(tq_ctx *ctx, double beta, long n_tau, long n_elem, const tq_complex *table, long n_pts, const double *taus,
                         tq_complex *out);
 
+/* Replaces  gf_evaluator<imfreq>::operator()(g, matsubara_freq)  c++/triqs/gfs/evaluator.hpp:47-75, batched: g(i w_n) for arbitrary
+ * Matsubara indices ns[n_pts] -- the mesh value inside the window, the fitted tail  sum_p A_p / (i w_n)^p  outside (one default
+ * fit_tail per gf, tail_fitter.hpp:92,95; the reference refits on every call).
+ *   g [batch][n_w][n_cols] on the full mesh, ns long[n_pts] (host or device), out [batch][n_pts][n_cols],
+ *   tail_err host double[batch] or NULL (0 when every index is inside the mesh and no fit was made). */
+tq_status tq_evaluate_imfreq(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_cols, long batch, const tq_complex *g, long n_pts,
+                             const long *ns, tq_complex *out, double *tail_err);
+
 /* ---- multi-GPU (one process per GPU; replaces mpi::all_reduce of gf data, c++/triqs/gfs/gf/gf.hpp:347-351) --- */
 
 #define TQ_COMM_ID_BYTES 128

@@ -232,6 +232,16 @@ def test_imfreq_evaluator_uses_the_tail_outside_the_mesh():
         ref = O.tail_eval(tail, iw).reshape(2, 2)
         assert np.max(np.abs(g(n) - ref)) < 1e-10
         assert np.max(np.abs(g(n) - exact)) < 1e-6
+    # batched: many indices in one call (tq_evaluate_imfreq), inside and outside the window
+    ns = np.array([-3 * n_iw, -n_iw - 1, -n_iw, -1, 0, 5, n_iw - 1, n_iw, n_iw + 10, 5000])
+    vals = g(ns)
+    tail, _ = O.fit_tail(g.flat(), beta, O.FERMION)
+    for i, n in enumerate(ns):
+        if -n_iw <= n <= n_iw - 1:
+            assert np.array_equal(vals[i], d[n + n_iw])
+        else:
+            ref = O.tail_eval(tail, 1j * np.pi * (2 * n + 1) / beta).reshape(2, 2)
+            assert np.max(np.abs(vals[i] - ref)) < 1e-10
 
 
 def test_torch_producer_and_consumer_need_no_manual_sync():

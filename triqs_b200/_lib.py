@@ -64,6 +64,7 @@ SIGNATURES = {
     "tq_dyson_ksum": (c_int, [c_void_p, c_int, c_long, c_long, c_double, c_int, c_double, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                               c_int]),
     "tq_interp_tau": (c_int, [c_void_p, c_double, c_long, c_long, c_void_p, c_long, c_void_p, c_void_p]),
+    "tq_evaluate_imfreq": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_void_p, c_long, c_void_p, c_void_p, POINTER(c_double)]),
     "tq_comm_unique_id": (c_int, [c_void_p]),
     "tq_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "tq_all_reduce_sum": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -430,6 +430,19 @@ class Context:
         self._check(self._run("tq_interp_tau", beta, n_tau, n_elem, _ptr(table), n_pts, _ptr(taus), _ptr(y)))
         return y
 
+    def evaluate_imfreq(self, g, beta, statistic, ns, out=None, return_err=False):
+        """g [batch, n_w, n_cols] (full mesh), ns: Matsubara indices (ints, any range) -> [batch, len(ns), n_cols]  (tq_evaluate_imfreq)."""
+        g = _as_c128(g)
+        batch, n_w, n_cols = g.shape
+        n_iw = n_w // 2 if statistic == FERMION else (n_w + 1) // 2
+        ns = np.ascontiguousarray(np.asarray(ns, dtype=np.int64).reshape(-1))
+        res = out if out is not None else _empty_like_kind(g, (batch, len(ns), n_cols))
+        err = (ctypes.c_double * batch)()
+        self._check(self._run("tq_evaluate_imfreq", beta, statistic, n_iw, n_cols, batch, _ptr(g), len(ns), _ptr(ns), _ptr(res), err))
+        if return_err:
+            return res, np.frombuffer(err, dtype=np.float64).copy()
+        return res
+
     # -- multi GPU ---------------------------------------------------------------------------------
     def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
         buf = (ctypes.c_ubyte * L.TQ_COMM_ID_BYTES).from_buffer_copy(unique_id)

@@ -140,3 +140,83 @@ extern "C" tq_status tq_replace_by_tail(tq_ctx *ctx, double beta, int statistic,
   }
   return TQ_OK;
 }
+
+
+// -------------------------------------------------------------------------------------------------
+// gf_evaluator<imfreq>   c++/triqs/gfs/evaluator.hpp:47-75:  g(i w_n) for ANY Matsubara index n -- the mesh value inside the window,
+// the fitted high-frequency tail  sum_p A_p / (i w_n)^p  outside (fit_tail_no_normalize with x = |w_max| / i w is the same sum).
+// Batched: one fit per gf (the reference refits on every call), then one thread per (point, column).
+// -------------------------------------------------------------------------------------------------
+tq_status tq_fit_tail_device(tq_ctx *ctx, double beta, int statistic, long n_iw, double tail_fraction, int n_tail_max, int expansion_order,
+                             int hermitian, int inner_dim, long n_cols, long batch, const cd *d_g, const cd *d_known, int n_known,
+                             cd *d_out_moments, int *n_moments, double *d_err);
+
+__global__ void k_eval_imfreq(const cd *__restrict__ g, const cd *__restrict__ tail, int n_moments, long n_w, int n_cols, long n_pts,
+                              const long *__restrict__ ns, long total, double beta, int stat, long first, cd *__restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long q = i / n_cols;
+  const int c = (int)(i - q * n_cols);
+  const long gf = q / n_pts, p = q - gf * n_pts;
+  const long n = ns[p];
+  if (n >= first && n < first + n_w) {
+    out[i] = g[((size_t)gf * n_w + (n - first)) * n_cols + c];
+    return;
+  }
+  const double w = M_PI * (double)(2 * n + stat) / beta; // matsubara.hpp:55
+  const cd *t = tail + (size_t)gf * n_moments * n_cols + c; // (tq_fit_tail_device: dense [batch][n_moments][n_cols])
+  cd z = cmk(1.0, 0.0), res = cmk(0.0, 0.0);
+  for (int m = 0; m < n_moments; ++m) {
+    res = cfma(t[(size_t)m * n_cols], z, res);
+    z = cmk(z.y / w, -z.x / w); // z / (i w)
+  }
+  out[i] = res;
+}
+
+extern "C" tq_status tq_evaluate_imfreq(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_cols, long batch, const tq_complex *g, long n_pts,
+                                        const long *ns, tq_complex *out, double *tail_err) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!g || !out || !ns || n_iw < 1 || n_cols < 1 || batch < 1 || n_pts < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_evaluate_imfreq: invalid argument");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long last = n_iw - 1, first = -(last + (statistic == TQ_FERMION ? 1 : 0)), n_w = last - first + 1;
+  const void *d_g = nullptr, *d_ns = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  TQ_TRY(tq_stage_in(ctx, g, sizeof(cd) * (size_t)batch * n_w * n_cols, ctx->stage_in, &d_g));
+  TQ_TRY(tq_stage_in(ctx, ns, sizeof(long) * (size_t)n_pts, ctx->stage_in2, &d_ns));
+  TQ_TRY(tq_stage_out_begin(ctx, out, sizeof(cd) * (size_t)batch * n_pts * n_cols, ctx->stage_out, &d_out, &out_host));
+  bool outside = true; // host-visible indices: fit only when a point lies outside the mesh
+  if (!tq_is_device_ptr(ns)) {
+    outside = false;
+    for (long p = 0; p < n_pts; ++p) outside |= (ns[p] < first || ns[p] > last);
+  }
+  const size_t mom_bytes = sizeof(cd) * (size_t)batch * TQ_MAX_MOMENTS * n_cols;
+  const size_t err_off = (mom_bytes + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->leg_tmp, err_off + sizeof(double) * batch));
+  cd *d_mom = (cd *)ctx->leg_tmp.p;
+  double *d_err = (double *)((char *)ctx->leg_tmp.p + err_off);
+  int n_moments = 0;
+  if (outside) {
+    TQ_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(double) * batch, ctx->stream));
+    TQ_TRY(tq_fit_tail_device(ctx, beta, statistic, n_iw, 0.2, 30, -1, 0, 1, n_cols, batch, (const cd *)d_g, nullptr, 0, d_mom, &n_moments, d_err));
+  }
+  const long total = batch * n_pts * n_cols;
+  {
+    KernelScope ks(ctx, "evaluate_imfreq");
+    k_eval_imfreq<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_g, d_mom, n_moments, n_w, (int)n_cols, n_pts, (const long *)d_ns,
+                                                                           total, beta, statistic, first, (cd *)d_out);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  if (tail_err) {
+    if (outside) {
+      TQ_CUDA(ctx, cudaMemcpyAsync(tail_err, d_err, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+      TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+      for (long b = 0; b < batch; ++b) tail_err[b] = 0.0;
+    }
+  }
+  TQ_TRY(tq_stage_out_finish(ctx, out, sizeof(cd) * (size_t)batch * n_pts * n_cols, d_out, out_host));
+  return TQ_OK;
+}

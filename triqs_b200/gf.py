@@ -212,8 +212,12 @@ class Gf:
         """off-mesh evaluation: linear interpolation on an imtime mesh (c++/triqs/gfs/evaluator.hpp:35-43; a scalar or an array
         of tau), or g(n) on an imfreq mesh -- the mesh value inside the window, the fitted tail outside (evaluator.hpp:50-76)."""
         if isinstance(self.mesh, MeshImFreq):
-            n = int(tau)
             m = self.mesh
+            if not np.isscalar(tau):  # an array of Matsubara indices: one batched call (tq_evaluate_imfreq)
+                ns = np.asarray(tau, dtype=np.int64).reshape(-1)
+                out = self.ctx.evaluate_imfreq(self.flat()[None], m.beta, m.statistic, ns)[0]
+                return out.reshape((len(ns),) + tuple(self.target_shape))
+            n = int(tau)
             if m.first_index <= n <= m.last_index:
                 return self.data[n - m.first_index]
             tail, _ = fit_tail(self)  # moments A_p: g = sum_p A_p / (i w)^p  (fit_tail_no_normalize with x = |w_max| / i w is the same sum)
@@ -497,3 +501,19 @@ def dyson_k_sum(ctx: Context, eps_k, sigma: Gf, mu: float, weights=None, rank: i
     if reduce_fn is not None and n_ranks > 1:
         part = reduce_fn(part)
     return Gf(sigma.mesh, sigma.target_shape, part.reshape((len(sigma.mesh),) + sigma.target_shape), ctx)
+
+
+# ---------------------------------------------------------------------------------------------
+# HDF5 archives (c++/triqs/gfs/h5.hpp:72-91; mesh groups imfreq.hpp:261-292, imtime.hpp:83-106, brzone.hpp:311-343, prod.hpp:179-195)
+# ---------------------------------------------------------------------------------------------
+def h5_write(path, **objects):
+    """h5_write("file.h5", G=g, Sigma=bg): one group per object with the reference's layout (Format tags "Gf" / "BlockGf",
+    `data` with the __complex__ attribute, `mesh` sub-group).  No libhdf5 needed (triqs_b200/h5lite.py)."""
+    from . import h5lite
+    h5lite.write_gf(path, objects)
+
+
+def h5_read(path, name=None, ctx=None):
+    """-> the Gf / BlockGf stored under `name`, or a dict of all of them; reads archives written by TRIQS itself."""
+    from . import h5lite
+    return h5lite.read_gf(path, name, ctx)
