@@ -104,7 +104,7 @@ template <int SGN> static int run_fft2_rt(int RA, int RB, int generic, int tcw, 
   if (!tq_radix_in_registers(RA, true)) return -1;
   for (int item = 0; item < RB * tcw + 5; ++item) {
 #define CALL_A(R) fft2_item_a<R, SGN, false>(s.data(), pitch, tcw, RB, tw.data(), item, pre, magic);
-    TQ_RADIX_SWITCH32(RA, CALL_A)
+    TQ_RADIX_SWITCH_X(RA, CALL_A)
 #undef CALL_A
   }
   for (int item = 0; item < RA * tcw * (generic ? fft2_generic_groups(RB) : 1) + 5; ++item) {
@@ -113,7 +113,7 @@ template <int SGN> static int run_fft2_rt(int RA, int RB, int generic, int tcw, 
     } else {
       if (!tq_radix_in_registers(RB, true)) return -1;
 #define CALL_B(R) fft2_item_b<R, SGN>(s.data(), pitch, tcw, RA, item, post, magic);
-      TQ_RADIX_SWITCH32(RB, CALL_B)
+      TQ_RADIX_SWITCH_X(RB, CALL_B)
 #undef CALL_B
     }
   }

@@ -108,7 +108,7 @@ def test_register_inverse_threshold_no_interchange(lib, n):
     assert np.all(err < 1e-15 * 200 * np.linalg.cond(a[acc]))
 
 
-REG_RADICES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 20, 25, 32]
+REG_RADICES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 20, 25, 32, 41]
 
 
 @pytest.mark.parametrize("RA", REG_RADICES)

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --fmad=true"
 OUT=../libtqgpu.so
-SRCS="tq_ctx.cu tq_fft_plan.cu fourier_matsubara.cu fourier_pipe.cu fourier_pipe_planned0.cu fourier_pipe_planned1.cu fourier_pipe_planned2.cu fourier_pipe_planned3.cu fourier_col.cu tail_fit.cu lattice.cu lattice_pipe.cu dyson.cu interp.cu imfreq_ops.cu tight_binding.cu fourier_real.cu legendre.cu"
+SRCS="tq_ctx.cu tq_fft_plan.cu fourier_matsubara.cu fourier_pipe.cu fourier_pipe_planned0.cu fourier_pipe_planned1.cu fourier_pipe_planned2.cu fourier_pipe_planned3.cu fourier_pipe_heavy0.cu fourier_pipe_heavy1.cu fourier_pipe_heavy2.cu fourier_pipe_heavy3.cu fourier_col.cu tail_fit.cu lattice.cu lattice_pipe.cu dyson.cu interp.cu imfreq_ops.cu tight_binding.cu fourier_real.cu legendre.cu"
 mkdir -p build
 pids=()
 for s in $SRCS; do

@@ -2,17 +2,20 @@
 // tensor maps and launches.  The kernels are in fourier_pipe_kernel.cuh.
 #include "fourier_pipe_kernel.cuh"
 
-// fourier_pipe_planned{0..3}.cu: the run-time-radix instantiation of each mode (one translation unit per mode)
-tq_status tq_launch_pipe_planned_m0(tq_ctx *, const PipeArgs &, const CUtensorMap &, const CUtensorMap &, const char *);
-tq_status tq_launch_pipe_planned_m1(tq_ctx *, const PipeArgs &, const CUtensorMap &, const CUtensorMap &, const char *);
-tq_status tq_launch_pipe_planned_m2(tq_ctx *, const PipeArgs &, const CUtensorMap &, const CUtensorMap &, const char *);
-tq_status tq_launch_pipe_planned_m3(tq_ctx *, const PipeArgs &, const CUtensorMap &, const CUtensorMap &, const char *);
-static tq_status tq_launch_pipe_planned(tq_ctx *ctx, int mode, const PipeArgs &A, const CUtensorMap &t1, const CUtensorMap &t2, const char *tag) {
+// fourier_pipe_planned{0..3}.cu / fourier_pipe_heavy{0..3}.cu: the run-time-radix instantiations of each mode with the base / the
+// extended radix set (one translation unit each)
+#define TQ_DECL_PLANNED(name) tq_status name(tq_ctx *, const PipeArgs &, const CUtensorMap &, const CUtensorMap &, const char *);
+TQ_DECL_PLANNED(tq_launch_pipe_planned_m0) TQ_DECL_PLANNED(tq_launch_pipe_planned_m1) TQ_DECL_PLANNED(tq_launch_pipe_planned_m2)
+TQ_DECL_PLANNED(tq_launch_pipe_planned_m3) TQ_DECL_PLANNED(tq_launch_pipe_heavy_m0) TQ_DECL_PLANNED(tq_launch_pipe_heavy_m1)
+TQ_DECL_PLANNED(tq_launch_pipe_heavy_m2) TQ_DECL_PLANNED(tq_launch_pipe_heavy_m3)
+#undef TQ_DECL_PLANNED
+static tq_status tq_launch_pipe_planned(tq_ctx *ctx, int mode, bool heavy, const PipeArgs &A, const CUtensorMap &t1, const CUtensorMap &t2,
+                                        const char *tag) {
   switch (mode) {
-    case M_F1: return tq_launch_pipe_planned_m0(ctx, A, t1, t2, tag);
-    case M_F2: return tq_launch_pipe_planned_m1(ctx, A, t1, t2, tag);
-    case M_I1: return tq_launch_pipe_planned_m2(ctx, A, t1, t2, tag);
-    default: return tq_launch_pipe_planned_m3(ctx, A, t1, t2, tag);
+    case M_F1: return heavy ? tq_launch_pipe_heavy_m0(ctx, A, t1, t2, tag) : tq_launch_pipe_planned_m0(ctx, A, t1, t2, tag);
+    case M_F2: return heavy ? tq_launch_pipe_heavy_m1(ctx, A, t1, t2, tag) : tq_launch_pipe_planned_m1(ctx, A, t1, t2, tag);
+    case M_I1: return heavy ? tq_launch_pipe_heavy_m2(ctx, A, t1, t2, tag) : tq_launch_pipe_planned_m2(ctx, A, t1, t2, tag);
+    default: return heavy ? tq_launch_pipe_heavy_m3(ctx, A, t1, t2, tag) : tq_launch_pipe_planned_m3(ctx, A, t1, t2, tag);
   }
 }
 
@@ -137,8 +140,8 @@ static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2) {
   if (L == 100000) { // the headline mesh keeps its tuned, fully compile-time kernels
     tile_shape(250, t1);
     tile_shape(400, t2);
-    *t1 = TileShape{250, 10, 25, false, 2.0};
-    *t2 = TileShape{400, 20, 20, false, 2.0};
+    *t1 = TileShape{250, 10, 25, false, false, 2.0};
+    *t2 = TileShape{400, 20, 20, false, false, 2.0};
     return true;
   }
   bool found = false;
@@ -494,8 +497,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
         TQ_TRY((launch_pipe<M_F1, 250, 10, 25, TQ_NW_F1>(ctx, P1, tmap, tmap2, "tau2iw_pass1")));
         TQ_TRY((launch_pipe<M_F2, 400, 20, 20, TQ_NW_F2>(ctx, P2, tmap, tmap2, "tau2iw_pass2")));
       } else {
-        TQ_TRY(tq_launch_pipe_planned(ctx, M_F1, P1, tmap, tmap2, "tau2iw_pass1"));
-        TQ_TRY(tq_launch_pipe_planned(ctx, M_F2, P2, tmap, tmap2, "tau2iw_pass2"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_F1, T1.heavy, P1, tmap, tmap2, "tau2iw_pass1"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_F2, T2.heavy, P2, tmap, tmap2, "tau2iw_pass2"));
       }
     } else {
       set_mode(P1, M_I1);
@@ -514,8 +517,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
         TQ_TRY((launch_pipe<M_I1, 250, 10, 25, TQ_NW_I1>(ctx, P1, tmap, tmap2, "iw2tau_pass1")));
         TQ_TRY((launch_pipe<M_I2, 400, 20, 20, TQ_NW_I2>(ctx, P2, tmap, tmap2, "iw2tau_pass2")));
       } else {
-        TQ_TRY(tq_launch_pipe_planned(ctx, M_I1, P1, tmap, tmap2, "iw2tau_pass1"));
-        TQ_TRY(tq_launch_pipe_planned(ctx, M_I2, P2, tmap, tmap2, "iw2tau_pass2"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_I1, T1.heavy, P1, tmap, tmap2, "iw2tau_pass1"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_I2, T2.heavy, P2, tmap, tmap2, "iw2tau_pass2"));
       }
     }
   }

@@ -44,7 +44,7 @@ enum { M_F1 = 0, M_F2 = 1, M_I1 = 2, M_I2 = 3 };
 #endif
 __host__ __device__ constexpr int pipe_nbuf(int mode) { return (mode == 0 || mode == 2) ? TQ_PIPE_NBUF1 : TQ_PIPE_NBUF2; } // M_F1, M_I1 : M_F2, M_I2
 __host__ __device__ constexpr int pipe_ntab(int mode) { return pipe_nbuf(mode) + 1; } // table sets live until the end of pass B, one stage longer than the tile
-constexpr int PIPE_MAXR = 32; // largest register radix of a pass
+constexpr int PIPE_MAXR = 41; // largest register radix of a pass
 // worker warps per CTA (+ 1 producer warp).  The register file is 16 K registers per SM sub-partition: 12 warps (3 per
 // sub-partition) get 168 registers per thread, 16 warps only 128 (radix 20 / 25 then spill); measured: 7 workers reach 86 %
 // of the throughput of 11, 15 workers at 128 registers are slower.
@@ -378,7 +378,7 @@ struct TileDecoder {
   }
 };
 
-template <int MODE, int N, int RA, int RB, int NW>
+template <int MODE, int N, int RA, int RB, int NW, int SET = 0>
 __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_pipe_kernel(const __grid_constant__ PipeArgs A,
                                                                                              const __grid_constant__ CUtensorMap tmap,
                                                                                              const __grid_constant__ CUtensorMap tmap2) {
@@ -664,7 +664,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           fft2_pass_a<N, RA, RB, SGN, TW0>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w, fetch_next);
         } else {
 #define TQ_CALL_A(R) fft2_item_a<R, SGN, TW0>(tile, pitch, id.w, RBv, twS, it, pre, m_w, fetch_next);
-          TQ_RADIX_SWITCH(RAv, TQ_CALL_A)
+          if constexpr (SET == 1) {
+            TQ_RADIX_SWITCH_X(RAv, TQ_CALL_A)
+          } else {
+            TQ_RADIX_SWITCH(RAv, TQ_CALL_A)
+          }
 #undef TQ_CALL_A
         }
       };
@@ -675,7 +679,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           fft2_item_b_generic<SGN>(tile, pitch, id.w, RAv, RBv, gtwS, it, post, m_w, hook);
         } else {
 #define TQ_CALL_B(R) fft2_item_b<R, SGN>(tile, pitch, id.w, RAv, it, post, m_w, hook);
-          TQ_RADIX_SWITCH(RBv, TQ_CALL_B)
+          if constexpr (SET == 1) {
+            TQ_RADIX_SWITCH_X(RBv, TQ_CALL_B)
+          } else {
+            TQ_RADIX_SWITCH(RBv, TQ_CALL_B)
+          }
 #undef TQ_CALL_B
         }
       };
@@ -770,11 +778,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #undef TQ_LAP
 }
 
-template <int MODE, int N, int RA, int RB, int NW>
+template <int MODE, int N, int RA, int RB, int NW, int SET = 0>
 static tq_status launch_pipe(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &tmap, const CUtensorMap &tmap2, const char *tag) {
   constexpr int NT = (NW + 1) * 32;
   const size_t smem = PipeSmem<MODE>(N ? N : A.tN, RA ? RA : A.tRA, RB ? RB : A.tRB, A.tcw, A.pitch, A.wmax, N ? 0 : A.rb_generic).total;
-  auto k = matsubara_pipe_kernel<MODE, N, RA, RB, NW>;
+  auto k = matsubara_pipe_kernel<MODE, N, RA, RB, NW, SET>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
   static const bool phase_debug = TQ_DEV_ENV("TQ_PHASE_DEBUG") != nullptr;

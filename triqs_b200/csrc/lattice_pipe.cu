@@ -48,7 +48,7 @@ template <int N, int RA> struct PostLattice {
   }
 };
 
-template <int N, int RA, int RB, int SGN, int NW>
+template <int N, int RA, int RB, int SGN, int NW, int SET = 0>
 __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pipe_kernel(const __grid_constant__ LatPipeArgs A,
                                                                                            const __grid_constant__ CUtensorMap tmap) {
   constexpr int NT = (NW + 1) * 32;
@@ -148,7 +148,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
         } else {
           const unsigned m_w = fastdiv_magic((unsigned)w);
 #define TQ_CALL_A(R) fft2_item_a<R, SGN, false>(tile, TC, w, RBv, twS, it, pre, m_w);
-          TQ_RADIX_SWITCH32(RAv, TQ_CALL_A)
+          if constexpr (SET == 1) {
+            TQ_RADIX_SWITCH_X(RAv, TQ_CALL_A)
+          } else {
+            TQ_RADIX_SWITCH32(RAv, TQ_CALL_A)
+          }
 #undef TQ_CALL_A
         }
         __syncwarp();
@@ -164,7 +168,11 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
             fft2_item_b_generic<SGN>(tile, TC, w, RAv, RBv, gtwS, it, post, m_w);
           } else {
 #define TQ_CALL_B(R) fft2_item_b<R, SGN>(tile, TC, w, RAv, it, post, m_w);
-            TQ_RADIX_SWITCH32(RBv, TQ_CALL_B)
+            if constexpr (SET == 1) {
+              TQ_RADIX_SWITCH_X(RBv, TQ_CALL_B)
+            } else {
+              TQ_RADIX_SWITCH32(RBv, TQ_CALL_B)
+            }
 #undef TQ_CALL_B
           }
         }
@@ -190,10 +198,10 @@ static size_t lat_smem_bytes(int N, int RB, bool generic, long tc) {
   const size_t buf_stride = (sizeof(cd) * (size_t)N * tc + 127) & ~size_t(127);
   return LP_NBUF * buf_stride + sizeof(cd) * (N + (generic ? RB : 0)) + 8 * 3 * LP_NBUF + 16;
 }
-template <int N, int RA, int RB, int SGN> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
+template <int N, int RA, int RB, int SGN, int SET = 0> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
   constexpr int NW = 11;
   const size_t smem = lat_smem_bytes(N ? N : A.tN, N ? RB : A.tRB, N ? false : A.rb_generic != 0, A.TC);
-  auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW>;
+  auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW, SET>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
   {
@@ -206,7 +214,7 @@ template <int N, int RA, int RB, int SGN> static tq_status launch_lat(tq_ctx *ct
 }
 
 // N0 / RA0 / RB0 = 0: the planned instantiation with the run-time shape T
-template <int N0, int RA0, int RB0>
+template <int N0, int RA0, int RB0, int SET = 0>
 static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
   const int N = T.N, RA = T.RA, RB = T.RB;
   const size_t budget = (size_t)ctx->max_smem_optin - sizeof(cd) * (N + RB) - 256;
@@ -269,9 +277,9 @@ static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner
   }
   if (A.n_tiles >= (1L << 31)) return TQ_OK;
   if (sign > 0)
-    TQ_TRY((launch_lat<N0, RA0, RB0, 1>(ctx, A, tmap)));
+    TQ_TRY((launch_lat<N0, RA0, RB0, 1, SET>(ctx, A, tmap)));
   else
-    TQ_TRY((launch_lat<N0, RA0, RB0, -1>(ctx, A, tmap)));
+    TQ_TRY((launch_lat<N0, RA0, RB0, -1, SET>(ctx, A, tmap)));
   *handled = true;
   return TQ_OK;
 }
@@ -282,14 +290,17 @@ tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, cons
   if (ctx->opt_no_pipe) return TQ_OK;
   // compile-time instantiations of the benchmark shapes (256 = 16 x 16, 128 = 8 x 16, 64 = 8 x 8) ...
   switch (N) {
-    case 256: return run_lat<256, 16, 16>(ctx, TileShape{256, 16, 16, false, 2.0}, outer, inner, in, out, sign, scale, handled);
-    case 128: return run_lat<128, 8, 16>(ctx, TileShape{128, 8, 16, false, 2.0}, outer, inner, in, out, sign, scale, handled);
-    case 64: return run_lat<64, 8, 8>(ctx, TileShape{64, 8, 8, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    case 256: return run_lat<256, 16, 16>(ctx, TileShape{256, 16, 16, false, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    case 128: return run_lat<128, 8, 16>(ctx, TileShape{128, 8, 16, false, false, 2.0}, outer, inner, in, out, sign, scale, handled);
+    case 64: return run_lat<64, 8, 8>(ctx, TileShape{64, 8, 8, false, false, 2.0}, outer, inner, in, out, sign, scale, handled);
     default: break;
   }
   // ... and the planned one for every other axis length that splits into a register radix and a second radix (register or direct
   // sum): 32, 48, 96, 100, 512, 3 2^k, primes up to 127 ...   (fourier_common.cpp:30-44: FFTW takes any length)
   TileShape T;
   if (N < 4 || N > 1024 || !tile_shape((int)N, &T, true)) return TQ_OK;
-  return run_lat<0, 0, 0>(ctx, T, outer, inner, in, out, sign, scale, handled);
+  // (the Rader primes 11, 13, 17, 41 live in their own instantiation: their spills stay out of the kernel the smooth axes use)
+  const bool primes = T.heavy && (T.RA != 32 && T.RB != 32 ? true : (tq_radix_is_heavy(T.RA) && T.RA != 32) || (tq_radix_is_heavy(T.RB) && T.RB != 32));
+  if (primes) return run_lat<0, 0, 0, 1>(ctx, T, outer, inner, in, out, sign, scale, handled);
+  return run_lat<0, 0, 0, 0>(ctx, T, outer, inner, in, out, sign, scale, handled);
 }

@@ -16,6 +16,7 @@
 // __host__ __device__ so tests/hostsim can run the same code on the CPU box.
 #pragma once
 #include "tq_fft.cuh"
+#include "tq_fft_rader.cuh"
 
 
 // compile-time loops (the functors take the butterfly leg as a template argument so that per-leg constants
@@ -187,8 +188,7 @@ template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(c
     case 25: CALL(25) break;                                                                                                     \
     default: break;                                                                                                              \
   }
-// ... plus radix 32 (power-of-two lattice axes 512, 1024): its butterfly needs more than the 168 registers of the 12-warp kernels, so it
-// is offered only where the spills stay inside its own case (lattice_pipe.cu)
+// base set + radix 32: the default instantiation of the lattice kernel (power-of-two axes 512, 1024)
 #define TQ_RADIX_SWITCH32(r, CALL)                                                                                                 \
   switch (r) {                                                                                                                   \
     case 1: CALL(1) break;                                                                                                       \
@@ -209,9 +209,37 @@ template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(c
     case 32: CALL(32) break;                                                                                                     \
     default: break;                                                                                                              \
   }
-TQ_HD bool tq_radix_in_registers(int r, bool allow32 = false) {
+// ... plus the "heavy" radices: 32 (power-of-two lattice axes 512, 1024) and the primes 11, 13, 17, 41 by Rader's algorithm
+// (tq_fft_rader.cuh; 41 | 6150, the default Python mesh).  Their butterflies need more than the 168 registers of the 12-warp
+// kernels, so they live in separate kernel instantiations (SET = 1): the spills stay out of the kernels every smooth length uses.
+#define TQ_RADIX_SWITCH_X(r, CALL)                                                                                               \
+  switch (r) {                                                                                                                   \
+    case 1: CALL(1) break;                                                                                                       \
+    case 2: CALL(2) break;                                                                                                       \
+    case 3: CALL(3) break;                                                                                                       \
+    case 4: CALL(4) break;                                                                                                       \
+    case 5: CALL(5) break;                                                                                                       \
+    case 6: CALL(6) break;                                                                                                       \
+    case 7: CALL(7) break;                                                                                                       \
+    case 8: CALL(8) break;                                                                                                       \
+    case 9: CALL(9) break;                                                                                                       \
+    case 10: CALL(10) break;                                                                                                     \
+    case 11: CALL(11) break;                                                                                                     \
+    case 12: CALL(12) break;                                                                                                     \
+    case 13: CALL(13) break;                                                                                                     \
+    case 15: CALL(15) break;                                                                                                     \
+    case 16: CALL(16) break;                                                                                                     \
+    case 17: CALL(17) break;                                                                                                     \
+    case 20: CALL(20) break;                                                                                                     \
+    case 25: CALL(25) break;                                                                                                     \
+    case 32: CALL(32) break;                                                                                                     \
+    case 41: CALL(41) break;                                                                                                     \
+    default: break;                                                                                                              \
+  }
+TQ_HD bool tq_radix_is_heavy(int r) { return r == 11 || r == 13 || r == 17 || r == 32 || r == 41; }
+TQ_HD bool tq_radix_in_registers(int r, bool allow_heavy = false) {
   return r == 1 || r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 7 || r == 8 || r == 9 || r == 10 || r == 12 || r == 15 || r == 16 ||
-         r == 20 || r == 25 || (allow32 && r == 32);
+         r == 20 || r == 25 || (allow_heavy && tq_radix_is_heavy(r));
 }
 
 template <int RA, int SGN, bool TW0, class Pre, class Hook = NoHook>

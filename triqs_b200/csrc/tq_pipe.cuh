@@ -90,28 +90,37 @@ static inline EncodeTiledFn get_encode_tiled() {
 struct TileShape {
   int N = 0, RA = 0, RB = 0;
   bool generic = false;
+  bool heavy = false; // uses a radix of the extended set (tq_fft2.cuh TQ_RADIX_SWITCH_X): separate kernel instantiation
   double cost = 0; // ~ FP64 work per element relative to a register radix pass
 };
 constexpr int PIPE_MAX_GENERIC = 127;   // largest radix of the direct-sum pass B
-static const int kRegRadix[] = {32, 25, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
+static const int kRegRadix[] = {41, 32, 25, 20, 17, 16, 15, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1};
 
-static inline bool tile_shape(int N, TileShape *out, bool allow32 = false) {
+static inline bool tile_shape(int N, TileShape *out, bool allow_heavy = true) {
   bool found = false;
   TileShape best;
   for (int ra : kRegRadix) {
-    if (N % ra || (ra == 32 && !allow32)) continue;
+    if (N % ra || (tq_radix_is_heavy(ra) && !allow_heavy)) continue;
     const int rb = N / ra;
     TileShape t;
     t.N = N;
     t.RA = ra;
     t.RB = rb;
-    if (tq_radix_in_registers(rb, allow32)) {
+    if (tq_radix_in_registers(rb, allow_heavy)) {
       t.generic = false;
       // per-element work of a register pass grows slowly with the radix; two balanced passes beat a long and a trivial one
       // (a pass has RB x columns (A) / RA x columns (B) butterflies to spread over the warps: a lopsided pair starves one of them)
-      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.05 * std::abs(ra - rb);
+      t.cost = (ra == 1 ? 0.35 : 1.0) + (rb == 1 ? 0.35 : 1.0) + 0.05 * std::min(std::abs(ra - rb), 15);
+      // a Rader butterfly is two transforms of length P - 1 plus a pointwise product, and its kernel spills; next to a unit radix
+      // a tile has only `columns` such butterflies to spread over the warps
+      t.heavy = tq_radix_is_heavy(ra) || tq_radix_is_heavy(rb);
+      if (tq_radix_is_heavy(ra)) t.cost += ra == 32 ? 0.3 : 1.0;
+      if (tq_radix_is_heavy(rb)) t.cost += rb == 32 ? 0.3 : 1.0;
+      if (t.heavy && (ra == 1 || rb == 1)) t.cost += 1.5;
     } else if (rb <= PIPE_MAX_GENERIC) {
       t.generic = true;
+      t.heavy = tq_radix_is_heavy(ra);
+      if (t.heavy) continue; // (a heavy RA with a direct-sum RB: no such instantiation is worth having)
       t.cost = (ra == 1 ? 0.35 : 1.0) + 0.5 + rb / 9.0; // 4 rb FP64 instructions per element against ~40 for a register pass
     } else {
       continue;
