@@ -81,7 +81,10 @@ tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
  *   "scratch_chunk_mb" > 0: four-step scratch budget per launch pair in MiB (default: 1536 pipelined, 64 generic)
  *   "host_lanes"       1..8: internal lanes over which tq_fourier_tau_to_iw / tq_fourier_iw_to_tau cut a batch passed in HOST
  *                      buffers, so that H2D copies, kernels and D2H copies of different chunks overlap (default 3; 1 = off)
- *   "host_chunk_kb"    input KiB per chunk of such a call (default 98304 = 96 MiB) */
+ *   "host_chunk_kb"    input KiB per chunk of such a call (default 49152 = 48 MiB)
+ *   "bounce"           1 (default): inside a multi-lane call, pageable host buffers are staged through the lanes' own pinned slots,
+ *                      piecewise and overlapped with the DMA (the driver's pageable path is serialised per process at ~7 GB/s);
+ *                      0: always plain cudaMemcpyAsync */
 tq_status tq_set_option(tq_ctx *ctx, const char *name, long value);
 /* number of kernel launches issued by this context since creation (bench.py reports the delta) */
 uint64_t tq_launch_count(const tq_ctx *ctx);

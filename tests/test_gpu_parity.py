@@ -811,7 +811,7 @@ def test_host_buffer_calls_overlap_lanes_do_not_change_a_bit(ctx):
     w3 = ctx.fourier_tau_to_iw(gts, beta, F, n_iw)
     warn3 = np.array(ctx.last_warn)
     t3, e3 = ctx.fourier_iw_to_tau(w3, beta, F, n_tau, return_err=True)
-    ctx.set_option("host_chunk_kb", 96 << 10)
+    ctx.set_option("host_chunk_kb", 48 << 10)
     assert np.array_equal(w1, w3) and np.array_equal(t1, t3)
     assert np.array_equal(warn1, warn3) and warn1[4] & 1 and not warn1[0] & 1
     assert np.array_equal(e1, e3)

@@ -74,6 +74,9 @@ struct tq_ctx {
   DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w, leg_tmp;
   void *pinned = nullptr;
   size_t pinned_cap = 0;
+  // pinned bounce buffers for PAGEABLE user memory (tq_stage_in / tq_stage_out_finish): two slots each way, events per slot
+  void *bounce[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t bounce_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // caches (mesh-only data, like the reference's tail_fitter::_lss and FFTW plans)
   std::map<std::tuple<long, int>, std::shared_ptr<FftPlanHost>> fft_plans;                        // (N, dummy)
   std::map<std::tuple<double, int, long, long>, std::shared_ptr<MatsubaraPlan>> matsubara_plans;  // beta, stat, n_tau, n_iw
@@ -97,7 +100,8 @@ struct tq_ctx {
   long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)
-  long opt_host_chunk_kb = 96L << 10; // input bytes per chunk of a host-buffer call (KiB)
+  long opt_bounce = 1;           // stage pageable host buffers through the library's own pinned slots (tq_stage_in)
+  long opt_host_chunk_kb = 48L << 10; // input bytes per chunk of a host-buffer call (KiB): one C2 block (40 MB) per chunk
   std::vector<tq_ctx *> lanes;   // child contexts of the lanes (created on first use)
   // NCCL
   void *nccl_comm = nullptr;

@@ -60,6 +60,10 @@ extern "C" void tq_destroy(tq_ctx *ctx) {
   free_buf(ctx->pipe_w);
   free_buf(ctx->leg_tmp);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < 4; ++i) {
+    if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+    if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]);
+  }
   if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -114,6 +118,8 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
     ctx->opt_force_planned = value;
   else if (n == "scratch_chunk_mb")
     ctx->opt_scratch_chunk_mb = value;
+  else if (n == "bounce")
+    ctx->opt_bounce = value;
   else if (n == "host_chunk_kb")
     ctx->opt_host_chunk_kb = std::max<long>(1, value);
   else if (n == "host_lanes")
@@ -184,6 +190,27 @@ bool tq_is_device_ptr(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Pageable user memory (a TRIQS nda array, a NumPy array): a cudaMemcpy from / to it is staged by the driver through ONE internal
+// buffer per process at ~7 GB/s, whatever the number of threads (profiles/r02_e2e_lanes_probe_before_bounce.jsonl).  The library
+// stages such buffers itself: the calling thread copies 8 MiB pieces into its own pinned slots and issues asynchronous DMA copies from
+// there, so that the CPU copy of piece i + 1 overlaps the DMA of piece i, and different lanes (threads) proceed independently.
+constexpr size_t TQ_BOUNCE_BYTES = 8u << 20;
+static bool host_is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static tq_status bounce_init(tq_ctx *ctx) {
+  for (int i = 0; i < 4; ++i) {
+    if (!ctx->bounce[i]) TQ_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], TQ_BOUNCE_BYTES));
+    if (!ctx->bounce_ev[i]) TQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounce_ev[i], cudaEventDisableTiming));
+  }
+  return TQ_OK;
+}
+
 tq_status tq_stage_in(tq_ctx *ctx, const void *user, size_t bytes, DeviceBuffer &stage, const void **dev) {
   if (!user) {
     *dev = nullptr;
@@ -194,8 +221,25 @@ tq_status tq_stage_in(tq_ctx *ctx, const void *user, size_t bytes, DeviceBuffer 
     return TQ_OK;
   }
   TQ_TRY(tq_reserve(ctx, stage, bytes));
-  TQ_CUDA(ctx, cudaMemcpyAsync(stage.p, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
   *dev = stage.p;
+  // (only inside a multi-lane call: a single thread copying through its own slots is CPU bound at ~5 GB/s, below the driver's 7 GB/s)
+  if (bytes >= (1u << 20) && ctx->opt_bounce == 2 && host_is_pageable(user)) {
+    TQ_TRY(bounce_init(ctx));
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i, off += TQ_BOUNCE_BYTES) {
+      const int slot = i & 1;
+      const size_t n = std::min(TQ_BOUNCE_BYTES, bytes - off);
+      if (i >= 2) TQ_CUDA(ctx, cudaEventSynchronize(ctx->bounce_ev[slot])); // the DMA out of this slot has finished
+      memcpy(ctx->bounce[slot], (const char *)user + off, n);
+      TQ_CUDA(ctx, cudaMemcpyAsync((char *)stage.p + off, ctx->bounce[slot], n, cudaMemcpyHostToDevice, ctx->stream));
+      TQ_CUDA(ctx, cudaEventRecord(ctx->bounce_ev[slot], ctx->stream));
+    }
+    // the slots are reused by the next staging call of this context: drain them
+    TQ_CUDA(ctx, cudaEventSynchronize(ctx->bounce_ev[0]));
+    TQ_CUDA(ctx, cudaEventSynchronize(ctx->bounce_ev[1]));
+    return TQ_OK;
+  }
+  TQ_CUDA(ctx, cudaMemcpyAsync(stage.p, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return TQ_OK;
 }
 
@@ -212,10 +256,30 @@ tq_status tq_stage_out_begin(tq_ctx *ctx, void *user, size_t bytes, DeviceBuffer
 }
 
 tq_status tq_stage_out_finish(tq_ctx *ctx, void *user, size_t bytes, void *dev, bool is_host) {
-  if (is_host) {
-    TQ_CUDA(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!is_host) return TQ_OK;
+  if (bytes >= (1u << 20) && ctx->opt_bounce == 2 && host_is_pageable(user)) {
+    TQ_TRY(bounce_init(ctx));
+    // DMA of piece i into slot 2 + (i & 1) overlaps the CPU copy of piece i - 1 out of the other slot
+    const size_t np = (bytes + TQ_BOUNCE_BYTES - 1) / TQ_BOUNCE_BYTES;
+    for (size_t i = 0; i <= np; ++i) {
+      if (i < np) {
+        const int slot = 2 + (int)(i & 1);
+        const size_t off = i * TQ_BOUNCE_BYTES, n = std::min(TQ_BOUNCE_BYTES, bytes - off);
+        TQ_CUDA(ctx, cudaMemcpyAsync(ctx->bounce[slot], (const char *)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        TQ_CUDA(ctx, cudaEventRecord(ctx->bounce_ev[slot], ctx->stream));
+      }
+      if (i > 0) {
+        const int slot = 2 + (int)((i - 1) & 1);
+        const size_t off = (i - 1) * TQ_BOUNCE_BYTES, n = std::min(TQ_BOUNCE_BYTES, bytes - off);
+        TQ_CUDA(ctx, cudaEventSynchronize(ctx->bounce_ev[slot]));
+        memcpy((char *)user + off, ctx->bounce[slot], n);
+      }
+    }
     TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TQ_OK;
   }
+  TQ_CUDA(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TQ_OK;
 }
 
