@@ -817,3 +817,23 @@ def test_host_buffer_calls_overlap_lanes_do_not_change_a_bit(ctx):
     assert np.array_equal(e1, e3)
     for b in (0, 6):
         assert rel(w3[b], O.fourier_tau_to_iw(gts[b], beta, F, n_iw)) < TOL
+
+
+def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
+    """NumPy (pageable) buffers above 1 MB are staged piecewise through the lanes' own pinned slots (tq_stage_in / tq_stage_out_finish):
+    same bits as the single-stream call, also when a gf spans several 8 MiB pieces."""
+    beta, n_tau, n_iw, ncols = 10.0, 120001, 3000, 5     # 9.6 MB per gf: two pieces each way
+    rng = np.random.default_rng(21)
+    iw = O.imfreq_values(beta, F, n_iw)
+    gws = np.stack([sum((rng.normal(size=ncols) + 1j * rng.normal(size=ncols))[None, :] / (iw[:, None] - e) for e in rng.uniform(-2, 2, 3))
+                    for _ in range(5)])
+    ctx.set_option("host_lanes", 1)
+    t1 = ctx.fourier_iw_to_tau(gws, beta, F, n_tau)
+    w1 = ctx.fourier_tau_to_iw(t1, beta, F, n_iw)
+    ctx.set_option("host_lanes", 3)
+    ctx.set_option("host_chunk_kb", 10 << 10)            # one gf per chunk -> 5 chunks over 3 lanes
+    t3 = ctx.fourier_iw_to_tau(gws, beta, F, n_tau)
+    w3 = ctx.fourier_tau_to_iw(t3, beta, F, n_iw)
+    ctx.set_option("host_chunk_kb", 48 << 10)
+    assert np.array_equal(t1, t3) and np.array_equal(w1, w3)
+    assert rel(t3[4], O.fourier_iw_to_tau(gws[4], beta, F, n_tau)) < TOL
