@@ -151,6 +151,18 @@ void test_eval_and_inverse() { // meshes/eval.cpp:62-89, gf_inverse.cpp
   for (long i = 0; i < m.mesh().size(); ++i) m[i][0] = m.mesh()[i] - 0.3;
   auto mi = inverse(m);
   for (long i = 0; i < m.mesh().size(); ++i) EXPECT(std::abs(mi[i][0] - 1.0 / (m.mesh()[i] - 0.3)) < 1e-14);
+  // gf_evaluator<imfreq> (evaluator.hpp:47-75): inside the window the mesh value, outside the fitted tail ~ 1 / (i w - 0.3)
+  gf<mesh::imfreq, scalar_valued> gw{{10.0, Fermion, 400}};
+  for (long i = 0; i < gw.mesh().size(); ++i) gw[i][0] = 1.0 / (gw.mesh()[i] - 0.3);
+  auto ev = evaluate(gw, std::vector<long>{-5000, -400, 0, 7, 399, 400, 3000});
+  const double pi = 3.14159265358979323846;
+  for (size_t k = 0; k < 7; ++k) {
+    const long n = std::vector<long>{-5000, -400, 0, 7, 399, 400, 3000}[k];
+    const dcomplex iw{0.0, pi * double(2 * n + 1) / 10.0};
+    EXPECT(std::abs(ev[k] - 1.0 / (iw - 0.3)) < (n >= -400 && n <= 399 ? 1e-15 : 1e-7));
+  }
+  set_option("host_lanes", 2);
+  set_option("host_lanes", 3);
 }
 
 void test_density() { // gf_density.cpp:22-55, gf_base.cpp:69

@@ -598,6 +598,18 @@ namespace triqs_b200 {
                         detail::ptr(out)));
     return out;
   }
+  // gf_evaluator<imfreq> (evaluator.hpp:47-75), batched over Matsubara indices: the mesh value inside the window, the fitted
+  // high-frequency tail outside.  Returns [ns.size()][n_others].
+  template <typename T> std::vector<dcomplex> evaluate(gf<mesh::imfreq, T> const &g, std::vector<long> const &ns) {
+    std::vector<dcomplex> out(size_t(ns.size() * g.n_others()));
+    double err = 0;
+    check(tq_evaluate_imfreq(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), g.n_others(), 1, detail::cptr(g.data()),
+                             (long)ns.size(), ns.data(), detail::ptr(out), &err));
+    return out;
+  }
+  // engine options of the context (tq_set_option: never change results), e.g. set_option("host_lanes", 4)
+  inline void set_option(const char *name, long value) { check(tq_set_option(context(), name, value)); }
+
   template <typename Mesh, typename Target> std::vector<dcomplex> gf<Mesh, Target>::operator()(double x) const {
     static_assert(std::is_same<Mesh, mesh::imtime>::value, "g(x) is implemented for imtime gfs");
     return evaluate(*this, std::vector<double>{x});

@@ -235,7 +235,10 @@ extern "C" tq_status tq_invert_batched(tq_ctx *ctx, int n, long n_pts, tq_comple
 //   per k: M = A - eps_k (eps_k read with warp-uniform loads), M <- M^-1 in registers, acc += weight * M
 //   partial[chunk][w][n][n] is reduced by a second tiny kernel in fixed order (deterministic result).
 // -------------------------------------------------------------------------------------------------
-template <int N> __global__ void __launch_bounds__(128) k_dyson_partial(const cd *__restrict__ eps, const double *__restrict__ weights,
+#ifndef TQ_DYSON_MINB
+#define TQ_DYSON_MINB 1
+#endif
+template <int N> __global__ void __launch_bounds__(128, TQ_DYSON_MINB) k_dyson_partial(const cd *__restrict__ eps, const double *__restrict__ weights,
                                                                        double uniform_weight, const cd *__restrict__ sigma, int n_w, long n_k,
                                                                        long k_per_chunk, double beta, int stat, int first, double mu,
                                                                        cd *__restrict__ partial) {
