@@ -105,3 +105,49 @@ def test_planned_lattice_axes(ctx, dims, n_others):
     finally:
         ctx.set_option("no_pipe", 0)
     assert rel(yk_g, yk) < TOL
+
+
+NARROW = [
+    # L, n_iw, ncols, stat, batch        ("gfs as columns": batch * ncols >= 8, ncols < 4)
+    (6150, 1025, 1, F, 8), (6150, 1025, 1, B, 37), (6000, 1000, 2, F, 13), (10000, 1025, 1, F, 9), (10000, 1025, 3, F, 11), (9999, 1000, 1, F, 24),
+    (600, 100, 3, B, 40), (20000, 2000, 1, F, 10), (100000, 10000, 1, F, 8), (100000, 10000, 2, B, 5), (1200, 200, 1, F, 300), (6144, 1024, 3, F, 3),
+]
+
+
+def pole_gw_moments(beta, stat, n_iw, ncols, seed):
+    """sum_p r_p / (i w - E_p) and its exact moments [0, sum r, sum r E, sum r E^2]"""
+    rng = np.random.default_rng(seed)
+    iw = O.imfreq_values(beta, stat, n_iw)
+    E = rng.uniform(0.3, 2.0, (3, ncols)) * rng.choice([-1, 1], (3, ncols))
+    r = rng.normal(size=(3, ncols)) + 1j * rng.normal(size=(3, ncols))
+    gw = sum(r[p][None, :] / (iw[:, None] - E[p][None, :]) for p in range(3))
+    return gw, np.stack([np.zeros(ncols, complex), r.sum(0), (r * E).sum(0), (r * E * E).sum(0)])
+
+
+@pytest.mark.parametrize("L,n_iw,ncols,stat,batch", NARROW)
+def test_narrow_targets_run_as_columns_of_one_wide_gf(ctx, L, n_iw, ncols, stat, batch):
+    """Batches of scalar / 1-3 column gfs (configs[0] is one): the planned engine treats the batch as ONE gf whose columns are all
+    (gf, column) pairs, gathered by tensor maps; checked against the oracle on the first, middle and last gf and against the per-gf
+    kernels ("no_tr") on all of them."""
+    beta, n_tau = 15.0, L + 1
+    pick = sorted({0, batch // 2, batch - 1})
+    both = [pole_gw_moments(beta, stat, n_iw, ncols, 77 * L % 7919 + b) for b in range(batch)]
+    gws, tails = np.stack([x[0] for x in both]), np.stack([x[1] for x in both])
+    ctx.profile_enable(True)
+    gt = np.asarray(ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=tails))
+    rep = ctx.profile_report()
+    ctx.profile_enable(False)
+    assert "iw2tau_pass1" in rep and "iw2tau_pass2" in rep, rep
+    for b in pick:
+        assert rel(gt[b], O.fourier_iw_to_tau(gws[b], beta, stat, n_tau, known_moments=tails[b])) < TOL
+    gw2 = np.asarray(ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=tails))
+    for b in pick:
+        assert rel(gw2[b], O.fourier_tau_to_iw(gt[b], beta, stat, n_iw, known_moments=tails[b])) < TOL
+    ctx.set_option("no_tr", 1)
+    try:
+        gt_g = np.asarray(ctx.fourier_iw_to_tau(gws, beta, stat, n_tau, moments=tails))
+        gw_g = np.asarray(ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=tails))
+    finally:
+        ctx.set_option("no_tr", 0)
+    for b in range(batch):
+        assert rel(gt_g[b], gt[b]) < TOL and rel(gw_g[b], gw2[b]) < TOL

@@ -272,7 +272,7 @@ static tq_status get_col_plan(tq_ctx *ctx, double beta, int stat, long n_iw, std
 tq_status tq_col_matsubara_fwd(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in, cd *d_out,
                                const cd *d_mom, int mom_rows, bool *handled) {
   *handled = false;
-  if (n_tau - 1 != COL_L || n_cols != 1 || ctx->opt_no_pipe || TQ_DEV_ENV("TQ_NO_COL")) return TQ_OK;
+  if (n_tau - 1 != COL_L || n_cols != 1 || ctx->opt_no_pipe || ctx->opt_no_col || TQ_DEV_ENV("TQ_NO_COL")) return TQ_OK;
   if (((uintptr_t)d_in) & 15) return TQ_OK; // bulk copies need 16-byte aligned sources (rows are 16 B, so every gf is)
   std::shared_ptr<ColPlan> pl;
   TQ_TRY(get_col_plan(ctx, beta, stat, n_iw, &pl));

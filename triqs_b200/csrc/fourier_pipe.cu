@@ -325,6 +325,34 @@ static tq_status make_i1_tensor_map(tq_ctx *ctx, const cd *in, long row0, long n
   return TQ_OK;
 }
 
+// "gfs as columns" (narrow targets, nc = 1..3 columns per gf): G(tau) of `batch` gfs as the 4-D tensor [b][a][gf][2 nc doubles];
+// box = one F1 tile [box_rows][1][tcw / nc gfs][2 nc]  -> shared memory [row][tcw columns], column = gf * nc + c
+static tq_status make_f1_tr_tensor_map(tq_ctx *ctx, const cd *in, long batch, int Na, int Nb, int nc, long L, int tcw, int box_rows, CUtensorMap *out) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {(cuuint64_t)(2 * nc), (cuuint64_t)batch, (cuuint64_t)Na, (cuuint64_t)Nb};
+  cuuint64_t strides[3] = {(cuuint64_t)((L + 1) * nc * sizeof(cd)), (cuuint64_t)(nc * sizeof(cd)), (cuuint64_t)((long)Na * nc * sizeof(cd))};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * nc), (cuuint32_t)(tcw / nc), 1u, (cuuint32_t)box_rows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled (F1, gfs as columns) failed with CUresult " + std::to_string((int)r));
+  return TQ_OK;
+}
+// ... and G(i w) as the 3-D tensor [row][gf][2 nc doubles]; box = one window row of a tile, [1][tcw / nc gfs][2 nc]
+static tq_status make_i1_tr_tensor_map(tq_ctx *ctx, const cd *in, long batch, int nc, long n_w, int tcw, CUtensorMap *out) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)(2 * nc), (cuuint64_t)batch, (cuuint64_t)n_w};
+  cuuint64_t strides[2] = {(cuuint64_t)(n_w * nc * sizeof(cd)), (cuuint64_t)(nc * sizeof(cd))};
+  cuuint32_t box[3] = {(cuuint32_t)(2 * nc), (cuuint32_t)(tcw / nc), 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tq_fail(ctx, TQ_ERR_CUDA, "cuTensorMapEncodeTiled (I1, gfs as columns) failed with CUresult " + std::to_string((int)r));
+  return TQ_OK;
+}
+
 // widest balanced column tile for a tile length N: n_ct tiles of width ceil(n_cols / n_ct)
 static int env_int_early(const char *name, int dflt) {
   const char *e = TQ_DEV_ENV_NAME(name);
@@ -335,11 +363,14 @@ template <int MODE> static int pipe_pitch(int tc, int pad, int rows_per_box) {
   if (pad == 1 || (pad == 2 && (rows_per_box * tc) % 8 != 0)) return (tc + 7) & ~7;
   return tc;
 }
-template <int MODE> static int pipe_pick_tcw(tq_ctx *ctx, const TileShape &T, long n_cols, int wmax, int cap, int pad = 0, int rows_per_box = 0) {
+// step > 1 ("gfs as columns"): widths are multiples of `step` (whole gfs, and rows of a multiple of 128 bytes), no balancing
+template <int MODE> static int pipe_pick_tcw(tq_ctx *ctx, const TileShape &T, long n_cols, int wmax, int cap, int pad = 0, int rows_per_box = 0,
+                                             int step = 1) {
   int fit = 0;
-  for (int tc = 1; tc <= n_cols && tc <= cap; ++tc)
+  for (int tc = step; (tc <= n_cols || tc == step) && tc <= cap; tc += step)
     if (PipeSmem<MODE>(T.N, T.RA, T.RB, tc, pipe_pitch<MODE>(tc, pad, rows_per_box), wmax, T.generic).total <= (size_t)ctx->max_smem_optin) fit = tc;
   if (fit < 1) return 0;
+  if (step > 1) return fit;
   static const int unbalanced = env_int_early("TQ_PIPE_UNBALANCED", 0); // (tuning experiment: widest tiles + a narrow remainder)
   if (unbalanced) return fit;
   long n_ct = (n_cols + fit - 1) / fit;
@@ -357,15 +388,25 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   *handled = false;
   const long L = n_tau - 1;
   if (ctx->opt_no_pipe) return TQ_OK;
+  // "gfs as columns": a batch of narrow gfs (1-3 target columns) runs as ONE virtual gf whose columns are all (gf, column) pairs;
+  // the tiles are gathered / scattered with the gf stride by tensor maps (fourier_pipe_kernel.cuh, PipeArgs::tr)
+  int tr = 0;
   {
     TileShape a, b;
     if (!pipe_plan_lengths(L, &a, &b)) return TQ_OK;
-    // Narrow targets on meshes whose whole column fits one SM's shared memory stay with the single-kernel paths (one HBM read and
-    // one write, no scratch): the pipelined tiles would have rows of 16-48 bytes.  Everything else -- any mesh with >= 4 target
-    // columns and every long mesh -- takes the planned four-step path.
-    const bool single_kernel_fits = sizeof(cd) * (size_t)(L + 64) <= (size_t)ctx->max_smem_optin;
-    if (n_cols < 4 && single_kernel_fits) return TQ_OK;
     if (L < 256) return TQ_OK;
+    if (n_cols < 4) {
+      // the single-column kernel (fourier_col.cu: one HBM read, one write, no scratch) keeps its mesh
+      const bool col_kernel = fwd && L == 10000 && n_cols == 1 && !ctx->opt_no_col;
+      if (batch * n_cols >= 8 && !col_kernel && !ctx->opt_no_tr) {
+        tr = (int)n_cols;
+      } else {
+        // Narrow targets on meshes whose whole column fits one SM's shared memory stay with the single-kernel paths (one HBM read
+        // and one write, no scratch): the pipelined tiles would have rows of 16-48 bytes.
+        const bool single_kernel_fits = sizeof(cd) * (size_t)(L + 64) <= (size_t)ctx->max_smem_optin;
+        if (single_kernel_fits) return TQ_OK;
+      }
+    }
   }
   if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return TQ_OK; // bulk copies need 16-byte aligned rows
 #ifdef TQ_KNOCKOUT
@@ -378,23 +419,30 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
   const TileShape &T1 = pl->t1, &T2 = pl->t2;
   const int Na = pl->Na, Nb = pl->Nb;
-  const bool spec = pl->specialised && !ctx->opt_force_planned;
+  const bool spec = pl->specialised && !ctx->opt_force_planned && !tr;
+  const long n_cols_real = n_cols; // target columns of a gf
+  const size_t tr_budget = ctx->opt_scratch_chunk_mb > 0 ? (size_t)ctx->opt_scratch_chunk_mb << 20 : 1536ull << 20;
+  // gfs per launch pair ("gfs as columns"): bounded by the scratch and by 2^31 tiles / 2^31 columns
+  const long tr_chunk = std::min<long>(batch, std::max<long>(8, std::min<long>((long)(tr_budget / ((size_t)L * n_cols * sizeof(cd))), (1L << 22) / n_cols)));
+  if (tr) n_cols = tr_chunk * n_cols; // columns of the virtual gf of one chunk
+  const int tr_step = tr == 3 ? 24 : 8; // whole gfs per tile and rows of a multiple of 128 bytes (TMA destinations)
   const int wmax1 = pl->wmax1, wmax2 = pl->wmax2;
   static const int cap1 = env_int("TQ_PIPE_TCW1", 64), cap2 = env_int("TQ_PIPE_TCW2", 64); // (tile-width caps: tuning experiments)
   // I1: window rows with n >= 0 / n < 0; when both are whole groups of Na rows they are two rectangles of the [b][a] view
   const long n_pos = (long)pl->last + 1, n_neg = -(long)pl->first;
-  bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && n_pos / Na <= 256 && n_neg / Na <= 256 &&
+  bool i1_rect = n_pos % Na == 0 && n_neg % Na == 0 && n_pos > 0 && n_neg > 0 && n_pos / Na <= 256 && n_neg / Na <= 256 && !tr &&
                  !TQ_DEV_ENV("TQ_PIPE_NO_I1_BOXES");
   // (the pruned pass A exists in the compile-time instantiations only)
   const bool i1_edge = spec && i1_rect && n_pos == (long)Na * T1.RB && n_neg == (long)Na * T1.RB && !TQ_DEV_ENV("TQ_PIPE_NO_I1_EDGE");
   // F1 fetches its tile as tensor boxes of at most 256 rows (each box lands 128-byte aligned: rows padded to 8 columns then)
   int f1_boxes = 1;
   while (Nb % f1_boxes != 0 || Nb / f1_boxes > 256) ++f1_boxes;
-  const int f1_pad = f1_boxes > 1 ? 2 : 0;
+  const int f1_pad = (f1_boxes > 1 && !tr) ? 2 : 0;
   // I1: the two tensor tiles of the rectangle path land 128-byte aligned only with rows padded to 8 columns; when that does not fit
   // the ring (long tiles), the row-by-row path with dense rows is used instead
-  int tcw1 = fwd ? pipe_pick_tcw<M_F1>(ctx, T1, n_cols, wmax1, cap1, f1_pad, Nb / f1_boxes)
-                 : pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, (i1_rect && !i1_edge) ? 1 : 0);
+  int tcw1 = tr ? (fwd ? pipe_pick_tcw<M_F1>(ctx, T1, n_cols, wmax1, cap1, 0, 0, tr_step) : pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, 0, 0, tr_step))
+             : fwd ? pipe_pick_tcw<M_F1>(ctx, T1, n_cols, wmax1, cap1, f1_pad, Nb / f1_boxes)
+                   : pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, (i1_rect && !i1_edge) ? 1 : 0);
   if (!fwd && i1_rect && !i1_edge) {
     const int dense = pipe_pick_tcw<M_I1>(ctx, T1, n_cols, wmax1, cap1, 0);
     if (tcw1 < 1 || (n_cols + tcw1 - 1) / tcw1 > (n_cols + dense - 1) / std::max(dense, 1)) { // fewer column tiles without the padding
@@ -402,25 +450,29 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       tcw1 = dense;
     }
   }
-  const int tcw2 = fwd ? pipe_pick_tcw<M_F2>(ctx, T2, n_cols, wmax2, cap2) : pipe_pick_tcw<M_I2>(ctx, T2, n_cols, wmax2, cap2);
+  const int tcw2 = fwd ? pipe_pick_tcw<M_F2>(ctx, T2, n_cols, wmax2, cap2, 0, 0, tr ? tr_step : 1)
+                       : pipe_pick_tcw<M_I2>(ctx, T2, n_cols, wmax2, cap2, 0, 0, tr ? tr_step : 1);
   if (tcw1 < 1 || tcw2 < 1) return TQ_OK;
   PipeArgs A{};
   A.Na = Na;
   A.Nb = Nb;
   A.n_cols = (int)n_cols;
   A.tcw2 = tcw2;
-  // pole weights of all gfs (tiny): [2][batch][n_cols][4]
-  const size_t pw_elems = (size_t)batch * n_cols * 4;
+  // pole weights of all gfs (tiny): [2][batch][4][n_cols]   ("gfs as columns": [2][4][all columns], written per scratch chunk below)
+  const size_t pw_elems = (size_t)batch * n_cols_real * 4;
   TQ_TRY(tq_reserve(ctx, ctx->pipe_w, sizeof(cd) * 2 * pw_elems));
   cd *w_tau = (cd *)ctx->pipe_w.p, *w_freq = w_tau + pw_elems;
-  {
-    const long total = batch * n_cols;
+  const auto pole_weights = [&](long g0, long n_gf, cd *wt, cd *wf) -> tq_status {
+    const long total = n_gf * n_cols_real;
     KernelScope ks(ctx, "pole_weights");
-    k_pole_weights<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_mom, (long)mom_rows * n_cols, (int)n_cols, total, stat, fwd ? d_in : nullptr,
-                                                                            (L + 1) * n_cols, (int)L, 0.5 * (beta / (double)L), w_tau, w_freq);
+    k_pole_weights<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_mom + g0 * mom_rows * n_cols_real, (long)mom_rows * n_cols_real, (int)n_cols_real,
+                                                                            total, stat, fwd ? d_in + g0 * (L + 1) * n_cols_real : nullptr,
+                                                                            (L + 1) * n_cols_real, (int)L, 0.5 * (beta / (double)L), wt, wf, tr);
     tq_count_launch(ctx);
     TQ_CUDA(ctx, cudaGetLastError());
-  }
+    return TQ_OK;
+  };
+  if (!tr) TQ_TRY(pole_weights(0, batch, w_tau, w_freq));
   A.L = (int)L;
   A.first = pl->first;
   A.last = pl->last;
@@ -440,7 +492,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   if (ctx->opt_scratch_chunk_mb > 0) l2_budget = (size_t)ctx->opt_scratch_chunk_mb << 20;
   long chunk = std::max<long>(1, (long)(l2_budget / per_gf));
   chunk = std::min<long>(std::min<long>(chunk, batch), 1L << 18); // (keeps the tile count of a launch below 2^31)
-  TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));
+  if (!tr) TQ_TRY(tq_reserve(ctx, ctx->scratch, per_gf * chunk));
   A.scratch = (cd *)ctx->scratch.p;
   auto set_mode = [&](PipeArgs &P, int mode) {
     const ModeTables &m = pl->m[mode];
@@ -462,6 +514,56 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     P.rb_generic = T.generic ? 1 : 0;
     P.lag0 = (int)ctx->opt_pipe_lag0;
   };
+  if (tr) {
+    const long nc = n_cols_real;
+    TQ_TRY(tq_reserve(ctx, ctx->scratch, (size_t)L * n_cols * sizeof(cd)));
+    A.scratch = (cd *)ctx->scratch.p;
+    A.tr = tr;
+    A.col_stride_out = out_rows * nc;
+    for (long g0 = 0; g0 < batch; g0 += tr_chunk) {
+      const long ng = std::min(tr_chunk, batch - g0), ncv = ng * nc;
+      TQ_TRY(pole_weights(g0, ng, w_tau, w_freq));
+      PipeArgs P1 = A;
+      P1.n_cols = (int)ncv;
+      P1.in = d_in + g0 * in_rows * nc;
+      P1.out = d_out + g0 * out_rows * nc;
+      P1.in_gf_stride = P1.out_gf_stride = P1.scratch_gf_stride = 0; // one virtual gf
+      P1.polew = fwd ? w_tau : w_freq;
+      P1.tcw = P1.pitch = tcw1;
+      P1.n_ct = (int)((ncv + tcw1 - 1) / tcw1);
+      P1.n_items = Na;
+      P1.n_tiles = (long)Na * P1.n_ct;
+      P1.wmax = wmax1;
+      PipeArgs P2 = P1;
+      P2.tcw = P2.pitch = tcw2;
+      P2.n_ct = (int)((ncv + tcw2 - 1) / tcw2);
+      P2.n_items = Nb;
+      P2.n_tiles = (long)Nb * P2.n_ct;
+      P2.wmax = wmax2;
+      P2.polew = fwd ? w_freq : w_tau;
+      CUtensorMap tm1, tm2;
+      memset(&tm1, 0, sizeof(tm1));
+      memset(&tm2, 0, sizeof(tm2));
+      if (fwd) {
+        set_mode(P1, M_F1);
+        set_mode(P2, M_F2);
+        P1.f1_boxes = f1_boxes;
+        P1.f1_box_rows = Nb / f1_boxes;
+        TQ_TRY(make_f1_tr_tensor_map(ctx, P1.in, ng, Na, Nb, (int)nc, L, tcw1, P1.f1_box_rows, &tm1));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_F1, T1.heavy, P1, tm1, tm2, "tau2iw_pass1"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_F2, T2.heavy, P2, tm1, tm2, "tau2iw_pass2"));
+      } else {
+        set_mode(P1, M_I1);
+        set_mode(P2, M_I2);
+        P1.i1_rect = P1.i1_edge = 0;
+        TQ_TRY(make_i1_tr_tensor_map(ctx, P1.in, ng, (int)nc, pl->n_w, tcw1, &tm1));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_I1, T1.heavy, P1, tm1, tm2, "iw2tau_pass1"));
+        TQ_TRY(tq_launch_pipe_planned(ctx, M_I2, T2.heavy, P2, tm1, tm2, "iw2tau_pass2"));
+      }
+    }
+    *handled = true;
+    return TQ_OK;
+  }
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   for (long b0 = 0; b0 < batch; b0 += chunk) {

@@ -95,6 +95,12 @@ struct PipeArgs {
   long long *dbg; // developer phase timing (TQ_PHASE_DEBUG) or nullptr
   // planned (run-time radix) kernels: tile length and radix pair of THIS pass; rb_generic: pass B by direct summation
   int tN, tRA, tRB, rb_generic;
+  // "gfs as columns" (planned kernels, narrow targets, tr = target columns of a gf = 1..3, 0 = off): the batch is ONE virtual gf whose
+  // columns are all (gf, column) pairs, column cv = gf * tr + c.  Tiles are gathered by tensor maps whose innermost box is the tr
+  // contiguous columns of a gf (16 tr bytes), second box dimension = tcw / tr gfs; results go back with the gf stride
+  // col_stride_out between groups of tr columns.  Tiles are numbered item-fastest so that the CTAs of a wave touch neighbouring rows.
+  int tr;
+  long col_stride_out;
   int lag0; // packet order of the planned kernels: 1 = A(k) B(k) | A(k+1) ..., 0 = pass B one tile behind pass A
   int f1_boxes, f1_box_rows; // F1: the tile is fetched as f1_boxes tensor boxes of f1_box_rows rows (a TMA box has <= 256 rows)
   const cd *gtw;             // [tRB] exp(+2 pi i j / tRB)   (generic pass B)
@@ -114,6 +120,13 @@ TQ_HD Window tile_window(int item, int S, int N, int L, int first, int last) {
   w.r2 = lo <= 0 ? 0 : ((lo + S - 1) / S < N ? (lo + S - 1) / S : N);
   if (w.r2 < w.r1) w.r2 = w.r1;
   return w;
+}
+
+// "gfs as columns": element offset of tile column c = g * nc + cc (nc = 1..3 target columns per gf, gf stride cs); cs = 0: plain columns
+TQ_D long tr_col_offset(int c, int nc, long cs) {
+  if (cs == 0) return c;
+  const int g = nc == 1 ? c : nc == 2 ? (c >> 1) : (c * 43) >> 7; // c / 3 for c < 128
+  return (long)g * cs + (c - g * nc);
 }
 
 // ---- functors plugged into the two-pass engine -----------------------------------------------
@@ -202,6 +215,8 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
   Window win;
   cd *base; // out of this gf + c0
   int ra_rt = 0; // RA == 0: run-time radix
+  long cs = 0;   // "gfs as columns": stride between gfs of the output (0: the columns of the tile are contiguous)
+  int nc = 1;    // ... and target columns per gf (`n_cols` is the row stride)
   cd a1, D23, A23, ex;
   cd *p;
   int sidx;
@@ -212,7 +227,7 @@ template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows onl
     D23 = coef[c + tcw];
     A23 = coef[c + 2 * tcw];
     ex = coef[c + 3 * tcw];
-    p = base + c;
+    p = base + tr_col_offset(c, nc, cs);
   }
   template <int TT> TQ_D void store(cd v) const { store_rt(TT, v); }
   TQ_D void store_rt(int TT, cd v) const {
@@ -240,6 +255,8 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
   bool fermion;
   cd *base; // out of this gf + c0
   int ra_rt = 0; // RA == 0: run-time radix
+  long cs = 0;   // "gfs as columns": stride between gfs of the output (0: the columns of the tile are contiguous)
+  int nc = 1;    // ... and target columns per gf (`n_cols` is the row stride)
   cd a1, a2, a3, m1;
   cd *p;
   int j0;
@@ -251,7 +268,7 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
     a3 = cscale(e.z * ea.z, coef[c + 2 * A.tcw]);
     m1 = coef[c + 3 * A.tcw];
     j0 = item + Nb * s;
-    p = base + c + (long)j0 * n_cols;
+    p = base + tr_col_offset(c, nc, cs) + (long)j0 * n_cols;
   }
   template <int TT> TQ_D void store(cd z) const {
     cd v = TT == 0 ? z : cmul(z, A.phr[TT]); // the per-s part of the twist was folded into the pass-A twiddle row
@@ -286,7 +303,7 @@ template <int RA> struct PostI2 { // G(tau_j) = z e^{-i pi j/L} + sum_i at_i E_i
 //   w_freq [gf][4][c] = a1, a2 - a3, a2 + a3, trapezoid correction        (frequency side: F2 epilogue, I1 pre-transform)
 // The trapezoid end-point correction -0.5 (beta/L) (g_0 + m1 +/- g_L) (:181) exists on the forward leg only (gt != nullptr).
 static __global__ void k_pole_weights(const cd *mom, long mom_gf_stride, int n_cols, long total, int stat, const cd *gt, long gt_gf_stride, int L,
-                               double half_fact_fwd, cd *w_tau, cd *w_freq) {
+                               double half_fact_fwd, cd *w_tau, cd *w_freq, int tr) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long gf = i / n_cols;
@@ -315,15 +332,17 @@ static __global__ void k_pole_weights(const cd *mom, long mom_gf_stride, int n_c
   // [gf][4][n_cols]: the four weights of a tile's columns are four contiguous runs, so that lanes with consecutive columns read
   // consecutive 16-byte words of shared memory (the [c][4] layout cost a 4-way bank conflict on every read: 10-18 % of the
   // shared-memory wavefronts of the pipelined kernels, ncu source view)
-  cd *wt = w_tau + (size_t)gf * 4 * n_cols + c, *wf = w_freq + (size_t)gf * 4 * n_cols + c;
+  // ("gfs as columns": ONE virtual gf whose columns are all (gf, column) pairs -> [4][total])
+  const size_t ws = tr ? (size_t)total : (size_t)n_cols;
+  cd *wt = tr ? w_tau + i : w_tau + (size_t)gf * 4 * n_cols + c, *wf = tr ? w_freq + i : w_freq + (size_t)gf * 4 * n_cols + c;
   wt[0] = a1;
-  wt[(size_t)n_cols] = a2;
-  wt[(size_t)2 * n_cols] = a3;
-  wt[(size_t)3 * n_cols] = m1;
+  wt[ws] = a2;
+  wt[2 * ws] = a3;
+  wt[3 * ws] = m1;
   wf[0] = a1;
-  wf[(size_t)n_cols] = csub(a2, a3);
-  wf[(size_t)2 * n_cols] = cadd(a2, a3);
-  wf[(size_t)3 * n_cols] = ex;
+  wf[ws] = csub(a2, a3);
+  wf[2 * ws] = cadd(a2, a3);
+  wf[3 * ws] = ex;
 }
 
 // shared-memory carve-up (bytes); tile buffers first, each padded to 128 B (TMA tensor destination alignment)
@@ -362,13 +381,24 @@ struct TileDecoder {
   unsigned long long m_per_gf; // ceil(2^64 / (n_items n_ct)): exact quotient for t < 2^32
   unsigned m_nct;
   int per_gf, n_ct, tcw, n_cols;
-  TQ_D TileDecoder(int n_items, int n_ct_, int tcw_, int n_cols_) : n_ct(n_ct_), tcw(tcw_), n_cols(n_cols_) {
-    per_gf = n_items * n_ct;
-    m_per_gf = per_gf > 1 ? ~0ull / (unsigned long long)per_gf + 1ull : 0ull;
+  // item_fast ("gfs as columns": one virtual gf): t = item + n_items * column tile
+  TQ_D TileDecoder(int n_items, int n_ct_, int tcw_, int n_cols_, bool item_fast) : n_ct(n_ct_), tcw(tcw_), n_cols(n_cols_) {
+    per_gf = item_fast ? -n_items : n_items * n_ct;
+    const int d = item_fast ? n_items : per_gf;
+    m_per_gf = d > 1 ? ~0ull / (unsigned long long)d + 1ull : 0ull;
     m_nct = fastdiv_magic((unsigned)n_ct);
   }
   TQ_D TileId operator()(long t) const {
     TileId id;
+    if (per_gf < 0) {
+      const int n_items = -per_gf;
+      const int ct = n_items > 1 ? (int)__umul64hi((unsigned long long)t, m_per_gf) : (int)t;
+      id.gf = 0;
+      id.item = (int)(t - (long)ct * n_items);
+      id.c0 = ct * tcw;
+      id.w = min(tcw, n_cols - id.c0);
+      return id;
+    }
     id.gf = per_gf > 1 ? (long)__umul64hi((unsigned long long)t, m_per_gf) : t;
     const int rem = (int)(t - id.gf * per_gf);
     id.item = fastdiv(rem, m_nct);
@@ -458,7 +488,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   __syncthreads();
 
   const int nloc = (int)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
-  const TileDecoder decode(A.n_items, A.n_ct, TCW, n_cols);
+  const TileDecoder decode(A.n_items, A.n_ct, TCW, n_cols, PLANNED && A.tr != 0);
   const unsigned m_pa = fastdiv_magic((unsigned)pa), m_pab = fastdiv_magic((unsigned)(pa + pb));
   // With at least NW packets per 5 tiles no worker can be two ring cycles ahead of an unfinished packet, and the phase of
   // buffer b can be established by waiting on its `free` barrier; tiny tiles fall back to polling the producer's counter.
@@ -510,7 +540,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         if (MODE == M_F1)
           bytes = (uint32_t)(sizeof(cd) * NN * A.pitch); // the whole box, zero-filled past n_cols
         else if (MODE == M_I1)
-          bytes = i1_boxes ? (uint32_t)(sizeof(cd) * cnt * A.pitch) : (uint32_t)(sizeof(cd) * cnt * id.w);
+          bytes = (i1_boxes || (PLANNED && A.tr)) ? (uint32_t)(sizeof(cd) * cnt * A.pitch) : (uint32_t)(sizeof(cd) * cnt * id.w);
         else
           bytes = (uint32_t)(sizeof(cd) * NN * id.w);
         if (PASS1) bytes += (uint32_t)(sizeof(cd) * NN);
@@ -527,8 +557,12 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           if constexpr (!PLANNED) {
             tma_load_4d(dst, &tmap, 2 * id.c0, id.item, 0, (int)id.gf, &full[b]); // [gf][b = 0..Nb)[a = item][columns]
           } else {
-            for (int bx = 0; bx < A.f1_boxes; ++bx) // a TMA box has at most 256 rows
-              tma_load_4d(dst + (size_t)bx * A.f1_box_rows * A.pitch, &tmap, 2 * id.c0, id.item, bx * A.f1_box_rows, (int)id.gf, &full[b]);
+            for (int bx = 0; bx < A.f1_boxes; ++bx) { // a TMA box has at most 256 rows
+              if (A.tr) // tensor [b][a][gf][2 tr doubles]: the columns of the tile are (gf, column) pairs
+                tma_load_4d(dst + (size_t)bx * A.f1_box_rows * A.pitch, &tmap, 0, id.c0 / A.tr, id.item, bx * A.f1_box_rows, &full[b]);
+              else
+                tma_load_4d(dst + (size_t)bx * A.f1_box_rows * A.pitch, &tmap, 2 * id.c0, id.item, bx * A.f1_box_rows, (int)id.gf, &full[b]);
+            }
           }
         } else if (MODE == M_I1) {
           if (i1_boxes) {
@@ -563,7 +597,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
           const int r = r0 < win.r1 ? r0 : win.r2 + (r0 - win.r1);
           const int k = id.item + A.Na * r;
           const long di = (k <= A.last ? k : k - A.L) - A.first;
-          bulk_g2s(dst + (size_t)r * A.pitch, A.in + id.gf * A.in_gf_stride + di * n_cols + id.c0, (uint32_t)(sizeof(cd) * id.w), &full[b]);
+          if (PLANNED && A.tr) // one row of tcw / tr gfs: tensor [row][gf][2 tr doubles], box {2 tr, pitch / tr, 1}
+            tma_load_3d(dst + (size_t)r * A.pitch, &tmap, 0, id.c0 / A.tr, (int)di, &full[b]);
+          else
+            bulk_g2s(dst + (size_t)r * A.pitch, A.in + id.gf * A.in_gf_stride + di * n_cols + id.c0, (uint32_t)(sizeof(cd) * id.w), &full[b]);
         }
       }
       TQ_LAP(t_work)
@@ -724,12 +761,16 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
             run_b(post, fetch_next);
           } else if (MODE == M_F2) {
             const int4 wv = *reinterpret_cast<const int4 *>(tab + S.win_off);
-            PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
-                            A.out + id.gf * A.out_gf_stride + id.c0, RAv};
+            const bool tr = PLANNED && A.tr != 0;
+            PostF2<RA> post{reinterpret_cast<const cd *>(tab + S.wrec_off), coef, TCW, tr ? A.tr : n_cols, id.item, A.Nb, A.L, A.first, Window{wv.x, wv.y},
+                            tr ? A.out + (long)(id.c0 / A.tr) * A.col_stride_out : A.out + id.gf * A.out_gf_stride + id.c0, RAv, tr ? A.col_stride_out : 0L,
+                            tr ? A.tr : 1};
             run_b(post, fetch_next);
           } else {
-            PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), n_cols, id.item, A.Nb, A.L, fermion,
-                            A.out + id.gf * A.out_gf_stride + id.c0, RAv};
+            const bool tr = PLANNED && A.tr != 0;
+            PostI2<RA> post{A, coef, qtab, *reinterpret_cast<const double4 *>(tab + S.item_off), tr ? A.tr : n_cols, id.item, A.Nb, A.L, fermion,
+                            tr ? A.out + (long)(id.c0 / A.tr) * A.col_stride_out : A.out + id.gf * A.out_gf_stride + id.c0, RAv, tr ? A.col_stride_out : 0L,
+                            tr ? A.tr : 1};
             run_b(post, fetch_next);
           }
           __syncwarp(); // every lane's reads of the tile are done ...

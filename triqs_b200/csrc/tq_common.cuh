@@ -98,6 +98,8 @@ struct tq_ctx {
   long opt_force_planned = 0;    // 1: run the L = 10^5 mesh through the planned (run-time radix) kernels too (A/B measurements)
   long opt_pipe_lag0 = 0;        // packet order of the planned kernels (fourier_pipe_kernel.cuh)
   long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
+  long opt_no_col = 0;           // 1: skip the single-column kernel of fourier_col.cu (A/B measurements)
+  long opt_no_tr = 0;            // 1: narrow targets never run as "gfs as columns" through the planned kernels (A/B measurements)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)
   long opt_bounce = 1;           // stage pageable host buffers through the library's own pinned slots (tq_stage_in)

@@ -116,6 +116,10 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
     ctx->opt_pipe_lag0 = value;
   else if (n == "force_planned")
     ctx->opt_force_planned = value;
+  else if (n == "no_col")
+    ctx->opt_no_col = value;
+  else if (n == "no_tr")
+    ctx->opt_no_tr = value;
   else if (n == "scratch_chunk_mb")
     ctx->opt_scratch_chunk_mb = value;
   else if (n == "bounce")

@@ -39,6 +39,12 @@ TQ_D void tma_load_4d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, i
                "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                : "memory");
 }
+TQ_D void tma_load_3d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                  smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
 // L2 prefetch of a future tile (no shared-memory destination, no barrier): shortens the flight time of the real copy
 TQ_D void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
