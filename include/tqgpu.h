@@ -274,6 +274,25 @@ tq_status tq_interp_tau(tq_ctx *ctx, double beta, long n_tau, long n_elem, const
 tq_status tq_evaluate_imfreq(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_cols, long batch, const tq_complex *g, long n_pts,
                              const long *ns, tq_complex *out, double *tail_err);
 
+/* Replaces the product-mesh evaluation  evaluate(mesh::prod<M...>, f, x...)  c++/triqs/mesh/evaluate.hpp:97-114  (what
+ * g(k, w), g(t, t'), g(tau1, tau2) ... call for a gf on a product mesh), batched over n_pts points: multi-linear interpolation,
+ * one factor per component mesh, combined in the reference's recursion order (first component innermost).  Per component:
+ *   TQ_AXIS_LINEAR    linear::evaluate  c++/triqs/mesh/bases/linear.hpp:221-228  (imtime, retime, refreq): coordinate = the value x in
+ *                     [xmin, xmax], `size` points;
+ *   TQ_AXIS_PERIODIC  evaluate(brzone1d, f, vi)  c++/triqs/mesh/brzone.hpp:355-359: coordinate = vi in units of the mesh index (the
+ *                     caller applies  transpose(units_inv) * k  of brzone.hpp:368; a brzone is three such components), periodic;
+ *   TQ_AXIS_INDEX     an index passes through (evaluate.hpp:73): coordinate = the data index along this component (imfreq: n - first).
+ *   table [size_0]...[size_{n_dims-1}][n_elem], coords double[n_pts][n_dims], out [n_pts][n_elem]. */
+#define TQ_PROD_MAX_DIMS 4
+enum { TQ_AXIS_LINEAR = 0, TQ_AXIS_PERIODIC = 1, TQ_AXIS_INDEX = 2 };
+typedef struct {
+  int kind;
+  long size;
+  double xmin, xmax; /* TQ_AXIS_LINEAR only */
+} tq_axis;
+tq_status tq_evaluate_prod(tq_ctx *ctx, int n_dims, const tq_axis *axes, long n_elem, const tq_complex *table, long n_pts,
+                           const double *coords, tq_complex *out);
+
 /* ---- multi-GPU (one process per GPU; replaces mpi::all_reduce of gf data, c++/triqs/gfs/gf/gf.hpp:347-351) --- */
 
 #define TQ_COMM_ID_BYTES 128

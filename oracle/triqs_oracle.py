@@ -802,3 +802,48 @@ def interp_tau(table: np.ndarray, beta: float, taus: np.ndarray) -> np.ndarray:
     i = np.minimum(a.astype(np.int64), n_tau - 2)
     w = np.minimum(a - i, 1.0)
     return (1 - w)[:, None] * table[i] + w[:, None] * table[i + 1]
+
+
+def evaluate_prod(table: np.ndarray, axes, coords: np.ndarray) -> np.ndarray:
+    """Off-mesh evaluation on a product mesh: c++/triqs/mesh/evaluate.hpp:97-114 (recursion over the component meshes, the first
+    component innermost) with linear::evaluate (c++/triqs/mesh/bases/linear.hpp:221-228), brzone1d (c++/triqs/mesh/brzone.hpp:355-359)
+    and index pass-through (evaluate.hpp:73).  table [s_0, ..., s_{d-1}, n_elem]; axes[d] = ("linear", xmin, xmax) | "periodic" | "index";
+    coords [n_pts, d] (periodic: in units of the mesh index, i.e. after transpose(units_inv) * k of brzone.hpp:368)."""
+    table = np.asarray(table, dtype=np.complex128)
+    coords = np.asarray(coords, dtype=np.float64)
+    d = len(axes)
+    n_pts = coords.shape[0]
+    lo, hi, w = [], [], []
+    for j, a in enumerate(axes):
+        n = table.shape[j]
+        x = coords[:, j]
+        if a == "periodic":
+            i = np.floor(x).astype(np.int64)
+            w.append(x - i)
+            lo.append(np.mod(i, n))
+            hi.append(np.zeros_like(i) if n == 1 else np.mod(i + 1, n))
+        elif a == "index":
+            i = np.rint(x).astype(np.int64)
+            lo.append(i)
+            hi.append(i)
+            w.append(None)
+        else:
+            xmin, xmax = float(a[1]), float(a[2])
+            delta_inv = 1.0 / ((xmax - xmin) / (n - 1))
+            xc = np.maximum(x, xmin)
+            aa = (xc - xmin) * delta_inv
+            i = np.minimum(aa.astype(np.int64), n - 2)
+            lo.append(i)
+            hi.append(i + 1)
+            w.append(np.minimum(aa - i, 1.0))
+
+    def rec(j, idx):
+        # value with components j.. (j = d - 1 is the outermost sum) still to be combined; idx: chosen indices of components > j
+        if j < 0:
+            return table[tuple(idx[k] for k in range(d))]
+        if w[j] is None:
+            return rec(j - 1, {**idx, j: lo[j]})
+        A, B = rec(j - 1, {**idx, j: lo[j]}), rec(j - 1, {**idx, j: hi[j]})
+        return (1 - w[j])[:, None] * A + w[j][:, None] * B
+
+    return rec(d - 1, {}).reshape(n_pts, table.shape[-1])

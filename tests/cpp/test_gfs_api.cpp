@@ -163,6 +163,30 @@ void test_eval_and_inverse() { // meshes/eval.cpp:62-89, gf_inverse.cpp
   }
   set_option("host_lanes", 2);
   set_option("host_lanes", 3);
+  // product mesh: test/c++/gfs/multivar/g_k_om.cpp:76-114 -- g(k, w) re-evaluated on the mesh and on a 3 x finer k grid (within 5 %)
+  const long n_k = 40;
+  gf<mesh::prod<mesh::brzone, mesh::imfreq>, scalar_valued> gkw{{mesh::brzone{n_k, n_k}, mesh::imfreq{5.0, Fermion, 5}}};
+  auto const &wm = gkw.mesh().m2;
+  auto fk = [&](double kx, double ky, dcomplex w) { return 1.0 / (w + 3.0 + 2.0 * (std::cos(kx) + std::cos(ky))); };
+  for (long ix = 0; ix < n_k; ++ix)
+    for (long iy = 0; iy < n_k; ++iy)
+      for (long iw = 0; iw < wm.size(); ++iw) gkw[(ix * n_k + iy) * wm.size() + iw][0] = fk(2 * pi * ix / n_k, 2 * pi * iy / n_k, wm[iw]);
+  std::vector<std::array<double, 3>> ks;
+  std::vector<long> ns;
+  std::vector<dcomplex> want;
+  const long n2 = 3 * n_k;
+  for (long a = 0; a < n2; ++a)
+    for (long b = 0; b < n2; ++b)
+      for (long n = wm.first_index(); n <= wm.last_index(); ++n) {
+        ks.push_back({double(a) / 3.0, double(b) / 3.0, 0.0}); // transpose(units_inv) * k: in units of the mesh index (brzone.hpp:368)
+        ns.push_back(n);
+        want.push_back(fk(2 * pi * a / n2, 2 * pi * b / n2, wm[n - wm.first_index()]));
+      }
+  auto got = evaluate(gkw, ks, ns);
+  for (size_t i = 0; i < want.size(); ++i) {
+    const bool on_mesh = (i / wm.size() / n2) % 3 == 0 && (i / wm.size() % n2) % 3 == 0;
+    EXPECT(std::abs(got[i] - want[i]) <= (on_mesh ? 1e-14 : 0.05 * std::abs(want[i])));
+  }
 }
 
 void test_density() { // gf_density.cpp:22-55, gf_base.cpp:69

@@ -297,3 +297,36 @@ def test_gf_invert_strided_view_and_device_replace_by_tail():
     assert np.max(np.abs(gd.data.cpu().numpy() - ref)) < 1e-14
     gd.invert()
     assert np.max(np.abs(gd.data.cpu().numpy() - np.linalg.inv(ref))) / np.max(np.abs(np.linalg.inv(ref))) < 1e-12
+
+
+def test_product_mesh_evaluation_reads_like_the_reference_test():
+    """test/c++/gfs/multivar/g_k_om.cpp:76-114 (Gkom.Eval): g(k, w) on gf<prod<brzone, imfreq>, scalar_valued>"""
+    from triqs_b200 import gf as G
+    beta, n_k, n_w = 5.0, 40, 5
+    bz, wm = G.MeshBrZone((n_k, n_k)), G.MeshImFreq(beta, O.FERMION, n_w)
+    iw = wm.values()
+    k = np.arange(n_k) / n_k * 2 * np.pi
+    data = 1 / (iw[None, None, :] + 3 + 2 * (np.cos(k)[:, None, None] + np.cos(k)[None, :, None]))
+    g = G.Gf(G.MeshProduct((bz, wm)), (), data.reshape(n_k * n_k, len(iw)))
+    # re-evaluate on the mesh itself
+    ks = np.array([[k[ix], k[iy], 0.0] for ix in range(n_k) for iy in range(n_k)])
+    for n in range(wm.first_index, wm.last_index + 1):
+        r = g(ks, n)
+        assert np.max(np.abs(r - data[:, :, n - wm.first_index].reshape(-1))) < 1e-14
+    # a three times finer grid: within 5 % (the reference's bound)
+    n2 = 3 * n_k
+    kk = np.arange(n2) / n2 * 2 * np.pi
+    ks = np.array([[kx, ky, 0.0] for kx in kk for ky in kk])
+    for n in (wm.first_index, 0, wm.last_index):
+        w = iw[n - wm.first_index]
+        res = 1 / (w + 3 + 2 * (np.cos(ks[:, 0]) + np.cos(ks[:, 1])))
+        assert np.all(np.abs(g(ks, n) - res) <= 0.05 * np.abs(res))
+    assert abs(g(np.array([np.pi, np.pi, 0.0]), 0) - 1 / (iw[n_w] + 3 - 4)) < 1e-14  # a single point (pi, pi) is a mesh point
+    # g(tau, tau') on prod<imtime, imtime>: bilinear data are reproduced
+    tm = G.MeshImTime(2.0, O.FERMION, 21)
+    t = tm.values()
+    f = (1 + t[:, None] - 2 * t[None, :] + 0.25 * t[:, None] * t[None, :]).astype(complex)
+    g2 = G.Gf(G.MeshProduct((tm, tm)), (), f)
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(0, 2, 100), rng.uniform(0, 2, 100)
+    assert np.max(np.abs(g2(x, y) - (1 + x - 2 * y + 0.25 * x * y))) < 1e-13

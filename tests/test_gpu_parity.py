@@ -440,6 +440,39 @@ def test_dyson_sharded_sum_equals_whole(ctx):
 # ---------------------------------------------------------------------------------------------
 # interpolation
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,axes", [
+    ((64, 48, 6), [("linear", 0.0, 10.0), ("linear", 0.0, 10.0)]),                       # g(tau, tau')
+    ((12, 10, 8, 16, 4), ["periodic", "periodic", "periodic", "index"]),                # g(k, iw), gf<prod<brzone, imfreq>>
+    ((40, 40, 1, 10, 1), ["periodic", "periodic", "periodic", "index"]),                # test/c++/gfs/multivar/g_k_om.cpp:76-114
+    ((30, 9), [("linear", -2.0, 3.0)]),                                                  # one component
+    ((7, 9, 5, 1), [("linear", 0.0, 1.0), "periodic", ("linear", -1.0, 1.0)]),
+    ((5, 6, 7, 8, 2), [("linear", 0.0, 1.0), ("linear", 0.0, 2.0), ("linear", 0.0, 3.0), ("linear", 0.0, 4.0)]),
+])
+def test_evaluate_prod_bit_exact(ctx, shape, axes):
+    """product-mesh evaluation (mesh/evaluate.hpp:97-114): same roundings as the restated recursion, so bit-for-bit"""
+    rng = np.random.default_rng(len(shape) * 100 + shape[0])
+    table = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    n_pts = 20011
+    cols = []
+    for d, a in enumerate(axes):
+        if a == "periodic":
+            cols.append(rng.uniform(-2.5 * shape[d], 2.5 * shape[d], n_pts))   # any real index, wrapped (brzone.hpp:355-359)
+        elif a == "index":
+            cols.append(rng.integers(0, shape[d], n_pts).astype(float))
+        else:
+            x = rng.uniform(a[1], a[2], n_pts)
+            x[:3] = [a[1], a[2], 0.5 * (a[1] + a[2])]                              # end points (linear.hpp:224-227 clamps)
+            cols.append(x)
+    coords = np.stack(cols, axis=1)
+    ref = O.evaluate_prod(table, axes, coords)
+    out = ctx.evaluate_prod(table, axes, coords)
+    assert np.array_equal(np.asarray(out), ref)
+    import torch
+    td = torch.from_numpy(table).cuda()
+    out_d = ctx.evaluate_prod(td, axes, torch.from_numpy(coords).cuda())
+    assert np.array_equal(out_d.cpu().numpy(), ref)
+
+
 def test_interp_tau(ctx):
     beta, n_tau = 10.0, 8192
     _, H = matrix_gf(beta, 8, 5, 77)

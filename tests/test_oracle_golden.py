@@ -397,3 +397,40 @@ def test_fit_tail_real_known_answers():
     g = (1 / (w - a))[:, None]
     tail, err = O.fit_tail_refreq(g, -om, om, np.array([[0.0], [1.0]], complex))
     assert np.max(np.abs(tail[:5, 0] - np.array([0, 1, a, a ** 2, a ** 3]))) < 1e-7
+
+
+def test_evaluate_prod_reference_known_answers():
+    """test/c++/gfs/multivar/g_k_om.cpp:76-114 (Gkom.Eval): g(k, iw) on a 40 x 40 brzone x imfreq mesh re-evaluated on the mesh itself
+    (1e-14) and on a 3 x finer k grid (within 5 %, the reference's own bound); the interpolation rules are
+    mesh/evaluate.hpp:97-114, brzone.hpp:355-373, linear.hpp:221-228."""
+    beta, n_k, n_w = 5.0, 40, 5
+    iw = O.imfreq_values(beta, O.FERMION, n_w)
+    k = np.arange(n_k) / n_k * 2 * np.pi
+    g = 1 / (iw[None, None, None, :] + 3 + 2 * (np.cos(k)[:, None, None, None] + np.cos(k)[None, :, None, None]))
+    g = np.ascontiguousarray(np.broadcast_to(g, (n_k, n_k, 1, len(iw))))[..., None]
+    axes = ["periodic", "periodic", "periodic", "index"]
+    pts = np.array([[ix, iy, 0, n] for ix in range(n_k) for iy in range(n_k) for n in range(len(iw))], float)
+    r = O.evaluate_prod(g, axes, pts)
+    assert np.max(np.abs(r[:, 0] - g[..., 0].reshape(-1))) < 1e-14
+    n2 = 3 * n_k
+    pts, ref = [], []
+    for a in range(n2):
+        for b in range(n2):
+            kx, ky = a / n2 * 2 * np.pi, b / n2 * 2 * np.pi
+            for n in range(len(iw)):
+                pts.append([kx / (2 * np.pi) * n_k, ky / (2 * np.pi) * n_k, 0.0, n])  # transpose(units_inv) * k, brzone.hpp:368
+                ref.append(1 / (iw[n] + 3 + 2 * (np.cos(kx) + np.cos(ky))))
+    r = O.evaluate_prod(g, axes, np.array(pts))[:, 0]
+    ref = np.array(ref)
+    assert np.all(np.abs(r - ref) <= 0.05 * np.abs(ref))
+    # one linear component == gf_evaluator<imtime> (evaluator.hpp:35-43)
+    rng = np.random.default_rng(0)
+    tab = rng.normal(size=(101, 3)) + 1j * rng.normal(size=(101, 3))
+    taus = rng.uniform(0, 7.0, 500)
+    assert np.array_equal(O.evaluate_prod(tab, [("linear", 0.0, 7.0)], taus[:, None]), O.interp_tau(tab, 7.0, taus))
+    # a bilinear function is reproduced exactly by two linear components (evaluate.hpp:104-110: the first component is the inner sum)
+    t1, t2 = O.linear_values(0.0, 2.0, 11), O.linear_values(-1.0, 1.0, 21)
+    f = (1 + 2 * t1[:, None] - 3 * t2[None, :] + 0.5 * t1[:, None] * t2[None, :]).astype(complex)[..., None]
+    xy = np.stack([rng.uniform(0, 2, 300), rng.uniform(-1, 1, 300)], axis=1)
+    r = O.evaluate_prod(f, [("linear", 0.0, 2.0), ("linear", -1.0, 1.0)], xy)[:, 0]
+    assert np.max(np.abs(r - (1 + 2 * xy[:, 0] - 3 * xy[:, 1] + 0.5 * xy[:, 0] * xy[:, 1]))) < 1e-13

@@ -19,6 +19,14 @@ TQ_WARN_NOISY_TAU, TQ_WARN_SHORT_TAU_MESH, TQ_WARN_TAIL_ERR = 1, 2, 4
 TQ_MAX_MOMENTS = 10
 TQ_MAX_MATRIX_DIM = 64
 TQ_COMM_ID_BYTES = 128
+TQ_PROD_MAX_DIMS = 4
+TQ_AXIS_LINEAR, TQ_AXIS_PERIODIC, TQ_AXIS_INDEX = 0, 1, 2
+
+
+class TqAxis(ctypes.Structure):
+    """tq_axis of include/tqgpu.h"""
+    _fields_ = [("kind", c_int), ("size", c_long), ("xmin", c_double), ("xmax", c_double)]
+
 
 # every symbol include/tqgpu.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -65,6 +73,7 @@ SIGNATURES = {
                               c_int]),
     "tq_interp_tau": (c_int, [c_void_p, c_double, c_long, c_long, c_void_p, c_long, c_void_p, c_void_p]),
     "tq_evaluate_imfreq": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_void_p, c_long, c_void_p, c_void_p, POINTER(c_double)]),
+    "tq_evaluate_prod": (c_int, [c_void_p, c_int, POINTER(TqAxis), c_long, c_void_p, c_long, c_void_p, c_void_p]),
     "tq_comm_unique_id": (c_int, [c_void_p]),
     "tq_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "tq_all_reduce_sum": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -443,6 +443,31 @@ class Context:
             return res, np.frombuffer(err, dtype=np.float64).copy()
         return res
 
+    def evaluate_prod(self, table, axes, coords, out=None):
+        """Multi-linear interpolation on a product mesh (tq_evaluate_prod; c++/triqs/mesh/evaluate.hpp:97-114).
+        table [size_0, ..., size_{d-1}, n_elem]; axes: one entry per component mesh --
+          ("linear", xmin, xmax)   imtime / retime / refreq (linear.hpp:221-228), coordinate = the value,
+          "periodic"               one brzone direction (brzone.hpp:355-359), coordinate in units of the mesh index,
+          "index"                  pass-through (imfreq: n - first), coordinate = the data index;
+        coords [n_pts, d] -> [n_pts, n_elem]."""
+        table = _as_c128(table)
+        coords = _as_f64(coords)
+        n_dims = len(axes)
+        if table.ndim != n_dims + 1 or coords.ndim != 2 or coords.shape[1] != n_dims:
+            raise TqError("evaluate_prod: table must be [size_0, ..., size_{d-1}, n_elem] and coords [n_pts, d]")
+        arr = (L.TqAxis * n_dims)()
+        for d, a in enumerate(axes):
+            if a == "periodic":
+                arr[d] = L.TqAxis(L.TQ_AXIS_PERIODIC, table.shape[d], 0.0, 0.0)
+            elif a == "index":
+                arr[d] = L.TqAxis(L.TQ_AXIS_INDEX, table.shape[d], 0.0, 0.0)
+            else:
+                arr[d] = L.TqAxis(L.TQ_AXIS_LINEAR, table.shape[d], float(a[1]), float(a[2]))
+        n_pts, n_elem = coords.shape[0], table.shape[-1]
+        y = out if out is not None else _empty_like_kind(table, (n_pts, n_elem))
+        self._check(self._run("tq_evaluate_prod", n_dims, arr, n_elem, _ptr(table), n_pts, _ptr(coords), _ptr(y)))
+        return y
+
     # -- multi GPU ---------------------------------------------------------------------------------
     def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
         buf = (ctypes.c_ubyte * L.TQ_COMM_ID_BYTES).from_buffer_copy(unique_id)

@@ -192,6 +192,16 @@ namespace triqs_b200 {
     }
     inline brzone make_adjoint_mesh(cyclat const &m) { return brzone{m._dims[0], m._dims[1], m._dims[2]}; }
     inline cyclat make_adjoint_mesh(brzone const &m) { return cyclat{m._dims[0], m._dims[1], m._dims[2]}; }
+
+    // Cartesian product of two meshes (c++/triqs/mesh/prod.hpp:72-208): data index = i1 * size(m2) + i2
+    template <typename M1, typename M2> struct prod {
+      M1 m1;
+      M2 m2;
+      prod() = default;
+      prod(M1 a, M2 b) : m1(std::move(a)), m2(std::move(b)) {}
+      long size() const { return m1.size() * m2.size(); }
+      bool operator==(prod const &o) const { return m1 == o.m1 && m2 == o.m2; }
+    };
   } // namespace mesh
 
   // ------------------------------------------------------------------------------------------------
@@ -605,6 +615,40 @@ namespace triqs_b200 {
     double err = 0;
     check(tq_evaluate_imfreq(context(), g.mesh().beta(), g.mesh().statistic(), g.mesh().n_iw(), g.n_others(), 1, detail::cptr(g.data()),
                              (long)ns.size(), ns.data(), detail::ptr(out), &err));
+    return out;
+  }
+  // Product-mesh evaluation  g(x1, x2)  (c++/triqs/mesh/evaluate.hpp:97-114), batched over points: multi-linear interpolation with
+  // the per-component rules of linear.hpp:221-228 (imtime / retime / refreq: the value), brzone.hpp:355-373 (a k vector given in units
+  // of the mesh index, i.e. transpose(units_inv) * k) and index pass-through (imfreq: the Matsubara index n, inside the mesh).
+  namespace detail {
+    inline void push_axes(mesh::imtime const &m, std::vector<tq_axis> &a) { a.push_back(tq_axis{TQ_AXIS_LINEAR, m.size(), 0.0, m.beta()}); }
+    inline void push_axes(mesh::linear_mesh_base const &m, std::vector<tq_axis> &a) { a.push_back(tq_axis{TQ_AXIS_LINEAR, m.size(), m._xmin, m._xmax}); }
+    inline void push_axes(mesh::brzone const &m, std::vector<tq_axis> &a) {
+      for (int j = 0; j < 3; ++j) a.push_back(tq_axis{TQ_AXIS_PERIODIC, m._dims[j], 0.0, 0.0});
+    }
+    inline void push_axes(mesh::imfreq const &m, std::vector<tq_axis> &a) { a.push_back(tq_axis{TQ_AXIS_INDEX, m.size(), 0.0, 0.0}); }
+    inline void push_coord(mesh::imtime const &, double x, std::vector<double> &c) { c.push_back(x); }
+    inline void push_coord(mesh::linear_mesh_base const &, double x, std::vector<double> &c) { c.push_back(x); }
+    inline void push_coord(mesh::brzone const &, std::array<double, 3> const &k, std::vector<double> &c) { c.insert(c.end(), k.begin(), k.end()); }
+    inline void push_coord(mesh::imfreq const &m, long n, std::vector<double> &c) {
+      if (n < m.first_index() || n > m.last_index()) throw runtime_error("product-mesh evaluation: Matsubara index outside the mesh");
+      c.push_back(double(n - m.first_index()));
+    }
+  } // namespace detail
+  template <typename M1, typename M2, typename T, typename X1, typename X2>
+  std::vector<dcomplex> evaluate(gf<mesh::prod<M1, M2>, T> const &g, std::vector<X1> const &x1, std::vector<X2> const &x2) {
+    if (x1.size() != x2.size()) throw runtime_error("product-mesh evaluation: one coordinate per component and point");
+    std::vector<tq_axis> axes;
+    detail::push_axes(g.mesh().m1, axes);
+    detail::push_axes(g.mesh().m2, axes);
+    std::vector<double> coords;
+    for (size_t i = 0; i < x1.size(); ++i) {
+      detail::push_coord(g.mesh().m1, x1[i], coords);
+      detail::push_coord(g.mesh().m2, x2[i], coords);
+    }
+    std::vector<dcomplex> out(size_t(x1.size() * g.n_others()));
+    check(tq_evaluate_prod(context(), (int)axes.size(), axes.data(), g.n_others(), detail::cptr(g.data()), (long)x1.size(), coords.data(),
+                           detail::ptr(out)));
     return out;
   }
   // engine options of the context (tq_set_option: never change results), e.g. set_option("host_lanes", 4)

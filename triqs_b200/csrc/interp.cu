@@ -74,3 +74,139 @@ extern "C" tq_status tq_interp_tau(tq_ctx *ctx, double beta, long n_tau, long n_
   TQ_TRY(tq_stage_out_finish(ctx, out, out_bytes, d_out, out_host));
   return TQ_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Off-mesh evaluation on a PRODUCT mesh: multi-linear interpolation, one factor per component mesh.
+//
+// Restates  evaluate(std::tuple<M...>, f, x1, x...)   c++/triqs/mesh/evaluate.hpp:97-114  (the recursion: the sum over the FIRST
+//           component is the innermost one), with the per-component rules
+//             linear::evaluate          c++/triqs/mesh/bases/linear.hpp:221-228   (imtime, retime, refreq: clamped cell, weight w)
+//             evaluate(brzone1d, f, vi) c++/triqs/mesh/brzone.hpp:355-359         (periodic: floor, positive_modulo; dim == 1 -> 0)
+//             evaluate(m, f, index)     c++/triqs/mesh/evaluate.hpp:73            (an index passes through: imfreq n, cyclat index)
+// One thread per output element; the cell and weight of every (point, component) are computed once per point in shared memory.
+// Every two-point combination is (1 - w) * A + w * B with the products rounded separately, like the reference's expression.
+constexpr int PROD_PB = 128;
+struct ProdArgs {
+  int n_dims;
+  int kind[TQ_PROD_MAX_DIMS];
+  long dim[TQ_PROD_MAX_DIMS];
+  long stride[TQ_PROD_MAX_DIMS]; // in elements of n_elem complex numbers
+  double xmin[TQ_PROD_MAX_DIMS], delta_inv[TQ_PROD_MAX_DIMS];
+};
+TQ_D long prod_pmod(long i, long d) {
+  const long r = i % d;
+  return r < 0 ? r + d : r;
+}
+__global__ void __launch_bounds__(256) k_evaluate_prod(const __grid_constant__ ProdArgs P, const cd *__restrict__ table, int n_elem,
+                                                       const double *__restrict__ coords, long n_pts, cd *__restrict__ out) {
+  __shared__ long s_lo[TQ_PROD_MAX_DIMS][PROD_PB], s_hi[TQ_PROD_MAX_DIMS][PROD_PB];
+  __shared__ double s_w[TQ_PROD_MAX_DIMS][PROD_PB];
+  const int nd = P.n_dims;
+  const long n_chunks = (n_pts + PROD_PB - 1) / PROD_PB;
+  for (long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const long p0 = ch * PROD_PB;
+    const int np = (int)min((long)PROD_PB, n_pts - p0);
+    for (int t = threadIdx.x; t < np * nd; t += blockDim.x) {
+      const int pl = t / nd, d = t - pl * nd;
+      const double x = __ldg(&coords[(p0 + pl) * nd + d]);
+      long lo, hi;
+      double w;
+      if (P.kind[d] == TQ_AXIS_LINEAR) { // linear.hpp:221-228
+        const double xc = fmax(x, P.xmin[d]);
+        const double a = (xc - P.xmin[d]) * P.delta_inv[d];
+        lo = min((long)a, P.dim[d] - 2);
+        hi = lo + 1;
+        w = fmin(a - (double)lo, 1.0);
+      } else if (P.kind[d] == TQ_AXIS_PERIODIC) { // brzone.hpp:355-359
+        const long i = (long)floor(x);
+        w = x - (double)i;
+        lo = prod_pmod(i, P.dim[d]);
+        hi = P.dim[d] == 1 ? 0 : prod_pmod(i + 1, P.dim[d]);
+      } else { // an index: pass through (evaluate.hpp:73)
+        lo = hi = (long)llrint(x);
+        w = -1.0; // marks "no interpolation along this component"
+      }
+      s_lo[d][pl] = lo * P.stride[d];
+      s_hi[d][pl] = hi * P.stride[d];
+      s_w[d][pl] = w;
+    }
+    __syncthreads();
+    const long tot = (long)np * n_elem;
+    cd *o = out + (size_t)p0 * n_elem;
+    for (long t = threadIdx.x; t < tot; t += blockDim.x) {
+      const int pl = (int)(t / n_elem);
+      const int e = (int)(t - (long)pl * n_elem);
+      // corners: bit j of the corner number selects lo / hi of the j-th INTERPOLATED component (in mesh order)
+      int idim[TQ_PROD_MAX_DIMS], m = 0;
+      long base = 0;
+      for (int d = 0; d < nd; ++d) {
+        if (s_w[d][pl] < 0.0)
+          base += s_lo[d][pl];
+        else
+          idim[m++] = d;
+      }
+      cd v[1 << TQ_PROD_MAX_DIMS];
+      for (int c = 0; c < (1 << m); ++c) {
+        long off = base;
+        for (int j = 0; j < m; ++j) off += ((c >> j) & 1) ? s_hi[idim[j]][pl] : s_lo[idim[j]][pl];
+        v[c] = __ldg(&table[(size_t)off * n_elem + e]);
+      }
+      // the first component is the innermost sum of the recursion (evaluate.hpp:104-110)
+      for (int j = 0; j < m; ++j) {
+        const double w = s_w[idim[j]][pl], u = 1 - w;
+        for (int c = 0; c < (1 << (m - 1 - j)); ++c) {
+          const cd A = v[2 * c], B = v[2 * c + 1];
+          v[c] = cmk(__dadd_rn(__dmul_rn(u, A.x), __dmul_rn(w, B.x)), __dadd_rn(__dmul_rn(u, A.y), __dmul_rn(w, B.y)));
+        }
+      }
+      __stcs(&o[t], v[0]);
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" tq_status tq_evaluate_prod(tq_ctx *ctx, int n_dims, const tq_axis *axes, long n_elem, const tq_complex *table, long n_pts,
+                                      const double *coords, tq_complex *out) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!axes || !table || !coords || !out || n_dims < 1 || n_dims > TQ_PROD_MAX_DIMS || n_elem < 1 || n_pts < 0)
+    return tq_fail(ctx, TQ_ERR_INVALID, "tq_evaluate_prod: invalid argument");
+  ProdArgs P{};
+  P.n_dims = n_dims;
+  size_t total = 1;
+  for (int d = n_dims - 1; d >= 0; --d) {
+    const tq_axis &a = axes[d];
+    if (a.size < 1 || (a.kind != TQ_AXIS_LINEAR && a.kind != TQ_AXIS_PERIODIC && a.kind != TQ_AXIS_INDEX))
+      return tq_fail(ctx, TQ_ERR_INVALID, "tq_evaluate_prod: invalid axis");
+    if (a.kind == TQ_AXIS_LINEAR && (a.size < 2 || !(a.xmax > a.xmin))) // linear.hpp:222 EXPECTS(size() > 1)
+      return tq_fail(ctx, TQ_ERR_INVALID, "tq_evaluate_prod: a linear axis needs at least two points and xmax > xmin");
+    P.kind[d] = a.kind;
+    P.dim[d] = a.size;
+    P.stride[d] = (long)total;
+    P.xmin[d] = a.xmin;
+    if (a.kind == TQ_AXIS_LINEAR) {
+      const double delta = (a.xmax - a.xmin) / (double)(a.size - 1); // linear.hpp:51
+      P.delta_inv[d] = 1.0 / delta;                                   // linear.hpp:52
+    }
+    total *= (size_t)a.size;
+  }
+  if (n_pts == 0) return TQ_OK;
+  if (n_elem > (1 << 22)) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_evaluate_prod: target too large");
+  TQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void *d_tab = nullptr, *d_x = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  const size_t out_bytes = sizeof(cd) * (size_t)n_pts * n_elem;
+  TQ_TRY(tq_stage_in(ctx, table, sizeof(cd) * total * (size_t)n_elem, ctx->stage_in, &d_tab));
+  TQ_TRY(tq_stage_in(ctx, coords, sizeof(double) * (size_t)n_pts * n_dims, ctx->stage_in2, &d_x));
+  TQ_TRY(tq_stage_out_begin(ctx, out, out_bytes, ctx->stage_out, &d_out, &out_host));
+  long nb = (n_pts + PROD_PB - 1) / PROD_PB;
+  nb = std::min<long>(nb, (long)ctx->sm_count * 8 * 16);
+  {
+    KernelScope ks(ctx, "evaluate_prod");
+    k_evaluate_prod<<<(unsigned)nb, 256, 0, ctx->stream>>>(P, (const cd *)d_tab, (int)n_elem, (const double *)d_x, n_pts, (cd *)d_out);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  TQ_TRY(tq_stage_out_finish(ctx, out, out_bytes, d_out, out_host));
+  return TQ_OK;
+}

@@ -121,10 +121,22 @@ class MeshCycLat:
 
 @dataclass(frozen=True)
 class MeshBrZone:
+    """c++/triqs/mesh/brzone.hpp: dims = points per reciprocal direction; `units` (rows = the mesh steps in k space, brzone.hpp:60-75)
+    is only needed to evaluate at a k vector -- default: the simple (hyper)cubic lattice with unit lattice constant, 2 pi / dims."""
     dims: tuple
+    units: tuple | None = None
 
     def __len__(self):
         return int(np.prod(self.dims))
+
+    def k_to_index_units(self, k):
+        """transpose(units_inv) * k   (brzone.hpp:368): a k vector in units of the mesh index"""
+        d = tuple(self.dims) + (1,) * (3 - len(self.dims))
+        U = np.diag([2 * np.pi / x for x in d]) if self.units is None else np.asarray(self.units, dtype=float)
+        k = np.atleast_2d(np.asarray(k, dtype=float))
+        if k.shape[1] < 3:
+            k = np.concatenate([k, np.zeros((k.shape[0], 3 - k.shape[1]))], axis=1)
+        return k @ np.linalg.inv(U)
 
 
 @dataclass(frozen=True)
@@ -208,9 +220,60 @@ class Gf:
             self.data[...] = dense
         return self
 
-    def __call__(self, tau):
+    def _call_prod(self, args):
+        """g(x1, x2, ...) on a product mesh (or a single linear / brzone mesh): c++/triqs/mesh/evaluate.hpp:97-114 via tq_evaluate_prod.
+        Per component: imtime / retime / refreq take values, brzone a k vector (or an array [n_pts, 3] of them), imfreq a Matsubara
+        index inside the mesh, cyclat a linear index."""
+        meshes = self.mesh.meshes if isinstance(self.mesh, MeshProduct) else (self.mesh,)
+        if len(args) != len(meshes):
+            raise TriqsRuntimeError(f"evaluation of a gf on {len(meshes)} meshes needs {len(meshes)} arguments")
+        axes, cols, shape, scalar = [], [], [], True
+        for m, x in zip(meshes, args):
+            if isinstance(m, MeshImTime):
+                axes.append(("linear", 0.0, m.beta))
+                shape.append(len(m))
+                cols.append(np.atleast_1d(np.asarray(x, dtype=float)))
+                scalar = scalar and np.isscalar(x)
+            elif isinstance(m, _MeshLinear):
+                axes.append(("linear", m.xmin, m.xmax))
+                shape.append(len(m))
+                cols.append(np.atleast_1d(np.asarray(x, dtype=float)))
+                scalar = scalar and np.isscalar(x)
+            elif isinstance(m, MeshBrZone):
+                v = m.k_to_index_units(x)
+                d = tuple(m.dims) + (1,) * (3 - len(m.dims))
+                for j in range(3):
+                    axes.append("periodic")
+                    shape.append(d[j])
+                    cols.append(v[:, j])
+                scalar = scalar and np.ndim(x) == 1
+            elif isinstance(m, MeshImFreq):
+                n = np.atleast_1d(np.asarray(x, dtype=np.int64))
+                if np.any(n < m.first_index) or np.any(n > m.last_index):
+                    raise TriqsRuntimeError("product-mesh evaluation: Matsubara index outside the mesh")
+                axes.append("index")
+                shape.append(len(m))
+                cols.append((n - m.first_index).astype(float))
+                scalar = scalar and np.isscalar(x)
+            else:
+                axes.append("index")
+                shape.append(len(m))
+                cols.append(np.atleast_1d(np.asarray(x, dtype=float)))
+                scalar = scalar and np.isscalar(x)
+        n_pts = max(len(c) for c in cols)
+        coords = np.stack([np.broadcast_to(c, (n_pts,)) for c in cols], axis=1)
+        d = self.data
+        table = d.reshape(tuple(shape) + (-1,))
+        out = self.ctx.evaluate_prod(table, axes, coords)
+        out = out.reshape((n_pts,) + tuple(self.target_shape))
+        return out[0] if scalar else out
+
+    def __call__(self, tau, *more):
         """off-mesh evaluation: linear interpolation on an imtime mesh (c++/triqs/gfs/evaluator.hpp:35-43; a scalar or an array
-        of tau), or g(n) on an imfreq mesh -- the mesh value inside the window, the fitted tail outside (evaluator.hpp:50-76)."""
+        of tau), or g(n) on an imfreq mesh -- the mesh value inside the window, the fitted tail outside (evaluator.hpp:50-76);
+        product meshes, real-time / real-frequency and brzone meshes: multi-linear interpolation (mesh/evaluate.hpp:97-114)."""
+        if more or isinstance(self.mesh, (MeshProduct, MeshBrZone, _MeshLinear)):
+            return self._call_prod((tau,) + more)
         if isinstance(self.mesh, MeshImFreq):
             m = self.mesh
             if not np.isscalar(tau):  # an array of Matsubara indices: one batched call (tq_evaluate_imfreq)
