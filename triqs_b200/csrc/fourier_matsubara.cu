@@ -1096,6 +1096,9 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
   }
   for (int l = 0; l < lanes; ++l) {
     ctx->lanes[l]->opt_no_pipe = ctx->opt_no_pipe;
+    ctx->lanes[l]->opt_no_col = ctx->opt_no_col;
+    ctx->lanes[l]->opt_no_tr = ctx->opt_no_tr;
+    ctx->lanes[l]->call_batch = batch;
     ctx->lanes[l]->opt_scratch_chunk_mb = ctx->opt_scratch_chunk_mb;
     ctx->lanes[l]->opt_bounce = ctx->opt_bounce ? 2 : 0; // (2: this context is a lane of a multi-lane call)
     ctx->lanes[l]->opt_pipe_lag0 = ctx->opt_pipe_lag0;

@@ -398,7 +398,8 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
     if (n_cols < 4) {
       // the single-column kernel (fourier_col.cu: one HBM read, one write, no scratch) keeps its mesh
       const bool col_kernel = fwd && L == 10000 && n_cols == 1 && !ctx->opt_no_col;
-      if (batch * n_cols >= 8 && !col_kernel && !ctx->opt_no_tr) {
+      // (a lane of a chunked host-buffer call decides as the whole call would: the chunking must not change a bit)
+      if (std::max(batch, ctx->call_batch) * n_cols >= 8 && !col_kernel && !ctx->opt_no_tr) {
         tr = (int)n_cols;
       } else {
         // Narrow targets on meshes whose whole column fits one SM's shared memory stay with the single-kernel paths (one HBM read

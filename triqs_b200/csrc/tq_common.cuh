@@ -105,6 +105,7 @@ struct tq_ctx {
   long opt_bounce = 1;           // stage pageable host buffers through the library's own pinned slots (tq_stage_in)
   long opt_host_chunk_kb = 48L << 10; // input bytes per chunk of a host-buffer call (KiB): one C2 block (40 MB) per chunk
   std::vector<tq_ctx *> lanes;   // child contexts of the lanes (created on first use)
+  long call_batch = 0;           // lane contexts: batch of the whole host-buffer call (path decisions must not depend on the chunking)
   // NCCL
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
