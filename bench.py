@@ -462,6 +462,19 @@ def run_native(args):
     e2e["single_thread_pageable"] = pts_step * st1 / wall(one_thread(p_gt, p_gw, p_gt2), st1)
     e2e["single_thread_pageable_err"] = float(np.max(np.abs(p_gt2[:NBLOCK] - p_gt[:NBLOCK])))
     del p_gt, p_gw, p_gt2
+    # real-valued G(tau) (gf<imtime, matrix_real_valued>; fourier.hpp:78-81 promotes it): tq_fourier_tau_to_iw_real /
+    # tq_fourier_iw_to_tau_real move 8 bytes per point of the large side over PCIe instead of 16
+    r_gt = torch.empty((NBLOCK * R, N_TAU, NCOL), dtype=torch.float64).pin_memory()
+    r_gt2 = torch.empty_like(r_gt).pin_memory()
+    r_gt.numpy()[...] = h_gt.real
+    rin, rout = r_gt.numpy(), r_gt2.numpy()
+
+    def one_thread_real():
+        ctx.fourier_tau_to_iw(rin, BETA, F, N_IW, out=h_gw)
+        ctx.fourier_iw_to_tau(h_gw, BETA, F, N_TAU, out=rout)
+    e2e["single_thread_pinned_real_gtau"] = pts_step * st1 / wall(one_thread_real, st1)
+    e2e["single_thread_pinned_real_gtau_err"] = float(np.max(np.abs(rout[:NBLOCK] - rin[:NBLOCK])))
+    del r_gt, r_gt2, rin, rout
 
     # the literal configs[1]: ONE BlockGf (2 blocks) per call, device resident
     gt_1, gw_1, gt2_1 = gt[:NBLOCK], gw[:NBLOCK], gt2[:NBLOCK]

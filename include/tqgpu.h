@@ -133,6 +133,21 @@ tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_i
                                const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
                                double *tail_err);
 
+/* Real-valued G(tau)  (gf<imtime, T::real_t>).  The reference promotes a real-valued gf to complex before it transforms it
+ *   c++/triqs/gfs/transform/fourier.hpp:78-81  (`gfl_t{flatten_gf_2d<N>(gin)}`, gfl_t = ...::complex_t)
+ * and users take `real(g)` after `is_gf_real(g, tol)` on the way back (c++/triqs/gfs/functions/functions2.hpp:223-246).
+ * These two entry points move only the 8-byte reals between the caller's buffer and the GPU (half the PCIe / HBM bytes of
+ * the large side); the promotion / real-part extraction is a streaming kernel on the device.
+ *   tq_fourier_tau_to_iw_real : gt double[batch][n_tau][n_others]; everything else as tq_fourier_tau_to_iw (same bits as
+ *                               promoting on the host and calling it)
+ *   tq_fourier_iw_to_tau_real : gt double[batch][n_tau][n_others] receives Re G(tau); max_imag host double[batch] (required)
+ *                               receives max |Im G(tau)| per gf, the quantity is_gf_real compares with its tolerance */
+tq_status tq_fourier_tau_to_iw_real(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                                    const double *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn);
+tq_status tq_fourier_iw_to_tau_real(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                                    const tq_complex *gw, const tq_complex *moments, int n_moments, double *gt, int *warn,
+                                    double *tail_err, double *max_imag);
+
 /* density(G(i w)) of matrix-valued gfs on the full Matsubara mesh -- replaces
  *   nda::matrix<dcomplex> density(gf_const_view<imfreq> g, array_const_view<dcomplex, 3> known_moments)
  *     c++/triqs/gfs/functions/density.cpp:32-120   (scalar overload :123-128)

@@ -292,7 +292,39 @@ void test_legendre_and_tight_binding() { // gf_legendre.cpp:22-72;  g_r_k.cpp:40
     for (long j = 0; j < N; ++j) EXPECT(std::abs(ek[i * N + j][0] + 2 * (std::cos(2 * M_PI * i / N) + std::cos(2 * M_PI * j / N))) < 1e-14);
 }
 
+// real-valued G(tau): gf<imtime, matrix_real_valued> -> gf<imfreq, matrix_valued> (fourier.hpp:66, :78-81), and real(g) / is_gf_real
+// (functions2.hpp:223-246) on the way back
+static void test_real_valued_gtau() {
+  double beta = 10, E = -1;
+  int N_iw = 100, N_tau = 6 * N_iw + 1;
+  auto Gt = gf<mesh::imtime, matrix_real_valued>{{beta, Fermion, N_tau}, {2, 2}};
+  auto Gtc = gf<mesh::imtime, matrix_valued>{{beta, Fermion, N_tau}, {2, 2}};
+  for (long i = 0; i < Gt.mesh().size(); ++i) {
+    double t = Gt.mesh()[i];
+    for (long c = 0; c < 4; ++c) {
+      Gt[i][c] = (one_pole(E, t, beta, -1) + 0.5 * one_pole(-2 * E, t, beta, -1)) * (1 + 0.1 * c);
+      Gtc[i][c] = Gt[i][c];
+    }
+  }
+  gf<mesh::imfreq, matrix_valued> Gw = make_gf_from_fourier(Gt, N_iw);
+  auto Gwc = make_gf_from_fourier(Gtc, N_iw);
+  EXPECT(max_diff(Gw, Gwc) == 0.0); // same bits as promoting on the host
+  EXPECT(!is_gf_real(Gw));
+  auto Gt_back = make_gf_from_fourier(Gw, N_tau);
+  EXPECT(is_gf_real(Gt_back, 1e-6)); // (the fitted tail leaves ~1e-8)
+  gf<mesh::imtime, matrix_real_valued> Gr = real(Gt_back);
+  auto Gr2 = make_real_gf_from_fourier(Gw, N_tau, {}, 1e-6);
+  double d = 0, d2 = 0;
+  for (size_t i = 0; i < Gr.data().size(); ++i) {
+    d = std::max(d, std::abs(Gr.data()[i] - Gt.data()[i]));
+    d2 = std::max(d2, std::abs(Gr.data()[i] - Gr2.data()[i]));
+  }
+  EXPECT(d < 1e-5); // (round trip through a least-squares tail fit on a short mesh)
+  EXPECT(d2 == 0.0);
+}
+
 int main() {
+  test_real_valued_gtau();
   test_fourier_real<scalar_valued>({});
   test_fourier_real<matrix_valued>({2, 2});
   test_fourier_real<tensor_valued<3>>({2, 2, 2});

@@ -870,3 +870,59 @@ def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
     ctx.set_option("host_chunk_kb", 48 << 10)
     assert np.array_equal(t1, t3) and np.array_equal(w1, w3)
     assert rel(t3[4], O.fourier_iw_to_tau(gws[4], beta, F, n_tau)) < TOL
+
+
+def test_real_valued_gtau_moves_reals_only_and_matches_the_promoted_call(ctx):
+    """Real-valued G(tau) (gf<imtime, T::real_t>): the reference promotes it to complex before the transform (fourier.hpp:78-81).
+    tq_fourier_tau_to_iw_real takes the float64 buffer and promotes on the device: same bits as promoting on the host; and
+    tq_fourier_iw_to_tau_real hands back real(g) with max |Im| per gf (functions2.hpp:223-246).  Host buffers (chunked over the
+    lanes), device tensors, odd and even column counts."""
+    import torch
+    beta, n_iw = 10.0, 200
+    rng = np.random.default_rng(33)
+    for n_tau, ncols, B in [(1201, 5, 7), (6151, 4, 3), (10001, 1, 9)]:
+        gts = []
+        for b in range(B):
+            E = rng.uniform(-2, 2, 3)
+            gts.append(np.stack([poles_gtau(beta, n_tau, E * (1 + 0.1 * c), [0.2, 0.3, 0.5])[:] for c in range(ncols)], axis=1))
+        gc = np.stack(gts)
+        assert np.max(np.abs(gc.imag)) == 0.0
+        gr = np.ascontiguousarray(gc.real)
+        w_c = ctx.fourier_tau_to_iw(gc, beta, F, n_iw)
+        warn_c = np.array(ctx.last_warn)
+        ctx.set_option("host_chunk_kb", 2 * n_tau * ncols * 8 // 1024 + 1)  # two gfs per chunk
+        w_r = ctx.fourier_tau_to_iw(gr, beta, F, n_iw)
+        ctx.set_option("host_chunk_kb", 48 << 10)
+        assert np.array_equal(w_c, w_r) and np.array_equal(warn_c, np.array(ctx.last_warn))
+        assert rel(w_r[0], O.fourier_tau_to_iw(gc[0], beta, F, n_iw)) < TOL
+        # device-resident real input
+        w_d = ctx.fourier_tau_to_iw(torch.from_numpy(gr).cuda(), beta, F, n_iw)
+        assert np.array_equal(w_d.cpu().numpy(), w_c)
+        # and back: real part + max |Im|
+        t_c = ctx.fourier_iw_to_tau(w_c, beta, F, n_tau)
+        t_r = ctx.fourier_iw_to_tau(w_c, beta, F, n_tau, real_out=True)
+        assert t_r.dtype == np.float64 and np.array_equal(t_r, t_c.real)
+        assert np.array_equal(ctx.last_max_imag, np.max(np.abs(t_c.imag), axis=(1, 2)))
+        assert np.max(np.abs(t_r - gr)) < 5e-6  # (round trip: limited by the tail fit, like the complex path)
+        out = torch.empty(B, n_tau, ncols, dtype=torch.float64, device="cuda")
+        ctx.fourier_iw_to_tau(torch.from_numpy(w_c).cuda(), beta, F, n_tau, out=out)
+        assert np.array_equal(out.cpu().numpy(), t_r)
+
+
+def test_gf_mirror_real_valued_gf(ctx):
+    """Gf(..., is_real=True) / real(g) / is_gf_real(g): python/triqs/gf/gf.py `is_real`, functions2.hpp:223-248."""
+    from triqs_b200.gf import Gf, MeshImTime, make_gf_from_fourier, is_gf_real, real
+    beta, n_tau = 10.0, 1201
+    m = MeshImTime(beta, F, n_tau)
+    g = Gf(m, (2, 2), ctx=ctx, is_real=True)
+    assert g.data.dtype == np.float64
+    for i in range(2):
+        for j in range(2):
+            g.data[:, i, j] = poles_gtau(beta, n_tau, [0.3 + i, -0.7 * (j + 1)], [0.4, 0.6]).real * (1.0 if i == j else 0.1)
+    gw = make_gf_from_fourier(g)
+    gc = Gf(m, (2, 2), g.data.astype(complex), ctx)
+    assert np.array_equal(gw.data, make_gf_from_fourier(gc).data)
+    back = make_gf_from_fourier(gw)
+    assert is_gf_real(back, 1e-9) and not is_gf_real(gw)
+    rb = real(back)
+    assert rb.data.dtype == np.float64 and np.max(np.abs(rb.data - g.data)) < 1e-6

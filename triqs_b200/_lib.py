@@ -48,6 +48,10 @@ SIGNATURES = {
                                           POINTER(c_int)]),
     "tq_fourier_iw_to_tau": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
                                      POINTER(c_int), POINTER(c_double)]),
+    "tq_fourier_tau_to_iw_real": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
+                                          POINTER(c_int)]),
+    "tq_fourier_iw_to_tau_real": (c_int, [c_void_p, c_double, c_int, c_long, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p,
+                                          POINTER(c_int), POINTER(c_double), POINTER(c_double)]),
     "tq_density": (c_int, [c_void_p, c_double, c_int, c_long, c_int, c_long, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int),
                            POINTER(c_double)]),
     "tq_fourier_t_to_w": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_long, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p]),

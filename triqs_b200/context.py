@@ -51,6 +51,13 @@ def _as_c128(x):
     return np.ascontiguousarray(x, dtype=np.complex128)
 
 
+def _is_real_dtype(x):
+    """real-valued data (gf<mesh, T::real_t>): float64 / float32 NumPy arrays or torch tensors"""
+    if _is_torch(x):
+        return not x.dtype.is_complex
+    return not np.iscomplexobj(x)
+
+
 def _as_f64(x):
     if _is_torch(x):
         import torch
@@ -169,8 +176,11 @@ class Context:
     # -- Matsubara transforms -------------------------------------------------------------------
     def fourier_tau_to_iw(self, gt, beta, statistic, n_iw, moments=None, out=None, one_gf=False):
         """gt [batch, n_tau, n_others] -> gw [batch, n_w, n_others]  (tq_fourier_tau_to_iw).
-        one_gf: the leading index is an outer mesh of ONE gf (tq_fourier_tau_to_iw_axis): joint noise check, one warning."""
-        gt = _as_c128(gt)
+        one_gf: the leading index is an outer mesh of ONE gf (tq_fourier_tau_to_iw_axis): joint noise check, one warning.
+        A real-valued gt (float64) goes through tq_fourier_tau_to_iw_real: only the reals cross PCIe, the promotion to complex
+        (fourier.hpp:78-81) happens on the device."""
+        real_in = _is_real_dtype(gt) and not one_gf
+        gt = _as_f64(gt) if real_in else _as_c128(gt)
         batch, n_tau, n_others = gt.shape
         n_w = 2 * n_iw if statistic == FERMION else 2 * n_iw - 1
         n_mom = 0
@@ -179,7 +189,10 @@ class Context:
             n_mom = moments.shape[1]
         gw = out if out is not None else _empty_like_kind(gt, (batch, n_w, n_others))
         warn = (ctypes.c_int * (1 if one_gf else batch))()
-        if one_gf:
+        if real_in:
+            self._check(self._run("tq_fourier_tau_to_iw_real", beta, statistic, n_tau, n_iw, n_others, batch, _ptr(gt), _ptr(moments),
+                                  n_mom, _ptr(gw), warn))
+        elif one_gf:
             self._check(self._run("tq_fourier_tau_to_iw_axis", beta, statistic, n_tau, n_iw, batch, n_others, _ptr(gt), _ptr(moments),
                                                             n_mom, _ptr(gw), warn))
         else:
@@ -188,8 +201,10 @@ class Context:
         self._emit(np.frombuffer(warn, dtype=np.int32))
         return gw
 
-    def fourier_iw_to_tau(self, gw, beta, statistic, n_tau, moments=None, out=None, return_err=False):
-        """gw [batch, n_w, n_others] (full mesh) -> gt [batch, n_tau, n_others]  (tq_fourier_iw_to_tau)."""
+    def fourier_iw_to_tau(self, gw, beta, statistic, n_tau, moments=None, out=None, return_err=False, real_out=False):
+        """gw [batch, n_w, n_others] (full mesh) -> gt [batch, n_tau, n_others]  (tq_fourier_iw_to_tau).
+        real_out (or a float64 `out`): tq_fourier_iw_to_tau_real -- gt receives Re G(tau) as float64 (real(g), functions2.hpp:242)
+        and `last_max_imag` [batch] max |Im G(tau)|, what is_gf_real (functions2.hpp:223) compares with its tolerance."""
         gw = _as_c128(gw)
         batch, n_w, n_others = gw.shape
         if statistic == FERMION:
@@ -204,11 +219,22 @@ class Context:
         if moments is not None:
             moments = _as_c128(moments)
             n_mom = moments.shape[1]
-        gt = out if out is not None else _empty_like_kind(gw, (batch, n_tau, n_others))
+        real_out = real_out or (out is not None and _is_real_dtype(out))
+        if real_out and out is not None:
+            if not _is_real_dtype(out) or tuple(out.shape) != (batch, n_tau, n_others) or not (
+                    out.is_contiguous() if _is_torch(out) else (out.flags.c_contiguous and out.dtype == np.float64)):
+                raise ValueError("real_out: `out` must be a contiguous float64 [batch, n_tau, n_others] array")
+        gt = out if out is not None else _empty_like_kind(gw, (batch, n_tau, n_others), np.float64 if real_out else np.complex128)
         warn = (ctypes.c_int * batch)()
         err = (ctypes.c_double * batch)()
-        self._check(self._run("tq_fourier_iw_to_tau", beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
-                                                   _ptr(gt), warn, err))
+        if real_out:
+            mi = (ctypes.c_double * batch)()
+            self._check(self._run("tq_fourier_iw_to_tau_real", beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
+                                  _ptr(gt), warn, err, mi))
+            self.last_max_imag = np.frombuffer(mi, dtype=np.float64).copy()
+        else:
+            self._check(self._run("tq_fourier_iw_to_tau", beta, statistic, n_iw, n_tau, n_others, batch, _ptr(gw), _ptr(moments), n_mom,
+                                  _ptr(gt), warn, err))
         self._emit(np.frombuffer(warn, dtype=np.int32))
         if return_err:
             return gt, np.frombuffer(err, dtype=np.float64).copy()

@@ -14,6 +14,7 @@
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <complex>
 #include <iostream>
 #include <stdexcept>
@@ -209,13 +210,43 @@ namespace triqs_b200 {
   // ------------------------------------------------------------------------------------------------
   struct scalar_valued {
     static constexpr int rank = 0;
+    using scalar_t = dcomplex;
+    using complex_t = scalar_valued;
   };
   struct matrix_valued {
     static constexpr int rank = 2;
+    using scalar_t = dcomplex;
+    using complex_t = matrix_valued;
   };
   template <int R> struct tensor_valued {
     static constexpr int rank = R;
+    using scalar_t = dcomplex;
+    using complex_t = tensor_valued<R>;
   };
+  // real-valued targets (c++/triqs/gfs/gf/targets.hpp: scalar_real_valued, matrix_real_valued, tensor_real_valued<R>): double data;
+  // the Fourier transform of such a gf promotes it to T::complex_t (fourier.hpp:66, :78-81)
+  struct scalar_real_valued {
+    static constexpr int rank = 0;
+    using scalar_t = double;
+    using complex_t = scalar_valued;
+  };
+  struct matrix_real_valued {
+    static constexpr int rank = 2;
+    using scalar_t = double;
+    using complex_t = matrix_valued;
+  };
+  template <int R> struct tensor_real_valued {
+    static constexpr int rank = R;
+    using scalar_t = double;
+    using complex_t = tensor_valued<R>;
+  };
+  namespace detail {
+    template <typename T> struct real_of;
+    template <> struct real_of<scalar_valued> { using type = scalar_real_valued; };
+    template <> struct real_of<matrix_valued> { using type = matrix_real_valued; };
+    template <int R> struct real_of<tensor_valued<R>> { using type = tensor_real_valued<R>; };
+    template <typename T> constexpr bool is_real_target = std::is_same<typename T::scalar_t, double>::value;
+  } // namespace detail
 
   // moments / small dense arrays: C-order [n_rows, target...] flattened to [n_rows][n_others]
   struct moment_array {
@@ -229,17 +260,21 @@ namespace triqs_b200 {
   };
 
   template <typename Mesh, typename Target = matrix_valued> class gf {
-    Mesh _mesh;
-    std::vector<long> _tshape; // target shape (empty for scalar_valued)
-    std::vector<dcomplex> _data;
-
     public:
     using mesh_t = Mesh;
     using target_t = Target;
+    using scalar_t = typename Target::scalar_t; // dcomplex, or double for the *_real_valued targets
+
+    private:
+    Mesh _mesh;
+    std::vector<long> _tshape; // target shape (empty for scalar_valued)
+    std::vector<scalar_t> _data;
+
+    public:
     gf() = default;
     gf(Mesh m, std::vector<long> target_shape = {}) : _mesh(std::move(m)), _tshape(std::move(target_shape)) {
       if ((int)_tshape.size() != Target::rank) throw runtime_error("gf: target shape does not match the target rank");
-      _data.assign(size_t(_mesh.size() * n_others()), dcomplex{0, 0});
+      _data.assign(size_t(_mesh.size() * n_others()), scalar_t{});
     }
     Mesh const &mesh() const { return _mesh; }
     std::vector<long> const &target_shape() const { return _tshape; }
@@ -254,11 +289,11 @@ namespace triqs_b200 {
       if (Target::rank == 2 && _tshape[0] == _tshape[1]) return _tshape[0];
       throw runtime_error("Incompatible target_shape for fit_hermitian_tail");
     }
-    std::vector<dcomplex> &data() { return _data; }
-    std::vector<dcomplex> const &data() const { return _data; }
+    std::vector<scalar_t> &data() { return _data; }
+    std::vector<scalar_t> const &data() const { return _data; }
     // value of the target at mesh data index i (pointer to n_others contiguous entries, C order)
-    dcomplex *operator[](long i) { return _data.data() + size_t(i * n_others()); }
-    dcomplex const *operator[](long i) const { return _data.data() + size_t(i * n_others()); }
+    scalar_t *operator[](long i) { return _data.data() + size_t(i * n_others()); }
+    scalar_t const *operator[](long i) const { return _data.data() + size_t(i * n_others()); }
     // off-mesh evaluation g(tau): linear interpolation on the device (evaluator.hpp:35-43)
     std::vector<dcomplex> operator()(double x) const;
   };
@@ -315,6 +350,50 @@ namespace triqs_b200 {
                                detail::cptr(gw.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
                                (int)known_moments.n_rows, detail::ptr(gt.data()), &warn, nullptr));
     print_warnings(warn);
+  }
+  // real-valued G(tau): only the doubles go to the device, promoted there (fourier.hpp:66 static_assert T1::complex_t == T2, :78-81)
+  template <typename T, typename = std::enable_if_t<detail::is_real_target<T>>>
+  void set_from_fourier(gf<mesh::imfreq, typename T::complex_t> &gw, gf<mesh::imtime, T> const &gt, moment_array const &known_moments = {}) {
+    if (gw.target_shape() != gt.target_shape()) throw runtime_error("fourier: target shapes differ");
+    int warn = 0;
+    check(tq_fourier_tau_to_iw_real(context(), gt.mesh().beta(), gt.mesh().statistic(), gt.mesh().size(), gw.mesh().n_iw(), gt.n_others(), 1,
+                                    gt.data().data(), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                                    (int)known_moments.n_rows, detail::ptr(gw.data()), &warn));
+    print_warnings(warn);
+  }
+  // is_gf_real / real(g)  (functions2.hpp:223-246)
+  template <typename M, typename T> bool is_gf_real(gf<M, T> const &g, double tolerance = 1.e-13) {
+    if constexpr (detail::is_real_target<T>) {
+      return true;
+    } else {
+      for (auto const &z : g.data())
+        if (std::abs(z.imag()) > tolerance) return false;
+      return true;
+    }
+  }
+  template <typename M, typename T> gf<M, typename detail::real_of<T>::type> real(gf<M, T> const &g) {
+    gf<M, typename detail::real_of<T>::type> r{g.mesh(), g.target_shape()};
+    for (size_t i = 0; i < g.data().size(); ++i) r.data()[i] = g.data()[i].real();
+    return r;
+  }
+  // make_gf_from_fourier(gw) + is_gf_real + real(g) in one call: only Re G(tau) comes back from the device; throws if
+  // max |Im G(tau)| exceeds the tolerance
+  template <typename T>
+  gf<mesh::imtime, typename detail::real_of<T>::type> make_real_gf_from_fourier(gf<mesh::imfreq, T> const &gw, long n_tau = -1,
+                                                                                 moment_array const &known_moments = {}, double tolerance = 1.e-13) {
+    gf<mesh::imtime, typename detail::real_of<T>::type> gt{mesh::make_adjoint_mesh(gw.mesh(), n_tau), gw.target_shape()};
+    int warn = 0;
+    double max_imag = 0;
+    check(tq_fourier_iw_to_tau_real(context(), gw.mesh().beta(), gw.mesh().statistic(), gw.mesh().n_iw(), gt.mesh().size(), gw.n_others(), 1,
+                                    detail::cptr(gw.data()), known_moments.is_empty() ? nullptr : detail::cptr(known_moments.v),
+                                    (int)known_moments.n_rows, gt.data().data(), &warn, nullptr, &max_imag));
+    print_warnings(warn);
+    if (max_imag > tolerance) {
+      char buf[64];
+      std::snprintf(buf, sizeof buf, "%.3e", max_imag);
+      throw runtime_error(std::string("make_real_gf_from_fourier: G(tau) is not real, max |Im| = ") + buf);
+    }
+    return gt;
   }
   template <typename T> void set_from_fourier(gf<mesh::brzone, T> &gk, gf<mesh::cyclat, T> const &gr) {
     auto d = gr.mesh().dims();
@@ -383,8 +462,8 @@ namespace triqs_b200 {
 
   // factories  (fourier.hpp:122-144, 238-245)
   template <typename T>
-  gf<mesh::imfreq, T> make_gf_from_fourier(gf<mesh::imtime, T> const &gt, long n_iw = -1, moment_array const &known_moments = {}) {
-    gf<mesh::imfreq, T> gw{mesh::make_adjoint_mesh(gt.mesh(), n_iw), gt.target_shape()};
+  gf<mesh::imfreq, typename T::complex_t> make_gf_from_fourier(gf<mesh::imtime, T> const &gt, long n_iw = -1, moment_array const &known_moments = {}) {
+    gf<mesh::imfreq, typename T::complex_t> gw{mesh::make_adjoint_mesh(gt.mesh(), n_iw), gt.target_shape()};
     set_from_fourier(gw, gt, known_moments);
     return gw;
   }

@@ -983,8 +983,41 @@ struct StatusWords {
   unsigned long long joint_der[2];
 };
 
+// real <-> complex at the boundary (fourier.hpp:78-81 promotes a real-valued gf; functions2.hpp:223-246 is_gf_real / real(g))
+static __global__ void k_promote_real(const double *__restrict__ re, cd *__restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n2 = n >> 1; // two reals in, two complex numbers out per thread and step (16-byte loads, 2 x 16-byte stores)
+  if ((((uintptr_t)re) & 15) == 0) {
+    const double2 *re2 = reinterpret_cast<const double2 *>(re);
+    for (size_t j = i; j < n2; j += stride) {
+      const double2 v = re2[j];
+      out[2 * j] = cmk(v.x, 0.0);
+      out[2 * j + 1] = cmk(v.y, 0.0);
+    }
+    if (i == 0 && (n & 1)) out[n - 1] = cmk(re[n - 1], 0.0);
+  } else {
+    for (size_t j = i; j < n; j += stride) out[j] = cmk(re[j], 0.0);
+  }
+}
+// real part of every element, and per gf the largest |imaginary part| (is_gf_real's criterion)
+static __global__ void k_real_part(const cd *__restrict__ in, double *__restrict__ out, size_t per_gf, unsigned long long *__restrict__ max_im_bits) {
+  const size_t gf = blockIdx.y;
+  const cd *p = in + gf * per_gf;
+  double *q = out + gf * per_gf;
+  double m = 0.0;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_gf; j += (size_t)gridDim.x * blockDim.x) {
+    const cd v = p[j];
+    q[j] = v.x;
+    m = fmax(m, fabs(v.y));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(max_im_bits + gf, (unsigned long long)__double_as_longlong(m)); // (non-negative doubles order like their bits)
+}
+
 static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
-                                        const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn, bool joint) {
+                                        const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn, bool joint,
+                                        bool real_in = false) {
   if (!ctx) return TQ_ERR_INVALID;
   if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_tau_to_iw: invalid argument");
@@ -1005,7 +1038,23 @@ static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic,
   const void *d_in = nullptr, *d_known = nullptr;
   void *d_out = nullptr;
   bool out_host = false;
-  TQ_TRY(tq_stage_in(ctx, gt, in_bytes, ctx->stage_in, &d_in));
+  if (real_in) {
+    // real-valued G(tau) (gf<imtime, T::real_t>): the reference promotes it to complex before the transform (fourier.hpp:78-81);
+    // here only the 8-byte reals cross PCIe / are read from the caller's buffer, the promotion is one streaming kernel on the device
+    const size_t n_el = (size_t)batch * n_tau * n_others;
+    const void *d_re = nullptr;
+    TQ_TRY(tq_stage_in(ctx, gt, sizeof(double) * n_el, ctx->stage_in, &d_re));
+    TQ_TRY(tq_reserve(ctx, ctx->promote, in_bytes));
+    {
+      KernelScope ks(ctx, "promote_real");
+      k_promote_real<<<(unsigned)std::min<size_t>((n_el + 511) / 512, 148 * 16), 256, 0, ctx->stream>>>((const double *)d_re, (cd *)ctx->promote.p, n_el);
+    }
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+    d_in = ctx->promote.p;
+  } else {
+    TQ_TRY(tq_stage_in(ctx, gt, in_bytes, ctx->stage_in, &d_in));
+  }
   if (have_moments) TQ_TRY(tq_stage_in(ctx, moments, sizeof(cd) * (size_t)batch * n_moments * n_others, ctx->stage_in2, &d_known));
   TQ_TRY(tq_stage_out_begin(ctx, gw, out_bytes, ctx->stage_out, &d_out, &out_host));
   // small buffer: [batch][4][n_others] moments, int warn[batch], status words
@@ -1144,6 +1193,21 @@ extern "C" tq_status tq_fourier_tau_to_iw(tq_ctx *ctx, double beta, int statisti
   return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, n_others, batch, gt, moments, n_moments, gw, warn, false);
 }
 
+extern "C" tq_status tq_fourier_tau_to_iw_real(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
+                                               const double *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
+  if (ctx && gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
+      !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
+    const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
+    // (chunks are sized by the bytes that cross PCIe: twice as many gfs per chunk as in the complex call)
+    return run_host_lanes(ctx, batch, sizeof(double) * (size_t)n_tau * n_others, is_pageable(gt) || is_pageable(gw), [&](tq_ctx *c, long b0, long nb) {
+      return fourier_tau_to_iw_impl(c, beta, statistic, n_tau, n_iw, n_others, nb, (const tq_complex *)(gt + (size_t)b0 * n_tau * n_others),
+                                    (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
+                                    gw + (size_t)b0 * n_w * n_others, warn ? warn + b0 : nullptr, false, true);
+    });
+  }
+  return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, n_others, batch, (const tq_complex *)gt, moments, n_moments, gw, warn, false, true);
+}
+
 extern "C" tq_status tq_fourier_tau_to_iw_axis(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long outer, long inner,
                                                const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn) {
   return fourier_tau_to_iw_impl(ctx, beta, statistic, n_tau, n_iw, inner, outer, gt, moments, n_moments, gw, warn, true);
@@ -1151,7 +1215,8 @@ extern "C" tq_status tq_fourier_tau_to_iw_axis(tq_ctx *ctx, double beta, int sta
 
 static tq_status fourier_iw_to_tau_impl(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
                                         const tq_complex *gw, const tq_complex *moments, int n_moments, tq_complex *gt, int *warn,
-                                        double *tail_err) {
+                                        double *tail_err, double *max_imag = nullptr /* != nullptr: gt is double[...] (real part) */) {
+  const bool real_out = max_imag != nullptr;
   if (!ctx) return TQ_ERR_INVALID;
   if (!gt || !gw || n_tau < 2 || n_iw < 1 || n_others < 1 || batch < 1 || !(beta > 0) || (statistic != TQ_FERMION && statistic != TQ_BOSON))
     return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_iw_to_tau: invalid argument");
@@ -1211,11 +1276,34 @@ static tq_status fourier_iw_to_tau_impl(tq_ctx *ctx, double beta, int statistic,
     return tq_fail(ctx, TQ_ERR_RUNTIME,
                    "Inverse Fourier: The time mesh mush be at least twice as long as the freq mesh :\n gt.mesh().size() =  " +
                       std::to_string(n_tau) + " gw.mesh().last_index()" + std::to_string(last) + "\n");
-  TQ_TRY(tq_stage_out_begin(ctx, gt, out_bytes, ctx->stage_out, &d_out, &out_host));
-  TQ_TRY(run_transform<IN_FREQ>(ctx, *pl, n_others, batch, (const cd *)d_in, (cd *)d_out, d_mom, mom_rows));
-  TQ_TRY(tq_reserve_pinned(ctx, sizeof(double) * batch + sizeof(StatusWords)));
+  unsigned long long *d_maxim = nullptr;
+  if (real_out) {
+    // the transform writes complex G(tau) into a device temporary; the caller's buffer receives the real part only
+    // (real(g), functions2.hpp:242-246) and max |Im| per gf (the quantity is_gf_real compares with its tolerance, :223-226)
+    void *d_re = nullptr;
+    TQ_TRY(tq_stage_out_begin(ctx, gt, out_bytes / 2, ctx->stage_out, &d_re, &out_host));
+    TQ_TRY(tq_reserve(ctx, ctx->promote, out_bytes + sizeof(unsigned long long) * (size_t)batch));
+    d_maxim = (unsigned long long *)((char *)ctx->promote.p + out_bytes);
+    TQ_CUDA(ctx, cudaMemsetAsync(d_maxim, 0, sizeof(unsigned long long) * (size_t)batch, ctx->stream));
+    TQ_TRY(run_transform<IN_FREQ>(ctx, *pl, n_others, batch, (const cd *)d_in, (cd *)ctx->promote.p, d_mom, mom_rows));
+    const size_t per_gf = (size_t)n_tau * n_others;
+    {
+      KernelScope ks(ctx, "real_part");
+      const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((per_gf + 1023) / 1024, (148 * 16 + batch - 1) / batch));
+      k_real_part<<<dim3(gx, (unsigned)batch), 256, 0, ctx->stream>>>((const cd *)ctx->promote.p, (double *)d_re, per_gf, d_maxim);
+    }
+    tq_count_launch(ctx);
+    TQ_CUDA(ctx, cudaGetLastError());
+    d_out = d_re;
+  } else {
+    TQ_TRY(tq_stage_out_begin(ctx, gt, out_bytes, ctx->stage_out, &d_out, &out_host));
+    TQ_TRY(run_transform<IN_FREQ>(ctx, *pl, n_others, batch, (const cd *)d_in, (cd *)d_out, d_mom, mom_rows));
+  }
+  TQ_TRY(tq_reserve_pinned(ctx, sizeof(double) * batch * 2 + sizeof(StatusWords)));
   double *h_err = (double *)ctx->pinned;
-  StatusWords *h_st = (StatusWords *)((char *)ctx->pinned + sizeof(double) * batch);
+  double *h_maxim = h_err + batch;
+  StatusWords *h_st = (StatusWords *)((char *)ctx->pinned + sizeof(double) * batch * 2);
+  if (real_out) TQ_CUDA(ctx, cudaMemcpyAsync(h_maxim, d_maxim, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
   TQ_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx->stream));
   TQ_CUDA(ctx, cudaMemcpyAsync(h_st, d_st, sizeof(StatusWords), cudaMemcpyDeviceToHost, ctx->stream));
   TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1243,8 +1331,28 @@ static tq_status fourier_iw_to_tau_impl(tq_ctx *ctx, double beta, int statistic,
   (void)w_any;
   if (tail_err)
     for (long b = 0; b < batch; ++b) tail_err[b] = fitted ? h_err[b] : 0.0;
-  TQ_TRY(tq_stage_out_finish(ctx, gt, out_bytes, d_out, out_host));
+  if (real_out)
+    for (long b = 0; b < batch; ++b) max_imag[b] = h_maxim[b];
+  TQ_TRY(tq_stage_out_finish(ctx, gt, real_out ? out_bytes / 2 : out_bytes, d_out, out_host));
   return TQ_OK;
+}
+
+extern "C" tq_status tq_fourier_iw_to_tau_real(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,
+                                               const tq_complex *gw, const tq_complex *moments, int n_moments, double *gt, int *warn,
+                                               double *tail_err, double *max_imag) {
+  if (!ctx) return TQ_ERR_INVALID;
+  if (!max_imag) return tq_fail(ctx, TQ_ERR_INVALID, "tq_fourier_iw_to_tau_real: max_imag must not be NULL");
+  if (gt && gw && batch > 1 && n_tau >= 2 && n_iw >= 1 && n_others >= 1 && ctx->opt_host_lanes > 1 && !tq_is_device_ptr(gt) &&
+      !tq_is_device_ptr(gw) && !(moments && tq_is_device_ptr(moments))) {
+    const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
+    return run_host_lanes(ctx, batch, sizeof(double) * (size_t)n_tau * n_others, is_pageable(gt) || is_pageable(gw), [&](tq_ctx *c, long b0, long nb) {
+      return fourier_iw_to_tau_impl(c, beta, statistic, n_iw, n_tau, n_others, nb, gw + (size_t)b0 * n_w * n_others,
+                                    (moments && n_moments > 0) ? moments + (size_t)b0 * n_moments * n_others : nullptr, n_moments,
+                                    (tq_complex *)(gt + (size_t)b0 * n_tau * n_others), warn ? warn + b0 : nullptr, tail_err ? tail_err + b0 : nullptr,
+                                    max_imag + b0);
+    });
+  }
+  return fourier_iw_to_tau_impl(ctx, beta, statistic, n_iw, n_tau, n_others, batch, gw, moments, n_moments, (tq_complex *)gt, warn, tail_err, max_imag);
 }
 
 extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_iw, long n_tau, long n_others, long batch,

@@ -143,6 +143,7 @@ struct PreF1 { // x = phase (g - sum_i at_i E_i[row]),  row = q + RB r        fo
     a3 = cscale(e.z * ea.z, coef[c + 2 * A.tcw]);
   }
   template <int R> TQ_D cd load(const cd *p) const {
+    if (TQ_KNOCK(256)) return *p;
     cd v = caxpy(-A.er[0][R], a1, *p);
     v = caxpy(-A.er[1][R], a2, v);
     v = caxpy(-A.er[2][R], a3, v);
@@ -205,7 +206,7 @@ template <int RA> struct PostScratch { // Y = z T[beta]  -> scratch[beta][column
     p = base + ((long)h * tcw2 * Na + (long)item * w + cc) + (long)sidx * beta_stride;
     Ts = T + sidx;
   }
-  template <int TT> TQ_D void store(cd v) const { p[(long)(ra() * TT) * beta_stride] = cmul(v, Ts[ra() * TT]); }
+  template <int TT> TQ_D void store(cd v) const { p[(long)(ra() * TT) * beta_stride] = TQ_KNOCK(128) ? v : cmul(v, Ts[ra() * TT]); }
   TQ_D void store_rt(int t, cd v) const { p[(long)(ra() * t) * beta_stride] = cmul(v, Ts[ra() * t]); }
 };
 template <int RA> struct PostF2 { // G(i w_n) = z + corr + tail, window rows only      :181-183
@@ -501,8 +502,8 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   // item -> (butterfly, column) division magics of the two possible tile widths (full / last column tile)
   const unsigned m_w_full = fastdiv_magic((unsigned)TCW), m_w_last = fastdiv_magic((unsigned)(n_cols - (A.n_ct - 1) * TCW));
   // developer phase timing (TQ_PHASE_DEBUG): compiled in only with -DTQ_DEVELOPER -- the five 64-bit accumulators and the
-  // predicated clock reads cost registers and issue slots in kernels that sit at the register limit
-#ifdef TQ_DEVELOPER
+  // predicated clock reads cost registers and issue slots in kernels that sit at the register limit (-DTQ_PHASE_TIMING on top)
+#if defined(TQ_DEVELOPER) && defined(TQ_PHASE_TIMING)
   long long t0 = clock64(), t_wait = 0, t_work = 0, t_sched = 0, t_ready = 0;
 #define TQ_LAP(acc)                                                                                                              \
   if (A.dbg && lane == 0) {                                                                                                      \
@@ -808,7 +809,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       }
     }
   }
-#ifdef TQ_DEVELOPER
+#if defined(TQ_DEVELOPER) && defined(TQ_PHASE_TIMING)
   if (A.dbg && lane == 0) {
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp] = t_wait;
     A.dbg[(size_t)blockIdx.x * 64 + 4 * warp + 1] = t_work;

@@ -71,7 +71,7 @@ struct tq_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   // grow-only scratch / staging
-  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w, leg_tmp;
+  DeviceBuffer stage_in, stage_in2, stage_in3, stage_out, scratch, small, pipe_w, leg_tmp, promote;
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   // pinned bounce buffers for PAGEABLE user memory (tq_stage_in / tq_stage_out_finish): two slots each way, events per slot

@@ -70,7 +70,12 @@ TQ_HD void fft2_pass_a(cd *s, int pitch, int tcw, const cd *__restrict__ twq, in
     cd *p = s + q * pitch + c; // row q, column c
     pre.begin(q, c);
     cd a[RA];
-    tq_unroll_load<RA>(a, pre, p, stride);
+    if (!TQ_KNOCK(32)) {
+      tq_unroll_load<RA>(a, pre, p, stride);
+    } else {
+#pragma unroll
+      for (int r = 0; r < RA; ++r) a[r] = cmk(1.0 + i, (double)r);
+    }
     if (!TQ_KNOCK(1)) Dft<RA, SGN>::run(a);
     const cd *tw = twq + q * RA;
     if ((TW0 || q != 0) && !TQ_KNOCK(16)) {
@@ -99,8 +104,13 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
     const cd *p = s + sidx * (RB * pitch) + c;
     post.begin(sidx, c);
     cd a[RB];
+    if (!TQ_KNOCK(8)) {
 #pragma unroll
-    for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
+      for (int t = 0; t < RB; ++t) a[t] = p[t * pitch];
+    } else {
+#pragma unroll
+      for (int t = 0; t < RB; ++t) a[t] = cmk(1.0 + i, (double)t);
+    }
     if (!TQ_KNOCK(1)) Dft<RB, SGN>::run(a);
     before_store();
     if (!TQ_KNOCK(4)) {

@@ -178,12 +178,14 @@ def make_adjoint_mesh(m, n=-1):
 class Gf:
     """mesh + data[mesh, target...] (C order, complex128) -- c++/triqs/gfs/gf/gf.hpp:86-375."""
 
-    def __init__(self, mesh, target_shape=(), data=None, ctx: Context | None = None):
+    def __init__(self, mesh, target_shape=(), data=None, ctx: Context | None = None, is_real=False):
+        """is_real: real-valued target (python/triqs/gf/gf.py `is_real`, gf<mesh, T::real_t>): float64 data.  Fourier transforms
+        of a real-valued G(tau) move only the reals to the GPU (Context.fourier_tau_to_iw)."""
         self.mesh = mesh
         self.target_shape = tuple(target_shape)
         shape = (mesh.shape if isinstance(mesh, MeshProduct) else (len(mesh),)) + self.target_shape
         if data is None:
-            data = np.zeros(shape, dtype=np.complex128)
+            data = np.zeros(shape, dtype=np.float64 if is_real else np.complex128)
         elif tuple(data.shape) != shape:
             raise TriqsRuntimeError(f"Gf: data shape {tuple(data.shape)} does not match mesh/target {shape}")
         self.data = data
@@ -317,6 +319,28 @@ class BlockGf:
 
     def __len__(self):
         return len(self.blocks)
+
+
+def is_gf_real(g, tolerance=1e-13) -> bool:
+    """c++/triqs/gfs/functions/functions2.hpp:223-232: max |Im g| <= tolerance (a BlockGf: every block)."""
+    if isinstance(g, BlockGf):
+        return all(is_gf_real(b, tolerance) for b in g.blocks)
+    d = g.data
+    if _is_torch(d):
+        return (not d.dtype.is_complex) or float(d.imag.abs().max()) <= tolerance
+    return (not np.iscomplexobj(d)) or float(np.max(np.abs(d.imag))) <= tolerance
+
+
+def real(g):
+    """c++/triqs/gfs/functions/functions2.hpp:242-248: the real-valued gf {g.mesh(), real(g.data())}."""
+    if isinstance(g, BlockGf):
+        return BlockGf(g.names, [real(b) for b in g.blocks])
+    d = g.data
+    if _is_torch(d):
+        d = d.real.contiguous() if d.dtype.is_complex else d
+    else:
+        d = np.ascontiguousarray(d.real) if np.iscomplexobj(d) else d
+    return Gf(g.mesh, g.target_shape, d, g._ctx)
 
 
 def make_zero_tail(g: Gf, n_moments=10):
