@@ -330,3 +330,51 @@ def test_product_mesh_evaluation_reads_like_the_reference_test():
     rng = np.random.default_rng(3)
     x, y = rng.uniform(0, 2, 100), rng.uniform(0, 2, 100)
     assert np.max(np.abs(g2(x, y) - (1 + x - 2 * y + 0.25 * x * y))) < 1e-13
+
+
+@pytest.mark.gpu
+def test_lazy_descriptors_fourier_legendre_lshift():
+    """`gw << Fourier(gt)` / `gt << Fourier(gw)` / BlockGf `<<` / Legendre descriptors (python/triqs/gf/descriptors.py:156-196,
+    gf.py:486-519): the same numbers as the factory functions, written INTO the existing gf."""
+    import numpy as np
+    from oracle import triqs_oracle as O
+    import triqs_b200
+    from triqs_b200.gf import (BlockGf, Fourier, Gf, LegendreToMatsubara, MatsubaraToLegendre, MeshImFreq, MeshImTime, MeshLegendre,
+                               make_gf_from_fourier)
+    from triqs_b200.context import TriqsRuntimeError
+    F = triqs_b200.FERMION
+    beta, n_iw, n_tau = 10.0, 200, 1201
+    mw, mt = MeshImFreq(beta, F, n_iw), MeshImTime(beta, F, n_tau)
+    iw = O.imfreq_values(beta, F, n_iw)
+    gw = Gf(mw, (2, 2))
+    for i in range(2):
+        for j in range(2):
+            gw.data[:, i, j] = (1.0 if i == j else 0.2) / (iw - 0.5 * (i + 1) + 0.3 * j)
+    gt = Gf(mt, (2, 2))
+    assert (gt << Fourier(gw)) is gt
+    assert np.array_equal(gt.data, make_gf_from_fourier(gw, n_tau).data)
+    gw2 = Gf(mw, (2, 2))
+    gw2 << Fourier(gt)
+    assert np.max(np.abs(gw2.data - gw.data)) < 1e-6
+    # a BlockGf of equally shaped blocks: one batched launch
+    bw = BlockGf(["up", "down"], [gw, gw2])
+    bt = BlockGf(["up", "down"], [Gf(mt, (2, 2)), Gf(mt, (2, 2))])
+    bt << Fourier(bw)
+    assert np.array_equal(bt["up"].data, gt.data)
+    # scalars, gfs, mesh mismatch
+    gw2 << 0.5
+    assert gw2.data[3, 0, 0] == 0.5 and gw2.data[3, 0, 1] == 0
+    gw2 << gw
+    assert np.array_equal(gw2.data, gw.data)
+    with pytest.raises(TriqsRuntimeError):
+        gt << Fourier(gt)
+    with pytest.raises(TriqsRuntimeError):
+        Gf(MeshImTime(2 * beta, F, n_tau), (2, 2)) << Fourier(gw)
+    # Legendre
+    gl = Gf(MeshLegendre(beta, F, 30), (2, 2))
+    gl << MatsubaraToLegendre(gt)
+    gw3 = Gf(mw, (2, 2))
+    gw3 << LegendreToMatsubara(gl)
+    from triqs_b200.gf import legendre_to_matsubara
+    assert np.array_equal(gw3.data, legendre_to_matsubara(gl, mw).data)
+    assert np.max(np.abs(gw3.data - gw.data)) < 5e-3  # (30 Legendre coefficients)

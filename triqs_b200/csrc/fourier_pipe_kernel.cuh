@@ -409,8 +409,19 @@ struct TileDecoder {
   }
 };
 
+// registers per thread: the 16 K registers of a sub-partition over its warps (12 warps: 168; 8 warps: 255)
+__host__ __device__ constexpr int pipe_maxnreg(int nw) {
+  const int r = (16384 / (((nw + 1) + 3) / 4 * 32)) & ~7;
+  return r > 255 ? 255 : r;
+}
+// "dual" packets (compile-time kernels only, bit per mode): 64 butterflies per packet, two per lane (tq_fft2.cuh fft2_pass_*_dual) -- meant
+// for 7 worker warps with 255 registers (-DTQ_NW_F1=7 ...)
+#ifndef TQ_PIPE_DUAL
+#define TQ_PIPE_DUAL 0
+#endif
+
 template <int MODE, int N, int RA, int RB, int NW, int SET = 0>
-__global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_pipe_kernel(const __grid_constant__ PipeArgs A,
+__global__ void __maxnreg__(pipe_maxnreg(NW)) matsubara_pipe_kernel(const __grid_constant__ PipeArgs A,
                                                                                              const __grid_constant__ CUtensorMap tmap,
                                                                                              const __grid_constant__ CUtensorMap tmap2) {
   constexpr bool PASS1 = (MODE == M_F1 || MODE == M_I1);
@@ -434,7 +445,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
 #ifndef TQ_EARLY_FREE
 #define TQ_EARLY_FREE 4 // bit per mode; only the pass-1 kernels (PostScratch) have the code path
 #endif
-  constexpr bool EARLY_FREE = PASS1 && ((TQ_EARLY_FREE >> MODE) & 1) != 0;
+  constexpr bool DUAL = N != 0 && ((TQ_PIPE_DUAL >> MODE) & 1) != 0;
+  constexpr int PKL = DUAL ? 64 : 32; // butterflies per packet
+  constexpr bool EARLY_FREE = PASS1 && ((TQ_EARLY_FREE >> MODE) & 1) != 0 && !DUAL;
 #ifndef TQ_PIPE_L2PF
 #define TQ_PIPE_L2PF 10 // F2, I2 (contiguous scratch tiles): -1 %; no gain on the tensor-map gathers of F1 / I1
 #endif
@@ -467,7 +480,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   // work packets = 32 butterflies (one per lane): pa packets of pass A and pb packets of pass B per tile
   // (a direct-sum pass B splits every butterfly over fft2_generic_groups(RB) work items)
   const int bgroups = rb_generic ? fft2_generic_groups(RBv) : 1;
-  const int pa = (RBv * TCW + 31) >> 5, pb = (RAv * TCW * bgroups + 31) >> 5;
+  const int pa = (RBv * TCW + PKL - 1) / PKL, pb = (RAv * TCW * bgroups + PKL - 1) / PKL;
   cd *gtwS = reinterpret_cast<cd *>(smem_raw + S.gtw); // generic pass B: exp(+2 pi i j / RB)
 
   for (int i = tid; i < NN; i += NT) twS[i] = A.twq[i];
@@ -498,7 +511,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
   // packets of that tile (pass A waits on `full`, pass B on `adone`) block every warp that claims one, so if even the narrowest
   // column tile has at least NW non-empty packets no warp gets past them.  (Measured gain where it applies: 1 %.)
   const int w_min = n_cols - (A.n_ct - 1) * TCW;
-  const bool skip_guard = ((RBv * w_min + 31) >> 5) + ((RAv * w_min * bgroups + 31) >> 5) >= NW + 2 && !A.keep_guard;
+  const bool skip_guard = ((RBv * w_min + PKL - 1) / PKL) + ((RAv * w_min * bgroups + PKL - 1) / PKL) >= NW + 2 && !A.keep_guard;
   // item -> (butterfly, column) division magics of the two possible tile widths (full / last column tile)
   const unsigned m_w_full = fastdiv_magic((unsigned)TCW), m_w_last = fastdiv_magic((unsigned)(n_cols - (A.n_ct - 1) * TCW));
   // developer phase timing (TQ_PHASE_DEBUG): compiled in only with -DTQ_DEVELOPER -- the five 64-bit accumulators and the
@@ -678,9 +691,9 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       unsigned char *tab = smem_raw + S.tab0 + ts * S.tab_stride;
       const cd *coef = reinterpret_cast<const cd *>(tab + S.coef_off);
       const int pitch = (MODE == M_F1 || MODE == M_I1) ? A.pitch : id.w;
-      const int it = r * 32 + lane; // butterfly of this lane (the engine skips it when past the end)
+      const int it = r * PKL + lane; // butterfly of this lane (the engine skips it when past the end; dual packets: it and it + 32)
       // a packet of a narrower (last) column tile can be empty for lane 0: its hook never runs, claim the next packet here
-      if (PK_LATE && r * 32 >= (is_b ? RAv * bgroups : RBv) * id.w) fetch_next();
+      if (PK_LATE && r * PKL >= (is_b ? RAv * bgroups : RBv) * id.w) fetch_next();
       // (I2 sits at the register limit: one more live value makes it spill, so it recomputes the magic per packet)
       const unsigned m_w = (MODE == M_I2 && !PLANNED) ? ~0u : (id.w == TCW ? m_w_full : m_w_last);
       TQ_LAP(t_sched)
@@ -698,7 +711,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
       // radix table in the planned ones (tq_fft2.cuh)
       const auto run_a = [&](auto &pre, auto tw0) {
         constexpr bool TW0 = decltype(tw0)::value;
-        if constexpr (!PLANNED) {
+        if constexpr (DUAL) {
+          auto pre1 = pre;
+          fft2_pass_a_dual<N, RA, RB, SGN, TW0>(tile, pitch, id.w, twS, it, pre, pre1, m_w, fetch_next);
+        } else if constexpr (!PLANNED) {
           fft2_pass_a<N, RA, RB, SGN, TW0>(tile, pitch, id.w, twS, it, 1 << 30, pre, m_w, fetch_next);
         } else {
 #define TQ_CALL_A(R) fft2_item_a<R, SGN, TW0>(tile, pitch, id.w, RBv, twS, it, pre, m_w, fetch_next);
@@ -711,7 +727,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
         }
       };
       const auto run_b = [&](auto &post, const auto &hook) {
-        if constexpr (!PLANNED) {
+        if constexpr (DUAL) {
+          auto post1 = post;
+          fft2_pass_b_dual<N, RA, RB, SGN>(tile, pitch, id.w, it, post, post1, m_w, hook);
+        } else if constexpr (!PLANNED) {
           fft2_pass_b<N, RA, RB, SGN>(tile, pitch, id.w, it, 1 << 30, post, m_w, hook);
         } else if (rb_generic) {
           fft2_item_b_generic<SGN>(tile, pitch, id.w, RAv, RBv, gtwS, it, post, m_w, hook);
@@ -740,7 +759,10 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) matsubara_
               auto wedge = [&](int rr) { return A.wedge[rr]; };
               fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS, it,
                                                  1 << 30, pre, wedge, m_w);
-              if (r * 32 < RB * id.w) fetch_next(); // (an empty packet has claimed its successor above)
+              if constexpr (DUAL)
+                fft2_pass_a_edge<N, RA, RB, false>(tile, reinterpret_cast<const cd *>(smem_raw + b * S.buf_stride + S.stage_off), pitch, id.w, twS,
+                                                   it + 32, 1 << 30, pre, wedge, m_w);
+              if (r * PKL < RB * id.w) fetch_next(); // (an empty packet has claimed its successor above)
               done = true;
             }
           }

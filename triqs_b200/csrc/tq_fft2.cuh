@@ -124,6 +124,80 @@ TQ_HD void fft2_pass_b(const cd *s, int pitch, int tcw, int tid, int nthreads, P
   }
 }
 
+// ---- two butterflies per lane ("dual" packets of 64) ---------------------------------------------------------------------
+// The pipelined kernels with 8 fat warps (255 registers) run TWO independent butterflies per lane: both sets of loads are issued
+// first, the stores of the first butterfly overlap the arithmetic of the second, so a warp hides its own shared-memory / global
+// latencies instead of relying on the other two warps of its scheduler being in a different phase.  The second item is i0 + 32; when
+// it is past the end it recomputes the first one with its stores predicated off (straight-line code, no divergent phases).
+template <int N, int RA, int RB, int SGN, bool TW0, class Pre, class Hook = NoHook>
+TQ_HD void fft2_pass_a_dual(cd *s, int pitch, int tcw, const cd *__restrict__ twq, int i0, Pre &pre0, Pre &pre1, unsigned magic,
+                            const Hook &before_store = Hook()) {
+  static_assert(RA * RB == N, "N = RA * RB");
+  const int nitems = RB * tcw;
+  const int stride = RB * pitch;
+  if (i0 >= nitems) return;
+  if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw);
+  const bool v1 = i0 + 32 < nitems;
+  const int i1 = v1 ? i0 + 32 : i0;
+  const int q0 = fastdiv(i0, magic), q1 = fastdiv(i1, magic);
+  const int c0 = i0 - q0 * tcw, c1 = i1 - q1 * tcw;
+  cd *p0 = s + q0 * pitch + c0, *p1 = s + q1 * pitch + c1;
+  cd a[RA], b[RA];
+  pre0.begin(q0, c0);
+  tq_unroll_load<RA>(a, pre0, p0, stride);
+  pre1.begin(q1, c1);
+  tq_unroll_load<RA>(b, pre1, p1, stride);
+  Dft<RA, SGN>::run(a);
+  {
+    const cd *tw = twq + q0 * RA;
+    if (TW0 || q0 != 0) {
+#pragma unroll
+      for (int r = TW0 ? 0 : 1; r < RA; ++r) a[r] = cmul(a[r], tw[r]);
+    }
+  }
+  before_store();
+  // (the second butterfly's inputs are in registers: when it duplicates the first one, overwriting its rows here is harmless)
+#pragma unroll
+  for (int r = 0; r < RA; ++r) p0[r * stride] = a[r];
+  Dft<RA, SGN>::run(b);
+  {
+    const cd *tw = twq + q1 * RA;
+    if (TW0 || q1 != 0) {
+#pragma unroll
+      for (int r = TW0 ? 0 : 1; r < RA; ++r) b[r] = cmul(b[r], tw[r]);
+    }
+  }
+  if (v1) {
+#pragma unroll
+    for (int r = 0; r < RA; ++r) p1[r * stride] = b[r];
+  }
+}
+
+template <int N, int RA, int RB, int SGN, class Post, class Hook = NoHook>
+TQ_HD void fft2_pass_b_dual(const cd *s, int pitch, int tcw, int i0, Post &post0, Post &post1, unsigned magic, const Hook &before_store = Hook()) {
+  static_assert(RA * RB == N, "N = RA * RB");
+  const int nitems = RA * tcw;
+  if (i0 >= nitems) return;
+  if (magic == ~0u) magic = fastdiv_magic((unsigned)tcw);
+  const bool v1 = i0 + 32 < nitems;
+  const int i1 = v1 ? i0 + 32 : i0;
+  const int s0 = fastdiv(i0, magic), s1 = fastdiv(i1, magic);
+  const int c0 = i0 - s0 * tcw, c1 = i1 - s1 * tcw;
+  const cd *p0 = s + s0 * (RB * pitch) + c0, *p1 = s + s1 * (RB * pitch) + c1;
+  cd a[RB], b[RB];
+#pragma unroll
+  for (int t = 0; t < RB; ++t) a[t] = p0[t * pitch];
+#pragma unroll
+  for (int t = 0; t < RB; ++t) b[t] = p1[t * pitch];
+  post0.begin(s0, c0);
+  Dft<RB, SGN>::run(a);
+  before_store();
+  tq_unroll_store<RB>(a, post0);
+  post1.begin(s1, c1);
+  Dft<RB, SGN>::run(b);
+  if (v1) tq_unroll_store<RB>(b, post1);
+}
+
 // Pass A when only the first and the last leg of every butterfly are non-zero (inverse Matsubara transform: the frequency
 // window occupies rows [0, RB) and [N - RB, N) of the tile, everything between is zero-fill):
 //   y_s = x_0 + x_{RA-1} w_RA^{SGN (RA-1) s} = x_0 + x_{RA-1} wedge[s],   wedge[s] = exp(-SGN 2 pi i s / RA)

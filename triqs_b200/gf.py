@@ -222,6 +222,65 @@ class Gf:
             self.data[...] = dense
         return self
 
+    # -- the Python call surface of the transforms: `g << Fourier(g_other)` (python/triqs/gf/descriptors.py:156-196) ------------
+    def _assign(self, data):
+        if tuple(data.shape) != tuple(self.data.shape):
+            raise TriqsRuntimeError(f"Gf: cannot assign data of shape {tuple(data.shape)} to a gf of shape {tuple(self.data.shape)}")
+        if _is_torch(self.data) and not _is_torch(data):
+            import torch
+            data = torch.from_numpy(np.ascontiguousarray(data)).to(self.data.device)
+        elif _is_torch(data) and not _is_torch(self.data):
+            data = data.cpu().numpy()
+        if not _is_real_data(self.data) or _is_real_data(data):
+            self.data[...] = data
+        else:
+            raise TriqsRuntimeError("Gf: cannot store complex values in a real-valued gf (use real(g) after is_gf_real(g))")
+        return self
+
+    def set_from_fourier(self, g, known_moments=None):
+        """G2.set_from_fourier(G[, known_moments]) (python/triqs/gf/gf_fnt.py via cpp2py; fourier.hpp:257-276): the transform of `g`
+        ONTO this gf's mesh -- imtime <-> imfreq, retime <-> refreq, cyclat <-> brzone."""
+        if tuple(g.target_shape) != tuple(self.target_shape):
+            raise TriqsRuntimeError("set_from_fourier: target shapes differ")
+        pairs = {MeshImTime: MeshImFreq, MeshImFreq: MeshImTime, MeshReTime: MeshReFreq, MeshReFreq: MeshReTime, MeshCycLat: MeshBrZone,
+                 MeshBrZone: MeshCycLat}
+        if pairs.get(type(g.mesh)) is not type(self.mesh):  # (the reference: static_assert on the adjoint mesh types, fourier.hpp:101,106)
+            raise TriqsRuntimeError(f"set_from_fourier: {type(self.mesh).__name__} is not the adjoint mesh type of {type(g.mesh).__name__}")
+        for attr in ("beta", "statistic", "dims"):
+            if hasattr(g.mesh, attr) and getattr(g.mesh, attr) != getattr(self.mesh, attr):
+                raise TriqsRuntimeError(f"set_from_fourier: the meshes differ in {attr}")
+        res = make_gf_from_fourier(g, self.mesh, known_moments)
+        return self._assign(res.data)
+
+    def set_from_legendre(self, gl):
+        """descriptors.py:170-182"""
+        return self._assign(legendre_to_matsubara(gl, self.mesh).data)
+
+    def set_from_imfreq(self, g):
+        """descriptors.py:184-196 (MatsubaraToLegendre; the argument may live on an imfreq or an imtime mesh)"""
+        return self._assign(matsubara_to_legendre(g, len(self.mesh)).data)
+
+    set_from_imtime = set_from_imfreq
+
+    def __lshift__(self, rhs):
+        """`g << rhs` (python/triqs/gf/gf.py:486-519): a lazy descriptor (Fourier, LegendreToMatsubara, MatsubaraToLegendre), another gf
+        on the same mesh, an array, or a scalar (times the identity for a matrix-valued target)."""
+        if callable(rhs) and not isinstance(rhs, Gf):
+            return rhs(self)
+        if isinstance(rhs, Gf):
+            if rhs.mesh != self.mesh:
+                raise TriqsRuntimeError("Gf <<: the meshes differ")
+            return self._assign(rhs.data)
+        if np.isscalar(rhs):
+            self.data[...] = 0
+            if len(self.target_shape) == 2 and self.target_shape[0] == self.target_shape[1]:
+                for i in range(self.target_shape[0]):
+                    self.data[..., i, i] = rhs
+            else:
+                self.data[...] = rhs
+            return self
+        return self._assign(rhs)
+
     def _call_prod(self, args):
         """g(x1, x2, ...) on a product mesh (or a single linear / brzone mesh): c++/triqs/mesh/evaluate.hpp:97-114 via tq_evaluate_prod.
         Per component: imtime / retime / refreq take values, brzone a k vector (or an array [n_pts, 3] of them), imfreq a Matsubara
@@ -302,8 +361,67 @@ class Gf:
         return out[0] if scalar else out
 
 
+class _LazyTransform:
+    """BaseBlock of python/triqs/gf/descriptors.py: a lazy expression `X(G)`; `G2 << X(G)` calls X(G)(G2).  Applied to a BlockGf it
+    acts block by block -- equally shaped blocks in ONE batched launch (map_block_gf, block/map.hpp:35-40)."""
+    _method = None
+
+    def __init__(self, G, *args, **kw):
+        self.G, self.args, self.kw = G, args, kw
+
+    def __call__(self, G2):
+        if isinstance(G2, BlockGf):
+            src = self.G
+            if not isinstance(src, BlockGf) or len(src) != len(G2):
+                raise TriqsRuntimeError("lazy transform: BlockGf arguments of equal length are required")
+            b0, s0 = G2.blocks[0], src.blocks[0]
+            same = all(b.mesh == b0.mesh and b.target_shape == b0.target_shape for b in G2.blocks) and all(
+                b.mesh == s0.mesh and b.target_shape == s0.target_shape for b in src.blocks)
+            if same and self._method == "set_from_fourier" and not self.args and not self.kw:
+                res = make_gf_from_fourier(src, b0.mesh)
+                for b, r in zip(G2.blocks, res.blocks):
+                    b._assign(r.data)
+                return G2
+            for b, sb in zip(G2.blocks, src.blocks):
+                getattr(b, self._method)(sb, *self.args, **self.kw)
+            return G2
+        getattr(G2, self._method)(self.G, *self.args, **self.kw)
+        return G2
+
+
+class Fourier(_LazyTransform):
+    """descriptors.py:156-168: `gw << Fourier(gt)`, `gt << Fourier(gw)` (any pair of adjoint meshes)"""
+    _method = "set_from_fourier"
+
+
+class LegendreToMatsubara(_LazyTransform):
+    """descriptors.py:170-182"""
+    _method = "set_from_legendre"
+
+
+class MatsubaraToLegendre(_LazyTransform):
+    """descriptors.py:184-196"""
+    _method = "set_from_imfreq"
+
+
+def _is_real_data(d):
+    return (not d.dtype.is_complex) if _is_torch(d) else (not np.iscomplexobj(d))
+
+
 class BlockGf:
     """named list of Gf -- c++/triqs/gfs/block/block_gf.hpp:104-295, python/triqs/gf/block_gf.py."""
+
+    def __lshift__(self, rhs):
+        """`G << Fourier(G_other)` etc. block by block (python/triqs/gf/block_gf.py:306-316)"""
+        if callable(rhs) and not isinstance(rhs, BlockGf):
+            return rhs(self)
+        if isinstance(rhs, BlockGf):
+            for b, r in zip(self.blocks, rhs.blocks):
+                b << r
+            return self
+        for b in self.blocks:
+            b << rhs
+        return self
 
     def __init__(self, name_list, block_list):
         if len(name_list) != len(block_list):
