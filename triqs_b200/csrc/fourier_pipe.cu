@@ -399,12 +399,18 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
       // the single-column kernel (fourier_col.cu: one HBM read, one write, no scratch) keeps its mesh
       const bool col_kernel = fwd && L == 10000 && n_cols == 1 && !ctx->opt_no_col;
       // (a lane of a chunked host-buffer call decides as the whole call would: the chunking must not change a bit)
-      if (std::max(batch, ctx->call_batch) * n_cols >= 8 && !col_kernel && !ctx->opt_no_tr) {
+      // Single-column gfs, inverse leg: I2 writes one 16-byte element per (gf, time point) at the gf stride -- half a 32-byte sector each, 3x the
+      // time of the two-column case whether the lanes or a tensor-map store issue the writes (both measured).  On smooth lengths whose column
+      // fits one SM's shared memory the single-kernel path is faster for this one case (L = 6000: 1015 vs 750 GB/s, 10^4: 941 vs 683); lengths
+      // with a heavy / direct-sum radix (6150: 281 vs 643) and longer meshes (2 10^4: 175 vs 671) keep the planned kernels.
+      const bool single_kernel_fits = sizeof(cd) * (size_t)(L + 64) <= (size_t)ctx->max_smem_optin;
+      const bool smooth = !a.heavy && !a.generic && !b.heavy && !b.generic;
+      const bool tr_loses = !fwd && n_cols == 1 && single_kernel_fits && smooth;
+      if (std::max(batch, ctx->call_batch) * n_cols >= 8 && !col_kernel && !tr_loses && !ctx->opt_no_tr) {
         tr = (int)n_cols;
       } else {
         // Narrow targets on meshes whose whole column fits one SM's shared memory stay with the single-kernel paths (one HBM read
         // and one write, no scratch): the pipelined tiles would have rows of 16-48 bytes.
-        const bool single_kernel_fits = sizeof(cd) * (size_t)(L + 64) <= (size_t)ctx->max_smem_optin;
         if (single_kernel_fits) return TQ_OK;
       }
     }
