@@ -703,6 +703,41 @@ def test_matsubara_meshes_with_large_prime_factors(ctx):
             assert rel(back[b], O.fourier_tau_to_iw(rt, beta, stat, n_iw, mom[b])) < TOL
 
 
+@pytest.mark.parametrize("L,n_iw,stat,C,B", [(1999, 300, O.FERMION, 5, 3), (4999, 833, O.BOSON, 3, 2), (8191, 1024, O.FERMION, 25, 2),
+                                            (19999, 2000, O.FERMION, 4, 1), (2 * 10007, 1500, O.BOSON, 2, 2)])
+def test_bluestein_for_lengths_without_a_plan(ctx, L, n_iw, stat, C, B):
+    """Round n_tau values (2000, 5000, 8192, 20000 ...) are one off a smooth length and have a prime factor > 127: chirp-z (Bluestein)
+    convolution through the plain axis engine instead of the O(N^2) window DFT.  Checked against the oracle (1e-12) and against the
+    direct evaluation ("no_bluestein"), both legs, known moments and the library's own tail."""
+    rng = np.random.default_rng(L)
+    beta = 7.0
+    iw = O.imfreq_values(beta, stat, n_iw)
+    e = rng.uniform(0.3, 2.0, size=(B, C)) * rng.choice([-1.0, 1.0], size=(B, C))
+    gw = 1 / (iw[None, :, None] - e[:, None, :])
+    mom = np.zeros((B, 4, C), complex)
+    mom[:, 1], mom[:, 2], mom[:, 3] = 1, e, e ** 2
+    ctx.profile_enable(True)
+    gt = ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+    back = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=mom)
+    rep = ctx.profile_report()
+    ctx.profile_enable(False)
+    assert "iw2tau_bluestein_pre" in rep and "tau2iw_bluestein_post" in rep, rep
+    for b in range(B):
+        rt = O.fourier_iw_to_tau(gw[b], beta, stat, L + 1, mom[b])
+        assert rel(gt[b], rt) < TOL
+        assert rel(back[b], O.fourier_tau_to_iw(rt, beta, stat, n_iw, mom[b])) < TOL
+    ctx.set_option("no_bluestein", 1)
+    try:
+        gt_d = ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+        back_d = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=mom)
+    finally:
+        ctx.set_option("no_bluestein", 0)
+    assert rel(gt, gt_d) < TOL and rel(back, back_d) < TOL
+    # unknown moments: tau-derivative estimate forward, least-squares tail on the way back
+    w2 = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw)
+    assert rel(w2[0], O.fourier_tau_to_iw(np.asarray(gt[0]), beta, stat, n_iw)) < TOL
+
+
 def test_tau_to_iw_along_inner_mesh_is_one_gf(ctx):
     """tq_fourier_tau_to_iw_axis = _fourier<N>, N > 0 (fourier.hpp:78-84): [outer][n_tau][inner] is ONE gf with outer*inner
     columns; the noise check (fourier_matsubara.cpp:100-114) is joint.  Column (0, 0) is G = 1/(i w) whose G(tau) = -1/2 is

@@ -7,6 +7,7 @@
 // A transform whose columns fit one SM's shared memory runs as ONE kernel (HBM is read once and written
 // once); longer ones (L = 10^5) run as a two-kernel four-step FFT L = Na * Nb with an L2-resident scratch.
 #include "tq_fft.cuh"
+#include "tq_pipe.cuh" // tile_shape (Bluestein picks axis lengths the plain engine has a plan for)
 
 #include <algorithm>
 #include <cmath>
@@ -492,6 +493,227 @@ static tq_status run_direct(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw
 }
 
 // -------------------------------------------------------------------------------------------------
+// Bluestein (chirp-z) evaluation for mesh lengths WITHOUT a plan (a prime factor > 127: L = 1999, 4999, 8191, 19999 ... -- round
+// n_tau values are one off a smooth length; FFTW takes them through Rader / Bluestein as well, fourier_common.cpp:30-44).
+//   j n = (j^2 + n^2 - (n - j)^2) / 2   =>   X_n = C(n) sum_j [x_j C(j)] B(n - j),   C(m) = e^{i pi m^2 / L},  B = conj C
+// i.e. a linear convolution of the chirped input with a chirp, done as a circular one of a SMOOTH length M = M1 M2 >= n_in + n_out - 1
+// through the plain axis engine (lattice_pipe.cu): FFT_M as a four-step  [M1][M2]: axis M1, twiddle w_M^{j2 k1}, axis M2  (output
+// order [k1][k2], the order the kernel spectrum is stored in), pointwise product, and the same steps backwards.  Only the window is
+// wanted / non-zero (:182, :254): n_in = L, n_out = n_w forward and the other way round on the return leg.  The pre / post arithmetic
+// of the Matsubara transform is k_direct_pre / k_direct_post.  Cost ~ 9 streaming passes over M n_cols elements instead of
+// n_w L n_cols multiply-adds.
+// -------------------------------------------------------------------------------------------------
+tq_status tq_fft_axis_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign); // lattice.cu
+
+struct BlueDir {
+  const cd *pre = nullptr;   // [n_in]  chirp on the input
+  const cd *post = nullptr;  // [n_out] chirp on the output, times 1 / M
+  const cd *khat = nullptr;  // [M1][M2] spectrum of the circular kernel sequence
+};
+struct BluePlan {
+  int M1 = 0, M2 = 0;
+  long M = 0;
+  const cd *tw = nullptr; // [M1][M2] exp(-2 pi i j2 k1 / M)
+  BlueDir dir[2];         // 0: forward (imtime -> imfreq), 1: inverse
+  std::vector<void *> allocs;
+  ~BluePlan() {
+    for (void *p : allocs) cudaFree(p);
+  }
+};
+struct BluePlanCache {
+  std::map<std::tuple<long, long, long>, std::shared_ptr<BluePlan>> plans; // (L, n_w, first)
+};
+
+// z[gf][m][c] = x[gf][m][c] pre[m]  (m < n_in),  0  (n_in <= m < M)
+static __global__ void k_blue_load(const cd *__restrict__ x, const cd *__restrict__ pre, int n_in, long M, int n_cols, cd *__restrict__ z) {
+  const long per = M * n_cols;
+  const long gf = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / n_cols;
+    cd v = cmk(0.0, 0.0);
+    if (m < n_in) v = cmul(x[gf * (long)n_in * n_cols + i], pre[m]);
+    z[gf * per + i] = v;
+  }
+}
+// z[gf][m][c] *= tab[m]  (or its conjugate)
+static __global__ void k_blue_mul(cd *__restrict__ z, const cd *__restrict__ tab, long M, int n_cols, int conj) {
+  const long per = M * n_cols;
+  const long gf = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    cd t = tab[i / n_cols];
+    if (conj) t = cconj(t);
+    z[gf * per + i] = cmul(z[gf * per + i], t);
+  }
+}
+// partial[gf][o][c] = z[gf][o][c] post[o]   (o < n_out)
+static __global__ void k_blue_store(const cd *__restrict__ z, const cd *__restrict__ post, int n_out, long M, int n_cols, cd *__restrict__ partial) {
+  const long per = (long)n_out * n_cols;
+  const long gf = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x)
+    partial[gf * per + i] = cmul(z[gf * M * n_cols + i], post[i / n_cols]);
+}
+
+static cd blue_chirp(long m, long L, int sign) { // exp(sign i pi m^2 / L), m^2 reduced mod 2 L exactly
+  const long r = (long)(((unsigned long long)(m < 0 ? -m : m) * (unsigned long long)(m < 0 ? -m : m)) % (unsigned long long)(2 * L));
+  const long double a = 3.141592653589793238462643383279502884L * (long double)r / (long double)L;
+  return cmk((double)cosl(a), (double)(sign * sinl(a)));
+}
+
+// smooth axis lengths the plain engine runs through its pipelined kernel (two register radices), 16 ... 640
+static bool blue_axis_ok(int n) {
+  if (n < 16 || n > 640) return false;
+  int m = n;
+  for (int p : {2, 3, 5})
+    while (m % p == 0) m /= p;
+  if (m != 1) return false;
+  TileShape t;
+  return tile_shape(n, &t, false) && !t.generic && !t.heavy;
+}
+static bool blue_pick_lengths(long need, int *M1, int *M2) {
+  long best = 0;
+  for (int a = 16; a <= 640; ++a) {
+    if (!blue_axis_ok(a)) continue;
+    for (int b = a; b <= 640; ++b) {
+      if ((long)a * b < need || !blue_axis_ok(b)) continue;
+      if (!best || (long)a * b < best) {
+        best = (long)a * b;
+        *M1 = a;
+        *M2 = b;
+      }
+      break; // larger b only grow the product
+    }
+  }
+  return best != 0;
+}
+
+static tq_status blue_convolve(tq_ctx *ctx, const BluePlan &bp, const BlueDir *d /* nullptr: transform only (plan creation) */, cd *z, long n_gf,
+                               int n_cols) {
+  const long M = bp.M;
+  const unsigned gx = (unsigned)std::min<long>((M * n_cols + 255) / 256, 148 * 8);
+  TQ_TRY(tq_fft_axis_device(ctx, n_gf, bp.M1, (long)bp.M2 * n_cols, z, z, -1));
+  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, bp.tw, M, n_cols, 0);
+  TQ_TRY(tq_fft_axis_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, -1));
+  tq_count_launch(ctx);
+  if (!d) return TQ_OK;
+  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, d->khat, M, n_cols, 0);
+  TQ_TRY(tq_fft_axis_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, +1));
+  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, bp.tw, M, n_cols, 1);
+  TQ_TRY(tq_fft_axis_device(ctx, n_gf, bp.M1, (long)bp.M2 * n_cols, z, z, +1));
+  tq_count_launch(ctx, 2);
+  TQ_CUDA(ctx, cudaGetLastError());
+  return TQ_OK;
+}
+
+static tq_status get_blue_plan(tq_ctx *ctx, const MatsubaraDev &D, std::shared_ptr<BluePlan> *out) {
+  if (!ctx->blue_cache) ctx->blue_cache = std::make_shared<BluePlanCache>();
+  auto key = std::make_tuple((long)D.L, (long)D.n_w, (long)D.first);
+  auto it = ctx->blue_cache->plans.find(key);
+  if (it != ctx->blue_cache->plans.end()) {
+    *out = it->second;
+    return TQ_OK;
+  }
+  auto bp = std::make_shared<BluePlan>();
+  const long L = D.L, n_w = D.n_w, first = D.first;
+  if (!blue_pick_lengths(L + n_w - 1, &bp->M1, &bp->M2)) { // (meshes beyond 640 x 640 - n_w: the direct evaluation stays)
+    *out = nullptr;
+    return TQ_OK;
+  }
+  const long M = bp->M = (long)bp->M1 * bp->M2;
+  auto up = [&](const std::vector<cd> &h, const cd **d) -> tq_status {
+    void *p = nullptr;
+    TQ_CUDA(ctx, cudaMalloc(&p, sizeof(cd) * h.size()));
+    bp->allocs.push_back(p);
+    TQ_CUDA(ctx, cudaMemcpyAsync(p, h.data(), sizeof(cd) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *d = (const cd *)p;
+    return TQ_OK;
+  };
+  {
+    std::vector<cd> tw((size_t)M);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k1 = 0; k1 < bp->M1; ++k1)
+      for (int j2 = 0; j2 < bp->M2; ++j2) {
+        const long r = ((long)k1 * j2) % M;
+        const long double a = two_pi * (long double)r / (long double)M;
+        tw[(size_t)k1 * bp->M2 + j2] = cmk((double)cosl(a), (double)-sinl(a));
+      }
+    TQ_TRY(up(tw, &bp->tw));
+  }
+  const double inv_M = 1.0 / (double)M;
+  for (int dir = 0; dir < 2; ++dir) {
+    const long n_in = dir == 0 ? L : n_w, n_out = dir == 0 ? n_w : L;
+    std::vector<cd> pre((size_t)n_in), post((size_t)n_out), kc((size_t)M, cmk(0.0, 0.0));
+    if (dir == 0) { // X_o = C(first + o) sum_j [x_j C(j)] B(first + o - j)
+      for (long j = 0; j < n_in; ++j) pre[j] = blue_chirp(j, L, +1);
+      for (long o = 0; o < n_out; ++o) post[o] = cscale(inv_M, blue_chirp(first + o, L, +1));
+      for (long t = -(n_in - 1); t <= n_out - 1; ++t) kc[(size_t)(((t % M) + M) % M)] = blue_chirp(first + t, L, -1);
+    } else { // Y_j = B(j) sum_i [y_i B(first + i)] C(first + i - j)
+      for (long i = 0; i < n_in; ++i) pre[i] = blue_chirp(first + i, L, -1);
+      for (long j = 0; j < n_out; ++j) post[j] = cscale(inv_M, blue_chirp(j, L, -1));
+      for (long t = -(n_in - 1); t <= n_out - 1; ++t) kc[(size_t)(((t % M) + M) % M)] = blue_chirp(first - t, L, +1);
+    }
+    TQ_TRY(up(pre, &bp->dir[dir].pre));
+    TQ_TRY(up(post, &bp->dir[dir].post));
+    const cd *kd = nullptr;
+    TQ_TRY(up(kc, &kd));
+    TQ_TRY(blue_convolve(ctx, *bp, nullptr, const_cast<cd *>(kd), 1, 1)); // its spectrum, in the engine's own [k1][k2] order
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bp->dir[dir].khat = kd;
+  }
+  ctx->blue_cache->plans[key] = bp;
+  *out = bp;
+  return TQ_OK;
+}
+
+template <bool FWD>
+static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw, const BluePlan &bp, long n_cols, long batch, const cd *d_in,
+                               cd *d_out, const cd *d_mom, int mom_rows) {
+  DirectArgs A{};
+  A.D = D;
+  A.btw = btw;
+  A.n_cols = (int)n_cols;
+  A.n_in = FWD ? D.L : D.n_w;
+  A.n_out = FWD ? D.n_w : D.L;
+  A.chunk = A.n_in;
+  A.n_chunks = 1;
+  A.in_gf_stride = (long)(FWD ? D.L + 1 : D.n_w) * n_cols;
+  A.out_gf_stride = (long)(FWD ? D.n_w : D.L + 1) * n_cols;
+  A.mom_gf_stride = (long)mom_rows * n_cols;
+  const BlueDir &dir = bp.dir[FWD ? 0 : 1];
+  const size_t x_gf = sizeof(cd) * (size_t)A.n_in * n_cols, p_gf = sizeof(cd) * (size_t)A.n_out * n_cols, z_gf = sizeof(cd) * (size_t)bp.M * n_cols;
+  long per = std::max<long>(1, std::min<long>((long)((512ull << 20) / (x_gf + p_gf + z_gf)), 65535));
+  per = std::min(per, batch);
+  const size_t x_off = (p_gf * per + 255) & ~size_t(255), z_off = (x_off + x_gf * per + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, z_off + z_gf * per));
+  A.partial = (cd *)ctx->scratch.p;
+  A.x = (cd *)((char *)ctx->scratch.p + x_off);
+  cd *z = (cd *)((char *)ctx->scratch.p + z_off);
+  const unsigned gz = (unsigned)std::min<long>((bp.M * n_cols + 255) / 256, 148 * 8);
+  for (long b0 = 0; b0 < batch; b0 += per) {
+    const long nb = std::min(per, batch - b0);
+    A.in = d_in + b0 * A.in_gf_stride;
+    A.out = d_out + b0 * A.out_gf_stride;
+    A.moments = d_mom + b0 * A.mom_gf_stride;
+    {
+      KernelScope ks(ctx, FWD ? "tau2iw_bluestein_pre" : "iw2tau_bluestein_pre");
+      k_direct_pre<FWD><<<dim3((unsigned)(((long)A.n_in * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
+      k_blue_load<<<dim3(gz, (unsigned)nb), 256, 0, ctx->stream>>>(A.x, dir.pre, A.n_in, bp.M, (int)n_cols, z);
+    }
+    tq_count_launch(ctx, 2);
+    TQ_TRY(blue_convolve(ctx, bp, &dir, z, nb, (int)n_cols));
+    {
+      KernelScope ks(ctx, FWD ? "tau2iw_bluestein_post" : "iw2tau_bluestein_post");
+      k_blue_store<<<dim3((unsigned)std::min<long>(((long)A.n_out * n_cols + 255) / 256, 148 * 8), (unsigned)nb), 256, 0, ctx->stream>>>(
+         z, dir.post, A.n_out, bp.M, (int)n_cols, A.partial);
+      k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
+    }
+    tq_count_launch(ctx, 2);
+    TQ_CUDA(ctx, cudaGetLastError());
+  }
+  return TQ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // moments of G(tau) from one-sided finite differences  (fourier_matsubara.cpp:39-92, noise check :100-114)
 // -------------------------------------------------------------------------------------------------
 __constant__ double c_vinv[2][8] = {
@@ -884,8 +1106,13 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   }
   constexpr int SGN = fwd ? 1 : -1;
   Tiling t;
-  if (choose_tiling(ctx, L, n_cols, batch, &t) != TQ_OK) { // no factorisation the tile FFT supports: direct window DFT
+  if (choose_tiling(ctx, L, n_cols, batch, &t) != TQ_OK) { // no factorisation the tile FFT supports: Bluestein, or the direct window DFT
     ctx->err.clear();
+    if (!ctx->opt_no_bluestein && L >= 512) { // (short meshes: the direct sum is a handful of launches and as fast)
+      std::shared_ptr<BluePlan> bp;
+      TQ_TRY(get_blue_plan(ctx, D, &bp));
+      if (bp) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
+    }
     return run_direct<fwd>(ctx, D, pl.btw, n_cols, batch, d_in, d_out, d_mom, mom_rows);
   }
   TileArgs A{};
@@ -1147,6 +1374,7 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
     ctx->lanes[l]->opt_no_pipe = ctx->opt_no_pipe;
     ctx->lanes[l]->opt_no_col = ctx->opt_no_col;
     ctx->lanes[l]->opt_no_tr = ctx->opt_no_tr;
+    ctx->lanes[l]->opt_no_bluestein = ctx->opt_no_bluestein;
     ctx->lanes[l]->call_batch = batch;
     ctx->lanes[l]->opt_scratch_chunk_mb = ctx->opt_scratch_chunk_mb;
     ctx->lanes[l]->opt_bounce = ctx->opt_bounce ? 2 : 0; // (2: this context is a lane of a multi-lane call)

@@ -270,6 +270,11 @@ tq_status tq_wrapped_fft_axis(tq_ctx *ctx, long outer, long N, long inner, const
   return launch_plain(ctx, outer, N, inner, in, out, sign, 1.0, rin, rout, coef);
 }
 
+// fourier_matsubara.cu (Bluestein): one plain unnormalised axis transform of [outer][N][inner] on device pointers, in place allowed
+tq_status tq_fft_axis_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign) {
+  return launch_plain(ctx, outer, N, inner, in, out, sign, 1.0);
+}
+
 static tq_status fft_many_device(tq_ctx *ctx, int rank, const long *dims, long howmany, const cd *d_in, cd *d_out, int sign, double scale) {
   long total = 1;
   for (int d = 0; d < rank; ++d) total *= dims[d];

@@ -61,6 +61,7 @@ struct ColPlanCache;   // fourier_col.cu
 struct RealPlanCache;  // fourier_real.cu
 struct LegendrePlanCache; // legendre.cu
 struct DirectTwiddles;    // lattice.cu
+struct BluePlanCache;     // fourier_matsubara.cu (Bluestein plans)
 
 struct tq_ctx {
   int device = 0;
@@ -87,6 +88,7 @@ struct tq_ctx {
   std::shared_ptr<RealPlanCache> real_cache;
   std::shared_ptr<LegendrePlanCache> leg_cache;
   std::shared_ptr<DirectTwiddles> direct_tw;
+  std::shared_ptr<BluePlanCache> blue_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {
@@ -99,6 +101,7 @@ struct tq_ctx {
   long opt_pipe_lag0 = 0;        // packet order of the planned kernels (fourier_pipe_kernel.cuh)
   long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
   long opt_no_col = 0;           // 1: skip the single-column kernel of fourier_col.cu (A/B measurements)
+  long opt_no_bluestein = 0;     // 1: lengths without a plan always go through the direct O(N^2) window DFT (A/B measurements, tests)
   long opt_no_tr = 0;            // 1: narrow targets never run as "gfs as columns" through the planned kernels (A/B measurements)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)
