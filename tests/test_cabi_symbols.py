@@ -68,7 +68,8 @@ def test_pipelined_kernels_do_not_spill():
     for m in re.finditer(r"Function (\S*matsubara_pipe_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
         found += 1
         regs, stack = int(m.group(2)), int(m.group(3))
-        assert regs <= 168, (m.group(1), regs)
+        workers = int(re.search(r"ELi(\d+)ELi[01]EEv8PipeArgs", m.group(1)).group(1))  # NW: 11 workers + producer = 12 warps (168), 7 + 1 = 8 (255)
+        assert regs <= (168 if workers > 7 else 255), (m.group(1), regs)
         heavy = m.group(1).endswith("ELi1EEv8PipeArgs14CUtensorMap_stS1_")  # SET = 1: radix 32 and the Rader primes, expected to spill
         assert stack <= (2048 if heavy else 32), (m.group(1), stack)
     assert found == 12  # four compile-time instantiations (L = 10^5) + four planned + four planned with the extended radix set

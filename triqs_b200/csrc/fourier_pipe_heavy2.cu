@@ -4,5 +4,5 @@
 #include "fourier_pipe_kernel.cuh"
 
 tq_status tq_launch_pipe_heavy_m2(tq_ctx *ctx, const PipeArgs &A, const CUtensorMap &tmap, const CUtensorMap &tmap2, const char *tag) {
-  return launch_pipe<2, 0, 0, 0, PIPE_NW, 1>(ctx, A, tmap, tmap2, tag);
+  return launch_pipe<2, 0, 0, 0, TQ_NW_HEAVY, 1>(ctx, A, tmap, tmap2, tag);
 }

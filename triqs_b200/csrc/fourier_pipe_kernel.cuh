@@ -49,6 +49,10 @@ constexpr int PIPE_MAXR = 41; // largest register radix of a pass
 // sub-partition) get 168 registers per thread, 16 warps only 128 (radix 20 / 25 then spill); measured: 7 workers reach 86 %
 // of the throughput of 11, 15 workers at 128 registers are slower.
 constexpr int PIPE_NW = 11;
+// worker warps of the "heavy" instantiations (Rader radices 11, 13, 17, 41 and radix 32): see fourier_pipe_heavy*.cu
+#ifndef TQ_NW_HEAVY
+#define TQ_NW_HEAVY PIPE_NW
+#endif
 // per-kernel worker counts (developer A/B switches; > 11 workers means 128 registers per thread)
 #ifndef TQ_NW_F1
 #define TQ_NW_F1 PIPE_NW

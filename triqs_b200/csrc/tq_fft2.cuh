@@ -320,7 +320,14 @@ template <int N, int RA, int RB, int SGN, class Post> TQ_HD void fft2_b_finish(c
     case 41: CALL(41) break;                                                                                                     \
     default: break;                                                                                                              \
   }
-TQ_HD bool tq_radix_is_heavy(int r) { return r == 11 || r == 13 || r == 17 || r == 32 || r == 41; }
+// (-DTQ_NO_RADER=mask, developer A/B: bit 0 drops radix 41, bit 1 radix 17, bit 2 radix 13, bit 3 radix 11 from the register set, so that the
+//  planner takes the direct-sum pass B for them)
+#ifndef TQ_NO_RADER
+#define TQ_NO_RADER 0
+#endif
+TQ_HD bool tq_radix_is_heavy(int r) {
+  return (r == 11 && !(TQ_NO_RADER & 8)) || (r == 13 && !(TQ_NO_RADER & 4)) || (r == 17 && !(TQ_NO_RADER & 2)) || r == 32 || (r == 41 && !(TQ_NO_RADER & 1));
+}
 TQ_HD bool tq_radix_in_registers(int r, bool allow_heavy = false) {
   return r == 1 || r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 7 || r == 8 || r == 9 || r == 10 || r == 12 || r == 15 || r == 16 ||
          r == 20 || r == 25 || (allow_heavy && tq_radix_is_heavy(r));

@@ -107,6 +107,7 @@ static inline bool tile_shape(int N, TileShape *out, bool allow_heavy = true) {
   TileShape best;
   for (int ra : kRegRadix) {
     if (N % ra || (tq_radix_is_heavy(ra) && !allow_heavy)) continue;
+    if (!tq_radix_in_registers(ra, true)) continue; // (a radix dropped from the register set by -DTQ_NO_RADER)
     const int rb = N / ra;
     TileShape t;
     t.N = N;
