@@ -351,12 +351,20 @@ struct DirectArgs {
   cd *partial; // [gf][n_chunks][n_out][n_cols]
   const cd *moments;
   long in_gf_stride, out_gf_stride, mom_gf_stride;
+  // Bluestein: the pre kernel writes x chirp into rows [0, n_in) of z[gf][M][n_cols] and zeros into the rest; the post kernel reads
+  // row o of z times post_mul[o] instead of the partial sums
+  const cd *pre_mul, *post_mul;
+  long z_rows;
 };
 
 // x_j = phase_j (g_j - sum_i a_i h_i(tau_j))  (FWD, :159-173)   or   y_di = (g_di - tail(i w)) / beta  (:254)
 template <bool FWD> __global__ void k_direct_pre(const DirectArgs A) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long per_gf = (long)A.n_in * A.n_cols;
+  if (A.pre_mul && i >= per_gf) { // zero padding of the convolution buffer
+    if (i < A.z_rows * A.n_cols) A.x[(size_t)blockIdx.y * A.z_rows * A.n_cols + i] = cmk(0.0, 0.0);
+    return;
+  }
   if (i >= per_gf) return;
   const int gf = blockIdx.y, r = (int)(i / A.n_cols), c = (int)(i - (long)r * A.n_cols);
   const MatsubaraDev &D = A.D;
@@ -373,7 +381,10 @@ template <bool FWD> __global__ void k_direct_pre(const DirectArgs A) {
   } else {
     x = cscale(D.inv_beta, csub(x, tail_iw(D, load_w(D, r), a1, a2, a3)));
   }
-  A.x[(size_t)gf * per_gf + i] = x;
+  if (A.pre_mul)
+    A.x[(size_t)gf * A.z_rows * A.n_cols + i] = cmul(x, A.pre_mul[r]);
+  else
+    A.x[(size_t)gf * per_gf + i] = x;
 }
 
 // partial[chunk][o][c] = sum_{i in chunk} x[i][c] w^{+-(k j)},  FWD: o = frequency data index, i = j;  inverse: o = j, i = data index
@@ -431,7 +442,10 @@ template <bool FWD> __global__ void k_direct_post(const DirectArgs A) {
   cd a1, a2, a3;
   pole_weights(fermion, m1, mom[(size_t)2 * A.n_cols + c], mom[(size_t)3 * A.n_cols + c], a1, a2, a3);
   cd v = cmk(0.0, 0.0);
-  for (int k = 0; k < A.n_chunks; ++k) v = cadd(v, A.partial[((size_t)gf * A.n_chunks + k) * per_gf + i]);
+  if (A.post_mul)
+    v = cmul(A.partial[(size_t)gf * A.z_rows * A.n_cols + i], A.post_mul[r]);
+  else
+    for (int k = 0; k < A.n_chunks; ++k) v = cadd(v, A.partial[((size_t)gf * A.n_chunks + k) * per_gf + i]);
   cd *out = A.out + (size_t)gf * A.out_gf_stride;
   if (FWD) {
     const cd *g = A.in + (size_t)gf * A.in_gf_stride;
@@ -504,6 +518,8 @@ static tq_status run_direct(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw
 // n_w L n_cols multiply-adds.
 // -------------------------------------------------------------------------------------------------
 tq_status tq_fft_axis_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign); // lattice.cu
+tq_status tq_fft_axis_mul_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *tab, int omod, int os, int rs,
+                                 int cdiv, int conj, bool *fused);
 
 struct BlueDir {
   const cd *pre = nullptr;   // [n_in]  chirp on the input
@@ -524,17 +540,6 @@ struct BluePlanCache {
   std::map<std::tuple<long, long, long>, std::shared_ptr<BluePlan>> plans; // (L, n_w, first)
 };
 
-// z[gf][m][c] = x[gf][m][c] pre[m]  (m < n_in),  0  (n_in <= m < M)
-static __global__ void k_blue_load(const cd *__restrict__ x, const cd *__restrict__ pre, int n_in, long M, int n_cols, cd *__restrict__ z) {
-  const long per = M * n_cols;
-  const long gf = blockIdx.y;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
-    const long m = i / n_cols;
-    cd v = cmk(0.0, 0.0);
-    if (m < n_in) v = cmul(x[gf * (long)n_in * n_cols + i], pre[m]);
-    z[gf * per + i] = v;
-  }
-}
 // z[gf][m][c] *= tab[m]  (or its conjugate)
 static __global__ void k_blue_mul(cd *__restrict__ z, const cd *__restrict__ tab, long M, int n_cols, int conj) {
   const long per = M * n_cols;
@@ -545,14 +550,6 @@ static __global__ void k_blue_mul(cd *__restrict__ z, const cd *__restrict__ tab
     z[gf * per + i] = cmul(z[gf * per + i], t);
   }
 }
-// partial[gf][o][c] = z[gf][o][c] post[o]   (o < n_out)
-static __global__ void k_blue_store(const cd *__restrict__ z, const cd *__restrict__ post, int n_out, long M, int n_cols, cd *__restrict__ partial) {
-  const long per = (long)n_out * n_cols;
-  const long gf = blockIdx.y;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x)
-    partial[gf * per + i] = cmul(z[gf * M * n_cols + i], post[i / n_cols]);
-}
-
 static cd blue_chirp(long m, long L, int sign) { // exp(sign i pi m^2 / L), m^2 reduced mod 2 L exactly
   const long r = (long)(((unsigned long long)(m < 0 ? -m : m) * (unsigned long long)(m < 0 ? -m : m)) % (unsigned long long)(2 * L));
   const long double a = 3.141592653589793238462643383279502884L * (long double)r / (long double)L;
@@ -590,16 +587,26 @@ static tq_status blue_convolve(tq_ctx *ctx, const BluePlan &bp, const BlueDir *d
                                int n_cols) {
   const long M = bp.M;
   const unsigned gx = (unsigned)std::min<long>((M * n_cols + 255) / 256, 148 * 8);
-  TQ_TRY(tq_fft_axis_device(ctx, n_gf, bp.M1, (long)bp.M2 * n_cols, z, z, -1));
-  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, bp.tw, M, n_cols, 0);
-  TQ_TRY(tq_fft_axis_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, -1));
-  tq_count_launch(ctx);
-  if (!d) return TQ_OK;
-  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, d->khat, M, n_cols, 0);
-  TQ_TRY(tq_fft_axis_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, +1));
-  k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, bp.tw, M, n_cols, 1);
+  const auto mul = [&](const cd *tab, int conj) {
+    k_blue_mul<<<dim3(gx, (unsigned)n_gf), 256, 0, ctx->stream>>>(z, tab, M, n_cols, conj);
+    tq_count_launch(ctx);
+  };
+  bool fused = false;
+  // forward: axis M1 of [gf][M1][M2 cols], x w_M^{j2 k1}, axis M2 of [gf M1][M2][cols]  ->  [k1][k2] order.  The pointwise products ride
+  // on the stores of the axis kernels where the pipelined kernel takes the length (always, for the lengths blue_pick_lengths returns,
+  // unless "no_pipe" is set).
+  TQ_TRY(tq_fft_axis_mul_device(ctx, n_gf, bp.M1, (long)bp.M2 * n_cols, z, z, -1, bp.tw, 0, 0, bp.M2, n_cols, 0, &fused));
+  if (!fused) mul(bp.tw, 0);
+  if (!d) {
+    TQ_TRY(tq_fft_axis_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, -1));
+    return TQ_OK;
+  }
+  TQ_TRY(tq_fft_axis_mul_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, -1, d->khat, bp.M1, bp.M2, 1, 0, 0, &fused));
+  if (!fused) mul(d->khat, 0);
+  // ... and back
+  TQ_TRY(tq_fft_axis_mul_device(ctx, n_gf * bp.M1, bp.M2, n_cols, z, z, +1, bp.tw, bp.M1, bp.M2, 1, 0, 1, &fused));
+  if (!fused) mul(bp.tw, 1);
   TQ_TRY(tq_fft_axis_device(ctx, n_gf, bp.M1, (long)bp.M2 * n_cols, z, z, +1));
-  tq_count_launch(ctx, 2);
   TQ_CUDA(ctx, cudaGetLastError());
   return TQ_OK;
 }
@@ -680,15 +687,16 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
   A.out_gf_stride = (long)(FWD ? D.n_w : D.L + 1) * n_cols;
   A.mom_gf_stride = (long)mom_rows * n_cols;
   const BlueDir &dir = bp.dir[FWD ? 0 : 1];
-  const size_t x_gf = sizeof(cd) * (size_t)A.n_in * n_cols, p_gf = sizeof(cd) * (size_t)A.n_out * n_cols, z_gf = sizeof(cd) * (size_t)bp.M * n_cols;
-  long per = std::max<long>(1, std::min<long>((long)((512ull << 20) / (x_gf + p_gf + z_gf)), 65535));
+  A.pre_mul = dir.pre;
+  A.post_mul = dir.post;
+  A.z_rows = bp.M;
+  const size_t z_gf = sizeof(cd) * (size_t)bp.M * n_cols;
+  long per = std::max<long>(1, std::min<long>((long)((512ull << 20) / z_gf), 65535));
   per = std::min(per, batch);
-  const size_t x_off = (p_gf * per + 255) & ~size_t(255), z_off = (x_off + x_gf * per + 255) & ~size_t(255);
-  TQ_TRY(tq_reserve(ctx, ctx->scratch, z_off + z_gf * per));
-  A.partial = (cd *)ctx->scratch.p;
-  A.x = (cd *)((char *)ctx->scratch.p + x_off);
-  cd *z = (cd *)((char *)ctx->scratch.p + z_off);
-  const unsigned gz = (unsigned)std::min<long>((bp.M * n_cols + 255) / 256, 148 * 8);
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, z_gf * per));
+  cd *z = (cd *)ctx->scratch.p;
+  A.x = z;       // k_direct_pre writes the chirped, zero-padded input straight into the convolution buffer ...
+  A.partial = z; // ... and k_direct_post reads the window rows back out of it
   for (long b0 = 0; b0 < batch; b0 += per) {
     const long nb = std::min(per, batch - b0);
     A.in = d_in + b0 * A.in_gf_stride;
@@ -696,18 +704,15 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
     A.moments = d_mom + b0 * A.mom_gf_stride;
     {
       KernelScope ks(ctx, FWD ? "tau2iw_bluestein_pre" : "iw2tau_bluestein_pre");
-      k_direct_pre<FWD><<<dim3((unsigned)(((long)A.n_in * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
-      k_blue_load<<<dim3(gz, (unsigned)nb), 256, 0, ctx->stream>>>(A.x, dir.pre, A.n_in, bp.M, (int)n_cols, z);
+      k_direct_pre<FWD><<<dim3((unsigned)((bp.M * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
     }
-    tq_count_launch(ctx, 2);
+    tq_count_launch(ctx);
     TQ_TRY(blue_convolve(ctx, bp, &dir, z, nb, (int)n_cols));
     {
       KernelScope ks(ctx, FWD ? "tau2iw_bluestein_post" : "iw2tau_bluestein_post");
-      k_blue_store<<<dim3((unsigned)std::min<long>(((long)A.n_out * n_cols + 255) / 256, 148 * 8), (unsigned)nb), 256, 0, ctx->stream>>>(
-         z, dir.post, A.n_out, bp.M, (int)n_cols, A.partial);
       k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
     }
-    tq_count_launch(ctx, 2);
+    tq_count_launch(ctx);
     TQ_CUDA(ctx, cudaGetLastError());
   }
   return TQ_OK;

@@ -275,6 +275,17 @@ tq_status tq_fft_axis_device(tq_ctx *ctx, long outer, long N, long inner, const 
   return launch_plain(ctx, outer, N, inner, in, out, sign, 1.0);
 }
 
+// ... the same with a pointwise product fused into the stores where the pipelined kernel takes the length:
+//   out(o, k, i) *= tab[(o % omod) * os + k * rs + i / cdiv]  (conjugated if conj);  *fused = false: transformed, NOT multiplied
+tq_status tq_lattice_pipe_axis_mul(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *tab, int omod, int os,
+                                   int rs, int cdiv, int conj, bool *handled);
+tq_status tq_fft_axis_mul_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *tab, int omod, int os, int rs,
+                                 int cdiv, int conj, bool *fused) {
+  TQ_TRY(tq_lattice_pipe_axis_mul(ctx, outer, N, inner, in, out, sign, tab, omod, os, rs, cdiv, conj, fused));
+  if (*fused) return TQ_OK;
+  return launch_plain(ctx, outer, N, inner, in, out, sign, 1.0);
+}
+
 static tq_status fft_many_device(tq_ctx *ctx, int rank, const long *dims, long howmany, const cd *d_in, cd *d_out, int sign, double scale) {
   long total = 1;
   for (int d = 0; d < rank; ++d) total *= dims[d];

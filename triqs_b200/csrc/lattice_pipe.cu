@@ -30,6 +30,10 @@ struct LatPipeArgs {
   int tN, tRA, tRB, rb_generic;
   int boxes, box_rows; // the tile is fetched as `boxes` tensor boxes of box_rows rows (a TMA box has <= 256 rows)
   const cd *gtw;       // [tRB] exp(+2 pi i j / tRB) for the direct-sum pass B
+  // fused pointwise product on the way out (MUL instantiations; the Bluestein convolution of fourier_matsubara.cu multiplies by the
+  // four-step twiddles / the kernel spectrum between its axis transforms):  out(o, k, i) *= mul[(o % mul_omod) * mul_os + k * mul_rs + i / mul_cdiv]
+  const cd *mul;
+  int mul_omod, mul_os, mul_rs, mul_cdiv, mul_conj; // mul_omod = 0: no outer term; mul_cdiv = 0: no column term
 };
 
 template <int N, int RA> struct PostLattice {
@@ -47,8 +51,29 @@ template <int N, int RA> struct PostLattice {
     p[(long)(ra() * t) * inner] = v;
   }
 };
+// ... with the fused pointwise product (planned instantiation only)
+struct PostLatticeMul {
+  cd *base;
+  long inner;
+  const cd *mul; // mul + outer term
+  int mul_rs, mul_cdiv, mul_conj, c0;
+  int ra_rt;
+  cd *p;
+  const cd *m;
+  TQ_D int ra() const { return ra_rt; }
+  TQ_D void begin(int sidx, int c) {
+    p = base + (long)sidx * inner + c;
+    m = mul + (long)sidx * mul_rs + (mul_cdiv ? (c0 + c) / mul_cdiv : 0);
+  }
+  template <int TT> TQ_D void store(cd v) const { store_rt(TT, v); }
+  TQ_D void store_rt(int t, cd v) const {
+    cd f = __ldg(m + (long)(ra_rt * t) * mul_rs);
+    if (mul_conj) f = cconj(f);
+    p[(long)(ra_rt * t) * inner] = cmul(v, f);
+  }
+};
 
-template <int N, int RA, int RB, int SGN, int NW, int SET = 0>
+template <int N, int RA, int RB, int SGN, int NW, int SET = 0, bool MUL = false>
 __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pipe_kernel(const __grid_constant__ LatPipeArgs A,
                                                                                            const __grid_constant__ CUtensorMap tmap) {
   constexpr int NT = (NW + 1) * 32;
@@ -159,6 +184,15 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
         if (lane == 0) mbar_arrive(&adone[b]);
       } else {
         mbar_wait(&adone[b], (uint32_t)(u & 1));
+        if constexpr (MUL) {
+          static_assert(!MUL || (N == 0 && SET == 0), "the fused product exists for the planned instantiation only");
+          PostLatticeMul post{A.out + (o * NN) * A.inner + c0, A.inner, A.mul + (A.mul_omod ? (long)(o % A.mul_omod) * A.mul_os : 0L), A.mul_rs, A.mul_cdiv,
+                              A.mul_conj, c0, RAv, nullptr, nullptr};
+          const unsigned m_w = fastdiv_magic((unsigned)w);
+#define TQ_CALL_B(R) fft2_item_b<R, SGN>(tile, TC, w, RAv, it, post, m_w);
+          TQ_RADIX_SWITCH32(RBv, TQ_CALL_B)
+#undef TQ_CALL_B
+        } else {
         PostLattice<N, RA> post{A.out + (o * NN) * A.inner + c0, A.inner, A.scale, scaled, nullptr, RAv};
         if constexpr (!PLANNED) {
           fft2_pass_b<N, RA, RB, SGN>(tile, TC, w, it, 1 << 30, post);
@@ -176,6 +210,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
 #undef TQ_CALL_B
           }
         }
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&freeb[b]);
@@ -188,7 +223,7 @@ __global__ void __maxnreg__((16384 / (((NW + 1) + 3) / 4 * 32)) & ~7) lattice_pi
 // host
 // ---------------------------------------------------------------------------------------------
 struct LatTwiddles {
-  std::map<std::tuple<int, int>, cd *> tw; // (N, sign) -> device [RB][RA]; (-RB, 0) -> exp(+2 pi i j / RB)
+  std::map<std::tuple<int, int>, cd *> tw; // (64 N + RA, sign) -> device [RB][RA]; (-RB, 0) -> exp(+2 pi i j / RB)
   ~LatTwiddles() {
     for (auto &kv : tw) cudaFree(kv.second);
   }
@@ -198,10 +233,10 @@ static size_t lat_smem_bytes(int N, int RB, bool generic, long tc) {
   const size_t buf_stride = (sizeof(cd) * (size_t)N * tc + 127) & ~size_t(127);
   return LP_NBUF * buf_stride + sizeof(cd) * (N + (generic ? RB : 0)) + 8 * 3 * LP_NBUF + 16;
 }
-template <int N, int RA, int RB, int SGN, int SET = 0> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
+template <int N, int RA, int RB, int SGN, int SET = 0, bool MUL = false> static tq_status launch_lat(tq_ctx *ctx, LatPipeArgs A, const CUtensorMap &tmap) {
   constexpr int NW = 11;
   const size_t smem = lat_smem_bytes(N ? N : A.tN, N ? RB : A.tRB, N ? false : A.rb_generic != 0, A.TC);
-  auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW, SET>;
+  auto k = lattice_pipe_kernel<N, RA, RB, SGN, NW, SET, MUL>;
   TQ_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<long>(A.n_tiles, (long)ctx->sm_count);
   {
@@ -214,13 +249,27 @@ template <int N, int RA, int RB, int SGN, int SET = 0> static tq_status launch_l
 }
 
 // N0 / RA0 / RB0 = 0: the planned instantiation with the run-time shape T
+struct LatMul { // fused pointwise product of the planned instantiation (LatPipeArgs::mul ...)
+  const cd *tab = nullptr;
+  int omod = 0, os = 0, rs = 0, cdiv = 0, conj = 0;
+};
 template <int N0, int RA0, int RB0, int SET = 0>
-static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled) {
+static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner, const cd *in, cd *out, int sign, double scale, bool *handled,
+                         const LatMul *mul = nullptr) {
   const int N = T.N, RA = T.RA, RB = T.RB;
   const size_t budget = (size_t)ctx->max_smem_optin - sizeof(cd) * (N + RB) - 256;
   long tc = (long)(budget / LP_NBUF / (sizeof(cd) * N));
-  tc = std::min<long>(std::min<long>(tc, 128), inner);
-  if (tc >= 8) tc &= ~7L; // 128-byte runs
+  tc = std::min<long>(tc, 128);
+  if (tc >= inner)
+    tc = inner; // all columns in ONE tile (inner = 25: a 24-column tile would leave a second tile with a single column)
+  else if (tc >= 8)
+    tc &= ~7L; // 128-byte runs
+  if (tc < inner) { // balance the column tiles (inner = 200, tc = 128: 2 x 104 instead of 128 + 72)
+    const long nt = (inner + tc - 1) / tc;
+    long bal = (inner + nt - 1) / nt;
+    if (bal >= 8) bal = (bal + 7) & ~7L;
+    tc = std::min(tc, bal);
+  }
   int boxes = 1;
   while (N % boxes != 0 || N / boxes > 256) ++boxes;
   if (boxes > 1 && ((long)(N / boxes) * tc) % 8 != 0) return TQ_OK; // every box must land 128-byte aligned
@@ -232,7 +281,7 @@ static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return TQ_OK;
   if (!ctx->lat_tw) ctx->lat_tw = std::make_shared<LatTwiddles>();
-  cd *&twd = ctx->lat_tw->tw[std::make_tuple(N, sign)];
+  cd *&twd = ctx->lat_tw->tw[std::make_tuple(N * 64 + RA, sign)]; // (the rows depend on the radix split, and a length can have two: heavy radices allowed or not)
   if (!twd) {
     std::vector<cd> w, rows((size_t)N);
     tq_fft_twiddles_host(N, w);
@@ -276,12 +325,47 @@ static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner
     A.gtw = g;
   }
   if (A.n_tiles >= (1L << 31)) return TQ_OK;
+  if constexpr (N0 == 0 && SET == 0) {
+    if (mul) {
+      if (T.generic || scale != 1.0) return TQ_OK; // (not handled: the caller multiplies in a pass of its own)
+      A.mul = mul->tab;
+      A.mul_omod = mul->omod;
+      A.mul_os = mul->os;
+      A.mul_rs = mul->rs;
+      A.mul_cdiv = mul->cdiv;
+      A.mul_conj = mul->conj;
+      if (sign > 0)
+        TQ_TRY((launch_lat<0, 0, 0, 1, 0, true>(ctx, A, tmap)));
+      else
+        TQ_TRY((launch_lat<0, 0, 0, -1, 0, true>(ctx, A, tmap)));
+      *handled = true;
+      return TQ_OK;
+    }
+  }
+  if (mul) return TQ_OK;
   if (sign > 0)
     TQ_TRY((launch_lat<N0, RA0, RB0, 1, SET>(ctx, A, tmap)));
   else
     TQ_TRY((launch_lat<N0, RA0, RB0, -1, SET>(ctx, A, tmap)));
   *handled = true;
   return TQ_OK;
+}
+
+// Axis transform with a fused pointwise product on the output (Bluestein): only lengths the planned (smooth, non-heavy) instantiation takes
+tq_status tq_lattice_pipe_axis_mul(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *tab, int omod, int os,
+                                   int rs, int cdiv, int conj, bool *handled) {
+  *handled = false;
+  if (ctx->opt_no_pipe) return TQ_OK;
+  TileShape T;
+  if (N < 4 || N > 1024 || !tile_shape((int)N, &T, false) || T.generic || T.heavy) return TQ_OK;
+  LatMul m;
+  m.tab = tab;
+  m.omod = omod;
+  m.os = os;
+  m.rs = rs;
+  m.cdiv = cdiv;
+  m.conj = conj;
+  return run_lat<0, 0, 0, 0>(ctx, T, outer, inner, in, out, sign, 1.0, handled, &m);
 }
 
 // DFT along the middle axis of [outer][N][inner]; *handled = false when there is no specialisation for N (caller falls back)
