@@ -82,6 +82,7 @@ tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
  *   "no_tr"            1: batches of narrow gfs (1-3 target columns) are not run as one wide virtual gf ("gfs as columns")
  *   "no_bluestein"     1: mesh lengths with a prime factor > 127 use the direct O(N^2) window DFT instead of the Bluestein (chirp-z)
  *                      convolution (A/B measurements; results agree to 1e-12)
+ *   "force_bluestein"  1: every imtime <-> imfreq transform with L >= 512 uses that convolution (A/B measurements, tests)
  *   "scratch_chunk_mb" > 0: four-step scratch budget per launch pair in MiB (default: 1536 pipelined, 64 generic)
  *   "host_lanes"       1..8: internal lanes over which tq_fourier_tau_to_iw / tq_fourier_iw_to_tau cut a batch passed in HOST
  *                      buffers, so that H2D copies, kernels and D2H copies of different chunks overlap (default 3; 1 = off)

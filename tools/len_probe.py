@@ -5,6 +5,9 @@ sys.path.insert(0, ".")
 import triqs_b200
 F = triqs_b200.FERMION
 ctx = triqs_b200.Context(0, print_warnings=False)
+import os
+if os.environ.get("FORCE_BLUESTEIN"):
+    ctx.set_option("force_bluestein", 1)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 def timed(fn, reps=5, warm=2):

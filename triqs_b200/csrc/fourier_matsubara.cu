@@ -518,6 +518,7 @@ static tq_status run_direct(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw
 // n_w L n_cols multiply-adds.
 // -------------------------------------------------------------------------------------------------
 tq_status tq_fft_axis_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign); // lattice.cu
+double tq_pipe_plan_cost(long L);                                                                                // fourier_pipe.cu
 tq_status tq_fft_axis_mul_device(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, const cd *tab, int omod, int os, int rs,
                                  int cdiv, int conj, bool *fused);
 
@@ -572,7 +573,7 @@ static bool blue_pick_lengths(long need, int *M1, int *M2) {
     if (!blue_axis_ok(a)) continue;
     for (int b = a; b <= 640; ++b) {
       if ((long)a * b < need || !blue_axis_ok(b)) continue;
-      if (!best || (long)a * b < best) {
+      if (!best || (long)a * b <= best) { // (<=: a ascends, so among equal products the most balanced pair wins)
         best = (long)a * b;
         *M1 = a;
         *M2 = b;
@@ -1100,6 +1101,16 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   const MatsubaraDev &D = pl.dev;
   const long L = D.L;
   constexpr bool fwd = IN_KIND == IN_TAU;
+  // Two-radix plans whose second radix is a large prime handled by direct summation (101 | 9999, 89 x 97, ...) cost 4 R FP64 instructions per
+  // element and pass: measured 3400 / cost GB/s against 360-410 for the Bluestein convolution (six streaming passes), so beyond a plan cost
+  // of ~9.5 the convolution is taken -- 9999 = 99 x 101: 230 -> 395 GB/s, 8633 = 89 x 97: 152 -> 390, 7979 = 79 x 101: 160 -> 375,
+  // 5353 = 53 x 101: 184 -> 364 (profiles/r02_bluestein_vs_planned.log).
+  const bool costly_plan = n_cols >= 4 && !ctx->opt_no_bluestein && tq_pipe_plan_cost(L) > 9.5;
+  if ((ctx->opt_force_bluestein || costly_plan) && L >= 512) {
+    std::shared_ptr<BluePlan> bp;
+    TQ_TRY(get_blue_plan(ctx, D, &bp));
+    if (bp) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
+  }
   {
     bool handled = false;
     TQ_TRY(tq_pipe_matsubara(ctx, fwd, D.beta, D.stat, L + 1, (long)D.last + 1, n_cols, batch, d_in, d_out, d_mom, mom_rows, &handled));
@@ -1380,6 +1391,7 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
     ctx->lanes[l]->opt_no_col = ctx->opt_no_col;
     ctx->lanes[l]->opt_no_tr = ctx->opt_no_tr;
     ctx->lanes[l]->opt_no_bluestein = ctx->opt_no_bluestein;
+    ctx->lanes[l]->opt_force_bluestein = ctx->opt_force_bluestein;
     ctx->lanes[l]->call_batch = batch;
     ctx->lanes[l]->opt_scratch_chunk_mb = ctx->opt_scratch_chunk_mb;
     ctx->lanes[l]->opt_bounce = ctx->opt_bounce ? 2 : 0; // (2: this context is a lane of a multi-lane call)

@@ -382,6 +382,14 @@ static int env_int(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// Cost of the two-radix plan of a mesh length in units of a register-radix pass (2 = both passes in registers; a direct-sum radix R adds
+// ~R / 9); < 0: no plan.  fourier_matsubara.cu prefers the Bluestein convolution above ~9.5 (measured: 3400 / cost GB/s against 360-410).
+double tq_pipe_plan_cost(long L) {
+  TileShape a, b;
+  if (!pipe_plan_lengths(L, &a, &b)) return -1.0;
+  return a.cost + b.cost;
+}
+
 // Runs the transform if a pipelined specialisation exists for this mesh.  *handled tells the caller.
 tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in,
                             cd *d_out, const cd *d_mom, int mom_rows, bool *handled) {

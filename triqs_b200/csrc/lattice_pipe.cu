@@ -272,7 +272,8 @@ static tq_status run_lat(tq_ctx *ctx, const TileShape &T, long outer, long inner
   }
   int boxes = 1;
   while (N % boxes != 0 || N / boxes > 256) ++boxes;
-  if (boxes > 1 && ((long)(N / boxes) * tc) % 8 != 0) return TQ_OK; // every box must land 128-byte aligned
+  if (boxes > 1 && ((long)(N / boxes) * tc) % 8 != 0 && tc > 8) tc &= ~7L; // every box must land 128-byte aligned: whole 128-byte rows do
+  if (boxes > 1 && ((long)(N / boxes) * tc) % 8 != 0) return TQ_OK;
   if (const char *e = TQ_DEV_ENV("TQ_LP_TC")) tc = std::min<long>(tc, atol(e)); // (tuning experiments)
   if (tc < 1) return TQ_OK;
   // pointers: TMA needs 16-byte alignment (always true for complex<double> arrays from cudaMalloc / numpy)
