@@ -6,6 +6,8 @@ import triqs_b200
 F = triqs_b200.FERMION
 ctx = triqs_b200.Context(0, print_warnings=False)
 import os
+if os.environ.get("BLUE_CHUNK_MB"):
+    ctx.set_option("blue_chunk_mb", int(os.environ["BLUE_CHUNK_MB"]))
 if os.environ.get("FORCE_BLUESTEIN"):
     ctx.set_option("force_bluestein", 1)
 dev = torch.device("cuda", 0)

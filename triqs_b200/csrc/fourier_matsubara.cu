@@ -692,7 +692,7 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
   A.post_mul = dir.post;
   A.z_rows = bp.M;
   const size_t z_gf = sizeof(cd) * (size_t)bp.M * n_cols;
-  long per = std::max<long>(1, std::min<long>((long)((512ull << 20) / z_gf), 65535));
+  long per = std::max<long>(1, std::min<long>((long)(((size_t)ctx->opt_blue_chunk_mb << 20) / z_gf), 65535));
   per = std::min(per, batch);
   TQ_TRY(tq_reserve(ctx, ctx->scratch, z_gf * per));
   cd *z = (cd *)ctx->scratch.p;
@@ -1392,6 +1392,7 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
     ctx->lanes[l]->opt_no_tr = ctx->opt_no_tr;
     ctx->lanes[l]->opt_no_bluestein = ctx->opt_no_bluestein;
     ctx->lanes[l]->opt_force_bluestein = ctx->opt_force_bluestein;
+    ctx->lanes[l]->opt_blue_chunk_mb = ctx->opt_blue_chunk_mb;
     ctx->lanes[l]->call_batch = batch;
     ctx->lanes[l]->opt_scratch_chunk_mb = ctx->opt_scratch_chunk_mb;
     ctx->lanes[l]->opt_bounce = ctx->opt_bounce ? 2 : 0; // (2: this context is a lane of a multi-lane call)

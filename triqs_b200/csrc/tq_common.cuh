@@ -101,6 +101,7 @@ struct tq_ctx {
   long opt_pipe_lag0 = 0;        // packet order of the planned kernels (fourier_pipe_kernel.cuh)
   long opt_no_pipe = 0;          // 1: skip the TMA-pipelined / column specialisations (generic tile kernels only)
   long opt_no_col = 0;           // 1: skip the single-column kernel of fourier_col.cu (A/B measurements)
+  long opt_blue_chunk_mb = 512;  // convolution buffer of the Bluestein path per group of gfs (MiB)
   long opt_force_bluestein = 0;  // 1: every imtime <-> imfreq transform with L >= 512 goes through the Bluestein convolution (A/B measurements, tests)
   long opt_no_bluestein = 0;     // 1: lengths without a plan always go through the direct O(N^2) window DFT (A/B measurements, tests)
   long opt_no_tr = 0;            // 1: narrow targets never run as "gfs as columns" through the planned kernels (A/B measurements)

@@ -124,6 +124,8 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
     ctx->opt_no_bluestein = value;
   else if (n == "force_bluestein")
     ctx->opt_force_bluestein = value;
+  else if (n == "blue_chunk_mb")
+    ctx->opt_blue_chunk_mb = std::max<long>(1, value);
   else if (n == "scratch_chunk_mb")
     ctx->opt_scratch_chunk_mb = value;
   else if (n == "bounce")
