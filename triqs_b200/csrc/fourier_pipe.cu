@@ -45,7 +45,7 @@ struct PipePlan {
   }
 };
 struct PipePlanCache {
-  std::map<std::tuple<double, int, long, long>, std::shared_ptr<PipePlan>> plans;
+  std::map<std::tuple<double, int, long, long, int>, std::shared_ptr<PipePlan>> plans; // (..., orientation: see pipe_plan_lengths)
 };
 
 template <class T> static tq_status pp_upload(tq_ctx *ctx, PipePlan &pl, const std::vector<T> &h, const T **d) {
@@ -135,7 +135,10 @@ static std::vector<cd> twiddle_rows(int N, int RA, int RB, int sgn, const std::v
 // RA and a second radix RB that is either a register radix too or small enough for the direct-sum pass B.
 constexpr int PIPE_MAX_TILE = 640;      // longest tile (rows) the shared-memory ring is sized for
 
-static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2) {
+// dir: +1 imtime -> imfreq, -1 imfreq -> imtime, 0 either.  A tile length with a heavy (Rader) radix costs very differently in the four kernels
+// (1.2 GB per launch: F1 1.2 ms with 7 workers, I2 1.15, F2 2.0, I1 2.8 -- smooth tiles 0.45-0.65), so the forward leg wants it in pass 1 and the
+// return leg in pass 2: the two directions of such a mesh use transposed plans (L = 6150: forward 2.7 -> 1.8 ms; 61500: inverse 3.5 -> 1.9 ms).
+static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2, int dir = 0) {
   if (L < 64 || L > (long)PIPE_MAX_TILE * PIPE_MAX_TILE) return false;
   if (L == 100000) { // the headline mesh keeps its tuned, fully compile-time kernels
     tile_shape(250, t1);
@@ -159,6 +162,8 @@ static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2) {
     if (na < 16) cost += 0.5;
     if (nb > na) cost += 0.05;  // pass 1 keeps a deeper ring of (padded) tiles: give it the shorter length
     if (std::max(na, nb) > 512) cost += 0.3; // few columns of such a tile fit the ring
+    if (dir > 0 && b.heavy && !a.heavy) cost += 0.8; // (a: pass-1 tile, b: pass-2 tile)
+    if (dir < 0 && a.heavy && !b.heavy) cost += 0.8;
     if (!found || cost < best) {
       best = cost;
       *t1 = a;
@@ -169,10 +174,17 @@ static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2) {
   return found;
 }
 
-static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, std::shared_ptr<PipePlan> *out) {
+static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, long n_iw, bool fwd, std::shared_ptr<PipePlan> *out) {
   if (!ctx->pipe_cache) ctx->pipe_cache = std::make_shared<PipePlanCache>();
   auto &plans = ctx->pipe_cache->plans;
-  auto key = std::make_tuple(beta, stat, n_tau, n_iw);
+  // orientation: 0 when both directions pick the same plan (every smooth length), +-1 when a heavy tile makes them differ
+  int orient = 0;
+  {
+    TileShape f1, f2, i1, i2;
+    if (pipe_plan_lengths(n_tau - 1, &f1, &f2, +1) && pipe_plan_lengths(n_tau - 1, &i1, &i2, -1) && (f1.N != i1.N || f1.RA != i1.RA))
+      orient = fwd ? +1 : -1;
+  }
+  auto key = std::make_tuple(beta, stat, n_tau, n_iw, orient);
   auto it = plans.find(key);
   if (it != plans.end()) {
     *out = it->second;
@@ -180,7 +192,7 @@ static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, l
   }
   auto pl = std::make_shared<PipePlan>();
   const long L = n_tau - 1;
-  if (!pipe_plan_lengths(L, &pl->t1, &pl->t2)) return tq_fail(ctx, TQ_ERR_INVALID, "internal: pipe plan for an unsupported length");
+  if (!pipe_plan_lengths(L, &pl->t1, &pl->t2, orient)) return tq_fail(ctx, TQ_ERR_INVALID, "internal: pipe plan for an unsupported length");
   const TileShape &T1 = pl->t1, &T2 = pl->t2;
   const int Na = T2.N, Nb = T1.N;
   pl->specialised = (T1.N == 250 && T1.RA == 10 && T1.RB == 25 && T2.N == 400 && T2.RA == 20 && T2.RB == 20);
@@ -431,7 +443,7 @@ tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n
   }
 #endif
   std::shared_ptr<PipePlan> pl;
-  TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, &pl));
+  TQ_TRY(get_pipe_plan(ctx, beta, stat, n_tau, n_iw, fwd, &pl));
   const TileShape &T1 = pl->t1, &T2 = pl->t2;
   const int Na = pl->Na, Nb = pl->Nb;
   const bool spec = pl->specialised && !ctx->opt_force_planned && !tr;
