@@ -149,8 +149,11 @@ static bool pipe_plan_lengths(long L, TileShape *t1, TileShape *t2, int dir = 0)
   }
   bool found = false;
   double best = 0;
+  const char *force_nb_f = TQ_DEV_ENV("TQ_PLAN_NB_FWD"), *force_nb_i = TQ_DEV_ENV("TQ_PLAN_NB_INV"); // (developer: pass-1 tile length per direction)
+  const long force_nb = (dir > 0 && force_nb_f) ? atol(force_nb_f) : (dir < 0 && force_nb_i) ? atol(force_nb_i) : 0;
   for (long nb = 1; nb <= PIPE_MAX_TILE; ++nb) {
     if (L % nb) continue;
+    if (force_nb && nb != force_nb) continue;
     const long na = L / nb;
     if (na > PIPE_MAX_TILE) continue;
     TileShape a, b;
@@ -183,6 +186,7 @@ static tq_status get_pipe_plan(tq_ctx *ctx, double beta, int stat, long n_tau, l
     TileShape f1, f2, i1, i2;
     if (pipe_plan_lengths(n_tau - 1, &f1, &f2, +1) && pipe_plan_lengths(n_tau - 1, &i1, &i2, -1) && (f1.N != i1.N || f1.RA != i1.RA))
       orient = fwd ? +1 : -1;
+    if (TQ_DEV_ENV("TQ_PLAN_NB_FWD") || TQ_DEV_ENV("TQ_PLAN_NB_INV")) orient = fwd ? +1 : -1;
   }
   auto key = std::make_tuple(beta, stat, n_tau, n_iw, orient);
   auto it = plans.find(key);
