@@ -80,6 +80,8 @@ tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
  *                      instantiation (A/B measurements; same results)
  *   "no_col"           1: scalar gfs on the 10^4 mesh do not use the single-column kernel
  *   "no_tr"            1: batches of narrow gfs (1-3 target columns) are not run as one wide virtual gf ("gfs as columns")
+ *   "no_two_for_one"   1: tq_fourier_tau_to_iw_real promotes every real column to a complex one instead of packing two real columns into one
+ *                      complex column (A/B measurements; results agree to 1e-13)
  *   "no_bluestein"     1: mesh lengths with a prime factor > 127 use the direct O(N^2) window DFT instead of the Bluestein (chirp-z)
  *                      convolution (A/B measurements; results agree to 1e-12)
  *   "force_bluestein"  1: every imtime <-> imfreq transform with L >= 512 uses that convolution (A/B measurements, tests)
@@ -141,8 +143,10 @@ tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statistic, long n_i
  * and users take `real(g)` after `is_gf_real(g, tol)` on the way back (c++/triqs/gfs/functions/functions2.hpp:223-246).
  * These two entry points move only the 8-byte reals between the caller's buffer and the GPU (half the PCIe / HBM bytes of
  * the large side); the promotion / real-part extraction is a streaming kernel on the device.
- *   tq_fourier_tau_to_iw_real : gt double[batch][n_tau][n_others]; everything else as tq_fourier_tau_to_iw (same bits as
- *                               promoting on the host and calling it)
+ *   tq_fourier_tau_to_iw_real : gt double[batch][n_tau][n_others]; everything else as tq_fourier_tau_to_iw.  With 8 or more columns and moments that
+ *                               are absent or real (host pointer) two real columns are transformed as ONE complex column and separated through
+ *                               G(i w_-n) = conj G(i w_n): half the transform work; agrees with promoting on the host to rounding (1e-13).
+ *                               Otherwise the columns are promoted on the device (same bits as promoting on the host)
  *   tq_fourier_iw_to_tau_real : gt double[batch][n_tau][n_others] receives Re G(tau); max_imag host double[batch] (required)
  *                               receives max |Im G(tau)| per gf, the quantity is_gf_real compares with its tolerance */
 tq_status tq_fourier_tau_to_iw_real(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,

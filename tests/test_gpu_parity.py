@@ -909,39 +909,61 @@ def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
 
 def test_real_valued_gtau_moves_reals_only_and_matches_the_promoted_call(ctx):
     """Real-valued G(tau) (gf<imtime, T::real_t>): the reference promotes it to complex before the transform (fourier.hpp:78-81).
-    tq_fourier_tau_to_iw_real takes the float64 buffer and promotes on the device: same bits as promoting on the host; and
-    tq_fourier_iw_to_tau_real hands back real(g) with max |Im| per gf (functions2.hpp:223-246).  Host buffers (chunked over the
-    lanes), device tensors, odd and even column counts."""
+    tq_fourier_tau_to_iw_real takes the float64 buffer: with 8+ columns two real columns travel as ONE complex column ("two for one",
+    separated through G(i w_-n) = conj G(i w_n)): same result as the promoted call to rounding; otherwise (or with "no_two_for_one") the columns are
+    promoted on the device: same BITS as promoting on the host.  tq_fourier_iw_to_tau_real hands back real(g) with max |Im| per gf
+    (functions2.hpp:223-246).  Host buffers (chunked over the lanes), device tensors, odd and even column counts, both statistics, known moments."""
     import torch
     beta, n_iw = 10.0, 200
     rng = np.random.default_rng(33)
-    for n_tau, ncols, B in [(1201, 5, 7), (6151, 4, 3), (10001, 1, 9)]:
+    for n_tau, ncols, B, stat in [(1201, 5, 7, F), (6151, 4, 3, F), (10001, 1, 9, F), (6001, 25, 3, F), (4097, 16, 2, O.BOSON), (2000, 9, 2, F)]:
         gts = []
         for b in range(B):
             E = rng.uniform(-2, 2, 3)
-            gts.append(np.stack([poles_gtau(beta, n_tau, E * (1 + 0.1 * c), [0.2, 0.3, 0.5])[:] for c in range(ncols)], axis=1))
+            gts.append(np.stack([poles_gtau(beta, n_tau, E * (1 + 0.1 * c), [0.2, 0.3, 0.5], stat)[:] for c in range(ncols)], axis=1))
         gc = np.stack(gts)
         assert np.max(np.abs(gc.imag)) == 0.0
         gr = np.ascontiguousarray(gc.real)
-        w_c = ctx.fourier_tau_to_iw(gc, beta, F, n_iw)
+        w_c = ctx.fourier_tau_to_iw(gc, beta, stat, n_iw)
         warn_c = np.array(ctx.last_warn)
         ctx.set_option("host_chunk_kb", 2 * n_tau * ncols * 8 // 1024 + 1)  # two gfs per chunk
-        w_r = ctx.fourier_tau_to_iw(gr, beta, F, n_iw)
+        w_r = ctx.fourier_tau_to_iw(gr, beta, stat, n_iw)
         ctx.set_option("host_chunk_kb", 48 << 10)
-        assert np.array_equal(w_c, w_r) and np.array_equal(warn_c, np.array(ctx.last_warn))
-        assert rel(w_r[0], O.fourier_tau_to_iw(gc[0], beta, F, n_iw)) < TOL
+        assert np.array_equal(warn_c, np.array(ctx.last_warn))
+        if ncols >= 8:   # two for one
+            assert rel(w_r, w_c) < 1e-13
+        else:
+            assert np.array_equal(w_c, w_r)
+        ctx.set_option("no_two_for_one", 1)
+        assert np.array_equal(ctx.fourier_tau_to_iw(gr, beta, stat, n_iw), w_c)
+        ctx.set_option("no_two_for_one", 0)
+        assert rel(w_r[0], O.fourier_tau_to_iw(gc[0], beta, stat, n_iw)) < TOL
+        # known moments: real ones keep the packed path, complex ones (not the moments of a real G) fall back to the promoted one
+        mom = np.zeros((B, 4, ncols), complex)
+        mom[:, 1] = 1.0
+        mom[:, 2] = rng.normal(size=(B, ncols))
+        mom[:, 3] = rng.normal(size=(B, ncols))
+        assert rel(ctx.fourier_tau_to_iw(gr, beta, stat, n_iw, moments=mom), ctx.fourier_tau_to_iw(gc, beta, stat, n_iw, moments=mom)) < 1e-13
+        momc = mom + 1e-3j * rng.normal(size=mom.shape) * (np.arange(4)[None, :, None] > 1)
+        assert np.array_equal(ctx.fourier_tau_to_iw(gr, beta, stat, n_iw, moments=momc), ctx.fourier_tau_to_iw(gc, beta, stat, n_iw, moments=momc))
         # device-resident real input
-        w_d = ctx.fourier_tau_to_iw(torch.from_numpy(gr).cuda(), beta, F, n_iw)
-        assert np.array_equal(w_d.cpu().numpy(), w_c)
+        w_d = ctx.fourier_tau_to_iw(torch.from_numpy(gr).cuda(), beta, stat, n_iw)
+        assert np.array_equal(w_d.cpu().numpy(), w_r)
         # and back: real part + max |Im|
-        t_c = ctx.fourier_iw_to_tau(w_c, beta, F, n_tau)
-        t_r = ctx.fourier_iw_to_tau(w_c, beta, F, n_tau, real_out=True)
+        t_c = ctx.fourier_iw_to_tau(w_c, beta, stat, n_tau)
+        t_r = ctx.fourier_iw_to_tau(w_c, beta, stat, n_tau, real_out=True)
         assert t_r.dtype == np.float64 and np.array_equal(t_r, t_c.real)
         assert np.array_equal(ctx.last_max_imag, np.max(np.abs(t_c.imag), axis=(1, 2)))
         assert np.max(np.abs(t_r - gr)) < 5e-6  # (round trip: limited by the tail fit, like the complex path)
         out = torch.empty(B, n_tau, ncols, dtype=torch.float64, device="cuda")
-        ctx.fourier_iw_to_tau(torch.from_numpy(w_c).cuda(), beta, F, n_tau, out=out)
+        ctx.fourier_iw_to_tau(torch.from_numpy(w_c).cuda(), beta, stat, n_tau, out=out)
         assert np.array_equal(out.cpu().numpy(), t_r)
+    # the zeroth-moment assertion (:116-118) survives the packing
+    bad = np.zeros((1, 4, 9), complex)
+    bad[:, 0, 3] = 1e-3
+    bad[:, 1] = 1.0
+    with pytest.raises(Exception, match="0th moment"):
+        ctx.fourier_tau_to_iw(np.zeros((1, 1201, 9)), beta, F, n_iw, moments=bad)
 
 
 def test_gf_mirror_real_valued_gf(ctx):

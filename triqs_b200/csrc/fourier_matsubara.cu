@@ -748,8 +748,10 @@ __device__ double block_max(double v, double *sh) {
 // `joint` (or nullptr): the batch is ONE gf whose columns are spread over [outer][.][inner] (a transform along mesh N > 0 of a
 // product mesh, fourier.hpp:78-84): the reference's noise check is then a maximum over all of them.  First pass
 // (joint_pass == 1) accumulates the two maxima, second pass (joint_pass == 2) decides with them.
+// packed: every complex column holds TWO real-valued columns (Re, Im) -- the noise check looks at them separately, exactly as it would
+// at the two promoted columns (hypot(x, 0) = |x|)
 __global__ void __launch_bounds__(256) k_moments_from_tau(const cd *gt, long gf_stride, int n_tau, int n_cols, double beta, int stat, cd *mom4,
-                                                          int *warn, unsigned long long *joint = nullptr, int joint_pass = 0) {
+                                                          int *warn, unsigned long long *joint = nullptr, int joint_pass = 0, int packed = 0) {
   __shared__ double sh[32];
   const int gf = blockIdx.x;
   const cd *g = gt + (size_t)gf * gf_stride;
@@ -759,6 +761,12 @@ __global__ void __launch_bounds__(256) k_moments_from_tau(const cd *gt, long gf_
   for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
     cd g0 = g[c], g1 = g[(size_t)1 * n_cols + c], g2 = g[(size_t)2 * n_cols + c];
     cd gL = g[(size_t)L * n_cols + c], gL1 = g[(size_t)(L - 1) * n_cols + c], gL2 = g[(size_t)(L - 2) * n_cols + c];
+    if (packed) {
+      const cd d1 = csub(g1, g0), d1L = csub(gL1, gL), d2 = csub(g2, g0), d2L = csub(gL2, gL);
+      m1 = fmax(m1, fmax(fabs(d1.x) + fabs(d1L.x), fabs(d1.y) + fabs(d1L.y)));
+      m2 = fmax(m2, fmax(fabs(d2.x) + fabs(d2L.x), fabs(d2.y) + fabs(d2L.y)));
+      continue;
+    }
     cd d;
     d = csub(g1, g0);
     double a = hypot(d.x, d.y);
@@ -1258,6 +1266,84 @@ static __global__ void k_real_part(const cd *__restrict__ in, double *__restrict
   if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(max_im_bits + gf, (unsigned long long)__double_as_longlong(m)); // (non-negative doubles order like their bits)
 }
 
+// Two real-valued columns per complex column ("two for one"): z[., p] = x[., 2p] + i x[., 2p + 1] (a last odd column: + i 0).  Every step of the
+// Matsubara transform is linear over C, so Z = F(x_2p) + i F(x_2p+1), and for real x  F(x)(i w_{-n}) = conj F(x)(i w_n)  (data index i <-> n_w - 1 - i
+// for both statistics) separates the two:  F(x_2p)_i = (Z_i + conj Z_i') / 2,  F(x_2p+1)_i = (Z_i - conj Z_i') / (2 i).
+static __global__ void k_pack_real_pairs(const double *__restrict__ re, cd *__restrict__ z, long rows, int nc, int nc2) {
+  const long total = rows * nc2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nc2;
+    const int p = (int)(i - r * nc2);
+    const double *src = re + r * nc + 2 * p;
+    z[i] = cmk(src[0], 2 * p + 1 < nc ? src[1] : 0.0);
+  }
+}
+static __global__ void k_unpack_pairs(const cd *__restrict__ Z, cd *__restrict__ out, int n_w, int nc, int nc2) {
+  const long gf = blockIdx.y;
+  const long per = (long)n_w * nc2;
+  const cd *z = Z + gf * per;
+  cd *o = out + gf * (long)n_w * nc;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / nc2), p = (int)(i - (long)r * nc2);
+    const cd a = z[i], b = z[(long)(n_w - 1 - r) * nc2 + p];
+    o[(long)r * nc + 2 * p] = cmk(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+    if (2 * p + 1 < nc) o[(long)r * nc + 2 * p + 1] = cmk(0.5 * (a.y + b.y), 0.5 * (b.x - a.x));
+  }
+}
+
+// The forward transform of nct = ceil(n_others / 2) packed columns (see k_pack_real_pairs) and the separation of the result.
+static tq_status fourier_tau_to_iw_packed(tq_ctx *ctx, MatsubaraPlan &pl, double beta, int statistic, long n_tau, long n_iw, long n_others, long nct,
+                                          long batch, const cd *d_in, const tq_complex *packed_moments /* host or nullptr */, int n_moments,
+                                          tq_complex *gw, int *warn) {
+  const long L = n_tau - 1, last = n_iw - 1, n_w = pl.dev.n_w;
+  const bool have_moments = packed_moments != nullptr && n_moments > 0;
+  const size_t out_bytes = sizeof(cd) * (size_t)batch * n_w * n_others;
+  const void *d_known = nullptr;
+  void *d_out = nullptr;
+  bool out_host = false;
+  if (have_moments) TQ_TRY(tq_stage_in(ctx, packed_moments, sizeof(cd) * (size_t)batch * n_moments * nct, ctx->stage_in2, &d_known));
+  TQ_TRY(tq_stage_out_begin(ctx, gw, out_bytes, ctx->stage_out, &d_out, &out_host));
+  TQ_TRY(tq_reserve(ctx, ctx->stage_in3, sizeof(cd) * (size_t)batch * n_w * nct));
+  cd *d_Z = (cd *)ctx->stage_in3.p;
+  const size_t mom_bytes = sizeof(cd) * (size_t)batch * 4 * nct;
+  const size_t warn_off = (mom_bytes + 255) & ~size_t(255);
+  const size_t st_off = (warn_off + sizeof(int) * batch + 255) & ~size_t(255);
+  TQ_TRY(tq_reserve(ctx, ctx->small, st_off + sizeof(StatusWords)));
+  cd *d_mom = (cd *)ctx->small.p;
+  int *d_warn = (int *)((char *)ctx->small.p + warn_off);
+  StatusWords *d_st = (StatusWords *)((char *)ctx->small.p + st_off);
+  TQ_CUDA(ctx, cudaMemsetAsync(d_warn, 0, st_off - warn_off + sizeof(StatusWords), ctx->stream));
+  if (have_moments) {
+    const long total = batch * nct;
+    KernelScope ks(ctx, "prepare_known_moments");
+    k_prepare_known_moments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const cd *)d_known, n_moments, (int)nct, total, d_mom,
+                                                                                        &d_st->max_m0_bits);
+  } else {
+    if (batch > 0x7fffffffL) return tq_fail(ctx, TQ_ERR_INVALID, "batch too large");
+    KernelScope ks(ctx, "moments_from_tau");
+    k_moments_from_tau<<<(unsigned)batch, 256, 0, ctx->stream>>>(d_in, n_tau * nct, (int)n_tau, (int)nct, beta, statistic, d_mom, d_warn, nullptr, 0, 1);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  TQ_TRY(run_transform<IN_TAU>(ctx, pl, nct, batch, d_in, d_Z, d_mom, 4));
+  {
+    KernelScope ks(ctx, "unpack_pairs");
+    const unsigned gx = (unsigned)std::max<long>(1, std::min<long>(((long)n_w * nct + 255) / 256, (148 * 16 + batch - 1) / batch));
+    k_unpack_pairs<<<dim3(gx, (unsigned)batch), 256, 0, ctx->stream>>>(d_Z, (cd *)d_out, (int)n_w, (int)n_others, (int)nct);
+  }
+  tq_count_launch(ctx);
+  TQ_CUDA(ctx, cudaGetLastError());
+  TQ_TRY(tq_reserve_pinned(ctx, sizeof(int) * batch + sizeof(StatusWords)));
+  int *h_warn = (int *)ctx->pinned;
+  TQ_CUDA(ctx, cudaMemcpyAsync(h_warn, d_warn, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+  TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int mesh_warn = (L < 6 * (last + 1)) ? TQ_WARN_SHORT_TAU_MESH : 0; // :131-133
+  if (warn)
+    for (long b = 0; b < batch; ++b) warn[b] = h_warn[b] | mesh_warn;
+  TQ_TRY(tq_stage_out_finish(ctx, gw, out_bytes, d_out, out_host));
+  return TQ_OK;
+}
+
 static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic, long n_tau, long n_iw, long n_others, long batch,
                                         const tq_complex *gt, const tq_complex *moments, int n_moments, tq_complex *gw, int *warn, bool joint,
                                         bool real_in = false) {
@@ -1281,22 +1367,65 @@ static tq_status fourier_tau_to_iw_impl(tq_ctx *ctx, double beta, int statistic,
   const void *d_in = nullptr, *d_known = nullptr;
   void *d_out = nullptr;
   bool out_host = false;
+  // columns of the transform itself: n_others, or half of them when two real-valued columns share a complex one
+  long nct = n_others;
+  std::vector<cd> packed_moments;
   if (real_in) {
     // real-valued G(tau) (gf<imtime, T::real_t>): the reference promotes it to complex before the transform (fourier.hpp:78-81);
-    // here only the 8-byte reals cross PCIe / are read from the caller's buffer, the promotion is one streaming kernel on the device
+    // here only the 8-byte reals cross PCIe / are read from the caller's buffer
     const size_t n_el = (size_t)batch * n_tau * n_others;
     const void *d_re = nullptr;
     TQ_TRY(tq_stage_in(ctx, gt, sizeof(double) * n_el, ctx->stage_in, &d_re));
-    TQ_TRY(tq_reserve(ctx, ctx->promote, in_bytes));
-    {
-      KernelScope ks(ctx, "promote_real");
-      k_promote_real<<<(unsigned)std::min<size_t>((n_el + 511) / 512, 148 * 16), 256, 0, ctx->stream>>>((const double *)d_re, (cd *)ctx->promote.p, n_el);
+    // "two for one": needs real moments (those of a real G(tau) are) that the host can look at, and enough columns to stay wide
+    bool pack = !joint && n_others >= 8 && !ctx->opt_no_two_for_one && !(have_moments && tq_is_device_ptr(moments));
+    const long nc2 = (n_others + 1) / 2;
+    if (pack && have_moments) {
+      const cd *m = (const cd *)moments;
+      packed_moments.assign((size_t)batch * n_moments * nc2, cmk(0.0, 0.0));
+      for (long b = 0; b < batch && pack; ++b)
+        for (int r = 0; r < n_moments && pack; ++r)
+          for (long c = 0; c < n_others; ++c) {
+            const cd v = m[((size_t)b * n_moments + r) * n_others + c];
+            if (v.y != 0.0) {
+              pack = false;
+              break;
+            }
+            if (r == 0 && !(std::fabs(v.x) < 1e-8)) // :116-118 (checked here per column: the packed 0th moment would mix two of them)
+              return tq_fail(ctx, TQ_ERR_RUNTIME,
+                             "ERROR: Direct Fourier implementation requires vanishing 0th moment\n  error is :" + std::to_string(std::fabs(v.x)));
+            cd &z = packed_moments[((size_t)b * n_moments + r) * nc2 + c / 2];
+            if (r > 0) (c & 1 ? z.y : z.x) = v.x;
+          }
     }
-    tq_count_launch(ctx);
+    if (pack) {
+      nct = nc2;
+      if (n_others % 2 == 0 && ((uintptr_t)d_re & 15) == 0) {
+        d_in = d_re; // [rows][2 m] doubles ARE [rows][m] complex numbers
+      } else {
+        TQ_TRY(tq_reserve(ctx, ctx->promote, sizeof(cd) * (size_t)batch * n_tau * nc2));
+        KernelScope ks(ctx, "pack_real_pairs");
+        k_pack_real_pairs<<<(unsigned)std::min<size_t>(((size_t)batch * n_tau * nc2 + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(
+           (const double *)d_re, (cd *)ctx->promote.p, batch * n_tau, (int)n_others, (int)nc2);
+        tq_count_launch(ctx);
+        d_in = ctx->promote.p;
+      }
+    } else {
+      TQ_TRY(tq_reserve(ctx, ctx->promote, in_bytes));
+      {
+        KernelScope ks(ctx, "promote_real");
+        k_promote_real<<<(unsigned)std::min<size_t>((n_el + 511) / 512, 148 * 16), 256, 0, ctx->stream>>>((const double *)d_re, (cd *)ctx->promote.p, n_el);
+      }
+      tq_count_launch(ctx);
+      d_in = ctx->promote.p;
+    }
     TQ_CUDA(ctx, cudaGetLastError());
-    d_in = ctx->promote.p;
   } else {
     TQ_TRY(tq_stage_in(ctx, gt, in_bytes, ctx->stage_in, &d_in));
+  }
+  const bool packed = nct != n_others;
+  if (packed) {
+    moments = packed_moments.empty() ? nullptr : (const tq_complex *)packed_moments.data();
+    return fourier_tau_to_iw_packed(ctx, *pl, beta, statistic, n_tau, n_iw, n_others, nct, batch, (const cd *)d_in, moments, n_moments, gw, warn);
   }
   if (have_moments) TQ_TRY(tq_stage_in(ctx, moments, sizeof(cd) * (size_t)batch * n_moments * n_others, ctx->stage_in2, &d_known));
   TQ_TRY(tq_stage_out_begin(ctx, gw, out_bytes, ctx->stage_out, &d_out, &out_host));
@@ -1390,6 +1519,7 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
     ctx->lanes[l]->opt_no_pipe = ctx->opt_no_pipe;
     ctx->lanes[l]->opt_no_col = ctx->opt_no_col;
     ctx->lanes[l]->opt_no_tr = ctx->opt_no_tr;
+    ctx->lanes[l]->opt_no_two_for_one = ctx->opt_no_two_for_one;
     ctx->lanes[l]->opt_no_bluestein = ctx->opt_no_bluestein;
     ctx->lanes[l]->opt_force_bluestein = ctx->opt_force_bluestein;
     ctx->lanes[l]->opt_blue_chunk_mb = ctx->opt_blue_chunk_mb;

@@ -104,6 +104,7 @@ struct tq_ctx {
   long opt_blue_chunk_mb = 512;  // convolution buffer of the Bluestein path per group of gfs (MiB)
   long opt_force_bluestein = 0;  // 1: every imtime <-> imfreq transform with L >= 512 goes through the Bluestein convolution (A/B measurements, tests)
   long opt_no_bluestein = 0;     // 1: lengths without a plan always go through the direct O(N^2) window DFT (A/B measurements, tests)
+  long opt_no_two_for_one = 0;   // 1: real-valued G(tau) is promoted column by column instead of packed two columns per complex one (A/B, tests)
   long opt_no_tr = 0;            // 1: narrow targets never run as "gfs as columns" through the planned kernels (A/B measurements)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)

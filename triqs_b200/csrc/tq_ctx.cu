@@ -120,6 +120,8 @@ extern "C" tq_status tq_set_option(tq_ctx *ctx, const char *name, long value) {
     ctx->opt_no_col = value;
   else if (n == "no_tr")
     ctx->opt_no_tr = value;
+  else if (n == "no_two_for_one")
+    ctx->opt_no_two_for_one = value;
   else if (n == "no_bluestein")
     ctx->opt_no_bluestein = value;
   else if (n == "force_bluestein")
