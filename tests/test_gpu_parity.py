@@ -733,6 +733,13 @@ def test_bluestein_for_lengths_without_a_plan(ctx, L, n_iw, stat, C, B):
     finally:
         ctx.set_option("no_bluestein", 0)
     assert rel(gt, gt_d) < TOL and rel(back, back_d) < TOL
+    ctx.set_option("no_pipe", 1)   # the axis transforms through the generic tile kernel, the pointwise products in passes of their own
+    try:
+        gt_g = ctx.fourier_iw_to_tau(gw, beta, stat, L + 1, moments=mom)
+        back_g = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw, moments=mom)
+    finally:
+        ctx.set_option("no_pipe", 0)
+    assert rel(gt, gt_g) < TOL and rel(back, back_g) < TOL
     # unknown moments: tau-derivative estimate forward, least-squares tail on the way back
     w2 = ctx.fourier_tau_to_iw(gt, beta, stat, n_iw)
     assert rel(w2[0], O.fourier_tau_to_iw(np.asarray(gt[0]), beta, stat, n_iw)) < TOL
