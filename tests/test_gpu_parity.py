@@ -745,6 +745,25 @@ def test_bluestein_for_lengths_without_a_plan(ctx, L, n_iw, stat, C, B):
     assert rel(w2[0], O.fourier_tau_to_iw(np.asarray(gt[0]), beta, stat, n_iw)) < TOL
 
 
+def test_fft_many_bluestein_axes(ctx):
+    """_fourier_base takes any length (fourier_common.cpp:30-44): plain axes with a prime factor > 127 run as a Bluestein convolution
+    (N >= 512; shorter ones by direct summation), also beyond the 65536 points the direct sum was limited to.  Against numpy's FFT."""
+    rng = np.random.default_rng(5)
+    for dims, hm in [((1009,), 7), ((2 * 1013, 3), 5), ((4, 4999), 25), ((70001,), 3), ((8191,), 1)]:
+        n = int(np.prod(dims))
+        x = rng.normal(size=(n, hm)) + 1j * rng.normal(size=(n, hm))
+        for sign in (+1, -1):
+            y = ctx.fft_many(x, dims, sign)
+            xr = x.reshape(tuple(dims) + (hm,))
+            axes = tuple(range(len(dims)))
+            ref = (np.fft.ifftn(xr, axes=axes) * n if sign > 0 else np.fft.fftn(xr, axes=axes)).reshape(n, hm)
+            assert rel(y, ref) < TOL, (dims, hm, sign)
+    ctx.profile_enable(True)
+    ctx.fft_many(rng.normal(size=(1009, 4)) + 0j, (1009,), 1)
+    assert "fft_axis_bluestein" in ctx.profile_report()
+    ctx.profile_enable(False)
+
+
 def test_tau_to_iw_along_inner_mesh_is_one_gf(ctx):
     """tq_fourier_tau_to_iw_axis = _fourier<N>, N > 0 (fourier.hpp:78-84): [outer][n_tau][inner] is ONE gf with outer*inner
     columns; the noise check (fourier_matsubara.cpp:100-114) is joint.  Column (0, 0) is G = 1/(i w) whose G(tau) = -1/2 is

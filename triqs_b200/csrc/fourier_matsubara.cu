@@ -673,6 +673,105 @@ static tq_status get_blue_plan(tq_ctx *ctx, const MatsubaraDev &D, std::shared_p
   return TQ_OK;
 }
 
+// ---- the same convolution for a PLAIN axis transform (tq_fft_many / lattice / real-time axes whose length has a prime factor > 127:
+// _fourier_base takes any length, fourier_common.cpp:30-44): X_k = sum_j x_j e^{s 2 pi i jk / N} for all k, so M >= 2 N - 1.
+struct BlueAxisCache {
+  std::map<std::tuple<long, int>, std::shared_ptr<BluePlan>> plans; // (N, sign); dir[0] only
+};
+// z[g][m][c] = in[o0 + g][m][c0 + c] pre[m]  (m < N), 0 above;   out[o0 + g][k][c0 + c] = z[g][k][c] post[k] scale
+static __global__ void k_blue_axis_load(const cd *__restrict__ in, long N, long inner, long c0, int cw, const cd *__restrict__ pre, long M, cd *__restrict__ z) {
+  const long per = M * cw;
+  const long g = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / cw;
+    const int c = (int)(i - m * cw);
+    z[g * per + i] = m < N ? cmul(in[(g * N + m) * inner + c0 + c], pre[m]) : cmk(0.0, 0.0);
+  }
+}
+static __global__ void k_blue_axis_store(const cd *__restrict__ z, long N, long inner, long c0, int cw, const cd *__restrict__ post, long M, double scale,
+                                         cd *__restrict__ out) {
+  const long per = N * cw;
+  const long g = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    const long k = i / cw;
+    const int c = (int)(i - k * cw);
+    out[(g * N + k) * inner + c0 + c] = cscale(scale, cmul(z[g * M * cw + i], post[k]));
+  }
+}
+bool tq_bluestein_axis_possible(tq_ctx *ctx, long N) {
+  int a, b;
+  return !ctx->opt_no_bluestein && N >= 512 && blue_pick_lengths(2 * N - 1, &a, &b);
+}
+tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale) {
+  if (!ctx->blue_axis_cache) ctx->blue_axis_cache = std::make_shared<BlueAxisCache>();
+  auto &plans = ctx->blue_axis_cache->plans;
+  auto key = std::make_tuple(N, sign > 0 ? 1 : -1);
+  std::shared_ptr<BluePlan> bp;
+  auto it = plans.find(key);
+  if (it != plans.end()) {
+    bp = it->second;
+  } else {
+    bp = std::make_shared<BluePlan>();
+    if (!blue_pick_lengths(2 * N - 1, &bp->M1, &bp->M2)) return tq_fail(ctx, TQ_ERR_UNSUPPORTED, "tq_fft_many: axis length too long for the Bluestein path");
+    const long M = bp->M = (long)bp->M1 * bp->M2;
+    const int sg = sign > 0 ? 1 : -1;
+    auto up = [&](const std::vector<cd> &h, const cd **d) -> tq_status {
+      void *p = nullptr;
+      TQ_CUDA(ctx, cudaMalloc(&p, sizeof(cd) * h.size()));
+      bp->allocs.push_back(p);
+      TQ_CUDA(ctx, cudaMemcpyAsync(p, h.data(), sizeof(cd) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+      TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      *d = (const cd *)p;
+      return TQ_OK;
+    };
+    std::vector<cd> tw((size_t)M), pre((size_t)N), post((size_t)N), kc((size_t)M, cmk(0.0, 0.0));
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k1 = 0; k1 < bp->M1; ++k1)
+      for (int j2 = 0; j2 < bp->M2; ++j2) {
+        const long double a = two_pi * (long double)(((long)k1 * j2) % M) / (long double)M;
+        tw[(size_t)k1 * bp->M2 + j2] = cmk((double)cosl(a), (double)-sinl(a));
+      }
+    const double inv_M = 1.0 / (double)M;
+    for (long j = 0; j < N; ++j) {
+      pre[j] = blue_chirp(j, N, sg);
+      post[j] = cscale(inv_M, pre[j]);
+    }
+    for (long t = -(N - 1); t <= N - 1; ++t) kc[(size_t)(((t % M) + M) % M)] = blue_chirp(t, N, -sg);
+    TQ_TRY(up(tw, &bp->tw));
+    TQ_TRY(up(pre, &bp->dir[0].pre));
+    TQ_TRY(up(post, &bp->dir[0].post));
+    const cd *kd = nullptr;
+    TQ_TRY(up(kc, &kd));
+    TQ_TRY(blue_convolve(ctx, *bp, nullptr, const_cast<cd *>(kd), 1, 1));
+    TQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bp->dir[0].khat = kd;
+    plans[key] = bp;
+  }
+  const long M = bp->M;
+  const size_t budget = (size_t)ctx->opt_blue_chunk_mb << 20;
+  const long cw = std::max<long>(1, std::min<long>(inner, (long)(budget / (sizeof(cd) * (size_t)M))));
+  const long per = std::max<long>(1, std::min<long>(std::min<long>(outer, 65535), (long)(budget / (sizeof(cd) * (size_t)M * cw))));
+  TQ_TRY(tq_reserve(ctx, ctx->scratch, sizeof(cd) * (size_t)M * cw * per));
+  cd *z = (cd *)ctx->scratch.p;
+  for (long o0 = 0; o0 < outer; o0 += per) {
+    const long g = std::min(per, outer - o0);
+    for (long c0 = 0; c0 < inner; c0 += cw) {
+      const int w = (int)std::min(cw, inner - c0);
+      const unsigned gx = (unsigned)std::min<long>((M * w + 255) / 256, 148 * 8);
+      {
+        KernelScope ks(ctx, "fft_axis_bluestein");
+        k_blue_axis_load<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(in + o0 * N * inner, N, inner, c0, w, bp->dir[0].pre, M, z);
+      }
+      tq_count_launch(ctx);
+      TQ_TRY(blue_convolve(ctx, *bp, &bp->dir[0], z, g, w));
+      k_blue_axis_store<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(z, N, inner, c0, w, bp->dir[0].post, M, scale, out + o0 * N * inner);
+      tq_count_launch(ctx);
+      TQ_CUDA(ctx, cudaGetLastError());
+    }
+  }
+  return TQ_OK;
+}
+
 template <bool FWD>
 static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw, const BluePlan &bp, long n_cols, long batch, const cd *d_in,
                                cd *d_out, const cd *d_mom, int mom_rows) {

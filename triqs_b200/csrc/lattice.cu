@@ -197,6 +197,9 @@ static tq_status launch_direct(tq_ctx *ctx, long outer, long N, long inner, cons
   return TQ_OK;
 }
 
+// fourier_matsubara.cu: Bluestein convolution for axis lengths without a plan
+bool tq_bluestein_axis_possible(tq_ctx *ctx, long N);
+tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale);
 // lattice_pipe.cu: TMA-pipelined fast path for axis lengths with a compile-time two-pass plan
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled);
 
@@ -211,7 +214,12 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
   const size_t budget = (size_t)ctx->max_smem_optin;
   {
     FftPlan probe;
-    if (!tq_fft_factorize((int)N, probe) || sizeof(cd) * (size_t)N > budget) return launch_direct(ctx, outer, N, inner, in, out, sign, scale, rin, rout, coef);
+    if (!tq_fft_factorize((int)N, probe) || sizeof(cd) * (size_t)N > budget) {
+      // a prime factor > 127 (or a column longer than one SM's shared memory): Bluestein convolution through the pipelined axis kernel
+      // (fourier_matsubara.cu), the direct O(N^2) sum for short axes and for the wrapped (real-time) transforms
+      if (!wrap && tq_bluestein_axis_possible(ctx, N)) return tq_bluestein_plain_axis(ctx, outer, N, inner, in, out, sign, scale);
+      return launch_direct(ctx, outer, N, inner, in, out, sign, scale, rin, rout, coef);
+    }
   }
   std::shared_ptr<FftPlanHost> fp;
   TQ_TRY(tq_get_fft_plan(ctx, N, &fp));

@@ -62,6 +62,7 @@ struct RealPlanCache;  // fourier_real.cu
 struct LegendrePlanCache; // legendre.cu
 struct DirectTwiddles;    // lattice.cu
 struct BluePlanCache;     // fourier_matsubara.cu (Bluestein plans)
+struct BlueAxisCache;     // ... for plain axis transforms
 
 struct tq_ctx {
   int device = 0;
@@ -89,6 +90,7 @@ struct tq_ctx {
   std::shared_ptr<LegendrePlanCache> leg_cache;
   std::shared_ptr<DirectTwiddles> direct_tw;
   std::shared_ptr<BluePlanCache> blue_cache;
+  std::shared_ptr<BlueAxisCache> blue_axis_cache;
   // per-kernel event timing (tq_profile_enable)
   bool profiling = false;
   struct ProfRec {
