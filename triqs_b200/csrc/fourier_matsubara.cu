@@ -679,30 +679,46 @@ struct BlueAxisCache {
   std::map<std::tuple<long, int>, std::shared_ptr<BluePlan>> plans; // (N, sign); dir[0] only
 };
 // z[g][m][c] = in[o0 + g][m][c0 + c] pre[m]  (m < N), 0 above;   out[o0 + g][k][c0 + c] = z[g][k][c] post[k] scale
-static __global__ void k_blue_axis_load(const cd *__restrict__ in, long N, long inner, long c0, int cw, const cd *__restrict__ pre, long M, cd *__restrict__ z) {
+static __global__ void k_blue_axis_load(const cd *__restrict__ in, long N, long inner, long c0, int cw, const cd *__restrict__ pre, long M, cd *__restrict__ z,
+                                        const cd *__restrict__ rin, const cd *__restrict__ coef, long o0) {
   const long per = M * cw;
   const long g = blockIdx.y;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
     const long m = i / cw;
     const int c = (int)(i - m * cw);
-    z[g * per + i] = m < N ? cmul(in[(g * N + m) * inner + c0 + c], pre[m]) : cmk(0.0, 0.0);
+    cd v = cmk(0.0, 0.0);
+    if (m < N) {
+      v = in[(g * N + m) * inner + c0 + c];
+      if (rin) { // the affine wrap of the real-time transforms (fourier_real.cu, k_direct_axis<true>): (x - a1 h1 - a2 h2) p_in
+        const cd a1 = coef[2 * ((o0 + g) * inner + c0 + c)], a2 = coef[2 * ((o0 + g) * inner + c0 + c) + 1];
+        v = cmul(csub(csub(v, cmul(a1, rin[3 * m])), cmul(a2, rin[3 * m + 1])), rin[3 * m + 2]);
+      }
+      v = cmul(v, pre[m]);
+    }
+    z[g * per + i] = v;
   }
 }
 static __global__ void k_blue_axis_store(const cd *__restrict__ z, long N, long inner, long c0, int cw, const cd *__restrict__ post, long M, double scale,
-                                         cd *__restrict__ out) {
+                                         cd *__restrict__ out, const cd *__restrict__ rout, const cd *__restrict__ coef, long o0) {
   const long per = N * cw;
   const long g = blockIdx.y;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
     const long k = i / cw;
     const int c = (int)(i - k * cw);
-    out[(g * N + k) * inner + c0 + c] = cscale(scale, cmul(z[g * M * cw + i], post[k]));
+    cd v = cscale(scale, cmul(z[g * M * cw + i], post[k]));
+    if (rout) { // p_out v + a1 e1 + a2 e2
+      const cd a1 = coef[2 * ((o0 + g) * inner + c0 + c)], a2 = coef[2 * ((o0 + g) * inner + c0 + c) + 1];
+      v = cadd(cadd(cmul(rout[3 * k + 2], v), cmul(a1, rout[3 * k])), cmul(a2, rout[3 * k + 1]));
+    }
+    out[(g * N + k) * inner + c0 + c] = v;
   }
 }
 bool tq_bluestein_axis_possible(tq_ctx *ctx, long N) {
   int a, b;
   return !ctx->opt_no_bluestein && N >= 512 && blue_pick_lengths(2 * N - 1, &a, &b);
 }
-tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale) {
+tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, const cd *rin,
+                                  const cd *rout, const cd *coef) {
   if (!ctx->blue_axis_cache) ctx->blue_axis_cache = std::make_shared<BlueAxisCache>();
   auto &plans = ctx->blue_axis_cache->plans;
   auto key = std::make_tuple(N, sign > 0 ? 1 : -1);
@@ -760,11 +776,11 @@ tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, c
       const unsigned gx = (unsigned)std::min<long>((M * w + 255) / 256, 148 * 8);
       {
         KernelScope ks(ctx, "fft_axis_bluestein");
-        k_blue_axis_load<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(in + o0 * N * inner, N, inner, c0, w, bp->dir[0].pre, M, z);
+        k_blue_axis_load<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(in + o0 * N * inner, N, inner, c0, w, bp->dir[0].pre, M, z, rin, coef, o0);
       }
       tq_count_launch(ctx);
       TQ_TRY(blue_convolve(ctx, *bp, &bp->dir[0], z, g, w));
-      k_blue_axis_store<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(z, N, inner, c0, w, bp->dir[0].post, M, scale, out + o0 * N * inner);
+      k_blue_axis_store<<<dim3(gx, (unsigned)g), 256, 0, ctx->stream>>>(z, N, inner, c0, w, bp->dir[0].post, M, scale, out + o0 * N * inner, rout, coef, o0);
       tq_count_launch(ctx);
       TQ_CUDA(ctx, cudaGetLastError());
     }

@@ -199,7 +199,8 @@ static tq_status launch_direct(tq_ctx *ctx, long outer, long N, long inner, cons
 
 // fourier_matsubara.cu: Bluestein convolution for axis lengths without a plan
 bool tq_bluestein_axis_possible(tq_ctx *ctx, long N);
-tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale);
+tq_status tq_bluestein_plain_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, const cd *rin,
+                                  const cd *rout, const cd *coef);
 // lattice_pipe.cu: TMA-pipelined fast path for axis lengths with a compile-time two-pass plan
 tq_status tq_lattice_pipe_axis(tq_ctx *ctx, long outer, long N, long inner, const cd *in, cd *out, int sign, double scale, bool *handled);
 
@@ -216,8 +217,8 @@ static tq_status launch_plain(tq_ctx *ctx, long outer, long N, long inner, const
     FftPlan probe;
     if (!tq_fft_factorize((int)N, probe) || sizeof(cd) * (size_t)N > budget) {
       // a prime factor > 127 (or a column longer than one SM's shared memory): Bluestein convolution through the pipelined axis kernel
-      // (fourier_matsubara.cu), the direct O(N^2) sum for short axes and for the wrapped (real-time) transforms
-      if (!wrap && tq_bluestein_axis_possible(ctx, N)) return tq_bluestein_plain_axis(ctx, outer, N, inner, in, out, sign, scale);
+      // (fourier_matsubara.cu; the affine wrap of the real-time transforms rides on its load / store kernels), the direct O(N^2) sum for short axes
+      if (tq_bluestein_axis_possible(ctx, N)) return tq_bluestein_plain_axis(ctx, outer, N, inner, in, out, sign, scale, rin, rout, coef);
       return launch_direct(ctx, outer, N, inner, in, out, sign, scale, rin, rout, coef);
     }
   }
