@@ -1232,7 +1232,7 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   if ((ctx->opt_force_bluestein || costly_plan) && L >= 512) {
     std::shared_ptr<BluePlan> bp;
     TQ_TRY(get_blue_plan(ctx, D, &bp));
-    if (bp) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
+    if (bp && sizeof(cd) * (size_t)bp->M * n_cols <= (8ull << 30)) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
   }
   {
     bool handled = false;
@@ -1250,7 +1250,8 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
     if (!ctx->opt_no_bluestein && L >= 512) { // (short meshes: the direct sum is a handful of launches and as fast)
       std::shared_ptr<BluePlan> bp;
       TQ_TRY(get_blue_plan(ctx, D, &bp));
-      if (bp) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
+      // (the convolution buffer of ONE gf has to fit: 8 GB is M = 10^5 with 5000 columns)
+      if (bp && sizeof(cd) * (size_t)bp->M * n_cols <= (8ull << 30)) return run_bluestein<fwd>(ctx, D, pl.btw, *bp, n_cols, batch, d_in, d_out, d_mom, mom_rows);
     }
     return run_direct<fwd>(ctx, D, pl.btw, n_cols, batch, d_in, d_out, d_mom, mom_rows);
   }
