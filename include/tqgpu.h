@@ -89,6 +89,8 @@ tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
  *   "host_lanes"       1..8: internal lanes over which tq_fourier_tau_to_iw / tq_fourier_iw_to_tau cut a batch passed in HOST
  *                      buffers, so that H2D copies, kernels and D2H copies of different chunks overlap (default 3; 1 = off)
  *   "host_chunk_kb"    input KiB per chunk of such a call (default 49152 = 48 MiB)
+ *   "stage_threads"    helper threads that copy a large PAGEABLE host buffer (a NumPy / nda array) through pinned slots, several pieces in flight
+ *                      (0 = auto: min(8, cores / 2)); calls with pageable buffers are not cut into lanes, their copies are spread over these threads
  *   "bounce"           1 (default): inside a multi-lane call, pageable host buffers are staged through the lanes' own pinned slots,
  *                      piecewise and overlapped with the DMA (the driver's pageable path is serialised per process at ~7 GB/s);
  *                      0: always plain cudaMemcpyAsync */

@@ -914,8 +914,8 @@ def test_host_buffer_calls_overlap_lanes_do_not_change_a_bit(ctx):
 
 
 def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
-    """NumPy (pageable) buffers above 1 MB are staged piecewise through the lanes' own pinned slots (tq_stage_in / tq_stage_out_finish):
-    same bits as the single-stream call, also when a gf spans several 8 MiB pieces."""
+    """NumPy (pageable) buffers above 4 MiB are staged piecewise through pinned slots by a few helper threads (tq_stage_in /
+    tq_stage_out_finish, stage_parallel): same bits as the plain single-stream copy ("host_lanes" = 1), whatever the helper count."""
     beta, n_tau, n_iw, ncols = 10.0, 120001, 3000, 5     # 9.6 MB per gf: two pieces each way
     rng = np.random.default_rng(21)
     iw = O.imfreq_values(beta, F, n_iw)
@@ -930,6 +930,11 @@ def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
     w3 = ctx.fourier_tau_to_iw(t3, beta, F, n_iw)
     ctx.set_option("host_chunk_kb", 48 << 10)
     assert np.array_equal(t1, t3) and np.array_equal(w1, w3)
+    for helpers in (1, 3, 16):
+        ctx.set_option("stage_threads", helpers)
+        assert np.array_equal(ctx.fourier_iw_to_tau(gws, beta, F, n_tau), t1)
+        assert np.array_equal(ctx.fourier_tau_to_iw(t1, beta, F, n_iw), w1)
+    ctx.set_option("stage_threads", 0)
     assert rel(t3[4], O.fourier_iw_to_tau(gws[4], beta, F, n_tau)) < TOL
 
 

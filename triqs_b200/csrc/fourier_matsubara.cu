@@ -1622,7 +1622,11 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
   const long chunk_bytes = std::max<long>(1, ctx->opt_host_chunk_kb) << 10;
   const long per_chunk = std::max<long>(1, chunk_bytes / (long)std::max<size_t>(bytes_per_gf, 1));
   const long n_chunks = (batch + per_chunk - 1) / per_chunk;
-  const int lanes = (int)std::min<long>(want, n_chunks);
+  int lanes = (int)std::min<long>(want, n_chunks);
+  // Pageable buffers: a lane stages its chunk through its pinned slots at the speed of ONE core, so the overlap the lanes buy is worth less than
+  // spreading every copy over all the helper threads (tq_stage_in / tq_stage_out_finish, tq_ctx.cu: stage_parallel) in ONE un-chunked call.
+  // Measured, blocks of configs[1] in NumPy arrays, forward call: 2 blocks 5.0 -> 3.1 ms, 4: 8.0 -> 5.3, 8: 11.0 -> 9.8, 16: 22.9 -> 18.9, 32: 38.3 -> 36.9.
+  if (pageable && ctx->opt_bounce == 1 && (size_t)batch * bytes_per_gf >= (4u << 20)) lanes = 1;
   if (lanes <= 1) return fn(ctx, 0, batch);
   while ((int)ctx->lanes.size() < lanes) {
     tq_ctx *c = nullptr;
