@@ -914,7 +914,7 @@ def test_host_buffer_calls_overlap_lanes_do_not_change_a_bit(ctx):
 
 
 def test_pageable_buffers_through_the_lanes_pinned_slots(ctx):
-    """NumPy (pageable) buffers above 4 MiB are staged piecewise through pinned slots by a few helper threads (tq_stage_in /
+    """NumPy (pageable) buffers above 12 MiB are staged piecewise through pinned slots by a few helper threads (tq_stage_in /
     tq_stage_out_finish, stage_parallel): same bits as the plain single-stream copy ("host_lanes" = 1), whatever the helper count."""
     beta, n_tau, n_iw, ncols = 10.0, 120001, 3000, 5     # 9.6 MB per gf: two pieces each way
     rng = np.random.default_rng(21)

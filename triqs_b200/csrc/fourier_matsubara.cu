@@ -1626,7 +1626,7 @@ static tq_status run_host_lanes(tq_ctx *ctx, long batch, size_t bytes_per_gf, bo
   // Pageable buffers: a lane stages its chunk through its pinned slots at the speed of ONE core, so the overlap the lanes buy is worth less than
   // spreading every copy over all the helper threads (tq_stage_in / tq_stage_out_finish, tq_ctx.cu: stage_parallel) in ONE un-chunked call.
   // Measured, blocks of configs[1] in NumPy arrays, forward call: 2 blocks 5.0 -> 3.1 ms, 4: 8.0 -> 5.3, 8: 11.0 -> 9.8, 16: 22.9 -> 18.9, 32: 38.3 -> 36.9.
-  if (pageable && ctx->opt_bounce == 1 && (size_t)batch * bytes_per_gf >= (4u << 20)) lanes = 1;
+  if (pageable && ctx->opt_bounce == 1 && (size_t)batch * bytes_per_gf >= (12u << 20)) lanes = 1;
   if (lanes <= 1) return fn(ctx, 0, batch);
   while ((int)ctx->lanes.size() < lanes) {
     tq_ctx *c = nullptr;

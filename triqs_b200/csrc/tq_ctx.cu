@@ -231,7 +231,7 @@ static tq_status bounce_init(tq_ctx *ctx) {
 // is spread over a few helper threads, each staging its share of the pieces through the pinned slots of a helper context (the contexts the
 // lanes use, created on first use) on that context's stream.  One thread moves ~5-8 GB/s through its slots; eight reach the PCIe rate.
 // Measured for ONE BlockGf of configs[1] in NumPy arrays (80 MB in, 16 MB out): 5.0 -> ~2 ms per forward call.
-constexpr size_t TQ_PAR_STAGE_MIN = 4u << 20;
+constexpr size_t TQ_PAR_STAGE_MIN = 12u << 20; // (below: starting the helper threads costs more than the driver's pageable copy)
 static int stage_helpers(const tq_ctx *ctx) {
   if (ctx->opt_stage_threads > 0) return (int)std::min<long>(ctx->opt_stage_threads, 32);
   return (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
