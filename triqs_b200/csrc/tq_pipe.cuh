@@ -16,6 +16,20 @@ TQ_D void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 TQ_D void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 TQ_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef TQ_MBAR_HINT
+  // (developer A/B: try_wait with an explicit suspend-time hint, the form CUTLASS uses)
+  asm volatile(
+     "{\n"
+     ".reg .pred P1;\n"
+     "LAB_WAIT:\n"
+     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+     "@P1 bra DONE;\n"
+     "bra LAB_WAIT;\n"
+     "DONE:\n"
+     "}\n" ::"r"(smem_u32(bar)),
+     "r"(parity), "r"((uint32_t)TQ_MBAR_HINT)
+     : "memory");
+#else
   asm volatile(
      "{\n"
      ".reg .pred P1;\n"
@@ -27,6 +41,7 @@ TQ_D void mbar_wait(uint64_t *bar, uint32_t parity) {
      "}\n" ::"r"(smem_u32(bar)),
      "r"(parity)
      : "memory");
+#endif
 }
 TQ_D void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
