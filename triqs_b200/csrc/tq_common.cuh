@@ -110,6 +110,7 @@ struct tq_ctx {
   long opt_no_tr = 0;            // 1: narrow targets never run as "gfs as columns" through the planned kernels (A/B measurements)
   long opt_scratch_chunk_mb = 0; // > 0: four-step scratch budget per launch pair in MiB
   long opt_host_lanes = 3;       // internal lanes that overlap H2D / kernels / D2H of host-buffer calls (1: off)
+  long opt_stage_nt = 1;         // non-temporal stores in the staging copies of pageable buffers (x86-64)
   long opt_stage_threads = 0;    // helper threads that stage a large pageable buffer of an un-chunked call (0: min(8, cores / 2))
   long opt_bounce = 1;           // stage pageable host buffers through the library's own pinned slots (tq_stage_in)
   long opt_host_chunk_kb = 48L << 10; // input bytes per chunk of a host-buffer call (KiB): one C2 block (40 MB) per chunk
