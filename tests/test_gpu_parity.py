@@ -1014,3 +1014,29 @@ def test_gf_mirror_real_valued_gf(ctx):
     assert is_gf_real(back, 1e-9) and not is_gf_real(gw)
     rb = real(back)
     assert rb.data.dtype == np.float64 and np.max(np.abs(rb.data - g.data)) < 1e-6
+
+
+def test_large_pageable_buffers_of_the_other_entry_points(ctx):
+    """tq_stage_in / tq_stage_out_finish spread every large copy from / to pageable memory over helper threads (tq_ctx.cu, stage_parallel): lattice,
+    plain DFT, interpolation and k-sum calls with NumPy buffers above 12 MiB give the bits of the plain single-stream copies ("host_lanes" = 1)."""
+    rng = np.random.default_rng(2)
+
+    def both(fn):
+        ctx.set_option("host_lanes", 1)
+        a = fn()
+        ctx.set_option("host_lanes", 3)
+        return a, fn()
+    x = rng.normal(size=(128 * 128, 96)) + 1j * rng.normal(size=(128 * 128, 96))          # 25 MB each way
+    a, b = both(lambda: ctx.fourier_lattice(x, (128, 128, 1), True))
+    assert np.array_equal(a, b) and rel(a, O.fourier_lattice_r_to_k(x, (128, 128, 1))) < TOL
+    a, b = both(lambda: ctx.fft_many(x, (128, 128), -1))
+    assert np.array_equal(a, b)
+    table = rng.normal(size=(4096, 4)) + 1j * rng.normal(size=(4096, 4))
+    taus = rng.uniform(0, 10.0, size=2_000_000)                                            # 16 MB in, 128 MB out
+    a, b = both(lambda: ctx.interp_tau(table, 10.0, taus))
+    assert np.array_equal(a, b)
+    eps = rng.normal(size=(40000, 5, 5)) + 1j * rng.normal(size=(40000, 5, 5))            # 16 MB
+    eps = eps + eps.conj().transpose(0, 2, 1)
+    sig = np.stack([np.eye(5) / (w - 0.5) for w in O.imfreq_values(10.0, F, 16)])
+    a, b = both(lambda: ctx.dyson_ksum(eps, sig, 10.0, F, 0.1))
+    assert np.array_equal(a, b)
