@@ -355,6 +355,7 @@ struct DirectArgs {
   // row o of z times post_mul[o] instead of the partial sums
   const cd *pre_mul, *post_mul;
   long z_rows;
+  int z_wide; // 1: the convolution buffer is [row][gf][column] (all gfs of the launch side by side: narrow targets), 0: [gf][row][column]
 };
 
 // x_j = phase_j (g_j - sum_i a_i h_i(tau_j))  (FWD, :159-173)   or   y_di = (g_di - tail(i w)) / beta  (:254)
@@ -362,7 +363,11 @@ template <bool FWD> __global__ void k_direct_pre(const DirectArgs A) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long per_gf = (long)A.n_in * A.n_cols;
   if (A.pre_mul && i >= per_gf) { // zero padding of the convolution buffer
-    if (i < A.z_rows * A.n_cols) A.x[(size_t)blockIdx.y * A.z_rows * A.n_cols + i] = cmk(0.0, 0.0);
+    if (i < A.z_rows * A.n_cols) {
+      const long rr = i / A.n_cols;
+      const size_t zi = A.z_wide ? ((size_t)rr * gridDim.y + blockIdx.y) * A.n_cols + (size_t)(i - rr * A.n_cols) : (size_t)blockIdx.y * A.z_rows * A.n_cols + i;
+      A.x[zi] = cmk(0.0, 0.0);
+    }
     return;
   }
   if (i >= per_gf) return;
@@ -382,7 +387,7 @@ template <bool FWD> __global__ void k_direct_pre(const DirectArgs A) {
     x = cscale(D.inv_beta, csub(x, tail_iw(D, load_w(D, r), a1, a2, a3)));
   }
   if (A.pre_mul)
-    A.x[(size_t)gf * A.z_rows * A.n_cols + i] = cmul(x, A.pre_mul[r]);
+    A.x[A.z_wide ? ((size_t)r * gridDim.y + gf) * A.n_cols + c : (size_t)gf * A.z_rows * A.n_cols + i] = cmul(x, A.pre_mul[r]);
   else
     A.x[(size_t)gf * per_gf + i] = x;
 }
@@ -443,7 +448,7 @@ template <bool FWD> __global__ void k_direct_post(const DirectArgs A) {
   pole_weights(fermion, m1, mom[(size_t)2 * A.n_cols + c], mom[(size_t)3 * A.n_cols + c], a1, a2, a3);
   cd v = cmk(0.0, 0.0);
   if (A.post_mul)
-    v = cmul(A.partial[(size_t)gf * A.z_rows * A.n_cols + i], A.post_mul[r]);
+    v = cmul(A.partial[A.z_wide ? ((size_t)r * gridDim.y + gf) * A.n_cols + c : (size_t)gf * A.z_rows * A.n_cols + i], A.post_mul[r]);
   else
     for (int k = 0; k < A.n_chunks; ++k) v = cadd(v, A.partial[((size_t)gf * A.n_chunks + k) * per_gf + i]);
   cd *out = A.out + (size_t)gf * A.out_gf_stride;
@@ -813,6 +818,9 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
   cd *z = (cd *)ctx->scratch.p;
   A.x = z;       // k_direct_pre writes the chirped, zero-padded input straight into the convolution buffer ...
   A.partial = z; // ... and k_direct_post reads the window rows back out of it
+  // narrow targets (scalar gfs ...): all gfs of a group side by side as the columns of ONE wide buffer, so that the axis kernels see rows of
+  // hundreds of bytes instead of 16-112 (L = 4999 x 1 column: 115 -> see profiles/r02_bluestein_narrow.log)
+  A.z_wide = (n_cols < 8 && per > 1) ? 1 : 0;
   for (long b0 = 0; b0 < batch; b0 += per) {
     const long nb = std::min(per, batch - b0);
     A.in = d_in + b0 * A.in_gf_stride;
@@ -823,7 +831,10 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
       k_direct_pre<FWD><<<dim3((unsigned)((bp.M * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
     }
     tq_count_launch(ctx);
-    TQ_TRY(blue_convolve(ctx, bp, &dir, z, nb, (int)n_cols));
+    if (A.z_wide)
+      TQ_TRY(blue_convolve(ctx, bp, &dir, z, 1, (int)(nb * n_cols)));
+    else
+      TQ_TRY(blue_convolve(ctx, bp, &dir, z, nb, (int)n_cols));
     {
       KernelScope ks(ctx, FWD ? "tau2iw_bluestein_post" : "iw2tau_bluestein_post");
       k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
