@@ -1239,7 +1239,7 @@ static tq_status run_transform(tq_ctx *ctx, MatsubaraPlan &pl, long n_cols, long
   // element and pass: measured 3400 / cost GB/s against 360-410 for the Bluestein convolution (six streaming passes), so beyond a plan cost
   // of ~9.5 the convolution is taken -- 9999 = 99 x 101: 230 -> 395 GB/s, 8633 = 89 x 97: 152 -> 390, 7979 = 79 x 101: 160 -> 375,
   // 5353 = 53 x 101: 184 -> 364 (profiles/r02_bluestein_vs_planned.log).
-  const bool costly_plan = n_cols >= 4 && !ctx->opt_no_bluestein && tq_pipe_plan_cost(L) > 9.5;
+  const bool costly_plan = (n_cols >= 4 || batch * n_cols >= 8) && !ctx->opt_no_bluestein && tq_pipe_plan_cost(L) > 9.5; // (narrow targets: wide buffer)
   if ((ctx->opt_force_bluestein || costly_plan) && L >= 512) {
     std::shared_ptr<BluePlan> bp;
     TQ_TRY(get_blue_plan(ctx, D, &bp));
