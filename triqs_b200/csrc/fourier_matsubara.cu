@@ -523,6 +523,61 @@ template <bool FWD> __global__ void k_direct_post(const DirectArgs A) {
   }
 }
 
+// ... and the way out of the wide layout for scalar gfs: z[row][gf] is read along the gfs, the result written along the rows of each gf
+template <bool FWD> __global__ void __launch_bounds__(256) k_direct_post_wide1(const DirectArgs A, int n_gf) {
+  __shared__ cd tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+  const long r0 = (long)blockIdx.x * 32;
+  const int g0 = blockIdx.y * 32;
+  const MatsubaraDev &D = A.D;
+  const bool fermion = D.stat == TQ_FERMION;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long rr = r0 + ty + 8 * k;
+    const int g = g0 + tx;
+    tile[ty + 8 * k][tx] = (rr < A.n_out && g < n_gf) ? A.partial[(size_t)rr * n_gf + g] : cmk(0.0, 0.0);
+  }
+  __syncthreads();
+  const long r = r0 + tx;
+  if (r >= A.n_out) return;
+  const cd pm = A.post_mul[r];
+  double h[3] = {0, 0, 0};
+  cd ph = cmk(1.0, 0.0);
+  double4 wrow = make_double4(0, 0, 0, 0);
+  if (FWD) {
+    wrow = load_w(D, (int)r);
+  } else {
+    row_model(D, (int)r, h);
+    if (fermion) ph = phase_inv(D, (int)r);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int g = g0 + ty + 8 * k;
+    if (g >= n_gf) continue;
+    const cd *mom = A.moments + (size_t)g * A.mom_gf_stride;
+    const cd m1 = mom[1];
+    cd a1, a2, a3;
+    pole_weights(fermion, m1, mom[2], mom[3], a1, a2, a3);
+    cd v = cmul(tile[tx][ty + 8 * k], pm);
+    cd *out = A.out + (size_t)g * A.out_gf_stride;
+    if (FWD) {
+      const cd *gin = A.in + (size_t)g * A.in_gf_stride;
+      cd t = cadd(gin[0], m1);
+      const cd gL = gin[(size_t)D.L];
+      t = fermion ? cadd(t, gL) : csub(t, gL);
+      out[r] = cadd(cadd(v, cscale(-0.5 * D.fact_fwd, t)), tail_iw(D, wrow, a1, a2, a3));
+    } else {
+      if (fermion) v = cmul(v, ph);
+      v = caxpy(h[2], a3, caxpy(h[1], a2, caxpy(h[0], a1, v)));
+      out[r] = v;
+      if (r == 0) {
+        const cd t = cadd(v, m1);
+        out[(size_t)D.L] = fermion ? cneg(t) : t;
+      }
+    }
+  }
+}
+
 template <bool FWD>
 static tq_status run_direct(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &btw, long n_cols, long batch, const cd *d_in, cd *d_out, const cd *d_mom,
                             int mom_rows) {
@@ -892,7 +947,10 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
       TQ_TRY(blue_convolve(ctx, bp, &dir, z, nb, (int)n_cols));
     {
       KernelScope ks(ctx, FWD ? "tau2iw_bluestein_post" : "iw2tau_bluestein_post");
-      k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
+      if (A.z_wide && n_cols == 1)
+        k_direct_post_wide1<FWD><<<dim3((unsigned)((A.n_out + 31) / 32), (unsigned)((nb + 31) / 32)), 256, 0, ctx->stream>>>(A, (int)nb);
+      else
+        k_direct_post<FWD><<<dim3((unsigned)(((long)A.n_out * n_cols + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(A);
     }
     tq_count_launch(ctx);
     TQ_CUDA(ctx, cudaGetLastError());
