@@ -927,7 +927,7 @@ static tq_status run_bluestein(tq_ctx *ctx, const MatsubaraDev &D, const BigTw &
   A.partial = z; // ... and k_direct_post reads the window rows back out of it
   // narrow targets (scalar gfs ...): all gfs of a group side by side as the columns of ONE wide buffer, so that the axis kernels see rows of
   // hundreds of bytes instead of 16-112 (L = 4999 x 1 column: 115 -> see profiles/r02_bluestein_narrow.log)
-  A.z_wide = (n_cols < 8 && per > 1) ? 1 : 0;
+  A.z_wide = (n_cols < 16 && per > 1) ? 1 : 0;
   for (long b0 = 0; b0 < batch; b0 += per) {
     const long nb = std::min(per, batch - b0);
     A.in = d_in + b0 * A.in_gf_stride;
