@@ -81,7 +81,7 @@ def test_release_library_has_no_developer_switches():
     from triqs_b200 import _lib
     blob = open(_lib.LIB_PATH, "rb").read()
     for name in [b"TQ_SCRATCH_ALIAS", b"TQ_COL_SKIP", b"TQ_KNOCK", b"TQ_PIPE_GUARD", b"TQ_PHASE_DEBUG", b"TQ_NO_PIPE", b"TQ_TWOPASS_CHUNK_MB",
-                 b"TQ_PIPE_TCW1", b"TQ_TILE_BYTES", b"TQ_PIPE_NO_I1_EDGE", b"TQ_COL_NT", b"TQ_LP_TC"]:
+                 b"TQ_PIPE_TCW1", b"TQ_TILE_BYTES", b"TQ_PIPE_NO_I1_EDGE", b"TQ_COL_NT", b"TQ_LP_TC", b"TQ_PLAN_NB_FWD", b"TQ_PLAN_NB_INV"]:
         assert name not in blob, name
 
 
