@@ -95,6 +95,12 @@ tq_status tq_stream_signal_external(tq_ctx *ctx, void *other);
  *                      piecewise and overlapped with the DMA (the driver's pageable path is serialised per process at ~7 GB/s);
  *                      0: always plain cudaMemcpyAsync */
 tq_status tq_set_option(tq_ctx *ctx, const char *name, long value);
+/* Which engine an imtime <-> imfreq transform of this shape takes, as a JSON object (host only: no context, no device needed) -- the
+ * analogue of printing an FFTW plan (c++/triqs/gfs/transform/fourier_common.cpp:30 plans per call and shows nothing):
+ *   {"L", "n_w", "plan_cost", "engine_fwd", "engine_inv", "plan_fwd", "plan_inv", "bluestein_M"}
+ * engines: "planned" (two-radix pipelined kernels, plan = "Nb=250(10x25) Na=400(20x20) ..."), "bluestein" (chirp-z convolution of length M1 x M2),
+ * "single-column", "generic" (tile kernels), "direct" (O(N^2) window sum). */
+tq_status tq_plan_describe(long n_tau, long n_iw, int statistic, long n_cols, long batch, char *buf, size_t len);
 /* number of kernel launches issued by this context since creation (bench.py reports the delta) */
 uint64_t tq_launch_count(const tq_ctx *ctx);
 /* library build id string ("tqgpu <version> sm_100a") */

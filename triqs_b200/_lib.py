@@ -38,6 +38,7 @@ SIGNATURES = {
     "tq_stream_wait_external": (c_int, [c_void_p, c_void_p]),
     "tq_stream_signal_external": (c_int, [c_void_p, c_void_p]),
     "tq_set_option": (c_int, [c_void_p, c_char_p, c_long]),
+    "tq_plan_describe": (c_int, [c_long, c_long, c_int, c_long, c_long, ctypes.c_char_p, c_size_t]),
     "tq_launch_count": (c_uint64, [c_void_p]),
     "tq_version": (c_char_p, []),
     "tq_profile_enable": (c_int, [c_void_p, c_int]),

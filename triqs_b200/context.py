@@ -86,6 +86,17 @@ def _empty_like_kind(ref, shape, dtype=np.complex128):
     return np.empty(shape, dtype=dtype)
 
 
+def plan_describe(n_tau, n_iw, statistic, n_cols=1, batch=1) -> dict:
+    """tq_plan_describe: which engine an imtime <-> imfreq transform of this shape takes (host only, works without a GPU)."""
+    import json
+    lib = L.load()
+    buf = ctypes.create_string_buffer(1024)
+    st = lib.tq_plan_describe(int(n_tau), int(n_iw), int(statistic), int(n_cols), int(batch), buf, len(buf))
+    if st != 0:
+        raise ValueError("tq_plan_describe: invalid argument")
+    return json.loads(buf.value.decode())
+
+
 class Context:
     """One per process/GPU: owns the stream, the plan caches and (optionally) the NCCL communicator."""
 

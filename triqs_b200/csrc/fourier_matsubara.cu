@@ -1991,6 +1991,40 @@ extern "C" tq_status tq_fourier_iw_to_tau(tq_ctx *ctx, double beta, int statisti
 }
 
 // -------------------------------------------------------------------------------------------------
+// tq_plan_describe: which engine an imtime <-> imfreq transform of this shape takes (host only, no device needed) -- the analogue of
+// printing an FFTW plan.  JSON: {"L":..., "engine_fwd": "...", "engine_inv": "...", "plan_fwd": "...", "plan_inv": "...", "bluestein_M": [M1, M2] | null}
+// -------------------------------------------------------------------------------------------------
+std::string tq_pipe_plan_text(long L, int dir); // fourier_pipe.cu
+extern "C" tq_status tq_plan_describe(long n_tau, long n_iw, int statistic, long n_cols, long batch, char *buf, size_t len) {
+  if (!buf || len < 2 || n_tau < 2 || n_iw < 1 || n_cols < 1 || batch < 1 || (statistic != TQ_FERMION && statistic != TQ_BOSON)) return TQ_ERR_INVALID;
+  const long L = n_tau - 1;
+  const long n_w = statistic == TQ_FERMION ? 2 * n_iw : 2 * n_iw - 1;
+  const double cost = tq_pipe_plan_cost(L);
+  int M1 = 0, M2 = 0;
+  const bool blue_ok = L >= 512 && blue_pick_lengths(L + n_w - 1, &M1, &M2);
+  const bool costly = (n_cols >= 4 || batch * n_cols >= 8) && cost > 9.5;
+  FftPlan probe;
+  const bool generic_ok = tq_fft_factorize((int)std::min<long>(L, 1L << 30), probe);
+  auto engine = [&](bool fwd) -> std::string {
+    if (costly && blue_ok) return "bluestein";
+    if (cost >= 0 && L >= 256) {
+      if (n_cols >= 4) return "planned";
+      if (fwd && L == 10000 && n_cols == 1) return "single-column";
+      if (batch * n_cols >= 8) return "planned (gfs as columns) or single-kernel";
+      return "planned or single-kernel";
+    }
+    if (generic_ok) return "generic";
+    return blue_ok ? "bluestein" : "direct";
+  };
+  std::string s = "{\"L\": " + std::to_string(L) + ", \"n_w\": " + std::to_string(n_w) + ", \"plan_cost\": " + std::to_string(cost) +
+                  ", \"engine_fwd\": \"" + engine(true) + "\", \"engine_inv\": \"" + engine(false) + "\", \"plan_fwd\": \"" + tq_pipe_plan_text(L, +1) +
+                  "\", \"plan_inv\": \"" + tq_pipe_plan_text(L, -1) + "\", \"bluestein_M\": " +
+                  (blue_ok ? "[" + std::to_string(M1) + ", " + std::to_string(M2) + "]" : std::string("null")) + "}";
+  snprintf(buf, len, "%s", s.c_str());
+  return TQ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // density(G(i w))   c++/triqs/gfs/functions/density.cpp:32-120        (the consumer of G_loc in a DMFT loop)
 //   n = -xi [ (1/beta) sum_n (G(i w_n) - sum_i a_i / (i w_n - b_i)) + m1 + sum_i F(a_i, b_i) ],  F = xi a / (-xi + e^{-beta b})
 // One streaming pass over G(i w): k_density_partial sums row chunks (the per-row factors 1/(i w - b_i) are computed once per

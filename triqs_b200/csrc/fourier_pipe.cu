@@ -406,6 +406,16 @@ double tq_pipe_plan_cost(long L) {
   return a.cost + b.cost;
 }
 
+// Host-only description of the plan of a mesh length and direction (tq_plan_describe): "Nb=250(10x25) Na=400(20x20) cost=4.00 heavy=0 generic=0"
+std::string tq_pipe_plan_text(long L, int dir) {
+  TileShape a, b;
+  if (!pipe_plan_lengths(L, &a, &b, dir)) return "none";
+  char buf[192];
+  snprintf(buf, sizeof buf, "Nb=%d(%dx%d) Na=%d(%dx%d) cost=%.2f heavy=%d%d generic=%d%d", a.N, a.RA, a.RB, b.N, b.RA, b.RB, a.cost + b.cost, (int)a.heavy,
+           (int)b.heavy, (int)a.generic, (int)b.generic);
+  return buf;
+}
+
 // Runs the transform if a pipelined specialisation exists for this mesh.  *handled tells the caller.
 tq_status tq_pipe_matsubara(tq_ctx *ctx, bool fwd, double beta, int stat, long n_tau, long n_iw, long n_cols, long batch, const cd *d_in,
                             cd *d_out, const cd *d_mom, int mom_rows, bool *handled) {
