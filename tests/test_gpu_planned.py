@@ -153,3 +153,28 @@ def test_narrow_targets_run_as_columns_of_one_wide_gf(ctx, L, n_iw, ncols, stat,
         ctx.set_option("no_tr", 0)
     for b in range(batch):
         assert rel(gt_g[b], gt[b]) < TOL and rel(gw_g[b], gw2[b]) < TOL
+
+
+@pytest.mark.parametrize("n_tau,n_iw,ncols,batch", [(100001, 10000, 25, 2), (6151, 1025, 9, 2), (10000, 1000, 25, 2), (5000, 833, 5, 3), (10001, 1025, 1, 16),
+                                                    (10000, 1000, 2, 8), (8192, 1000, 1, 16), (12001, 2000, 4, 1)])
+def test_plan_describe_names_the_engine_that_runs(ctx, n_tau, n_iw, ncols, batch):
+    """tq_plan_describe (host only) against the kernels that actually run (profile tags of the forward call)"""
+    from triqs_b200 import plan_describe
+    d = plan_describe(n_tau, n_iw, F, ncols, batch)
+    rng = np.random.default_rng(3)
+    gt = rng.normal(size=(batch, n_tau, ncols)) * 1e-3 + 0j
+    mom = np.zeros((batch, 4, ncols), complex)
+    mom[:, 1] = 1.0
+    ctx.profile_enable(True)
+    ctx.fourier_tau_to_iw(gt, 10.0, F, n_iw, moments=mom)
+    rep = ctx.profile_report()
+    ctx.profile_enable(False)
+    eng = d["engine_fwd"]
+    if eng == "bluestein":
+        assert "tau2iw_bluestein_pre" in rep, (d, sorted(rep))
+    elif eng == "planned":
+        assert "tau2iw_pass1" in rep and "tau2iw_pass2" in rep, (d, sorted(rep))
+    elif eng == "single-column":
+        assert "tau2iw_col" in rep, (d, sorted(rep))
+    else:
+        assert "tau2iw_bluestein_pre" not in rep, (d, sorted(rep))
