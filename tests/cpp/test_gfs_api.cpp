@@ -324,6 +324,10 @@ static void test_real_valued_gtau() {
 }
 
 int main() {
+  {
+    std::string d = plan_describe(mesh::imtime{10.0, Fermion, 5000}, 833, 4, 2); // L = 4999 is prime
+    EXPECT(d.find("\"engine_fwd\": \"bluestein\"") != std::string::npos);
+  }
   test_real_valued_gtau();
   test_fourier_real<scalar_valued>({});
   test_fourier_real<matrix_valued>({2, 2});

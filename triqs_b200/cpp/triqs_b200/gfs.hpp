@@ -732,6 +732,12 @@ namespace triqs_b200 {
   }
   // engine options of the context (tq_set_option: never change results), e.g. set_option("host_lanes", 4)
   inline void set_option(const char *name, long value) { check(tq_set_option(context(), name, value)); }
+  // which engine / plan an imtime <-> imfreq transform of this shape takes, as JSON (host only: needs no device) -- tq_plan_describe
+  inline std::string plan_describe(mesh::imtime const &mt, long n_iw, long n_others = 1, long batch = 1) {
+    char buf[1024];
+    if (tq_plan_describe(mt.size(), n_iw, mt.statistic(), n_others, batch, buf, sizeof buf) != TQ_OK) throw runtime_error("plan_describe: invalid argument");
+    return buf;
+  }
 
   template <typename Mesh, typename Target> std::vector<dcomplex> gf<Mesh, Target>::operator()(double x) const {
     static_assert(std::is_same<Mesh, mesh::imtime>::value, "g(x) is implemented for imtime gfs");
