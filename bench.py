@@ -461,7 +461,10 @@ def run_native(args):
     p_gt2 = np.empty_like(h_gt2)
     e2e["single_thread_pageable"] = pts_step * st1 / wall(one_thread(p_gt, p_gw, p_gt2), st1)
     e2e["single_thread_pageable_err"] = float(np.max(np.abs(p_gt2[:NBLOCK] - p_gt[:NBLOCK])))
-    del p_gt, p_gw, p_gt2
+    # the literal drop-in call: ONE BlockGf (2 blocks) in plain NumPy arrays, forward and back
+    q_gt, q_gw, q_gt2 = p_gt[:NBLOCK].copy(), p_gw[:NBLOCK].copy(), p_gt2[:NBLOCK].copy()
+    e2e["single_blockgf_pageable_round_trip_ms"] = 1e3 * wall(one_thread(q_gt, q_gw, q_gt2), 10) / 10
+    del p_gt, p_gw, p_gt2, q_gt, q_gw, q_gt2
     # real-valued G(tau) (gf<imtime, matrix_real_valued>; fourier.hpp:78-81 promotes it): tq_fourier_tau_to_iw_real /
     # tq_fourier_iw_to_tau_real move 8 bytes per point of the large side over PCIe instead of 16
     r_gt = torch.empty((NBLOCK * R, N_TAU, NCOL), dtype=torch.float64).pin_memory()
